@@ -1,0 +1,475 @@
+// Stage 4: DBSCAN on the sparse k-NN matrix + precursor-tolerance split.
+//
+// DBSCAN (A.4): neighbourhood(i) = CSR row entries with dist <= eps, core(i) =
+// |neighbourhood| >= min_samples.  sklearn's dbscan_inner
+// (sklearn/cluster/_dbscan_inner.pyx:11-41) visits points in index order and
+// grows clusters along edges that LEAVE core points, so on this asymmetric
+// k-NN graph a point's cluster is the rank of the minimum-index core point it
+// is reachable from -- not an undirected component.  The
+// kernels compute that fix-point: m[core u] = u, every core u pushes
+// atomicMin(m[w], m[u]) along its out-edges, chains are shortcut by pointer
+// jumping (m[u] is itself a core point that reaches u, so m[m[u]] reaches u),
+// repeat until nothing changes; labels = rank of m[v] among the seeds
+// (m[s] == s) by prefix sum.
+//
+// Precursor split (falcon/cluster/cluster.py:334-509): inside each DBSCAN
+// cluster the members, ascending in precursor m/z, are agglomerated with 1-D
+// complete linkage and the dendrogram is cut at the tolerance.  The reference
+// merges the globally closest adjacent pair first; because complete linkage is
+// reducible, merging every adjacent pair that is a local minimum of the
+// merge distance (strict on the left, non-strict on the right = "first minimum
+// wins") in parallel rounds yields the same flat clusters.  One warp per
+// cluster keeps the list of run starts in global scratch and compacts it each
+// round with ballots.
+//
+// HBM/latency-bound: nnz * 8 bytes for the eps mask pass, then
+// sweeps * (nnz_eps * 4 + N * 8), one 32-bit key sort of N rows.
+#include <cub/cub.cuh>
+
+#include "common.cuh"
+
+namespace flc {
+
+constexpr int32_t kInf = 0x7fffffff;
+constexpr uint32_t kNoiseKey = 0xffffffffu;
+
+// ---------------------------------------------------------------- DBSCAN
+__global__ void dbscan_core_kernel(const float* __restrict__ dist, const int64_t* __restrict__ indptr,
+                                   int64_t n, float eps, int32_t min_samples, int32_t* __restrict__ m,
+                                   uint8_t* __restrict__ core) {
+  const int lane = threadIdx.x & 31;
+  const int64_t i = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  if (i >= n) return;
+  const int64_t a = indptr[i], b = indptr[i + 1];
+  int cnt = 0;
+  for (int64_t p = a + lane; p < b; p += 32) cnt += (dist[p] <= eps) ? 1 : 0;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  if (lane == 0) {
+    const bool c = cnt >= min_samples;
+    core[i] = c ? 1 : 0;
+    m[i] = c ? static_cast<int32_t>(i) : kInf;
+  }
+}
+
+__global__ void dbscan_propagate_kernel(const float* __restrict__ dist, const int32_t* __restrict__ indices,
+                                        const int64_t* __restrict__ indptr, int64_t n, float eps,
+                                        const uint8_t* __restrict__ core, int32_t* m,
+                                        int32_t* __restrict__ changed) {
+  const int lane = threadIdx.x & 31;
+  const int64_t u = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  if (u >= n || !core[u]) return;
+  // Shortcut: follow the chain of minimum ancestors to its current end.
+  int32_t mu = m[u];
+  if (lane == 0) {
+    int32_t r = mu;
+    while (true) {
+      const int32_t next = *reinterpret_cast<volatile int32_t*>(m + r);
+      if (next >= r) break;
+      r = next;
+    }
+    if (r < mu) {
+      atomicMin(m + u, r);
+      *changed = 1;
+      mu = r;
+    }
+  }
+  mu = __shfl_sync(0xffffffffu, mu, 0);
+  const int64_t a = indptr[u], b = indptr[u + 1];
+  bool any = false;
+  for (int64_t p = a + lane; p < b; p += 32) {
+    if (dist[p] <= eps) {
+      const int32_t w = indices[p];
+      if (*reinterpret_cast<volatile int32_t*>(m + w) > mu) {
+        const int32_t old = atomicMin(m + w, mu);
+        any |= old > mu;
+      }
+    }
+  }
+  if (any) *changed = 1;
+}
+
+__global__ void dbscan_seed_kernel(const int32_t* __restrict__ m, const uint8_t* __restrict__ core, int64_t n,
+                                   int32_t* __restrict__ seed) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i <= n) seed[i] = (i < n && core[i] && m[i] == static_cast<int32_t>(i)) ? 1 : 0;
+}
+
+__global__ void dbscan_label_kernel(const int32_t* __restrict__ m, const int32_t* __restrict__ rank, int64_t n,
+                                    int32_t* __restrict__ labels) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) {
+    const int32_t r = m[i];
+    labels[i] = r == kInf ? -1 : rank[r];
+  }
+}
+
+struct DbscanLayout {
+  int32_t* m;
+  uint8_t* core;
+  int32_t* seed;
+  int32_t* rank;
+  int32_t* changed;
+  void* cub_tmp;
+  size_t cub_bytes;
+};
+
+static void dbscan_layout(Workspace& ws, int64_t n, DbscanLayout& L) {
+  L.m = ws.take<int32_t>(n + 1);
+  L.core = ws.take<uint8_t>(n + 1);
+  L.seed = ws.take<int32_t>(n + 1);
+  L.rank = ws.take<int32_t>(n + 1);
+  L.changed = ws.take<int32_t>(1);
+  size_t b = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, b, (int32_t*)nullptr, (int32_t*)nullptr, static_cast<int>(n + 1));
+  L.cub_bytes = b;
+  L.cub_tmp = ws.take<char>(b);
+}
+
+// ---------------------------------------------------------------- precursor split
+__global__ void split_key_kernel(const int32_t* __restrict__ labels, int64_t n, uint32_t* __restrict__ key,
+                                 int32_t* __restrict__ idx) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) {
+    const int32_t l = labels[i];
+    key[i] = l < 0 ? kNoiseKey : static_cast<uint32_t>(l);
+    idx[i] = static_cast<int32_t>(i);
+  }
+}
+
+__global__ void split_mzkey_kernel(const double* __restrict__ mz, int64_t n, uint64_t* __restrict__ key,
+                                   int32_t* __restrict__ idx) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) {
+    uint64_t b = static_cast<uint64_t>(__double_as_longlong(mz[i]));
+    key[i] = (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+    idx[i] = static_cast<int32_t>(i);
+  }
+}
+
+// After sorting by label: gather the values, flag group heads (label change).
+__global__ void split_prepare_kernel(const uint32_t* __restrict__ key_sorted, const int32_t* __restrict__ perm,
+                                     const double* __restrict__ mz, int64_t n, double* __restrict__ vs,
+                                     uint8_t* __restrict__ ghead, uint8_t* __restrict__ runhead) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  vs[i] = mz[perm[i]];
+  const uint32_t k = key_sorted[i];
+  const bool head = (i == 0) || (k != key_sorted[i - 1]);
+  ghead[i] = head ? 1 : 0;
+  // Noise rows are runs of their own; cluster members start out as heads only at
+  // the group start, the split kernel adds the interior run starts.
+  runhead[i] = (head || k == kNoiseKey) ? 1 : 0;
+}
+
+__device__ __forceinline__ double split_distance(double lo, double hi, int tol_mode) {
+  const double d = hi - lo;
+  return tol_mode == FLC_TOL_PPM ? d / lo * 1000000.0 : d;
+}
+
+// One warp per DBSCAN cluster.  list_a / list_b: per-element scratch holding
+// the current run starts (offsets inside the group), ping-pong.
+__global__ void split_group_kernel(const int64_t* __restrict__ gstart, const int64_t* __restrict__ n_groups_ptr,
+                                   const uint32_t* __restrict__ key_sorted, const double* __restrict__ vs,
+                                   int64_t n, double tol, int tol_mode, int32_t* list_a, int32_t* list_b,
+                                   uint8_t* __restrict__ runhead) {
+  const int lane = threadIdx.x & 31;
+  const int64_t g = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  if (g >= *n_groups_ptr) return;
+  const int64_t s = gstart[g];
+  const int64_t e = (g + 1 < *n_groups_ptr) ? gstart[g + 1] : n;
+  if (key_sorted[s] == kNoiseKey) return;
+  const int32_t m = static_cast<int32_t>(e - s);
+  if (m < 2) return;
+  const double* v = vs + s;
+  int32_t* cur = list_a + s;
+  int32_t* nxt = list_b + s;
+  for (int32_t j = lane; j < m; j += 32) cur[j] = j;
+  __syncwarp();
+  int32_t r = m;
+  // boundary j (1 <= j < r) separates run j-1 = [cur[j-1], cur[j]) from run j.
+  auto run_start = [&](int32_t j) -> int32_t { return __ldcg(cur + j); };
+  auto run_end = [&](int32_t j) -> int32_t { return j + 1 < r ? __ldcg(cur + j + 1) : m; };
+  while (r > 1) {
+    int32_t r_new = 0;
+    bool merged_any = false;
+    for (int32_t base = 0; base < r; base += 32) {
+      const int32_t j = base + lane;
+      const bool valid = j < r;
+      bool merge = false;
+      if (valid && j >= 1) {
+        const double d = split_distance(v[run_start(j - 1)], v[run_end(j) - 1], tol_mode);
+        if (d <= tol) {
+          merge = true;
+          if (j >= 2) {
+            const double dl = split_distance(v[run_start(j - 2)], v[run_end(j - 1) - 1], tol_mode);
+            if (!(d < dl)) merge = false;
+          }
+          if (merge && j + 1 < r) {
+            const double dr = split_distance(v[run_start(j)], v[run_end(j + 1) - 1], tol_mode);
+            if (!(d <= dr)) merge = false;
+          }
+        }
+      }
+      const bool keep = valid && !merge;
+      const uint32_t ballot = __ballot_sync(0xffffffffu, keep);
+      if (keep) __stcg(nxt + r_new + __popc(ballot & ((1u << lane) - 1u)), run_start(j));
+      r_new += __popc(ballot);
+      merged_any |= __any_sync(0xffffffffu, merge);
+    }
+    __syncwarp();
+    if (!merged_any) break;
+    int32_t* t = cur; cur = nxt; nxt = t;
+    r = r_new;
+  }
+  for (int32_t j = lane; j < r; j += 32) runhead[s + __ldcg(cur + j)] = 1;
+}
+
+// run id of every element = inclusive scan of runhead - 1; run start positions
+// compacted into rstart; a run is kept when it has >= min_samples members and is
+// not noise.
+__global__ void split_keep_kernel(const int64_t* __restrict__ rstart, const int64_t* __restrict__ n_runs_ptr,
+                                  const uint32_t* __restrict__ key_sorted, int64_t n, int32_t min_samples,
+                                  int32_t* __restrict__ kept) {
+  const int64_t r = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t n_runs = *n_runs_ptr;
+  if (r > n) return;
+  if (r >= n_runs) {
+    kept[r] = 0;
+    return;
+  }
+  const int64_t a = rstart[r];
+  const int64_t b = (r + 1 < n_runs) ? rstart[r + 1] : n;
+  kept[r] = (key_sorted[a] != kNoiseKey && (b - a) >= min_samples) ? 1 : 0;
+}
+
+__global__ void split_label_kernel(const int32_t* __restrict__ run_id_incl, const int32_t* __restrict__ kept,
+                                   const int32_t* __restrict__ new_id, const int32_t* __restrict__ perm,
+                                   int64_t n, int32_t* __restrict__ labels_out) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int32_t r = run_id_incl[i] - 1;
+  labels_out[perm[i]] = kept[r] ? new_id[r] : -1;
+}
+
+__global__ void u8_to_i32_kernel(const uint8_t* __restrict__ in, int64_t n, int32_t* __restrict__ out) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = in[i];
+}
+
+struct SplitLayout {
+  uint32_t* key_a;
+  uint32_t* key_b;
+  int32_t* idx_a;
+  int32_t* idx_b;
+  uint64_t* mzkey_a;
+  uint64_t* mzkey_b;
+  double* vs;
+  uint8_t* ghead;
+  uint8_t* runhead;
+  int64_t* gstart;
+  int64_t* rstart;
+  int64_t* n_groups;
+  int64_t* n_runs;
+  int32_t* list_a;
+  int32_t* list_b;
+  int32_t* run_i32;
+  int32_t* run_id;
+  int32_t* kept;
+  int32_t* new_id;
+  void* cub_tmp;
+  size_t cub_bytes;
+};
+
+static void split_layout(Workspace& ws, int64_t n, SplitLayout& L) {
+  L.key_a = ws.take<uint32_t>(n);
+  L.key_b = ws.take<uint32_t>(n);
+  L.idx_a = ws.take<int32_t>(n);
+  L.idx_b = ws.take<int32_t>(n);
+  L.mzkey_a = ws.take<uint64_t>(n);
+  L.mzkey_b = ws.take<uint64_t>(n);
+  L.vs = ws.take<double>(n);
+  L.ghead = ws.take<uint8_t>(n);
+  L.runhead = ws.take<uint8_t>(n);
+  L.gstart = ws.take<int64_t>(n + 1);
+  L.rstart = ws.take<int64_t>(n + 1);
+  L.n_groups = ws.take<int64_t>(1);
+  L.n_runs = ws.take<int64_t>(1);
+  L.list_a = ws.take<int32_t>(n);
+  L.list_b = ws.take<int32_t>(n);
+  L.run_i32 = ws.take<int32_t>(n);
+  L.run_id = ws.take<int32_t>(n);
+  L.kept = ws.take<int32_t>(n + 1);
+  L.new_id = ws.take<int32_t>(n + 1);
+  const int num = static_cast<int>(n);
+  size_t b1 = 0, b2 = 0, b3 = 0, b4 = 0, b5 = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, b1, (uint32_t*)nullptr, (uint32_t*)nullptr, (int32_t*)nullptr,
+                                  (int32_t*)nullptr, num);
+  cub::DeviceRadixSort::SortPairs(nullptr, b2, (uint64_t*)nullptr, (uint64_t*)nullptr, (int32_t*)nullptr,
+                                  (int32_t*)nullptr, num);
+  cub::DeviceSelect::Flagged(nullptr, b3, cub::CountingInputIterator<int64_t>(0), (uint8_t*)nullptr,
+                             (int64_t*)nullptr, (int64_t*)nullptr, num);
+  cub::DeviceScan::InclusiveSum(nullptr, b4, (int32_t*)nullptr, (int32_t*)nullptr, num);
+  cub::DeviceScan::ExclusiveSum(nullptr, b5, (int32_t*)nullptr, (int32_t*)nullptr, num + 1);
+  size_t b = b1;
+  if (b2 > b) b = b2;
+  if (b3 > b) b = b3;
+  if (b4 > b) b = b4;
+  if (b5 > b) b = b5;
+  L.cub_bytes = b;
+  L.cub_tmp = ws.take<char>(b);
+}
+
+}  // namespace flc
+
+extern "C" {
+
+size_t flc_dbscan_workspace_bytes(int64_t n) {
+  if (n <= 0) return 256;
+  flc::Workspace ws(nullptr, 0);
+  flc::DbscanLayout L;
+  flc::dbscan_layout(ws, n, L);
+  return ws.used + 256;
+}
+
+int flc_dbscan(const float* dist, const int32_t* indices, const int64_t* indptr, int64_t n, float eps,
+               int32_t min_samples, int32_t* labels, int64_t* n_clusters, void* workspace,
+               size_t workspace_bytes, flc_stream_t stream_) {
+  using namespace flc;
+  FLC_REQUIRE(n >= 0 && n < (int64_t(1) << 31) - 1, "n out of range");
+  FLC_REQUIRE(min_samples >= 1, "min_samples must be >= 1");
+  FLC_REQUIRE(n_clusters != nullptr, "null n_clusters");
+  cudaStream_t stream = as_stream(stream_);
+  if (n == 0) {
+    *n_clusters = 0;
+    return FLC_OK;
+  }
+  Workspace ws(workspace, workspace_bytes);
+  DbscanLayout L;
+  dbscan_layout(ws, n, L);
+  if (!ws.ok) return set_error(FLC_ERR_WORKSPACE, "dbscan workspace too small: need %zu", ws.used);
+  const unsigned wblocks = static_cast<unsigned>((n * 32 + 255) / 256);
+  const unsigned tblocks = static_cast<unsigned>((n + 1 + 255) / 256);
+  dbscan_core_kernel<<<wblocks, 256, 0, stream>>>(dist, indptr, n, eps, min_samples, L.m, L.core);
+  FLC_LAUNCH_CHECK();
+  int32_t changed = 1;
+  int sweeps = 0;
+  while (changed) {
+    FLC_CUDA(cudaMemsetAsync(L.changed, 0, sizeof(int32_t), stream));
+    for (int rep = 0; rep < 2; ++rep) {
+      dbscan_propagate_kernel<<<wblocks, 256, 0, stream>>>(dist, indices, indptr, n, eps, L.core, L.m,
+                                                           L.changed);
+      FLC_LAUNCH_CHECK();
+    }
+    FLC_CUDA(cudaMemcpyAsync(&changed, L.changed, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+    FLC_CUDA(cudaStreamSynchronize(stream));
+    if (++sweeps > 100000) return set_error(FLC_ERR_CUDA, "dbscan propagation did not converge");
+  }
+  dbscan_seed_kernel<<<tblocks, 256, 0, stream>>>(L.m, L.core, n, L.seed);
+  FLC_LAUNCH_CHECK();
+  size_t tmp = L.cub_bytes;
+  FLC_CUDA(cub::DeviceScan::ExclusiveSum(L.cub_tmp, tmp, L.seed, L.rank, static_cast<int>(n + 1), stream));
+  count_launch(2);
+  dbscan_label_kernel<<<tblocks, 256, 0, stream>>>(L.m, L.rank, n, labels);
+  FLC_LAUNCH_CHECK();
+  int32_t total = 0;
+  FLC_CUDA(cudaMemcpyAsync(&total, L.rank + n, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+  FLC_CUDA(cudaStreamSynchronize(stream));
+  *n_clusters = total;
+  return FLC_OK;
+}
+
+size_t flc_split_workspace_bytes(int64_t n) {
+  if (n <= 0) return 256;
+  flc::Workspace ws(nullptr, 0);
+  flc::SplitLayout L;
+  flc::split_layout(ws, n, L);
+  return ws.used + 256;
+}
+
+int flc_split_clusters(const int32_t* labels_in, const double* precursor_mz, int64_t n, double tol,
+                       int tol_mode, double rt_tol, int32_t min_samples, int values_sorted,
+                       int32_t* labels_out, int64_t* n_clusters, void* workspace, size_t workspace_bytes,
+                       flc_stream_t stream_) {
+  using namespace flc;
+  FLC_REQUIRE(n >= 0 && n < (int64_t(1) << 31) - 1, "n out of range");
+  FLC_REQUIRE(tol_mode == FLC_TOL_DA || tol_mode == FLC_TOL_PPM, "Unknown precursor tolerance mode");
+  FLC_REQUIRE(n_clusters != nullptr, "null n_clusters");
+  if (rt_tol >= 0.0)
+    return set_error(FLC_ERR_UNSUPPORTED,
+                     "retention-time split (rt_tol) is not implemented on the device yet");
+  cudaStream_t stream = as_stream(stream_);
+  if (n == 0) {
+    *n_clusters = 0;
+    return FLC_OK;
+  }
+  Workspace ws(workspace, workspace_bytes);
+  SplitLayout L;
+  split_layout(ws, n, L);
+  if (!ws.ok) return set_error(FLC_ERR_WORKSPACE, "split workspace too small: need %zu", ws.used);
+  const int num = static_cast<int>(n);
+  const unsigned tblocks = static_cast<unsigned>((n + 255) / 256);
+  size_t tmp;
+  const int32_t* idx_in;
+  if (!values_sorted) {
+    // rows by precursor m/z first, then (stable) by label
+    split_mzkey_kernel<<<tblocks, 256, 0, stream>>>(precursor_mz, n, L.mzkey_a, L.idx_a);
+    FLC_LAUNCH_CHECK();
+    tmp = L.cub_bytes;
+    FLC_CUDA(cub::DeviceRadixSort::SortPairs(L.cub_tmp, tmp, L.mzkey_a, L.mzkey_b, L.idx_a, L.idx_b, num, 0,
+                                             64, stream));
+    count_launch(9);
+    // key of the m/z-sorted rows
+    split_key_kernel<<<tblocks, 256, 0, stream>>>(labels_in, n, L.key_b, L.idx_a);
+    FLC_LAUNCH_CHECK();
+    FLC_TRY(flc_gather(L.key_b, L.idx_b, n, 4, L.key_a, stream_));
+    idx_in = L.idx_b;
+  } else {
+    split_key_kernel<<<tblocks, 256, 0, stream>>>(labels_in, n, L.key_a, L.idx_a);
+    FLC_LAUNCH_CHECK();
+    idx_in = L.idx_a;
+  }
+  // stable sort by label; perm -> L.idx_out
+  int32_t* perm = (idx_in == L.idx_a) ? L.idx_b : L.idx_a;
+  tmp = L.cub_bytes;
+  FLC_CUDA(cub::DeviceRadixSort::SortPairs(L.cub_tmp, tmp, L.key_a, L.key_b, idx_in, perm, num, 0, 32, stream));
+  count_launch(5);
+  const uint32_t* key_sorted = L.key_b;
+  split_prepare_kernel<<<tblocks, 256, 0, stream>>>(key_sorted, perm, precursor_mz, n, L.vs, L.ghead,
+                                                    L.runhead);
+  FLC_LAUNCH_CHECK();
+  tmp = L.cub_bytes;
+  FLC_CUDA(cub::DeviceSelect::Flagged(L.cub_tmp, tmp, cub::CountingInputIterator<int64_t>(0), L.ghead,
+                                      L.gstart, L.n_groups, num, stream));
+  count_launch(2);
+  // Upper bound on the number of groups is n: launch one warp per possible group.
+  const unsigned gblocks = static_cast<unsigned>((n * 32 + 255) / 256);
+  split_group_kernel<<<gblocks, 256, 0, stream>>>(L.gstart, L.n_groups, key_sorted, L.vs, n, tol, tol_mode,
+                                                  L.list_a, L.list_b, L.runhead);
+  FLC_LAUNCH_CHECK();
+  tmp = L.cub_bytes;
+  FLC_CUDA(cub::DeviceSelect::Flagged(L.cub_tmp, tmp, cub::CountingInputIterator<int64_t>(0), L.runhead,
+                                      L.rstart, L.n_runs, num, stream));
+  count_launch(2);
+  u8_to_i32_kernel<<<tblocks, 256, 0, stream>>>(L.runhead, n, L.run_i32);
+  FLC_LAUNCH_CHECK();
+  tmp = L.cub_bytes;
+  FLC_CUDA(cub::DeviceScan::InclusiveSum(L.cub_tmp, tmp, L.run_i32, L.run_id, num, stream));
+  count_launch(2);
+  split_keep_kernel<<<static_cast<unsigned>((n + 1 + 255) / 256), 256, 0, stream>>>(L.rstart, L.n_runs,
+                                                                                   key_sorted, n, min_samples,
+                                                                                   L.kept);
+  FLC_LAUNCH_CHECK();
+  tmp = L.cub_bytes;
+  FLC_CUDA(cub::DeviceScan::ExclusiveSum(L.cub_tmp, tmp, L.kept, L.new_id, num + 1, stream));
+  count_launch(2);
+  split_label_kernel<<<tblocks, 256, 0, stream>>>(L.run_id, L.kept, L.new_id, perm, n, labels_out);
+  FLC_LAUNCH_CHECK();
+  int32_t total = 0;
+  FLC_CUDA(cudaMemcpyAsync(&total, L.new_id + n, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+  FLC_CUDA(cudaStreamSynchronize(stream));
+  *n_clusters = total;
+  return FLC_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,370 @@
+// Stage 3b: candidate pairs -> exact re-score -> top-k -> precursor filter -> CSR.
+//
+// The tensor-core scan (scan_tc.cu) produces (query, candidate) pairs whose
+// bf16 inner product clears `1 - eps - margin`.  This file groups them by
+// query (histogram + scan + scatter), and with one warp per query
+//   * checks inverted-list membership (candidate's list is one the query probes),
+//   * recomputes the inner product exactly: float32 inputs, float64 accumulate,
+//     rounded once to float32 (order independent, so it matches the oracle bit
+//     for bit; faiss' float32 SIMD sum differs by ~1e-7 < the 1e-5 bar),
+//   * applies the eps cut (dist = max(1 - ip, 0) <= eps),
+//   * orders candidates by (ip descending, id ascending) with a warp bitonic
+//     sort and keeps n_neighbors_ann (faiss index.search semantics, A.2),
+//   * applies the precursor m/z / RT tolerance filter in that order and keeps
+//     n_neighbors (A.2 _filter_neighbors_mz),
+// then builds the CSR arrays with a prefix sum over the row counts.
+//
+// HBM-bound: algorithmic bytes = pairs * 8 (read) + pairs * 4 * low_dim worst
+// case for the re-score rows (L2-resident in practice: a bucket's rows were just
+// read by the scan) + N * 16 (m/z, RT) + nnz * 8 + (N + 1) * 8.
+#include <cub/cub.cuh>
+
+#include "common.cuh"
+
+namespace flc {
+
+constexpr int kRefineWarps = 4;
+constexpr uint64_t kKeyMax = ~uint64_t(0);
+
+__global__ void pair_hist_kernel(const uint64_t* __restrict__ pairs, const uint64_t* __restrict__ pair_count,
+                                 uint64_t capacity, int64_t n, uint32_t* __restrict__ cnt) {
+  const uint64_t total = min(*pair_count, capacity);
+  for (uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
+    const uint32_t q = static_cast<uint32_t>(pairs[i] >> 32);
+    if (q < n) atomicAdd(cnt + q, 1u);
+  }
+}
+
+__global__ void pair_scatter_kernel(const uint64_t* __restrict__ pairs, const uint64_t* __restrict__ pair_count,
+                                    uint64_t capacity, int64_t n, const int64_t* __restrict__ off,
+                                    uint32_t* __restrict__ cursor, uint64_t* __restrict__ grouped) {
+  const uint64_t total = min(*pair_count, capacity);
+  for (uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
+    const uint64_t p = pairs[i];
+    const uint32_t q = static_cast<uint32_t>(p >> 32);
+    if (q < n) {
+      const uint32_t slot = atomicAdd(cursor + q, 1u);
+      grouped[off[q] + slot] = p & 0xffffffffull;
+    }
+  }
+}
+
+// Order-preserving float -> uint (ascending), then inverted so that a larger
+// inner product gives a smaller key.
+__device__ __forceinline__ uint32_t ip_key_desc(float ip) {
+  uint32_t u = __float_as_uint(ip);
+  u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+  return ~u;
+}
+__device__ __forceinline__ float ip_from_key(uint32_t k) {
+  uint32_t u = ~k;
+  u = (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u;
+  return __uint_as_float(u);
+}
+
+__device__ __forceinline__ uint64_t shfl_xor_u64(uint64_t v, int m) {
+  uint32_t lo = __shfl_xor_sync(0xffffffffu, static_cast<uint32_t>(v), m);
+  uint32_t hi = __shfl_xor_sync(0xffffffffu, static_cast<uint32_t>(v >> 32), m);
+  return (static_cast<uint64_t>(hi) << 32) | lo;
+}
+
+// Ascending bitonic sort of one key per lane.
+__device__ __forceinline__ uint64_t warp_sort32(uint64_t key, int lane) {
+#pragma unroll
+  for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      const uint64_t other = shfl_xor_u64(key, j);
+      const bool up = ((lane & k) == 0);
+      const bool lower = ((lane & j) == 0);
+      const bool take_min = (up == lower);
+      key = take_min ? (key < other ? key : other) : (key > other ? key : other);
+    }
+  }
+  return key;
+}
+
+// Ascending bitonic sort of `len` (power of two >= 64) keys in shared memory by one warp.
+__device__ __forceinline__ void warp_sort_smem(uint64_t* buf, int len, int lane) {
+  for (int k = 2; k <= len; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int t = lane; t < (len >> 1); t += 32) {
+        const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+        const int p = i | j;
+        const bool up = ((i & k) == 0);
+        const uint64_t a = buf[i], b = buf[p];
+        if ((a > b) == up) {
+          buf[i] = b;
+          buf[p] = a;
+        }
+      }
+      __syncwarp();
+    }
+  }
+}
+
+struct RefineParams {
+  const float* x;
+  int64_t ld;
+  int64_t n;
+  uint32_t low_dim;
+  const double* mz;
+  const float* rt;
+  const int32_t* list_id;
+  const int32_t* probes;
+  int32_t max_nprobe;
+  double tol;
+  int tol_mode;
+  double rt_tol;
+  int32_t k;
+  int32_t k_ann;
+  int32_t ka_pow2;  // power of two >= max(k_ann, 32)
+  float eps;
+  int use_eps;
+};
+
+__device__ __forceinline__ bool tolerance_ok(const RefineParams& P, double mq, float rq, uint32_t c) {
+  const double mc = P.mz[c];
+  const double dm = fabs(mq - mc);
+  bool ok = P.tol_mode == FLC_TOL_DA ? (dm < P.tol) : (dm / mc * 1000000.0 < P.tol);
+  if (ok && P.rt != nullptr && P.rt_tol >= 0.0)
+    ok = fabs(static_cast<double>(rq) - static_cast<double>(P.rt[c])) < P.rt_tol;
+  return ok;
+}
+
+__global__ void __launch_bounds__(kRefineWarps * 32)
+refine_kernel(RefineParams P, const int64_t* __restrict__ off, uint64_t* __restrict__ grouped,
+              int32_t* __restrict__ row_count) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const size_t per_warp = static_cast<size_t>(2) * P.ka_pow2 * sizeof(uint64_t) +
+                          ((static_cast<size_t>(P.low_dim) * sizeof(float) + 15) & ~size_t(15));
+  uint64_t* buf = reinterpret_cast<uint64_t*>(smem_raw + warp * per_warp);
+  float* xq = reinterpret_cast<float*>(buf + 2 * P.ka_pow2);
+
+  const int64_t q = static_cast<int64_t>(blockIdx.x) * kRefineWarps + warp;
+  if (q >= P.n) return;
+  const int64_t base = off[q];
+  const int64_t m = off[q + 1] - base;
+  if (m == 0) {
+    if (lane == 0) row_count[q] = 0;
+    return;
+  }
+  const float* xrow = P.x + q * P.ld;
+  for (uint32_t i = lane; i < P.low_dim; i += 32) xq[i] = xrow[i];
+  __syncwarp();
+  const double mq = P.mz[q];
+  const float rq = P.rt ? P.rt[q] : 0.f;
+
+  // Phase A: exact score of every candidate -> sort key (in place).
+  for (int64_t j = 0; j < m; ++j) {
+    const uint32_t c = static_cast<uint32_t>(grouped[base + j]);
+    bool member = true;
+    if (P.list_id != nullptr) {
+      const int32_t lc = P.list_id[c];
+      bool hit = false;
+      for (int32_t t = lane; t < P.max_nprobe; t += 32) hit |= (P.probes[q * P.max_nprobe + t] == lc);
+      member = __any_sync(0xffffffffu, hit);
+    }
+    uint64_t key = kKeyMax;
+    if (member) {
+      const float* xc = P.x + static_cast<int64_t>(c) * P.ld;
+      double acc = 0.0;
+      for (uint32_t i = lane; i < P.low_dim; i += 32)
+        acc = fma(static_cast<double>(xq[i]), static_cast<double>(__ldg(xc + i)), acc);
+      acc = warp_sum_f64(acc);
+      const float ip = static_cast<float>(acc);
+      const float dist = fmaxf(1.0f - ip, 0.0f);
+      if (!P.use_eps || dist <= P.eps) key = (static_cast<uint64_t>(ip_key_desc(ip)) << 32) | c;
+    }
+    if (lane == 0) grouped[base + j] = key;
+  }
+  __syncwarp();
+
+  int32_t kept = 0;
+  if (m <= 32) {
+    uint64_t key = lane < m ? grouped[base + lane] : kKeyMax;
+    key = warp_sort32(key, lane);
+    const bool valid = key != kKeyMax && lane < P.k_ann;
+    const uint32_t c = static_cast<uint32_t>(key);
+    const bool pass = valid && tolerance_ok(P, mq, rq, c);
+    const uint32_t ballot = __ballot_sync(0xffffffffu, pass);
+    const int rank = __popc(ballot & ((1u << lane) - 1u));
+    if (pass && rank < P.k) {
+      const float ip = ip_from_key(static_cast<uint32_t>(key >> 32));
+      const float dist = fmaxf(1.0f - ip, 0.0f);
+      grouped[base + rank] = (static_cast<uint64_t>(__float_as_uint(dist)) << 32) | c;
+    }
+    kept = min(__popc(ballot), P.k);
+  } else {
+    const int KA = P.ka_pow2;
+    for (int t = lane; t < KA; t += 32) buf[t] = kKeyMax;
+    for (int64_t blk = 0; blk < m; blk += KA) {
+      for (int t = lane; t < KA; t += 32) buf[KA + t] = (blk + t < m) ? grouped[base + blk + t] : kKeyMax;
+      __syncwarp();
+      warp_sort_smem(buf, 2 * KA, lane);
+    }
+    // Phase C: tolerance filter in similarity order.
+    for (int s = 0; s < P.k_ann && kept < P.k; s += 32) {
+      const int t = s + lane;
+      const uint64_t key = (t < P.k_ann && t < KA) ? buf[t] : kKeyMax;
+      const bool valid = key != kKeyMax;
+      const uint32_t c = static_cast<uint32_t>(key);
+      const bool pass = valid && tolerance_ok(P, mq, rq, c);
+      const uint32_t ballot = __ballot_sync(0xffffffffu, pass);
+      const int rank = kept + __popc(ballot & ((1u << lane) - 1u));
+      if (pass && rank < P.k) {
+        const float ip = ip_from_key(static_cast<uint32_t>(key >> 32));
+        const float dist = fmaxf(1.0f - ip, 0.0f);
+        grouped[base + rank] = (static_cast<uint64_t>(__float_as_uint(dist)) << 32) | c;
+      }
+      kept = min(kept + __popc(ballot), P.k);
+      if (__ballot_sync(0xffffffffu, valid) != 0xffffffffu) break;
+    }
+  }
+  if (lane == 0) row_count[q] = kept;
+}
+
+__global__ void csr_compact_kernel(const uint64_t* __restrict__ grouped, const int64_t* __restrict__ off,
+                                   const int64_t* __restrict__ indptr, int64_t n, uint64_t nnz_capacity,
+                                   float* __restrict__ dist, int32_t* __restrict__ indices) {
+  const int lane = threadIdx.x & 31;
+  const int64_t q = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  if (q >= n) return;
+  const int64_t src = off[q];
+  const int64_t dst = indptr[q];
+  const int64_t cnt = indptr[q + 1] - dst;
+  for (int64_t t = lane; t < cnt; t += 32) {
+    if (static_cast<uint64_t>(dst + t) < nnz_capacity) {
+      const uint64_t e = grouped[src + t];
+      dist[dst + t] = __uint_as_float(static_cast<uint32_t>(e >> 32));
+      indices[dst + t] = static_cast<int32_t>(static_cast<uint32_t>(e));
+    }
+  }
+}
+
+struct KnnLayout {
+  uint32_t* cnt;     // [n + 1]
+  uint32_t* cursor;  // [n]
+  int64_t* off;      // [n + 1]
+  int32_t* row_count;  // [n + 1]
+  uint64_t* grouped;   // [n_pairs]
+  void* cub_tmp;
+  size_t cub_bytes;
+};
+
+static void knn_layout(Workspace& ws, int64_t n, uint64_t n_pairs, KnnLayout& L) {
+  L.cnt = ws.take<uint32_t>(n + 1);
+  L.cursor = ws.take<uint32_t>(n + 1);
+  L.off = ws.take<int64_t>(n + 1);
+  L.row_count = ws.take<int32_t>(n + 1);
+  L.grouped = ws.take<uint64_t>(n_pairs ? n_pairs : 1);
+  size_t b1 = 0, b2 = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, b1, (uint32_t*)nullptr, (int64_t*)nullptr, static_cast<int>(n + 1));
+  cub::DeviceScan::ExclusiveSum(nullptr, b2, (int32_t*)nullptr, (int64_t*)nullptr, static_cast<int>(n + 1));
+  L.cub_bytes = b1 > b2 ? b1 : b2;
+  L.cub_tmp = ws.take<char>(L.cub_bytes);
+}
+
+}  // namespace flc
+
+extern "C" {
+
+size_t flc_knn_csr_workspace_bytes(int64_t n, uint64_t n_pairs) {
+  if (n <= 0) return 256;
+  flc::Workspace ws(nullptr, 0);
+  flc::KnnLayout L;
+  flc::knn_layout(ws, n, n_pairs, L);
+  return ws.used + 256;
+}
+
+int flc_knn_csr(const uint64_t* pairs, const uint64_t* pair_count, uint64_t pair_capacity,
+                const float* x, int64_t ld, int64_t n, uint32_t low_dim,
+                const double* precursor_mz, const float* rt, const int32_t* list_id,
+                const int32_t* probes, int32_t max_nprobe, double tol, int tol_mode, double rt_tol,
+                int32_t n_neighbors, int32_t n_neighbors_ann, float eps_cut, float* dist,
+                int32_t* indices, uint64_t nnz_capacity, int64_t* indptr, int64_t* nnz,
+                void* workspace, size_t workspace_bytes, flc_stream_t stream_) {
+  using namespace flc;
+  FLC_REQUIRE(n >= 0 && n < (int64_t(1) << 31), "n out of range");
+  FLC_REQUIRE(tol_mode == FLC_TOL_DA || tol_mode == FLC_TOL_PPM, "Unknown precursor tolerance mode");
+  FLC_REQUIRE(n_neighbors > 0 && n_neighbors_ann >= n_neighbors,
+              "n_neighbors_ann must be >= n_neighbors > 0");
+  FLC_REQUIRE(n_neighbors_ann <= 1024, "n_neighbors_ann > 1024 not supported");
+  FLC_REQUIRE((list_id == nullptr) == (probes == nullptr), "list_id and probes go together");
+  FLC_REQUIRE(nnz != nullptr, "null nnz");
+  cudaStream_t stream = as_stream(stream_);
+  if (n == 0) {
+    *nnz = 0;
+    FLC_CUDA(cudaMemsetAsync(indptr, 0, sizeof(int64_t), stream));
+    FLC_CUDA(cudaStreamSynchronize(stream));
+    return FLC_OK;
+  }
+  // The pair count decides the layout: read it (this op returns nnz anyway).
+  uint64_t total = 0;
+  FLC_CUDA(cudaMemcpyAsync(&total, pair_count, sizeof(total), cudaMemcpyDeviceToHost, stream));
+  FLC_CUDA(cudaStreamSynchronize(stream));
+  if (total > pair_capacity)
+    return set_error(FLC_ERR_CAPACITY, "scan produced %llu candidate pairs, capacity %llu",
+                     static_cast<unsigned long long>(total),
+                     static_cast<unsigned long long>(pair_capacity));
+  Workspace ws(workspace, workspace_bytes);
+  KnnLayout L;
+  knn_layout(ws, n, total, L);
+  if (!ws.ok)
+    return set_error(FLC_ERR_WORKSPACE, "knn_csr workspace too small: need %zu bytes for %llu pairs",
+                     ws.used, static_cast<unsigned long long>(total));
+  FLC_CUDA(cudaMemsetAsync(L.cnt, 0, sizeof(uint32_t) * (n + 1), stream));
+  FLC_CUDA(cudaMemsetAsync(L.cursor, 0, sizeof(uint32_t) * (n + 1), stream));
+  FLC_CUDA(cudaMemsetAsync(L.row_count, 0, sizeof(int32_t) * (n + 1), stream));
+  const unsigned pair_blocks =
+      static_cast<unsigned>(std::min<uint64_t>((total + 255) / 256 + 1, uint64_t(kNumSMs) * 32));
+  pair_hist_kernel<<<pair_blocks, 256, 0, stream>>>(pairs, pair_count, pair_capacity, n, L.cnt);
+  FLC_LAUNCH_CHECK();
+  size_t tmp = L.cub_bytes;
+  FLC_CUDA(cub::DeviceScan::ExclusiveSum(L.cub_tmp, tmp, L.cnt, L.off, static_cast<int>(n + 1), stream));
+  count_launch(2);
+  pair_scatter_kernel<<<pair_blocks, 256, 0, stream>>>(pairs, pair_count, pair_capacity, n, L.off,
+                                                       L.cursor, L.grouped);
+  FLC_LAUNCH_CHECK();
+
+  RefineParams P;
+  P.x = x; P.ld = ld; P.n = n; P.low_dim = low_dim; P.mz = precursor_mz; P.rt = rt;
+  P.list_id = list_id; P.probes = probes; P.max_nprobe = max_nprobe;
+  P.tol = tol; P.tol_mode = tol_mode; P.rt_tol = rt_tol;
+  P.k = n_neighbors; P.k_ann = n_neighbors_ann;
+  int ka = 32;
+  while (ka < n_neighbors_ann) ka <<= 1;
+  P.ka_pow2 = ka;
+  P.use_eps = !(eps_cut != eps_cut);  // NaN disables the cut
+  P.eps = eps_cut;
+  const size_t per_warp = static_cast<size_t>(2) * ka * sizeof(uint64_t) +
+                          ((static_cast<size_t>(low_dim) * sizeof(float) + 15) & ~size_t(15));
+  const size_t smem = per_warp * kRefineWarps;
+  FLC_REQUIRE(smem <= 200 * 1024, "low_dim / n_neighbors_ann too large for the refine kernel");
+  if (smem > 48 * 1024)
+    FLC_CUDA(cudaFuncSetAttribute(refine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  static_cast<int>(smem)));
+  const unsigned rblocks = static_cast<unsigned>((n + kRefineWarps - 1) / kRefineWarps);
+  refine_kernel<<<rblocks, kRefineWarps * 32, smem, stream>>>(P, L.off, L.grouped, L.row_count);
+  FLC_LAUNCH_CHECK();
+  tmp = L.cub_bytes;
+  FLC_CUDA(cub::DeviceScan::ExclusiveSum(L.cub_tmp, tmp, L.row_count, indptr, static_cast<int>(n + 1), stream));
+  count_launch(2);
+  int64_t total_nnz = 0;
+  FLC_CUDA(cudaMemcpyAsync(&total_nnz, indptr + n, sizeof(int64_t), cudaMemcpyDeviceToHost, stream));
+  FLC_CUDA(cudaStreamSynchronize(stream));
+  *nnz = total_nnz;
+  if (static_cast<uint64_t>(total_nnz) > nnz_capacity)
+    return set_error(FLC_ERR_CAPACITY, "CSR needs %lld entries, capacity %llu",
+                     static_cast<long long>(total_nnz), static_cast<unsigned long long>(nnz_capacity));
+  const unsigned cblocks = static_cast<unsigned>((n * 32 + 255) / 256);
+  csr_compact_kernel<<<cblocks, 256, 0, stream>>>(L.grouped, L.off, indptr, n, nnz_capacity, dist, indices);
+  FLC_LAUNCH_CHECK();
+  return FLC_OK;
+}
+
+}  // extern "C"

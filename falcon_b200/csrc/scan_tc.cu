@@ -1,0 +1,415 @@
+// Stage 3a: inverted-list inner-product scan on tcgen05 tensor cores.
+//
+// For every precursor bucket the kernel forms S = X_b * X_b^T tile by tile
+// (128 queries x up to 256 candidates, K = low_dim) and emits the (query,
+// candidate) pairs whose bf16 inner product clears the threshold
+// `1 - eps - margin`; the exact re-score, top-k and filter run on the few
+// survivors (refine.cu).  This is the dense contraction of faiss'
+// IndexIVFFlat/IndexFlatIP scanner restated for Blackwell:
+//
+//   warp 0  TMA producer: one elected lane streams 128x64 bf16 boxes of the
+//           query rows (A) and candidate rows (B) through a 4-stage shared-memory
+//           ring (cp.async.bulk.tensor, SWIZZLE_128B, completion on mbarriers).
+//           Rows past the end of the matrix and columns past low_dim are
+//           zero-filled by TMA, so low_dim = 400 needs no padded copy.
+//   warp 1  MMA issuer: one lane issues tcgen05.mma.cta_group::1.kind::f16
+//           (M = 128, N = candidates rounded up to 16, K = 16 per instruction)
+//           from shared-memory descriptors into one of two 256-column fp32
+//           accumulators in TMEM; tcgen05.commit releases ring slots / publishes
+//           the accumulator.
+//   warps 2-5  epilogue: tcgen05.ld (32 lanes x 32 columns per warp), threshold
+//           compare into a per-row bit mask, warp prefix sum, ONE atomicAdd per
+//           warp and 32-column chunk that has survivors, coalesced pair stores.
+//
+// Persistent grid: one CTA per SM, each walking a contiguous range of the
+// bucket-major tile sequence (queries outer, candidates inner, so the A rows of
+// consecutive tiles hit L2).
+//
+// Roofline: tensor-core bound for buckets >~ 4k rows, 2 * low_dim * n_b^2 FLOP
+// per bucket; HBM/L2-latency bound for small buckets (n_b * low_dim * 2 bytes
+// read once).
+#include <cuda.h>
+
+#include "scan.cuh"
+
+namespace flc {
+
+constexpr int kStages = 4;
+constexpr int kBoxRows = 128;
+constexpr int kBoxBytes = kBoxRows * kBoxK * 2;           // 16 KiB
+constexpr int kABytes = kBoxBytes;                        // 128 x 64 bf16
+constexpr int kBBytes = 2 * kBoxBytes;                    // 256 x 64 bf16
+constexpr int kStageBytes = kABytes + kBBytes;            // 48 KiB
+constexpr int kScanThreads = 192;                         // 6 warps
+constexpr int kTmemCols = 512;                            // 2 accumulators x 256 columns
+constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+constexpr long long kWatchdogCycles = 4000000000ll;       // ~2 s: trap instead of hanging
+
+// ---------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > kWatchdogCycles) __trap();
+  }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int32_t c0, int32_t c1,
+                                            uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_ld_32x32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// Shared-memory matrix descriptor: K-major operand, SWIZZLE_128B, rows of 128
+// bytes, 8-row groups 1024 bytes apart (cute::UMMA::SmemDescriptor bit layout:
+// start >> 4 [0,14), LBO >> 4 [16,30), SBO >> 4 [32,46), version = 1 [46,48),
+// layout type SWIZZLE_128B = 2 [61,64)).
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+// Instruction descriptor, kind::f16: D = f32, A = B = bf16, both K-major
+// (cute::UMMA::InstrDescriptor: c_format [4,6), a_format [7,10), b_format
+// [10,13), n >> 3 [17,23), m >> 4 [24,29)).
+__device__ __forceinline__ uint32_t make_idesc(uint32_t m, uint32_t n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((n >> 3) << 17) | ((m >> 4) << 24);
+}
+
+// ---------------------------------------------------------------- tile walker
+struct Tile {
+  int64_t q0;   // first query row
+  int64_t c0;   // first candidate row
+  int64_t end;  // end row of the bucket
+};
+
+struct TileWalker {
+  const int64_t* bucket_ptr;
+  const int64_t* tile_off;
+  int64_t n_buckets;
+  int64_t b, b_start, b_end, tiles_c, local, b_tiles;
+
+  __device__ void load_bucket() {
+    b_start = bucket_ptr[b];
+    b_end = bucket_ptr[b + 1];
+    const int64_t nb = b_end - b_start;
+    tiles_c = (nb + kTileN - 1) / kTileN;
+    b_tiles = ((nb + kTileM - 1) / kTileM) * tiles_c;
+  }
+  __device__ void init(const int64_t* bp, const int64_t* to, int64_t nbk, int64_t t) {
+    bucket_ptr = bp; tile_off = to; n_buckets = nbk;
+    int64_t lo = 0, hi = nbk;  // last b with tile_off[b] <= t
+    while (hi - lo > 1) {
+      const int64_t mid = (lo + hi) >> 1;
+      if (tile_off[mid] <= t) lo = mid; else hi = mid;
+    }
+    b = lo;
+    local = t - tile_off[b];
+    load_bucket();
+  }
+  __device__ Tile get() const {
+    Tile t;
+    t.q0 = b_start + (local / tiles_c) * kTileM;
+    t.c0 = b_start + (local % tiles_c) * kTileN;
+    t.end = b_end;
+    return t;
+  }
+  __device__ void next() {
+    if (++local >= b_tiles) {
+      local = 0;
+      do {
+        ++b;
+        if (b >= n_buckets) return;
+        load_bucket();
+      } while (b_tiles == 0);
+    }
+  }
+};
+
+// ---------------------------------------------------------------- kernel
+__global__ void __launch_bounds__(kScanThreads, 1)
+scan_tc_kernel(const __grid_constant__ CUtensorMap tmap, uint32_t low_dim,
+               const int64_t* __restrict__ bucket_ptr, int64_t n_buckets,
+               const int64_t* __restrict__ tile_off, float threshold,
+               uint64_t* __restrict__ pairs, uint64_t capacity, unsigned long long* __restrict__ pair_count) {
+  extern __shared__ unsigned char smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t tiles_base = (raw + 1023u) & ~1023u;  // SWIZZLE_128B wants 1024-byte alignment
+  const uint32_t bar_base = tiles_base + kStages * kStageBytes;
+  // barriers: full[kStages], empty[kStages], tmem_full[2], tmem_empty[2]; then the TMEM pointer
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * kStages + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * kStages + 2 + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * kStages + 4);
+  volatile uint32_t* tmem_slot_ptr =
+      reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), 4);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot),
+                 "n"(kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  // Contiguous range of tiles for this CTA.
+  const int64_t total = tile_off[n_buckets];
+  const int64_t per = (total + gridDim.x - 1) / gridDim.x;
+  const int64_t t_begin = min(total, per * static_cast<int64_t>(blockIdx.x));
+  const int64_t t_end = min(total, t_begin + per);
+  const int num_kb = static_cast<int>((low_dim + kBoxK - 1) / kBoxK);
+
+  if (t_begin < t_end) {
+    if (warp == 0) {
+      // ===================== TMA producer =====================
+      if (lane == 0) {
+        TileWalker w;
+        w.init(bucket_ptr, tile_off, n_buckets, t_begin);
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int64_t t = t_begin; t < t_end; ++t, w.next()) {
+          const Tile tile = w.get();
+          const bool two = (tile.end - tile.c0) > kBoxRows;
+          const uint32_t bytes = kABytes + (two ? 2 : 1) * kBoxBytes;
+          for (int kb = 0; kb < num_kb; ++kb) {
+            mbar_wait(empty_bar(stage), phase ^ 1u);
+            mbar_arrive_expect_tx(full_bar(stage), bytes);
+            const uint32_t sa = tiles_base + stage * kStageBytes;
+            const uint32_t sb = sa + kABytes;
+            tma_load_2d(sa, &tmap, kb * kBoxK, static_cast<int32_t>(tile.q0), full_bar(stage));
+            tma_load_2d(sb, &tmap, kb * kBoxK, static_cast<int32_t>(tile.c0), full_bar(stage));
+            if (two)
+              tma_load_2d(sb + kBoxBytes, &tmap, kb * kBoxK, static_cast<int32_t>(tile.c0 + kBoxRows),
+                          full_bar(stage));
+            if (++stage == kStages) { stage = 0; phase ^= 1u; }
+          }
+        }
+      }
+    } else if (warp == 1) {
+      // ===================== MMA issuer =====================
+      TileWalker w;
+      w.init(bucket_ptr, tile_off, n_buckets, t_begin);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int64_t t = t_begin; t < t_end; ++t, w.next()) {
+        const Tile tile = w.get();
+        const int64_t nc = min(static_cast<int64_t>(kTileN), tile.end - tile.c0);
+        const uint32_t n_mma = static_cast<uint32_t>(max(static_cast<int64_t>(16), (nc + 15) & ~int64_t(15)));
+        const uint32_t idesc = make_idesc(kTileM, n_mma);
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * kTileN);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          if (lane == 0) {
+            const uint32_t sa = tiles_base + stage * kStageBytes;
+            const uint32_t sb = sa + kABytes;
+            const int rem = static_cast<int>(low_dim) - kb * kBoxK;
+            const int ksteps = rem >= kBoxK ? kBoxK / 16 : (rem + 15) / 16;
+            for (int k = 0; k < ksteps; ++k) {
+              const uint64_t adesc = make_smem_desc(sa + k * 32);
+              const uint64_t bdesc = make_smem_desc(sb + k * 32);
+              tc_mma_bf16(d_tmem, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+            }
+            tc_commit(empty_bar(stage));
+            if (kb == num_kb - 1) tc_commit(tfull_bar(acc));
+          }
+          __syncwarp();
+          if (++stage == kStages) { stage = 0; phase ^= 1u; }
+        }
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1u;
+      }
+    } else {
+      // ===================== epilogue (warps 2..5) =====================
+      const int quarter = warp & 3;  // TMEM lanes [32 * quarter, 32 * quarter + 32)
+      TileWalker w;
+      w.init(bucket_ptr, tile_off, n_buckets, t_begin);
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int64_t t = t_begin; t < t_end; ++t, w.next()) {
+        const Tile tile = w.get();
+        const int64_t nc = min(static_cast<int64_t>(kTileN), tile.end - tile.c0);
+        const int64_t q = tile.q0 + quarter * 32 + lane;
+        const bool q_valid = q < tile.end;
+        mbar_wait(tfull_bar(acc), acc_phase);
+        tc_fence_after();
+        const int chunks = static_cast<int>((nc + 31) >> 5);
+        for (int ch = 0; ch < chunks; ++ch) {
+          uint32_t v[32];
+          const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
+                                 static_cast<uint32_t>(acc * kTileN + ch * 32);
+          tc_ld_32x32(taddr, v);
+          uint32_t mask = 0;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) mask |= (__uint_as_float(v[j]) >= threshold ? 1u : 0u) << j;
+          const int64_t cols_left = nc - ch * 32;
+          if (cols_left < 32) mask &= (1u << cols_left) - 1u;
+          if (!q_valid) mask = 0;
+          const uint32_t cnt = __popc(mask);
+          uint32_t incl = cnt;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t up = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += up;
+          }
+          const uint32_t warp_total = __shfl_sync(0xffffffffu, incl, 31);
+          if (warp_total != 0) {
+            unsigned long long base = 0;
+            if (lane == 31) base = atomicAdd(pair_count, static_cast<unsigned long long>(warp_total));
+            base = __shfl_sync(0xffffffffu, base, 31);
+            unsigned long long pos = base + incl - cnt;
+            const uint64_t qhi = static_cast<uint64_t>(q) << 32;
+            const uint64_t cbase = static_cast<uint64_t>(tile.c0 + ch * 32);
+            while (mask) {
+              const int j = __ffs(mask) - 1;
+              mask &= mask - 1;
+              if (pos < capacity) pairs[pos] = qhi | (cbase + j);
+              ++pos;
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar(acc));
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1u;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols)
+                 : "memory");
+  }
+}
+
+// ---------------------------------------------------------------- host
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
+      qres != cudaDriverEntryPointSuccess)
+    return nullptr;
+  fn = reinterpret_cast<EncodeTiledFn>(p);
+  return fn;
+}
+
+int launch_scan_tc(const uint16_t* x_bf16, int64_t ld_bf16, int64_t n, uint32_t low_dim,
+                   const int64_t* bucket_ptr, int64_t n_buckets, const int64_t* tile_off, float threshold,
+                   uint64_t* pairs, uint64_t pair_capacity, unsigned long long* pair_count,
+                   cudaStream_t stream) {
+  EncodeTiledFn encode = get_encode_fn();
+  if (!encode) return set_error(FLC_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+  FLC_REQUIRE((reinterpret_cast<uintptr_t>(x_bf16) & 15) == 0, "x_bf16 must be 16-byte aligned");
+  CUtensorMap tmap;
+  const cuuint64_t gdim[2] = {static_cast<cuuint64_t>(low_dim), static_cast<cuuint64_t>(n)};
+  const cuuint64_t gstride[1] = {static_cast<cuuint64_t>(ld_bf16) * 2};
+  const cuuint32_t box[2] = {kBoxK, kBoxRows};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult rc = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                             const_cast<uint16_t*>(x_bf16), gdim, gstride, box, estr,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (rc != CUDA_SUCCESS) return set_error(FLC_ERR_CUDA, "cuTensorMapEncodeTiled failed with %d", (int)rc);
+  static bool attr_set = false;
+  if (!attr_set) {
+    FLC_CUDA(cudaFuncSetAttribute(scan_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    attr_set = true;
+  }
+  scan_tc_kernel<<<kNumSMs, kScanThreads, kSmemBytes, stream>>>(tmap, low_dim, bucket_ptr, n_buckets, tile_off,
+                                                               threshold, pairs, pair_capacity, pair_count);
+  FLC_LAUNCH_CHECK();
+  return FLC_OK;
+}
+
+}  // namespace flc

@@ -1,0 +1,351 @@
+"""Device-resident clustering hot path: buckets -> vectors -> (IVF) -> scan ->
+k-NN CSR -> DBSCAN -> precursor split.
+
+Python only orchestrates: every stage is one call through the C ABI
+(``include/falcon_b200.h``) on raw device pointers; torch owns the buffers and
+the stream.  The stage order is the per-charge loop of published falcon
+(the surviving skeleton is /root/reference/falcon/falcon.py:151-203):
+``vectorize`` -> ``compute_pairwise_distances`` -> ``generate_clusters``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import dataclasses
+import math
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import check, lib, ptr
+
+# bf16 inner products of unit vectors differ from the exact value by at most
+# 2^-8 (two roundings of relative size 2^-9 on operands whose product sums are
+# bounded by 1); candidates are kept down to eps + SCAN_MARGIN and re-scored.
+SCAN_MARGIN = 2.0 ** -7
+
+
+@dataclasses.dataclass
+class Settings:
+    """falcon's clustering settings (published flag set; snapshot
+    defaults at /root/reference/falcon/config.py:77-183 where they survive)."""
+
+    precursor_tol_mass: float = 20.0
+    precursor_tol_mode: str = "ppm"
+    rt_tol: Optional[float] = None
+    fragment_tol: float = 0.05
+    eps: float = 0.1
+    mz_interval: int = 1
+    low_dim: int = 400
+    n_neighbors: int = 64
+    n_neighbors_ann: int = 128
+    batch_size: int = 2 ** 16
+    n_probe: int = 32
+    min_mz: float = 101.0
+    max_mz: float = 1500.0
+    min_samples: int = 2
+    exhaustive: bool = False  # north_star "n_probe = nlist" mode
+    hash_seed: int = 0
+    kmeans_iters: int = 10
+    scan_impl: int = 0  # 0 = tcgen05, 1 = SIMT verification kernel
+    eps_cut: bool = True  # keep only dist <= eps in the CSR (what generate_clusters reads)
+
+
+def get_dim(min_mz: float, max_mz: float, bin_size: float):
+    """(vec_len, min_mz, max_mz) -- /root/reference/falcon/cluster/spectrum.py:172-199."""
+    n, s, e = C.c_uint32(), C.c_float(), C.c_float()
+    check(lib.flc_get_dim(min_mz, max_mz, bin_size, C.byref(n), C.byref(s), C.byref(e)))
+    return int(n.value), float(s.value), float(e.value)
+
+
+def _stream() -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def require_cuda(device=None) -> torch.device:
+    if not torch.cuda.is_available():
+        raise RuntimeError("falcon_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+    dev = torch.device("cuda", torch.cuda.current_device() if device is None else device) \
+        if not isinstance(device, torch.device) else device
+    check(lib.flc_check_device(dev.index if dev.index is not None else torch.cuda.current_device()))
+    return dev
+
+
+class _Timer:
+    """Per-stage CUDA-event timing on the current stream (optional)."""
+
+    def __init__(self, enabled: bool):
+        self.enabled = enabled
+        self.events: list[tuple[str, torch.cuda.Event, torch.cuda.Event]] = []
+
+    def __call__(self, name: str):
+        return _TimerCtx(self, name)
+
+    def result(self) -> dict:
+        if not self.enabled:
+            return {}
+        torch.cuda.synchronize()
+        out: dict[str, float] = {}
+        for name, a, b in self.events:
+            out[name] = out.get(name, 0.0) + a.elapsed_time(b)
+        return out
+
+
+class _TimerCtx:
+    def __init__(self, timer: _Timer, name: str):
+        self.t, self.name = timer, name
+
+    def __enter__(self):
+        if self.t.enabled:
+            self.a = torch.cuda.Event(enable_timing=True)
+            self.a.record()
+
+    def __exit__(self, *exc):
+        if self.t.enabled:
+            b = torch.cuda.Event(enable_timing=True)
+            b.record()
+            self.t.events.append((self.name, self.a, b))
+
+
+@dataclasses.dataclass
+class KnnGraph:
+    """Sparse k-NN matrix on the device, rows in bucket order."""
+
+    dist: torch.Tensor  # float32 [nnz]
+    indices: torch.Tensor  # int32 [nnz]
+    indptr: torch.Tensor  # int64 [n + 1]
+    nnz: int
+    n_pairs: int
+
+
+@dataclasses.dataclass
+class Buckets:
+    order: torch.Tensor  # int32 [n] sorted position -> input row
+    key: torch.Tensor  # uint32 (as int32 storage) [n]
+    mz: torch.Tensor  # float64 [n] precursor m/z in bucket order
+    rt: Optional[torch.Tensor]  # float32 [n] in bucket order
+    bucket_ptr: torch.Tensor  # int64 [n_buckets + 1] (view of an [n + 1] buffer)
+    n_buckets: int
+
+
+@dataclasses.dataclass
+class IvfIndex:
+    nlist: torch.Tensor
+    nprobe: torch.Tensor
+    centroid_ptr: torch.Tensor
+    centroids: torch.Tensor
+    list_id: torch.Tensor
+    probes: torch.Tensor
+    max_nprobe: int
+    total_centroids: int
+
+
+class HotPath:
+    """The stage functions, each a thin wrapper over one C-ABI entry point."""
+
+    def __init__(self, settings: Settings | None = None, device=None, profile: bool = False):
+        self.s = settings or Settings()
+        if self.s.precursor_tol_mode not in _lib.TOL_MODES:
+            raise ValueError("Unknown precursor tolerance mode")
+        self.device = require_cuda(device)
+        self.vec_len, self.min_mz, self.max_mz = get_dim(self.s.min_mz, self.s.max_mz, self.s.fragment_tol)
+        self.timer = _Timer(profile)
+        self.ld_bf16 = (self.s.low_dim + 7) // 8 * 8
+
+    # ------------------------------------------------------------------ helpers
+    def _empty(self, n, dtype):
+        return torch.empty(int(n), dtype=dtype, device=self.device)
+
+    def _ws(self, nbytes: int) -> torch.Tensor:
+        return torch.empty(int(nbytes) + 256, dtype=torch.uint8, device=self.device)
+
+    # ------------------------------------------------------------------ a5
+    def bucket_sort(self, precursor_mz: torch.Tensor, charge: torch.Tensor,
+                    rt: Optional[torch.Tensor] = None) -> Buckets:
+        n = precursor_mz.shape[0]
+        order = self._empty(n, torch.int32)
+        key = self._empty(n, torch.int32)
+        mz_sorted = self._empty(n, torch.float64)
+        bucket_ptr = self._empty(n + 1, torch.int64)
+        nb = C.c_int64(0)
+        with self.timer("bucket_sort"):
+            ws = self._ws(lib.flc_bucket_sort_workspace_bytes(n))
+            check(lib.flc_bucket_sort(ptr(precursor_mz), ptr(charge), n, self.s.mz_interval,
+                                      ptr(order), ptr(key), ptr(mz_sorted), ptr(bucket_ptr),
+                                      C.byref(nb), ptr(ws), ws.numel(), _stream()))
+            rt_sorted = None
+            if rt is not None:
+                rt_sorted = self._empty(n, torch.float32)
+                check(lib.flc_gather(ptr(rt), ptr(order), n, 4, ptr(rt_sorted), _stream()))
+        return Buckets(order, key, mz_sorted, rt_sorted, bucket_ptr[: nb.value + 1], int(nb.value))
+
+    # ------------------------------------------------------------------ a2-a4
+    def vectorize(self, mz: torch.Tensor, intensity: torch.Tensor, indptr: torch.Tensor,
+                  order: Optional[torch.Tensor] = None, want_bf16: bool = True,
+                  want_hash_idx: bool = False, norm: bool = True):
+        n = indptr.shape[0] - 1
+        d = self.s.low_dim
+        x = torch.empty((n, d), dtype=torch.float32, device=self.device)
+        xb = torch.empty((n, self.ld_bf16), dtype=torch.bfloat16, device=self.device) if want_bf16 else None
+        hidx = self._empty(mz.shape[0], torch.int32) if want_hash_idx else None
+        with self.timer("vectorize"):
+            check(lib.flc_vectorize(ptr(mz), ptr(intensity), ptr(indptr), ptr(order), n,
+                                    self.min_mz, self.s.fragment_tol, self.vec_len, d, self.s.hash_seed,
+                                    1 if norm else 0, ptr(x), d, ptr(xb), self.ld_bf16, ptr(hidx), _stream()))
+        return x, xb, hidx
+
+    def hash_table(self) -> torch.Tensor:
+        out = self._empty(self.vec_len, torch.int32)
+        check(lib.flc_hash_table(self.vec_len, self.s.low_dim, self.s.hash_seed, ptr(out), _stream()))
+        return out
+
+    # ------------------------------------------------------------------ a6
+    def ivf_plan(self, buckets: Buckets):
+        nb = buckets.n_buckets
+        nlist = self._empty(nb + 1, torch.int32)
+        nprobe = self._empty(nb + 1, torch.int32)
+        cptr = self._empty(nb + 2, torch.int64)
+        total, maxp = C.c_int64(0), C.c_int32(0)
+        check(lib.flc_ivf_plan(ptr(buckets.bucket_ptr), nb, self.s.n_probe, 0, ptr(nlist), ptr(nprobe),
+                               ptr(cptr), C.byref(total), C.byref(maxp), _stream()))
+        return nlist, nprobe, cptr, int(total.value), int(maxp.value)
+
+    def build_ivf(self, x: torch.Tensor, buckets: Buckets,
+                  centroids: Optional[torch.Tensor] = None) -> IvfIndex:
+        n, d = x.shape
+        with self.timer("ivf_train"):
+            nlist, nprobe, cptr, total, maxp = self.ivf_plan(buckets)
+            if centroids is None:
+                centroids = torch.empty((max(total, 1), d), dtype=torch.float32, device=self.device)
+                ws = self._ws(lib.flc_kmeans_workspace_bytes(n, total, d))
+                check(lib.flc_kmeans_train(ptr(x), x.stride(0), n, d, ptr(buckets.bucket_ptr),
+                                           buckets.n_buckets, ptr(nlist), ptr(cptr), total,
+                                           self.s.kmeans_iters, ptr(centroids), ptr(ws), ws.numel(), _stream()))
+            elif centroids.shape[0] < total:
+                raise ValueError("centroids array too small for the bucket plan")
+        with self.timer("ivf_assign"):
+            list_id = self._empty(n, torch.int32)
+            probes = torch.empty((n, maxp), dtype=torch.int32, device=self.device)
+            check(lib.flc_ivf_assign(ptr(x), x.stride(0), n, d, ptr(buckets.bucket_ptr), buckets.n_buckets,
+                                     ptr(nlist), ptr(nprobe), ptr(cptr), ptr(centroids), maxp,
+                                     ptr(list_id), ptr(probes), _stream()))
+        return IvfIndex(nlist, nprobe, cptr, centroids, list_id, probes, maxp, total)
+
+    # ------------------------------------------------------------------ a7-a9
+    def scan_threshold(self) -> float:
+        if not self.s.eps_cut:
+            return -math.inf
+        return float(np.float32(1.0) - np.float32(self.s.eps) - np.float32(SCAN_MARGIN))
+
+    def knn_graph(self, x: torch.Tensor, xb: torch.Tensor, buckets: Buckets,
+                  ivf: Optional[IvfIndex] = None, pair_capacity: Optional[int] = None) -> KnnGraph:
+        n, d = x.shape
+        s = self.s
+        thr = self.scan_threshold()
+        if pair_capacity is None:
+            pair_capacity = 32 * n + (1 << 20) if s.eps_cut else None
+        if pair_capacity is None:
+            sizes = (buckets.bucket_ptr[1:] - buckets.bucket_ptr[:-1])
+            pair_capacity = int((sizes * sizes).sum().item()) + 1024
+        pair_count = torch.zeros(1, dtype=torch.int64, device=self.device)
+        ws = self._ws(lib.flc_scan_workspace_bytes(n, buckets.n_buckets))
+        while True:
+            pairs = self._empty(pair_capacity, torch.int64)
+            with self.timer("scan"):
+                check(lib.flc_scan_pairs(ptr(xb), xb.stride(0), n, d, ptr(buckets.bucket_ptr),
+                                         buckets.n_buckets,
+                                         ptr(ivf.list_id) if ivf else None, ptr(ivf.probes) if ivf else None,
+                                         ivf.max_nprobe if ivf else 0, ptr(ivf.nlist) if ivf else None,
+                                         thr, s.scan_impl, ptr(pairs), pair_capacity, ptr(pair_count),
+                                         ptr(ws), ws.numel(), _stream()))
+            n_pairs = int(pair_count.item())
+            if n_pairs <= pair_capacity:
+                break
+            pair_capacity = n_pairs + 1024  # candidate buffer was too small: rescan
+        nnz_cap = max(1, min(n_pairs, n * s.n_neighbors))
+        dist = self._empty(nnz_cap, torch.float32)
+        indices = self._empty(nnz_cap, torch.int32)
+        indptr = self._empty(n + 1, torch.int64)
+        nnz = C.c_int64(0)
+        with self.timer("knn_csr"):
+            ws2 = self._ws(lib.flc_knn_csr_workspace_bytes(n, n_pairs))
+            check(lib.flc_knn_csr(ptr(pairs), ptr(pair_count), pair_capacity, ptr(x), x.stride(0), n, d,
+                                  ptr(buckets.mz), ptr(buckets.rt) if s.rt_tol is not None else None,
+                                  ptr(ivf.list_id) if ivf else None, ptr(ivf.probes) if ivf else None,
+                                  ivf.max_nprobe if ivf else 0,
+                                  s.precursor_tol_mass, _lib.TOL_MODES[s.precursor_tol_mode],
+                                  -1.0 if s.rt_tol is None else float(s.rt_tol),
+                                  s.n_neighbors, s.n_neighbors_ann,
+                                  float(np.float32(s.eps)) if s.eps_cut else float("nan"),
+                                  ptr(dist), ptr(indices), nnz_cap, ptr(indptr), C.byref(nnz),
+                                  ptr(ws2), ws2.numel(), _stream()))
+        return KnnGraph(dist[: nnz.value], indices[: nnz.value], indptr, int(nnz.value), n_pairs)
+
+    # ------------------------------------------------------------------ a10
+    def dbscan(self, g: KnnGraph, n: int):
+        labels = self._empty(n, torch.int32)
+        nc = C.c_int64(0)
+        with self.timer("dbscan"):
+            ws = self._ws(lib.flc_dbscan_workspace_bytes(n))
+            check(lib.flc_dbscan(ptr(g.dist), ptr(g.indices), ptr(g.indptr), n,
+                                 float(np.float32(self.s.eps)), self.s.min_samples, ptr(labels),
+                                 C.byref(nc), ptr(ws), ws.numel(), _stream()))
+        return labels, int(nc.value)
+
+    # ------------------------------------------------------------------ a11-a15
+    def split(self, labels: torch.Tensor, mz: torch.Tensor, values_sorted: bool):
+        n = labels.shape[0]
+        out = self._empty(n, torch.int32)
+        nc = C.c_int64(0)
+        with self.timer("split"):
+            ws = self._ws(lib.flc_split_workspace_bytes(n))
+            check(lib.flc_split_clusters(ptr(labels), ptr(mz), n, self.s.precursor_tol_mass,
+                                         _lib.TOL_MODES[self.s.precursor_tol_mode],
+                                         -1.0 if self.s.rt_tol is None else float(self.s.rt_tol),
+                                         self.s.min_samples, 1 if values_sorted else 0, ptr(out),
+                                         C.byref(nc), ptr(ws), ws.numel(), _stream()))
+        return out, int(nc.value)
+
+    # ------------------------------------------------------------------ whole path
+    def run(self, mz, intensity, indptr, precursor_mz, charge, rt=None, keep=False):
+        """All stages on device tensors; returns labels in INPUT order (int32,
+        -1 = noise) and the number of clusters.  ``keep`` also returns the
+        intermediates (bucket order) for parity checks."""
+        n = precursor_mz.shape[0]
+        if n == 0:
+            empty = self._empty(0, torch.int32)
+            return (empty, 0, {}) if keep else (empty, 0)
+        buckets = self.bucket_sort(precursor_mz, charge, rt if self.s.rt_tol is not None else None)
+        x, xb, _ = self.vectorize(mz, intensity, indptr, buckets.order)
+        ivf = None if self.s.exhaustive else self.build_ivf(x, buckets)
+        graph = self.knn_graph(x, xb, buckets, ivf)
+        db_labels, _ = self.dbscan(graph, n)
+        sorted_labels, n_clusters = self.split(db_labels, buckets.mz, values_sorted=True)
+        labels = self._empty(n, torch.int32)
+        with self.timer("scatter"):
+            check(lib.flc_scatter32(ptr(sorted_labels), ptr(buckets.order), n, ptr(labels), _stream()))
+        if keep:
+            return labels, n_clusters, dict(buckets=buckets, x=x, xb=xb, ivf=ivf, graph=graph,
+                                            db_labels=db_labels, sorted_labels=sorted_labels)
+        return labels, n_clusters
+
+
+def cluster_host(spectra, settings: Settings | None = None, device=None, profile=False):
+    """End-to-end on HOST arrays (a ``synth.SpectrumSet``-like object): H2D copy,
+    all stages, D2H of the labels.  This is the call ``bench.py`` times as e2e."""
+    hp = HotPath(settings, device, profile)
+    dev = hp.device
+
+    def up(a, dtype):
+        t = torch.from_numpy(np.ascontiguousarray(a, dtype=dtype))
+        return t.to(dev, non_blocking=True)
+
+    mz = up(spectra.mz, np.float32)
+    inten = up(spectra.intensity, np.float32)
+    indptr = up(spectra.indptr, np.int64)
+    pmz = up(spectra.precursor_mz, np.float64)
+    z = up(spectra.precursor_charge, np.int32)
+    rt = up(spectra.retention_time, np.float32) if hp.s.rt_tol is not None else None
+    labels, n_clusters = hp.run(mz, inten, indptr, pmz, z, rt)
+    return labels.cpu().numpy(), n_clusters, hp.timer.result()

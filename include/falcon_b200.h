@@ -1,0 +1,198 @@
+/*
+ * falcon_b200 -- C ABI of the B200-native falcon clustering hot path.
+ *
+ * Every entry point is plain C: raw device pointers + sizes + a CUDA stream, no
+ * torch types.  All functions return 0 (FLC_OK) or a negative error code and
+ * leave a message retrievable with flc_last_error() (thread local).  Unless
+ * stated otherwise pointers are DEVICE pointers owned by the caller; the
+ * library never allocates device memory behind the caller's back -- each op
+ * has a *_workspace_bytes() query and takes the scratch buffer explicitly.
+ * Ops are asynchronous on `stream` unless they return a host value (those
+ * synchronise the stream; said in the comment).
+ *
+ * Reference interfaces each entry point replaces are cited as
+ * /root/reference/<file>:<line>; "A.n" refers to SURVEY.md Appendix A (the
+ * published falcon 0.1.x pipeline that north_star names, absent from the
+ * mounted snapshot).
+ */
+#ifndef FALCON_B200_H_
+#define FALCON_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define FLC_API __attribute__((visibility("default")))
+#else
+#define FLC_API
+#endif
+
+typedef void* flc_stream_t; /* cudaStream_t */
+
+enum {
+  FLC_OK = 0,
+  FLC_ERR_INVALID = -1,   /* bad argument (reference raises ValueError) */
+  FLC_ERR_CUDA = -2,      /* CUDA runtime/driver error */
+  FLC_ERR_CAPACITY = -3,  /* caller-provided buffer too small; see message */
+  FLC_ERR_WORKSPACE = -4, /* workspace too small */
+  FLC_ERR_UNSUPPORTED = -5
+};
+
+enum { FLC_TOL_DA = 0, FLC_TOL_PPM = 1 };
+
+/* ------------------------------------------------------------------ misc */
+FLC_API const char* flc_last_error(void);
+FLC_API int flc_version(void);
+/* Kernels launched by this library since load / last reset (all threads). */
+FLC_API uint64_t flc_launch_count(void);
+FLC_API void flc_reset_launch_count(void);
+/* Compute capability of `device` must be 10.x; returns FLC_ERR_UNSUPPORTED otherwise. */
+FLC_API int flc_check_device(int device);
+
+/* ------------------------------------------------------------------ a1: get_dim
+ * falcon/cluster/spectrum.py:172-199 (float32 arithmetic forced by the numba
+ * signature at :172).  Host function. */
+FLC_API int flc_get_dim(float min_mz, float max_mz, float bin_size,
+                uint32_t* vec_len, float* start_dim, float* end_dim);
+
+/* ------------------------------------------------------------------ a3: hash_lookup
+ * A.1: hash_lookup[i] = murmurhash3_32(int32 i, seed, positive=True) % low_dim. */
+FLC_API int flc_hash_table(uint32_t vec_len, uint32_t low_dim, uint32_t seed,
+                   uint32_t* out /*[vec_len]*/, flc_stream_t stream);
+
+/* ------------------------------------------------------------------ a2 + a4: vectorise
+ * Binning (falcon/cluster/spectrum.py:250-296, expression :291 in float64),
+ * feature hashing + L2 norm (A.1; snapshot sibling spectrum.py:202-247).
+ * Row r of the outputs is spectrum order[r] (order == NULL: identity).
+ *   out_f32   [n, ld_f32]  float32 (nullable)
+ *   out_bf16  [n, ld_bf16] bfloat16 bits, columns >= low_dim zeroed (nullable)
+ *   out_hash_idx [n_peaks] hashed column of every peak in input peak order,
+ *                -1 for peaks outside [0, vec_len) (nullable; parity checks) */
+FLC_API int flc_vectorize(const float* mz, const float* intensity, const int64_t* indptr,
+                  const int32_t* order, int64_t n,
+                  double min_mz, double bin_size, uint32_t vec_len,
+                  uint32_t low_dim, uint32_t seed, int norm,
+                  float* out_f32, int64_t ld_f32,
+                  uint16_t* out_bf16, int64_t ld_bf16,
+                  int32_t* out_hash_idx, flc_stream_t stream);
+
+/* ------------------------------------------------------------------ a5: buckets
+ * A.2 bucket rule: round(((mz - 1.00794) * max(|z|,1)) / 1.0005079) // mz_interval,
+ * spectra ordered by (charge, interval, precursor m/z) (stable).
+ *   order      [n] int32   sorted position -> input index
+ *   key_sorted [n] uint32  charge << 24 | interval, in sorted order
+ *   mz_sorted  [n] float64 precursor m/z in sorted order
+ *   bucket_ptr [n + 1] int64, first *n_buckets + 1 entries valid
+ * Synchronises the stream (returns *n_buckets on the host). */
+FLC_API size_t flc_bucket_sort_workspace_bytes(int64_t n);
+FLC_API int flc_bucket_sort(const double* precursor_mz, const int32_t* charge, int64_t n,
+                    int32_t mz_interval,
+                    int32_t* order, uint32_t* key_sorted, double* mz_sorted,
+                    int64_t* bucket_ptr, int64_t* n_buckets /*host*/,
+                    void* workspace, size_t workspace_bytes, flc_stream_t stream);
+/* out[i] = in[order[i]] for 4- or 8-byte elements. */
+FLC_API int flc_gather(const void* in, const int32_t* order, int64_t n, int elem_bytes,
+               void* out, flc_stream_t stream);
+/* out[order[i]] = in[i] for 4-byte elements. */
+FLC_API int flc_scatter32(const void* in, const int32_t* order, int64_t n, void* out,
+                  flc_stream_t stream);
+
+/* ------------------------------------------------------------------ a6: IVF train / assign
+ * A.2 (faiss IndexIVFFlat over IndexFlatIP): per bucket
+ * n_list = 0 (flat) if n < 100 else 2^floor(log2(n/39)) (..., see flc_ivf_plan),
+ * spherical k-means (niter iterations), assignment = arg-max inner product. */
+/*  nlist[b], nprobe[b] (int32) and centroid_ptr[b] (int64 exclusive scan of nlist)
+ *  for every bucket; exhaustive != 0 lifts the nprobe cap (nprobe = nlist).
+ *  Synchronises the stream; returns the total number of centroids on the host. */
+FLC_API int flc_ivf_plan(const int64_t* bucket_ptr, int64_t n_buckets, int32_t n_probe,
+                 int exhaustive, int32_t* nlist, int32_t* nprobe,
+                 int64_t* centroid_ptr /*[n_buckets+1]*/, int64_t* total_centroids /*host*/,
+                 int32_t* max_nprobe /*host*/, flc_stream_t stream);
+FLC_API size_t flc_kmeans_workspace_bytes(int64_t n, int64_t total_centroids, uint32_t low_dim);
+FLC_API int flc_kmeans_train(const float* x, int64_t ld, int64_t n, uint32_t low_dim,
+                     const int64_t* bucket_ptr, int64_t n_buckets,
+                     const int32_t* nlist, const int64_t* centroid_ptr,
+                     int64_t total_centroids, int niter,
+                     float* centroids /*[total_centroids, low_dim]*/,
+                     void* workspace, size_t workspace_bytes, flc_stream_t stream);
+/*  list_id[i] (int32, bucket-local list of row i, 0 for flat buckets) and
+ *  probes[i * max_nprobe + j] (int32 list ids best first, -1 padded), both from
+ *  float64 inner products with ties to the lower id. */
+FLC_API int flc_ivf_assign(const float* x, int64_t ld, int64_t n, uint32_t low_dim,
+                   const int64_t* bucket_ptr, int64_t n_buckets,
+                   const int32_t* nlist, const int32_t* nprobe,
+                   const int64_t* centroid_ptr, const float* centroids,
+                   int32_t max_nprobe, int32_t* list_id, int32_t* probes,
+                   flc_stream_t stream);
+
+/* ------------------------------------------------------------------ a7: inverted-list scan
+ * A.2 index.search: bf16 inner products of every query against the members
+ * of its bucket (exhaustive) or of the lists it probes, on tcgen05 tensor
+ * cores; (query, candidate) pairs with ip >= threshold are appended to
+ * `pairs` (uint64: query << 32 | candidate, global bucket-order row numbers).
+ *   impl: 0 = tcgen05/TMA kernel, 1 = SIMT verification kernel (same bf16
+ *         inputs, fp32 accumulation on CUDA cores; for bring-up and tests).
+ *   list_id/probes NULL: exhaustive within the bucket.
+ * *pair_count (device uint64) receives the number of pairs produced (may
+ * exceed pair_capacity: then FLC_ERR_CAPACITY is reported by flc_knn_csr). */
+FLC_API size_t flc_scan_workspace_bytes(int64_t n, int64_t n_buckets);
+FLC_API int flc_scan_pairs(const uint16_t* x_bf16, int64_t ld_bf16, int64_t n, uint32_t low_dim,
+                   const int64_t* bucket_ptr, int64_t n_buckets,
+                   const int32_t* list_id, const int32_t* probes, int32_t max_nprobe,
+                   const int32_t* nlist,
+                   float threshold, int impl,
+                   uint64_t* pairs, uint64_t pair_capacity, uint64_t* pair_count,
+                   void* workspace, size_t workspace_bytes, flc_stream_t stream);
+
+/* ------------------------------------------------------------------ a7 (tail) + a8 + a9: top-k, filter, CSR
+ * For every query: exact re-score of its candidate pairs (float64 accumulate,
+ * rounded once to float32), IVF membership check, optional eps cut
+ * (dist = max(1 - ip, 0) <= eps; pass NaN to disable), order by (ip desc, id asc),
+ * keep n_neighbors_ann, precursor (Da: |d| < tol; ppm: |d| / mz_cand * 1e6 < tol)
+ * and RT (|d| < rt_tol, rt == NULL or rt_tol < 0: off) filter in that order,
+ * keep n_neighbors, write CSR (float32 dist, int32 column, int64 indptr).
+ * Synchronises the stream; returns nnz on the host. */
+FLC_API size_t flc_knn_csr_workspace_bytes(int64_t n, uint64_t n_pairs);
+FLC_API int flc_knn_csr(const uint64_t* pairs, const uint64_t* pair_count, uint64_t pair_capacity,
+                const float* x, int64_t ld, int64_t n, uint32_t low_dim,
+                const double* precursor_mz, const float* rt,
+                const int32_t* list_id, const int32_t* probes, int32_t max_nprobe,
+                double tol, int tol_mode, double rt_tol,
+                int32_t n_neighbors, int32_t n_neighbors_ann, float eps_cut,
+                float* dist, int32_t* indices, uint64_t nnz_capacity, int64_t* indptr /*[n+1]*/,
+                int64_t* nnz /*host*/,
+                void* workspace, size_t workspace_bytes, flc_stream_t stream);
+
+/* ------------------------------------------------------------------ a10: DBSCAN
+ * A.4 + sklearn dbscan_inner semantics (sklearn/cluster/_dbscan_inner.pyx:11-41):
+ * neighbourhood = row entries with dist <= eps, core = |neighbourhood| >= min_samples,
+ * label = rank of the minimum-index core point the point is reachable from
+ * along edges leaving core points; -1 = noise.  Synchronises the stream;
+ * returns the number of clusters on the host. */
+FLC_API size_t flc_dbscan_workspace_bytes(int64_t n);
+FLC_API int flc_dbscan(const float* dist, const int32_t* indices, const int64_t* indptr, int64_t n,
+               float eps, int32_t min_samples, int32_t* labels, int64_t* n_clusters /*host*/,
+               void* workspace, size_t workspace_bytes, flc_stream_t stream);
+
+/* ------------------------------------------------------------------ a11-a15: precursor split
+ * falcon/cluster/cluster.py:334-509: inside every DBSCAN cluster, 1-D complete
+ * linkage on precursor m/z cut at tol (inclusive); sub-clusters with fewer than
+ * min_samples members become noise; labels renumbered consecutively.
+ * values_sorted != 0 promises precursor_mz ascending inside every cluster in
+ * row order (true for bucket-sorted rows) and skips the m/z sort.
+ * rt_tol >= 0 (retention-time cut, cluster.py:418-429) is not implemented on the
+ * device yet: FLC_ERR_UNSUPPORTED.  Synchronises; returns #clusters on the host. */
+FLC_API size_t flc_split_workspace_bytes(int64_t n);
+FLC_API int flc_split_clusters(const int32_t* labels_in, const double* precursor_mz, int64_t n,
+                       double tol, int tol_mode, double rt_tol, int32_t min_samples,
+                       int values_sorted, int32_t* labels_out, int64_t* n_clusters /*host*/,
+                       void* workspace, size_t workspace_bytes, flc_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FALCON_B200_H_ */

@@ -1,0 +1,138 @@
+"""End-to-end parity (partitions identical to the oracle), the facades, and
+size-independent properties at BASELINE sizes."""
+import functools
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+from falcon_b200 import pipeline, synth  # noqa: E402
+from falcon_b200.cluster import cluster, spectrum  # noqa: E402
+from oracle import dbscan as odb  # noqa: E402
+from oracle import ivf as oivf  # noqa: E402
+from tests import helpers  # noqa: E402
+
+
+def _cpu(t):
+    return t.cpu().numpy()
+
+
+@pytest.mark.parametrize("n,lo,hi", [(50000, 700.0, 3500.0), (20000, 1000.0, 1020.0)])
+def test_end_to_end_exhaustive_partition_identical(n, lo, hi):
+    """BASELINE config 0 size (50k): identical partitions in exhaustive mode."""
+    sp = helpers.dataset(n, 42, lo, hi)
+    labels, nc, _ = pipeline.cluster_host(sp, pipeline.Settings(exhaustive=True))
+    o = helpers.oracle_pipeline(sp, exhaustive=True)
+    ref = np.empty(n, np.int64)
+    ref[o["order"]] = o["labels"]
+    assert nc == ref.max() + 1
+    assert odb.same_partition(labels, ref)
+
+
+def test_end_to_end_default_nprobe_shared_centroids():
+    sp = helpers.dataset(20000, 43, 1000.0, 1020.0)
+    h = pipeline.HotPath(pipeline.Settings(exhaustive=False))
+    d = helpers.to_device(sp, h.device)
+    labels, nc, keep = h.run(d["mz"], d["intensity"], d["indptr"], d["precursor_mz"], d["charge"], keep=True)
+    ivf, b = keep["ivf"], keep["buckets"]
+    nlist, cptr, cents = _cpu(ivf.nlist), _cpu(ivf.centroid_ptr), _cpu(ivf.centroids)
+    assert (nlist > 0).sum() > 10
+    shared = [cents[cptr[i]: cptr[i] + nlist[i]] if nlist[i] else None for i in range(b.n_buckets)]
+    o = helpers.oracle_pipeline(sp, exhaustive=False, centroids=shared, vectors=_cpu(keep["x"]))
+    ref = np.empty(len(sp), np.int64)
+    ref[o["order"]] = o["labels"]
+    assert odb.same_partition(_cpu(labels), ref)
+
+
+def test_facade_to_vector_parallel_and_errors():
+    sp = helpers.dataset(2000, 3)
+    vec_len, lo, hi = spectrum.get_dim(101.0, 1500.0, 0.05)
+    table = spectrum.hash_lookup(vec_len, 400)
+    v = spectrum.to_vector_parallel(sp.as_dicts(), dim=400, min_mz=lo, max_mz=hi, bin_size=0.05,
+                                    hash_lookup=table, norm=True)
+    np.testing.assert_allclose(v, helpers.oracle_vectors(sp), rtol=0, atol=1e-6)
+    with pytest.raises(NotImplementedError):
+        spectrum.to_vector_parallel(sp.as_dicts()[:4], 400, lo, hi, 0.05, hash_lookup=np.zeros(vec_len, np.uint32))
+    assert spectrum.to_vector_parallel([], 400, lo, hi, 0.05).shape == (0, 400)
+
+
+def test_facade_compute_pairwise_distances_and_generate_clusters(tmp_path):
+    import joblib
+
+    sp = helpers.dataset(6000, 5, 1000.0, 1010.0)
+    order, bptr, _ = oivf.bucket_sort(sp.precursor_mz, sp.precursor_charge)
+    dicts = sp.as_dicts()
+    files = []
+    for i, (s, e) in enumerate(zip(bptr[:-1], bptr[1:])):  # per-bucket files like the reference's work_dir
+        f = tmp_path / f"bucket_{i}.pkl"
+        joblib.dump([dicts[j] for j in order[s:e]], f)
+        files.append(str(f))
+    vec_len, lo, hi = spectrum.get_dim(101.0, 1500.0, 0.05)
+    vectorize = functools.partial(spectrum.to_vector_parallel, dim=400, min_mz=lo, max_mz=hi, bin_size=0.05,
+                                  hash_lookup=None, norm=True)
+    mat, meta = cluster.compute_pairwise_distances(len(sp), files, None, vectorize, 20.0, "ppm", None, 64, 128,
+                                                   2 ** 16, 32, eps=0.1, exhaustive=True)
+    o = helpers.oracle_pipeline(sp, exhaustive=True)
+    assert np.array_equal(mat.indptr, o["csr_cut"].indptr) and np.array_equal(mat.indices, o["csr_cut"].indices)
+    assert mat.dtype == np.float32 and mat.shape == (len(sp), len(sp))
+    assert np.array_equal(meta["precursor_mz"].values, o["sorted"].precursor_mz)
+    labels = cluster.generate_clusters(mat, 0.1, meta["precursor_mz"].values, None, 20.0, "ppm", None)
+    assert odb.same_partition(labels, o["labels"])
+    # the oracle's own full matrix through the GPU generate_clusters
+    labels2 = cluster.generate_clusters(o["csr"], 0.1, o["sorted"].precursor_mz, None, 20.0, "ppm")
+    assert odb.same_partition(labels2, o["labels"])
+    with pytest.raises(ValueError, match="tolerance mode"):
+        cluster.generate_clusters(mat, 0.1, meta["precursor_mz"].values, None, 20.0, "mDa")
+    with pytest.raises(ValueError):
+        cluster.compute_pairwise_distances(len(sp) + 1, files, None, vectorize, 20.0, "ppm", None, 64, 128, 1, 32)
+
+
+def test_empty_and_tiny_inputs():
+    h = pipeline.HotPath(pipeline.Settings(exhaustive=True))
+    e = synth.generate(0)
+    labels, nc, _ = pipeline.cluster_host(e)
+    assert labels.shape == (0,) and nc == 0
+    one = synth.generate(1, 5)
+    labels, nc, _ = pipeline.cluster_host(one, pipeline.Settings(exhaustive=True))
+    assert labels.tolist() == [-1] and nc == 0
+    two = one.take(np.array([0, 0]))
+    labels, nc, _ = pipeline.cluster_host(two, pipeline.Settings(exhaustive=True))
+    assert labels.tolist() == [0, 0] and nc == 1
+
+
+def test_full_size_properties_1m():
+    """BASELINE config 1 (1M spectra, defaults): properties that need no oracle."""
+    n = 1_000_000
+    sp = helpers.dataset(n, 42)
+    s = pipeline.Settings()
+    labels, nc, _ = pipeline.cluster_host(sp, s)
+    labels2, nc2, _ = pipeline.cluster_host(sp, s)
+    assert nc == nc2 and np.array_equal(labels, labels2)  # deterministic
+    m = labels >= 0
+    assert nc > n // 20 and labels.max() == nc - 1
+    sizes = np.bincount(labels[m], minlength=nc)
+    assert sizes.min() >= 2  # min_samples
+    # precursor tolerance: complete linkage span of every cluster within 20 ppm of its lightest member
+    lo = np.full(nc, np.inf)
+    hi = np.zeros(nc)
+    np.minimum.at(lo, labels[m], sp.precursor_mz[m])
+    np.maximum.at(hi, labels[m], sp.precursor_mz[m])
+    assert ((hi - lo) / lo * 1e6 <= 20.0).all()
+    # one charge per cluster (buckets never mix charges)
+    zmin = np.full(nc, 99)
+    zmax = np.zeros(nc, np.int64)
+    np.minimum.at(zmin, labels[m], sp.precursor_charge[m])
+    np.maximum.at(zmax, labels[m], sp.precursor_charge[m])
+    assert (zmin == zmax).all()
+    # clusters are pure w.r.t. the generating templates on this synthetic set
+    tmin = np.full(nc, np.iinfo(np.int64).max)
+    tmax = np.zeros(nc, np.int64)
+    np.minimum.at(tmin, labels[m], sp.template[m])
+    np.maximum.at(tmax, labels[m], sp.template[m])
+    assert (tmin == tmax).mean() > 0.999
+    # exhaustive mode finds a superset of the default-n_probe neighbours: never fewer clustered spectra
+    labels_ex, _, _ = pipeline.cluster_host(sp, pipeline.Settings(exhaustive=True))
+    assert (labels_ex >= 0).sum() >= m.sum()

@@ -1,0 +1,342 @@
+"""Stage-by-stage parity of the CUDA path (through the C ABI) against the oracle."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+from falcon_b200 import pipeline, synth  # noqa: E402
+from oracle import dbscan as odb  # noqa: E402
+from oracle import hashing  # noqa: E402
+from oracle import ivf as oivf  # noqa: E402
+from oracle import vectorize as ovec  # noqa: E402
+from tests import helpers  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def hp():
+    return pipeline.HotPath(pipeline.Settings(exhaustive=True))
+
+
+def _cpu(t):
+    return t.cpu().numpy()
+
+
+# ------------------------------------------------------------------ stage 1
+def test_hash_table_bit_exact(hp):
+    got = _cpu(hp.hash_table()).view(np.uint32)
+    assert np.array_equal(got, hashing.hash_lookup(hp.vec_len, 400))
+
+
+def test_vectorize_golden_bins_bit_exact(hp, golden_dir):
+    g = np.load(os.path.join(golden_dir, "binning.npz"))
+    dev = hp.device
+    mz, inten, indptr = (torch.from_numpy(g[k]).to(dev) for k in ("mz", "intensity", "indptr"))
+    x, xb, hidx = hp.vectorize(mz, inten, indptr, want_hash_idx=True)
+    table = hashing.hash_lookup(hp.vec_len, 400)
+    assert np.array_equal(_cpu(hidx), table[g["bins"]].astype(np.int32))  # bins from the reference itself
+    ref = ovec.to_vector(g["mz"], g["intensity"], g["indptr"], hp.min_mz, 0.05, hp.vec_len, 400)
+    np.testing.assert_allclose(_cpu(x), ref, rtol=0, atol=1e-6)
+    assert (_cpu(x) != ref).mean() < 1e-5
+    assert np.array_equal(_cpu(xb.view(torch.int16)).view(np.uint16)[:, :400], ovec.to_bf16_bits(_cpu(x)))
+
+
+@pytest.mark.parametrize("low_dim", [400, 200, 800, 100])
+def test_vectorize_synthetic(low_dim):
+    h = pipeline.HotPath(pipeline.Settings(low_dim=low_dim))
+    sp = helpers.dataset(5000, 1)
+    d = helpers.to_device(sp, h.device)
+    x, xb, hidx = h.vectorize(d["mz"], d["intensity"], d["indptr"], want_hash_idx=True)
+    ref, ref_idx = helpers.oracle_vectors(sp, low_dim, return_hash_idx=True)
+    assert np.array_equal(_cpu(hidx), ref_idx)
+    np.testing.assert_allclose(_cpu(x), ref, rtol=0, atol=1e-6)
+    xb_bits = _cpu(xb.view(torch.int16)).view(np.uint16)
+    assert np.array_equal(xb_bits[:, :low_dim], ovec.to_bf16_bits(_cpu(x)))
+    assert (xb_bits[:, low_dim:] == 0).all()
+    # un-normalised and permuted
+    order = torch.randperm(len(sp), device=h.device).to(torch.int32)
+    x2, _, _ = h.vectorize(d["mz"], d["intensity"], d["indptr"], order=order, want_bf16=False, norm=False)
+    ref2 = helpers.oracle_vectors(sp, low_dim, norm=False)[_cpu(order)]
+    assert np.array_equal(_cpu(x2), ref2)
+
+
+def test_vectorize_edge_cases(hp):
+    dev = hp.device
+    # spectrum 0 empty, spectrum 1 has out-of-range peaks and 3 peaks in one bin, spectrum 2 has 70 peaks
+    mz = np.r_[np.float32([50.0, 200.01, 200.02, 200.03, 1600.0]),
+               np.sort(np.random.default_rng(0).uniform(101, 1500, 70)).astype(np.float32)]
+    inten = np.random.default_rng(1).random(mz.shape[0]).astype(np.float32)
+    indptr = np.array([0, 0, 5, 75], np.int64)
+    x, _, hidx = hp.vectorize(*(torch.from_numpy(a).to(dev) for a in (mz, inten, indptr)), want_hash_idx=True)
+    ref, ref_idx = ovec.to_vector(mz, inten, indptr, hp.min_mz, 0.05, hp.vec_len, 400, return_hash_idx=True)
+    assert np.array_equal(_cpu(hidx), ref_idx) and ref_idx[0] == -1 and ref_idx[4] == -1
+    np.testing.assert_allclose(_cpu(x), ref, rtol=0, atol=1e-6)
+    assert (_cpu(x)[0] == 0).all()
+    e = torch.empty(0, device=dev)
+    x0, _, _ = hp.vectorize(e.float(), e.float(), torch.zeros(1, dtype=torch.int64, device=dev))
+    assert x0.shape == (0, 400)
+
+
+# ------------------------------------------------------------------ buckets
+@pytest.mark.parametrize("mz_interval", [1, 4])
+def test_bucket_sort(mz_interval):
+    h = pipeline.HotPath(pipeline.Settings(mz_interval=mz_interval))
+    sp = helpers.dataset(20000, 5)
+    d = helpers.to_device(sp, h.device)
+    b = h.bucket_sort(d["precursor_mz"], d["charge"], d["rt"])
+    order, bptr, keys = oivf.bucket_sort(sp.precursor_mz, sp.precursor_charge, mz_interval)
+    assert b.n_buckets == bptr.shape[0] - 1
+    assert np.array_equal(_cpu(b.bucket_ptr), bptr)
+    assert np.array_equal(_cpu(b.order), order)
+    assert np.array_equal(_cpu(b.mz), sp.precursor_mz[order])
+    assert np.array_equal(_cpu(b.rt), sp.retention_time[order])
+    assert np.array_equal(_cpu(b.key).view(np.uint32)[bptr[:-1]], keys)
+
+
+# ------------------------------------------------------------------ scan
+def _pairs(h, xb, buckets, n, impl, thr, cap=1 << 22):
+    import ctypes as C
+
+    from falcon_b200._lib import check, lib, ptr
+
+    pairs = torch.empty(cap, dtype=torch.int64, device=h.device)
+    cnt = torch.zeros(1, dtype=torch.int64, device=h.device)
+    ws = torch.empty(lib.flc_scan_workspace_bytes(n, buckets.n_buckets) + 256, dtype=torch.uint8, device=h.device)
+    check(lib.flc_scan_pairs(ptr(xb), xb.stride(0), n, h.s.low_dim, ptr(buckets.bucket_ptr), buckets.n_buckets,
+                             None, None, 0, None, thr, impl, ptr(pairs), cap, ptr(cnt), ptr(ws), ws.numel(),
+                             C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    k = int(cnt.item())
+    assert k <= cap
+    p = _cpu(pairs[:k]).view(np.uint64)
+    return set(zip((p >> np.uint64(32)).astype(np.int64).tolist(), (p & np.uint64(0xFFFFFFFF)).astype(np.int64).tolist()))
+
+
+@pytest.mark.parametrize("n,lo,hi,low_dim", [(4000, 700.0, 3500.0, 400), (6000, 1000.0, 1012.0, 400),
+                                             (3000, 1000.0, 1003.0, 200), (3000, 1000.0, 1003.0, 800)])
+def test_scan_pairs_tc_and_simt(n, lo, hi, low_dim):
+    """Both scan kernels return every pair whose exact ip clears 1 - eps, nothing
+    outside the bucket, nothing below the bf16 threshold by more than rounding."""
+    h = pipeline.HotPath(pipeline.Settings(low_dim=low_dim, exhaustive=True))
+    sp = helpers.dataset(n, 9, lo, hi)
+    d = helpers.to_device(sp, h.device)
+    b = h.bucket_sort(d["precursor_mz"], d["charge"])
+    x, xb, _ = h.vectorize(d["mz"], d["intensity"], d["indptr"], b.order)
+    thr = h.scan_threshold()
+    xf = _cpu(xb.float())[:, :low_dim].astype(np.float64)
+    xe = _cpu(x).astype(np.float64)
+    bptr = _cpu(b.bucket_ptr)
+    must, may = set(), set()
+    for s, e in zip(bptr[:-1], bptr[1:]):
+        sb = xf[s:e] @ xf[s:e].T
+        se = (xe[s:e] @ xe[s:e].T).astype(np.float32)
+        for q, c in zip(*np.nonzero(np.maximum(np.float32(1) - se, 0) <= np.float32(helpers.EPS))):
+            must.add((q + s, c + s))
+        for q, c in zip(*np.nonzero(sb >= thr - 1e-3)):
+            may.add((q + s, c + s))
+    assert len(must) > n
+    for impl in (1, 0):
+        got = _pairs(h, xb, b, n, impl, thr)
+        assert must <= got, f"impl {impl} missed {len(must - got)} pairs"
+        assert got <= may, f"impl {impl} produced {len(got - may)} spurious pairs"
+
+
+# ------------------------------------------------------------------ k-NN CSR, exhaustive
+@pytest.mark.parametrize("n,lo,hi,scan_impl", [(5000, 700.0, 3500.0, 0), (6000, 1000.0, 1012.0, 0),
+                                               (6000, 1000.0, 1012.0, 1)])
+def test_knn_csr_exhaustive_exact(n, lo, hi, scan_impl):
+    h = pipeline.HotPath(pipeline.Settings(exhaustive=True, scan_impl=scan_impl))
+    sp = helpers.dataset(n, 13, lo, hi)
+    d = helpers.to_device(sp, h.device)
+    b = h.bucket_sort(d["precursor_mz"], d["charge"])
+    x, xb, _ = h.vectorize(d["mz"], d["intensity"], d["indptr"], b.order)
+    g = h.knn_graph(x, xb, b)
+    o = helpers.oracle_pipeline(sp, exhaustive=True, vectors=_cpu(x))
+    ref = o["csr_cut"]
+    assert np.array_equal(_cpu(g.indptr), ref.indptr)
+    assert np.array_equal(_cpu(g.indices), ref.indices)  # neighbour sets AND order identical
+    np.testing.assert_allclose(_cpu(g.dist), ref.data, rtol=0, atol=1e-5)  # north_star tolerance
+    assert (_cpu(g.dist) != ref.data).mean() < 1e-4  # in fact bit-identical up to double rounding
+
+
+def test_knn_csr_without_eps_cut_matches_full_reference_matrix():
+    h = pipeline.HotPath(pipeline.Settings(exhaustive=True, eps_cut=False))
+    sp = helpers.dataset(3000, 17)
+    d = helpers.to_device(sp, h.device)
+    b = h.bucket_sort(d["precursor_mz"], d["charge"])
+    x, xb, _ = h.vectorize(d["mz"], d["intensity"], d["indptr"], b.order)
+    g = h.knn_graph(x, xb, b)
+    ref = helpers.oracle_pipeline(sp, exhaustive=True, vectors=_cpu(x))["csr"]
+    assert np.array_equal(_cpu(g.indptr), ref.indptr)
+    assert np.array_equal(_cpu(g.indices), ref.indices)
+    np.testing.assert_allclose(_cpu(g.dist), ref.data, rtol=0, atol=1e-5)
+
+
+def test_knn_csr_da_mode_and_small_k():
+    s = pipeline.Settings(exhaustive=True, precursor_tol_mass=0.01, precursor_tol_mode="Da", n_neighbors=3,
+                          n_neighbors_ann=5, eps=0.3)
+    h = pipeline.HotPath(s)
+    sp = helpers.dataset(4000, 19, 1000.0, 1004.0)
+    d = helpers.to_device(sp, h.device)
+    b = h.bucket_sort(d["precursor_mz"], d["charge"])
+    x, xb, _ = h.vectorize(d["mz"], d["intensity"], d["indptr"], b.order)
+    g = h.knn_graph(x, xb, b)
+    order, bptr, _ = oivf.bucket_sort(sp.precursor_mz, sp.precursor_charge)
+    mat, _ = oivf.compute_pairwise_distances(_cpu(x), sp.precursor_mz[order], None, bptr, 0.01, "Da", None,
+                                             3, 5, 32, True)
+    ref = oivf.eps_cut(mat, 0.3)
+    assert np.array_equal(_cpu(g.indptr), ref.indptr)
+    assert np.array_equal(_cpu(g.indices), ref.indices)
+
+
+# ------------------------------------------------------------------ IVF
+def test_ivf_shared_centroids_exact_and_recall():
+    """Default n_probe with centroids shared between the CUDA path and the oracle:
+    neighbour sets identical (north_star asks recall >= 0.99)."""
+    h = pipeline.HotPath(pipeline.Settings(exhaustive=False))
+    sp = helpers.dataset(8000, 23, 1000.0, 1008.0)
+    d = helpers.to_device(sp, h.device)
+    b = h.bucket_sort(d["precursor_mz"], d["charge"])
+    x, xb, _ = h.vectorize(d["mz"], d["intensity"], d["indptr"], b.order)
+    ivf = h.build_ivf(x, b)
+    assert ivf.total_centroids > 0
+    nlist, cptr = _cpu(ivf.nlist), _cpu(ivf.centroid_ptr)
+    bptr = _cpu(b.bucket_ptr)
+    assert nlist[:-1].tolist() == [oivf.n_list_rule(int(e - s)) for s, e in zip(bptr[:-1], bptr[1:])]
+    cents = _cpu(ivf.centroids)
+    shared = [cents[cptr[i]: cptr[i] + nlist[i]] if nlist[i] else None for i in range(b.n_buckets)]
+    # coarse assignment / probes equal the oracle's
+    xs = _cpu(x)
+    lid, probes = _cpu(ivf.list_id), _cpu(ivf.probes)
+    for i in range(b.n_buckets):
+        if nlist[i]:
+            s, e = bptr[i], bptr[i + 1]
+            assert np.array_equal(lid[s:e], oivf.assign_lists(xs[s:e], shared[i]))
+            p = oivf.n_probe_rule(int(nlist[i]), 32)
+            assert np.array_equal(probes[s:e, :p], oivf.probe_lists(xs[s:e], shared[i], p))
+            assert (probes[s:e, p:] == -1).all()
+    g = h.knn_graph(x, xb, b, ivf)
+    o = helpers.oracle_pipeline(sp, exhaustive=False, centroids=shared, vectors=xs)
+    ref = o["csr_cut"]
+    gi, gp = _cpu(g.indices), _cpu(g.indptr)
+    hit = sum(len(set(gi[gp[q]: gp[q + 1]]) & set(ref.indices[ref.indptr[q]: ref.indptr[q + 1]]))
+              for q in range(len(sp)))
+    assert hit / max(ref.nnz, 1) >= 0.99
+    assert np.array_equal(gp, ref.indptr) and np.array_equal(gi, ref.indices)
+
+
+def test_kmeans_quality_close_to_oracle():
+    h = pipeline.HotPath(pipeline.Settings(exhaustive=False))
+    sp = helpers.dataset(6000, 29, 1000.0, 1003.0)
+    d = helpers.to_device(sp, h.device)
+    b = h.bucket_sort(d["precursor_mz"], d["charge"])
+    x, _, _ = h.vectorize(d["mz"], d["intensity"], d["indptr"], b.order, want_bf16=False)
+    ivf = h.build_ivf(x, b)
+    xs, bptr, nlist, cptr = _cpu(x), _cpu(b.bucket_ptr), _cpu(ivf.nlist), _cpu(ivf.centroid_ptr)
+    cents = _cpu(ivf.centroids)
+    checked = 0
+    for i in range(b.n_buckets):
+        if nlist[i] and checked < 3:
+            xb_ = xs[bptr[i]: bptr[i + 1]]
+            c_gpu = cents[cptr[i]: cptr[i] + nlist[i]]
+            c_cpu = oivf.kmeans_train(xb_, int(nlist[i]))
+            np.testing.assert_allclose(np.linalg.norm(c_gpu, axis=1), 1.0, atol=1e-5)
+            obj_gpu = (xb_ @ c_gpu.T).max(axis=1).sum()
+            obj_cpu = (xb_ @ c_cpu.T).max(axis=1).sum()
+            assert obj_gpu >= 0.98 * obj_cpu
+            checked += 1
+    assert checked > 0
+
+
+# ------------------------------------------------------------------ DBSCAN + split
+def _random_graph(rng, n, max_deg):
+    deg = rng.integers(1, max_deg + 1, n)
+    indptr = np.r_[0, np.cumsum(deg)].astype(np.int64)
+    indices = np.concatenate([np.r_[i, rng.integers(max(0, i - 40), min(n, i + 40), dd - 1)]
+                              for i, dd in enumerate(deg)]).astype(np.int32)
+    data = (rng.random(indices.shape[0]) * 0.2).astype(np.float32)
+    data[indptr[:-1]] = 0
+    return data, indices, indptr
+
+
+@pytest.mark.parametrize("n,max_deg,seed", [(1, 1, 0), (50, 3, 1), (5000, 4, 2), (20000, 3, 3), (3000, 8, 4)])
+def test_dbscan_random_directed_graphs(hp, n, max_deg, seed):
+    data, indices, indptr = _random_graph(np.random.default_rng(seed), n, max_deg)
+    dev = hp.device
+    g = pipeline.KnnGraph(torch.from_numpy(data).to(dev), torch.from_numpy(indices).to(dev),
+                          torch.from_numpy(indptr).to(dev), len(data), 0)
+    labels, nc = hp.dbscan(g, n)
+    ref = odb.dbscan_sklearn(data, indices, indptr, 0.1)
+    assert np.array_equal(_cpu(labels), ref)  # labels, not just the partition
+    assert nc == ref.max() + 1
+
+
+def test_dbscan_long_chain(hp):
+    """A 30k-long one-way chain: pointer jumping must converge and give one cluster."""
+    n = 30000
+    indptr = np.arange(0, 2 * n + 1, 2, dtype=np.int64)
+    indices = np.stack([np.arange(n), np.minimum(np.arange(n) + 1, n - 1)], 1).reshape(-1).astype(np.int32)
+    data = np.zeros(2 * n, np.float32)
+    dev = hp.device
+    g = pipeline.KnnGraph(torch.from_numpy(data).to(dev), torch.from_numpy(indices).to(dev),
+                          torch.from_numpy(indptr).to(dev), 2 * n, 0)
+    labels, nc = hp.dbscan(g, n)
+    assert nc == 1 and (_cpu(labels) == 0).all()
+
+
+@pytest.mark.parametrize("mode,tol", [("ppm", 20.0), ("Da", 0.02)])
+@pytest.mark.parametrize("values_sorted", [False, True])
+def test_split_clusters(mode, tol, values_sorted):
+    h = pipeline.HotPath(pipeline.Settings(precursor_tol_mass=tol, precursor_tol_mode=mode))
+    rng = np.random.default_rng(31)
+    n = 30000
+    labels = rng.integers(-1, 4000, n).astype(np.int32)
+    labels[rng.random(n) < 0.2] = -1
+    big = rng.random(n) < 0.1
+    labels[big] = 4000 + rng.integers(0, 3, big.sum())  # a few clusters with ~1000 members
+    centre = 400.0 + (np.maximum(labels, 0) % 997)
+    mz = centre + rng.normal(0, 1.0, n) * (centre * 12e-6 if mode == "ppm" else 0.012)
+    dup = rng.random(n) < 0.05
+    mz[dup] = centre[dup]  # exact ties
+    if values_sorted:
+        order = np.argsort(mz, kind="stable")
+        labels, mz = labels[order], mz[order]
+    dev = h.device
+    out, nc = h.split(torch.from_numpy(labels).to(dev), torch.from_numpy(mz).to(dev), values_sorted)
+    out = _cpu(out)
+    ref = np.full(n, -1, np.int64)
+    nxt = 0
+    for l in np.unique(labels[labels >= 0]):
+        members = np.flatnonzero(labels == l)
+        sub, k = odb.postprocess_cluster(mz[members], None, tol, mode, None)
+        ref[members[sub >= 0]] = sub[sub >= 0] + nxt
+        nxt += k
+    assert nc == nxt
+    assert odb.same_partition(out, ref)
+    assert sorted(np.unique(out[out >= 0]).tolist()) == list(range(nc))
+
+
+def test_split_golden_cases(hp, golden_dir):
+    """The reference's own _postprocess_cluster outputs (tests/golden/postprocess.npz)."""
+    g = np.load(os.path.join(golden_dir, "postprocess.npz"))
+    dev = hp.device
+    n_checked = 0
+    for i in range(int(g["n_post"])):
+        if float(g[f"post_rttol{i}"]) >= 0:
+            continue
+        v, mode, tol = g[f"post_v{i}"], str(g[f"post_mode{i}"]), float(g[f"post_tol{i}"])
+        h = pipeline.HotPath(pipeline.Settings(precursor_tol_mass=tol, precursor_tol_mode=mode))
+        out, nc = h.split(torch.zeros(len(v), dtype=torch.int32, device=dev), torch.from_numpy(v).to(dev), False)
+        assert nc == int(g[f"post_k{i}"])
+        assert odb.same_partition(_cpu(out), g[f"post_labels{i}"])
+        n_checked += 1
+    assert n_checked >= 30
+
+
+def test_rt_tolerance_split_is_reported_unsupported(hp):
+    h = pipeline.HotPath(pipeline.Settings(rt_tol=5.0))
+    z = torch.zeros(4, dtype=torch.int32, device=h.device)
+    with pytest.raises(NotImplementedError, match="rt_tol"):
+        h.split(z, torch.ones(4, dtype=torch.float64, device=h.device), False)

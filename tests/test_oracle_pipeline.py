@@ -1,0 +1,90 @@
+"""Self-consistency of the oracle's unpinned stages (buckets / IVF / DBSCAN)."""
+import numpy as np
+from hypothesis import given, settings
+from hypothesis import strategies as st
+
+from oracle import dbscan as odb
+from oracle import ivf as oivf
+from tests import helpers
+
+
+def test_nlist_rule():
+    assert oivf.n_list_rule(99) == 0
+    assert oivf.n_list_rule(100) == 2
+    assert oivf.n_list_rule(155) == 2 and oivf.n_list_rule(156) == 4
+    assert oivf.n_list_rule(39 * 64) == 64 and oivf.n_list_rule(39 * 64 - 1) == 32
+    assert oivf.n_list_rule(10 ** 6) == 2 ** 16
+    assert oivf.n_probe_rule(64, 32) == 8 and oivf.n_probe_rule(1024, 32) == 32
+    assert oivf.n_probe_rule(2, 32) == 1 and oivf.n_probe_rule(64, 32, exhaustive=True) == 64
+
+
+def test_bucket_rule_and_sort():
+    mz = np.array([500.2, 500.7, 500.2004, 334.1, 500.1])
+    z = np.array([2, 2, 2, 3, 2])
+    b = oivf.bucket_ids(mz, z)
+    assert b.tolist() == [int(round((m - 1.00794) * c / 1.0005079)) for m, c in zip(mz, z)]
+    order, ptr, keys = oivf.bucket_sort(mz, z)
+    ks = ((z.astype(np.int64) << 24) | b)[order]
+    assert (np.diff(ks) >= 0).all() and ptr[0] == 0 and ptr[-1] == 5
+    for s, e in zip(ptr[:-1], ptr[1:]):
+        assert (np.diff(mz[order][s:e]) >= 0).all()
+
+
+def test_exhaustive_equals_brute_force():
+    sp = helpers.dataset(3000, 3, 1000.0, 1010.0)
+    o = helpers.oracle_pipeline(sp, exhaustive=True)
+    x, mzs, bptr = o["x"], o["sorted"].precursor_mz, o["bucket_ptr"]
+    sim = (x.astype(np.float64) @ x.astype(np.float64).T).astype(np.float32)
+    csr = o["csr"]
+    assert np.diff(bptr).max() >= 100
+    for q in range(0, 3000, 97):
+        b = np.searchsorted(bptr, q, "right") - 1
+        s, e = bptr[b], bptr[b + 1]
+        cand = np.arange(s, e)
+        order = cand[np.argsort(-sim[q, s:e], kind="stable")][:128]
+        ok = np.abs(mzs[q] - mzs[order]) / mzs[order] * 1e6 < helpers.TOL
+        exp = order[ok][:64]
+        got = csr.indices[csr.indptr[q]: csr.indptr[q + 1]]
+        assert np.array_equal(got, exp)
+        np.testing.assert_array_equal(csr.data[csr.indptr[q]: csr.indptr[q + 1]],
+                                      np.maximum(np.float32(1) - sim[q, exp], 0))
+        assert q in got
+
+
+def test_ivf_is_subset_and_recall_reasonable():
+    sp = helpers.dataset(3000, 3, 1000.0, 1010.0)
+    ex = helpers.oracle_pipeline(sp, exhaustive=True)
+    iv = helpers.oracle_pipeline(sp, exhaustive=False)
+    a, b = ex["csr_cut"], iv["csr_cut"]
+    hit = tot = 0
+    for q in range(3000):
+        ea = set(a.indices[a.indptr[q]: a.indptr[q + 1]].tolist())
+        eb = set(b.indices[b.indptr[q]: b.indptr[q + 1]].tolist())
+        assert eb <= ea
+        hit += len(eb)
+        tot += len(ea)
+    assert hit / tot > 0.5
+
+
+@settings(max_examples=150, deadline=None)
+@given(st.integers(2, 40), st.integers(0, 2 ** 31 - 1))
+def test_dbscan_min_ancestor_equals_sklearn(n, seed):
+    """dbscan_inner == rank of the minimum-index core ancestor."""
+    rng = np.random.default_rng(seed)
+    deg = rng.integers(1, 5, n)
+    indptr = np.r_[0, np.cumsum(deg)]
+    indices = np.concatenate([np.r_[i, rng.integers(0, n, d - 1)] for i, d in enumerate(deg)])
+    data = rng.random(indices.shape[0]).astype(np.float32) * 0.2
+    data[indptr[:-1]] = 0
+    a = odb.dbscan_sklearn(data, indices, indptr, 0.1)
+    b = odb.dbscan_min_ancestor(data, indices, indptr, 0.1)
+    assert np.array_equal(a, b)
+
+
+def test_oracle_clusters_are_pure_on_synthetic_data():
+    sp = helpers.dataset(4000, 11)
+    o = helpers.oracle_pipeline(sp, exhaustive=True)
+    lab, tmpl = o["labels"], o["sorted"].template
+    assert lab.max() > 300
+    for l in np.unique(lab[lab >= 0])[:200]:
+        assert np.unique(tmpl[lab == l]).shape[0] == 1
