@@ -1,0 +1,400 @@
+#!/usr/bin/env python
+"""Benchmark of the falcon clustering hot path (BASELINE.json metric: spectra/sec).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --steps K --warmup W    # CPU reference arm (oracle)
+
+One "step" = one pass of the whole hot path (buckets -> vectors -> IVF -> scan ->
+k-NN CSR -> DBSCAN -> precursor split [-> NCCL label gather]) over the workload
+of BASELINE.json configs[1]: 1 M synthetic spectra with falcon's defaults per
+GPU.  With N > 1 every rank clusters its own 1 M spectra (precursor buckets are
+independent units, so there is no data-path collective; "weak" scaling) and the
+labels are gathered over NCCL inside the step.
+
+Prints ONE JSON line (rank 0).  `value` = spectra/s with the inputs resident in
+HBM; `e2e` = the same through the host-buffer API (pinned H2D + D2H inside the
+timed region); `roofline` = the dominant hand-written kernel against the
+measured peaks of MEASURED_PEAKS.json; `cpu_baseline` = the CPU oracle timed on
+a bounded sample of the same workload on this box's host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "spectra_per_sec_end_to_end"
+UNIT = "spectra/s"
+FALLBACK_PEAKS = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        d["_source"] = "measured"
+        return d
+    d = dict(FALLBACK_PEAKS)
+    d["_source"] = "fallback"
+    return d
+
+
+# --------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device_index: int):
+        self.idx = device_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.idx)], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in open(self.path):
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        os.unlink(self.path)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------- CPU reference
+def bucket_sample(spectra, target: int):
+    """A contiguous range of whole precursor buckets of `spectra` holding about
+    `target` spectra (same bucket-size distribution as the full workload)."""
+    from oracle import ivf as oivf
+
+    order, bptr, _ = oivf.bucket_sort(spectra.precursor_mz, spectra.precursor_charge)
+    nb = bptr.shape[0] - 1
+    b0 = nb // 3
+    b1 = int(np.searchsorted(bptr, bptr[b0] + target, "left"))
+    b1 = min(max(b1, b0 + 1), nb)
+    idx = order[bptr[b0]: bptr[b1]]
+    return spectra.take(np.sort(idx)), b1 - b0
+
+
+def cpu_reference_time(sample, cores: int, exhaustive: bool):
+    from oracle import pipeline as opipe
+
+    t0 = time.perf_counter()
+    labels, stages, _ = opipe.run(sample, n_jobs=cores, exhaustive=exhaustive)
+    return time.perf_counter() - t0, stages, int(labels.max()) + 1
+
+
+def run_reference_arm(args):
+    """CPU arm: the oracle (restatement of the reference's faiss/numba/sklearn
+    path; the reference itself cannot be installed offline) on a bounded sample
+    of the same workload, all host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from falcon_b200 import synth
+
+    cores = len(os.sched_getaffinity(0))
+    full = synth.generate(args.n, 42)
+    sample, n_buckets = bucket_sample(full, args.cpu_sample)
+    times = []
+    for i in range(args.warmup + args.steps):
+        dt, stages, _ = cpu_reference_time(sample, cores, args.exhaustive)
+        log(f"[reference] step {i}: {dt:.2f}s {stages}")
+        if i >= args.warmup:
+            times.append(dt)
+    t = float(np.mean(times))
+    value = len(sample) / t
+    desc = (f"{len(sample)} spectra = {n_buckets} whole precursor buckets of the {args.n}-spectrum workload")
+    out = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc,
+                         "note": "CPU restatement (faiss-cpu/lance/fastcluster unavailable offline): "
+                                 "numpy/OpenBLAS per-bucket IVF + sklearn dbscan_inner, joblib over buckets"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(out), flush=True)
+
+
+def workload_config(args):
+    return {
+        "workload": f"{args.n} synthetic spectra per GPU (seed 42+rank, charge 2/3, 101-1500 m/z, <=50 peaks), "
+                    "falcon defaults low_dim=400 eps=0.10 n_probe=32 n_neighbors=64/128 precursor_tol=20ppm"
+                    + (" exhaustive (n_probe=nlist)" if args.exhaustive else ""),
+        "baseline_config": "configs[1]: 1M synthetic spectra, defaults, single B200",
+        "spectra_per_gpu": args.n, "low_dim": 400, "eps": 0.1, "n_probe": 32, "exhaustive": bool(args.exhaustive),
+        "l2": "inputs larger than L2 (peaks 270 MB, vectors 2.4 GB per step vs 126 MB L2); no flush",
+    }
+
+
+# --------------------------------------------------------------------------- roofline
+def kernel_rooflines(stats: dict, peaks: dict) -> dict:
+    """Algorithmic work per launch of every hand-written kernel."""
+    n, p, d, ldb = stats["n"], stats["n_peaks"], stats["low_dim"], stats["ld_bf16"]
+    pairs, nnz = stats["n_pairs"], stats["nnz"]
+    hbm = peaks["hbm_gbs"]
+    work = {
+        # bytes: peaks (m/z + intensity) + indptr + order + f32 row + bf16 row
+        "vectorize": ("hbm", p * 8 + (n + 1) * 8 + n * 4 + n * d * 4 + n * ldb * 2),
+        # HBM floor of the scan: every bf16 row read once, pairs written once
+        "scan_tc": ("hbm", n * ldb * 2 + pairs * 8),
+        # pairs in/out + exact re-score rows (L2-resident in practice) + m/z + row counts
+        "refine": ("hbm", pairs * 16 + pairs * d * 4 + n * (d * 4 + 8 + 8 + 4)),
+        "pair_hist": ("hbm", pairs * 8 + pairs * 4),
+        "pair_scatter": ("hbm", pairs * 16 + pairs * 12),
+        "csr_compact": ("hbm", nnz * 16 + (n + 1) * 24),
+        "dbscan_core": ("hbm", nnz * 4 + (n + 1) * 8 + n * 5),
+        "dbscan_propagate": ("hbm", nnz * 8 + (n + 1) * 8 + n * 9),
+        "ivf_assign": ("hbm", n * d * 4 + n * 4 * (1 + stats.get("max_nprobe", 1))),
+        "kmeans_assign": ("hbm", n * d * 4 + n * 4),
+        "kmeans_update": ("hbm", stats.get("ivf_rows", 0) * d * 4),
+    }
+    out = {}
+    for name, (bound, bytes_) in work.items():
+        if name in stats["kernels"]:
+            ms, launches = stats["kernels"][name]
+            if launches and ms > 0:
+                ach = bytes_ / (ms / launches * 1e-3) / 1e9
+                out[name] = {"bound": bound, "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm,
+                             "ms_per_launch": ms / launches, "launches_per_step": launches / stats["steps"],
+                             "algorithmic_bytes_per_launch": bytes_}
+    # tensor view of the scan: FLOPs the IVF semantics require
+    if "scan_tc" in stats["kernels"]:
+        ms, launches = stats["kernels"]["scan_tc"]
+        tf = 2.0 * d * stats["required_pairs"] / (ms / launches * 1e-3) / 1e12
+        pk = peaks["bf16_tflops"]
+        out["scan_tc"]["tensor"] = {"achieved": tf, "peak": pk, "unit": "TFLOP/s", "frac": tf / pk,
+                                    "required_pairs": stats["required_pairs"],
+                                    "computed_pairs": stats["computed_pairs"]}
+    return out
+
+
+# --------------------------------------------------------------------------- main arm
+def run_ours(args):
+    import torch
+
+    from falcon_b200 import _lib, distributed as fdist, pipeline, synth
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: falcon_b200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist  # noqa: F811
+
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    peaks = load_peaks()
+    settings = pipeline.Settings(exhaustive=args.exhaustive)
+    hp = pipeline.HotPath(settings, dev)
+
+    t0 = time.perf_counter()
+    sp = synth.generate(args.n, 42 + rank)
+    log(f"[rank {rank}] generated {len(sp)} spectra / {sp.n_peaks} peaks in {time.perf_counter() - t0:.1f}s")
+    host = {k: torch.from_numpy(np.ascontiguousarray(v)).pin_memory() for k, v in dict(
+        mz=sp.mz, intensity=sp.intensity, indptr=sp.indptr, precursor_mz=sp.precursor_mz,
+        charge=sp.precursor_charge).items()}
+    h2d_bytes = sum(t.numel() * t.element_size() for t in host.values())
+    d = {k: v.to(dev) for k, v in host.items()}
+    labels_host = torch.empty(len(sp), dtype=torch.int32).pin_memory()
+
+    def gather(labels, n_clusters):
+        if world > 1:
+            return fdist.gather_labels(labels, n_clusters)[0]
+        return labels
+
+    def step_resident():
+        labels, nc = hp.run(d["mz"], d["intensity"], d["indptr"], d["precursor_mz"], d["charge"])
+        return gather(labels, nc), nc
+
+    def step_e2e():
+        dd = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+        labels, nc = hp.run(dd["mz"], dd["intensity"], dd["indptr"], dd["precursor_mz"], dd["charge"])
+        labels_host.copy_(labels, non_blocking=True)
+        out = gather(labels, nc)
+        torch.cuda.current_stream().synchronize()
+        return out, nc
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup, sample_clocks=False, profile=False):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        sampler = ClockSampler(local) if sample_clocks else None
+        if sampler:
+            sampler.start()
+        if profile:
+            _lib.profile_reset()
+            _lib.profile_enable(True)
+        _lib.reset_launch_count()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(steps):
+            out = fn()
+        b.record()
+        torch.cuda.synchronize()
+        launches = _lib.launch_count()
+        if profile:
+            _lib.profile_enable(False)
+        clocks = sampler.stop() if sampler else None
+        barrier()
+        ms = a.elapsed_time(b) / steps
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, out, launches, clocks
+
+    ms, (labels, n_clusters), launches, clocks = timed(step_resident, args.steps, args.warmup,
+                                                       sample_clocks=True, profile=True)
+    kernels = _lib.profile_summary()
+    ms_e2e, _, _, _ = timed(step_e2e, args.steps, max(1, args.warmup - 1))
+    total = args.n * world
+
+    # one instrumented pass for the roofline statistics (outside the timed regions)
+    hp2 = pipeline.HotPath(settings, dev, profile=True)
+    _, _, keep = hp2.run(d["mz"], d["intensity"], d["indptr"], d["precursor_mz"], d["charge"], keep=True)
+    stage_ms = hp2.timer.result()
+    sizes = (keep["buckets"].bucket_ptr[1:] - keep["buckets"].bucket_ptr[:-1]).double()
+    computed_pairs = float((sizes * sizes).sum().item())
+    required_pairs = computed_pairs
+    ivf = keep["ivf"]
+    stats_extra = {}
+    if ivf is not None:
+        bp = keep["buckets"].bucket_ptr
+        b_of_row = torch.searchsorted(bp, torch.arange(args.n, device=dev), right=True) - 1
+        max_l = int(ivf.nlist.max().item()) + 1
+        lsize = torch.bincount(b_of_row * max_l + ivf.list_id.long(), minlength=int(bp.shape[0]) * max_l)
+        pr = ivf.probes.long()
+        valid = pr >= 0
+        idx = (b_of_row[:, None] * max_l + pr.clamp(min=0))
+        required_pairs = float((lsize[idx] * valid).sum().item())
+        nl = ivf.nlist[:-1].long()
+        stats_extra = {"max_nprobe": ivf.max_nprobe, "ivf_rows": int(sizes[nl > 0].sum().item()),
+                       "total_centroids": ivf.total_centroids}
+    stats = {"n": args.n, "n_peaks": sp.n_peaks, "low_dim": settings.low_dim, "ld_bf16": hp.ld_bf16,
+             "n_pairs": keep["graph"].n_pairs, "nnz": keep["graph"].nnz, "kernels": kernels,
+             "steps": args.steps, "required_pairs": required_pairs, "computed_pairs": computed_pairs,
+             **stats_extra}
+    roof_all = kernel_rooflines(stats, peaks)
+    hand = {k: v for k, v in kernels.items() if k in roof_all}
+    dominant = max(hand, key=lambda k: hand[k][0]) if hand else None
+    roofline = None
+    if dominant:
+        r = roof_all[dominant]
+        roofline = {"kernel": dominant, "bound": r["bound"], "achieved": r["achieved"], "peak": r["peak"],
+                    "unit": r["unit"], "frac": r["frac"], "traffic": None,
+                    "peak_source": f"{peaks['_source']} (MEASURED_PEAKS.json hbm_gbs; kernel timed alone -> burst figure)",
+                    "ms_per_launch": r["ms_per_launch"],
+                    "share_of_step": hand[dominant][0] / args.steps / ms}
+        if "tensor" in r:
+            roofline["tensor"] = r["tensor"]
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = len(os.sched_getaffinity(0))
+        sample, nb = bucket_sample(sp, args.cpu_sample)
+        cpu_reference_time(bucket_sample(sp, 4000)[0], cores, args.exhaustive)  # warm the worker pool / imports
+        dt, stages, _ = cpu_reference_time(sample, cores, args.exhaustive)
+        cpu_baseline = {"value": len(sample) / dt, "unit": UNIT, "cores": cores, "kind": "port",
+                        "sample": f"{len(sample)} spectra = {nb} whole precursor buckets of the workload, "
+                                  f"{dt:.1f}s of CPU work",
+                        "stages_s": stages}
+
+    if rank == 0:
+        bsz = sizes.cpu().numpy()
+        out = {
+            "metric": METRIC, "value": total / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16 scan / f32 vectors / f64 re-score", "data": "synthetic",
+            "config": workload_config(args),
+            "e2e": {"value": total / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
+                    "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": args.n * 4},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
+            "n_clusters": int(n_clusters),
+            "stage_ms": stage_ms,
+            "kernels_ms_per_step": {k: v[0] / args.steps for k, v in kernels.items()},
+            "kernel_rooflines": {k: {"frac": v["frac"], "achieved": v["achieved"], "unit": v["unit"],
+                                     "ms_per_launch": v["ms_per_launch"]} for k, v in roof_all.items()},
+            "bucket_sizes": {"n_buckets": int(bsz.shape[0]), "mean": float(bsz.mean()), "p50": float(np.median(bsz)),
+                             "p99": float(np.percentile(bsz, 99)), "max": float(bsz.max())},
+            "n_pairs": keep["graph"].n_pairs, "nnz": keep["graph"].nnz,
+        }
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n", type=int, default=1_000_000, help="spectra per GPU")
+    ap.add_argument("--exhaustive", action="store_true", help="n_probe = nlist (BASELINE configs[2])")
+    ap.add_argument("--cpu-sample", type=int, default=150_000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -47,6 +47,10 @@ SIGNATURES = {
     "flc_launch_count": (_u64, []),
     "flc_reset_launch_count": (None, []),
     "flc_check_device": (C.c_int, [C.c_int]),
+    "flc_profile_enable": (None, [C.c_int]),
+    "flc_profile_reset": (None, []),
+    "flc_profile_count": (C.c_int, []),
+    "flc_profile_get": (C.c_int, [C.c_int, C.c_char_p, C.c_int, C.POINTER(_f64), C.POINTER(C.c_int)]),
     "flc_get_dim": (C.c_int, [_f32, _f32, _f32, C.POINTER(_u32), C.POINTER(_f32), C.POINTER(_f32)]),
     "flc_hash_table": (C.c_int, [_u32, _u32, _u32, _p, _p]),
     "flc_vectorize": (C.c_int, [_p, _p, _p, _p, _i64, _f64, _f64, _u32, _u32, _u32, C.c_int,
@@ -112,3 +116,22 @@ def launch_count() -> int:
 
 def reset_launch_count() -> None:
     lib.flc_reset_launch_count()
+
+
+def profile_enable(on: bool) -> None:
+    lib.flc_profile_enable(1 if on else 0)
+
+
+def profile_reset() -> None:
+    lib.flc_profile_reset()
+
+
+def profile_summary() -> dict:
+    """{kernel name: (total device ms, launches)} since the last reset."""
+    out = {}
+    for i in range(lib.flc_profile_count()):
+        name = C.create_string_buffer(64)
+        ms, k = C.c_double(0), C.c_int(0)
+        check(lib.flc_profile_get(i, name, 64, C.byref(ms), C.byref(k)))
+        out[name.value.decode()] = (ms.value, k.value)
+    return out

@@ -123,28 +123,28 @@ int flc_bucket_sort(const double* precursor_mz, const int32_t* charge, int64_t n
   if (!ws.ok) return set_error(FLC_ERR_WORKSPACE, "bucket_sort workspace too small: need %zu", ws.used);
   const unsigned blocks = static_cast<unsigned>((n + 255) / 256);
   const int num = static_cast<int>(n);
-  bucket_key_kernel<<<blocks, 256, 0, stream>>>(precursor_mz, charge, n, mz_interval, L.key_a, L.mz_a,
-                                                L.idx_a);
+  timed("bucket_key", stream, [&] { bucket_key_kernel<<<blocks, 256, 0, stream>>>(precursor_mz, charge, n, mz_interval, L.key_a, L.mz_a,
+                                                L.idx_a); });
   FLC_LAUNCH_CHECK();
   size_t tmp = L.cub_bytes;
   FLC_CUDA(cub::DeviceRadixSort::SortPairs(L.cub_tmp, tmp, L.mz_a, L.mz_b, L.idx_a, L.idx_b, num, 0, 64,
                                            stream));
   count_launch(9);
-  gather_kernel<uint32_t><<<blocks, 256, 0, stream>>>(L.key_a, L.idx_b, n, L.key_b);
+  timed("gather", stream, [&] { gather_kernel<uint32_t><<<blocks, 256, 0, stream>>>(L.key_a, L.idx_b, n, L.key_b); });
   FLC_LAUNCH_CHECK();
   tmp = L.cub_bytes;
   FLC_CUDA(cub::DeviceRadixSort::SortPairs(L.cub_tmp, tmp, L.key_b, key_sorted, L.idx_b, order, num, 0, 32,
                                            stream));
   count_launch(5);
-  gather_kernel<double><<<blocks, 256, 0, stream>>>(precursor_mz, order, n, mz_sorted);
+  timed("gather", stream, [&] { gather_kernel<double><<<blocks, 256, 0, stream>>>(precursor_mz, order, n, mz_sorted); });
   FLC_LAUNCH_CHECK();
-  bucket_head_kernel<<<blocks, 256, 0, stream>>>(key_sorted, n, L.flag);
+  timed("bucket_head", stream, [&] { bucket_head_kernel<<<blocks, 256, 0, stream>>>(key_sorted, n, L.flag); });
   FLC_LAUNCH_CHECK();
   tmp = L.cub_bytes;
   FLC_CUDA(cub::DeviceSelect::Flagged(L.cub_tmp, tmp, cub::CountingInputIterator<int64_t>(0), L.flag,
                                       bucket_ptr, L.n_sel, num, stream));
   count_launch(2);
-  bucket_close_kernel<<<1, 1, 0, stream>>>(bucket_ptr, L.n_sel, n);
+  timed("bucket_close", stream, [&] { bucket_close_kernel<<<1, 1, 0, stream>>>(bucket_ptr, L.n_sel, n); });
   FLC_LAUNCH_CHECK();
   FLC_CUDA(cudaMemcpyAsync(n_buckets, L.n_sel, sizeof(int64_t), cudaMemcpyDeviceToHost, stream));
   FLC_CUDA(cudaStreamSynchronize(stream));
@@ -158,11 +158,11 @@ int flc_gather(const void* in, const int32_t* order, int64_t n, int elem_bytes, 
   if (n <= 0) return FLC_OK;
   const unsigned blocks = static_cast<unsigned>((n + 255) / 256);
   if (elem_bytes == 4)
-    gather_kernel<uint32_t><<<blocks, 256, 0, as_stream(stream)>>>(
-        static_cast<const uint32_t*>(in), order, n, static_cast<uint32_t*>(out));
+    timed("gather", stream, [&] { gather_kernel<uint32_t><<<blocks, 256, 0, as_stream(stream)>>>(
+        static_cast<const uint32_t*>(in), order, n, static_cast<uint32_t*>(out)); });
   else
-    gather_kernel<uint64_t><<<blocks, 256, 0, as_stream(stream)>>>(
-        static_cast<const uint64_t*>(in), order, n, static_cast<uint64_t*>(out));
+    timed("gather", stream, [&] { gather_kernel<uint64_t><<<blocks, 256, 0, as_stream(stream)>>>(
+        static_cast<const uint64_t*>(in), order, n, static_cast<uint64_t*>(out)); });
   FLC_LAUNCH_CHECK();
   return FLC_OK;
 }
@@ -171,8 +171,8 @@ int flc_scatter32(const void* in, const int32_t* order, int64_t n, void* out, fl
   using namespace flc;
   if (n <= 0) return FLC_OK;
   const unsigned blocks = static_cast<unsigned>((n + 255) / 256);
-  scatter32_kernel<<<blocks, 256, 0, as_stream(stream)>>>(static_cast<const uint32_t*>(in), order, n,
-                                                        static_cast<uint32_t*>(out));
+  timed("scatter32", stream, [&] { scatter32_kernel<<<blocks, 256, 0, as_stream(stream)>>>(static_cast<const uint32_t*>(in), order, n,
+                                                        static_cast<uint32_t*>(out)); });
   FLC_LAUNCH_CHECK();
   return FLC_OK;
 }

@@ -48,6 +48,28 @@ inline void count_launch(uint64_t k = 1) { g_launches.fetch_add(k, std::memory_o
     if (rc__ != FLC_OK) return rc__;                                                        \
   } while (0)
 
+// ---------------------------------------------------------------- per-kernel timing
+// When enabled (flc_profile_enable), a ProfScope brackets a kernel launch with
+// CUDA events on the launching stream; flc_profile_get() reports the summed
+// device time and launch count per kernel name.
+struct ProfScope {
+  ProfScope(const char* name, cudaStream_t stream);
+  ~ProfScope();
+  int slot;
+  cudaStream_t stream;
+};
+
+template <typename F>
+inline void timed(const char* name, cudaStream_t stream, F&& launch) {
+  ProfScope scope(name, stream);
+  launch();
+}
+template <typename F>
+inline void timed(const char* name, flc_stream_t stream, F&& launch) {
+  ProfScope scope(name, static_cast<cudaStream_t>(stream));
+  launch();
+}
+
 // ---------------------------------------------------------------- workspace carving
 struct Workspace {
   char* base;

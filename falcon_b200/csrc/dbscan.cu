@@ -350,27 +350,27 @@ int flc_dbscan(const float* dist, const int32_t* indices, const int64_t* indptr,
   if (!ws.ok) return set_error(FLC_ERR_WORKSPACE, "dbscan workspace too small: need %zu", ws.used);
   const unsigned wblocks = static_cast<unsigned>((n * 32 + 255) / 256);
   const unsigned tblocks = static_cast<unsigned>((n + 1 + 255) / 256);
-  dbscan_core_kernel<<<wblocks, 256, 0, stream>>>(dist, indptr, n, eps, min_samples, L.m, L.core);
+  timed("dbscan_core", stream, [&] { dbscan_core_kernel<<<wblocks, 256, 0, stream>>>(dist, indptr, n, eps, min_samples, L.m, L.core); });
   FLC_LAUNCH_CHECK();
   int32_t changed = 1;
   int sweeps = 0;
   while (changed) {
     FLC_CUDA(cudaMemsetAsync(L.changed, 0, sizeof(int32_t), stream));
     for (int rep = 0; rep < 2; ++rep) {
-      dbscan_propagate_kernel<<<wblocks, 256, 0, stream>>>(dist, indices, indptr, n, eps, L.core, L.m,
-                                                           L.changed);
+      timed("dbscan_propagate", stream, [&] { dbscan_propagate_kernel<<<wblocks, 256, 0, stream>>>(dist, indices, indptr, n, eps, L.core, L.m,
+                                                           L.changed); });
       FLC_LAUNCH_CHECK();
     }
     FLC_CUDA(cudaMemcpyAsync(&changed, L.changed, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
     FLC_CUDA(cudaStreamSynchronize(stream));
     if (++sweeps > 100000) return set_error(FLC_ERR_CUDA, "dbscan propagation did not converge");
   }
-  dbscan_seed_kernel<<<tblocks, 256, 0, stream>>>(L.m, L.core, n, L.seed);
+  timed("dbscan_seed", stream, [&] { dbscan_seed_kernel<<<tblocks, 256, 0, stream>>>(L.m, L.core, n, L.seed); });
   FLC_LAUNCH_CHECK();
   size_t tmp = L.cub_bytes;
   FLC_CUDA(cub::DeviceScan::ExclusiveSum(L.cub_tmp, tmp, L.seed, L.rank, static_cast<int>(n + 1), stream));
   count_launch(2);
-  dbscan_label_kernel<<<tblocks, 256, 0, stream>>>(L.m, L.rank, n, labels);
+  timed("dbscan_label", stream, [&] { dbscan_label_kernel<<<tblocks, 256, 0, stream>>>(L.m, L.rank, n, labels); });
   FLC_LAUNCH_CHECK();
   int32_t total = 0;
   FLC_CUDA(cudaMemcpyAsync(&total, L.rank + n, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
@@ -413,19 +413,19 @@ int flc_split_clusters(const int32_t* labels_in, const double* precursor_mz, int
   const int32_t* idx_in;
   if (!values_sorted) {
     // rows by precursor m/z first, then (stable) by label
-    split_mzkey_kernel<<<tblocks, 256, 0, stream>>>(precursor_mz, n, L.mzkey_a, L.idx_a);
+    timed("split_mzkey", stream, [&] { split_mzkey_kernel<<<tblocks, 256, 0, stream>>>(precursor_mz, n, L.mzkey_a, L.idx_a); });
     FLC_LAUNCH_CHECK();
     tmp = L.cub_bytes;
     FLC_CUDA(cub::DeviceRadixSort::SortPairs(L.cub_tmp, tmp, L.mzkey_a, L.mzkey_b, L.idx_a, L.idx_b, num, 0,
                                              64, stream));
     count_launch(9);
     // key of the m/z-sorted rows
-    split_key_kernel<<<tblocks, 256, 0, stream>>>(labels_in, n, L.key_b, L.idx_a);
+    timed("split_key", stream, [&] { split_key_kernel<<<tblocks, 256, 0, stream>>>(labels_in, n, L.key_b, L.idx_a); });
     FLC_LAUNCH_CHECK();
     FLC_TRY(flc_gather(L.key_b, L.idx_b, n, 4, L.key_a, stream_));
     idx_in = L.idx_b;
   } else {
-    split_key_kernel<<<tblocks, 256, 0, stream>>>(labels_in, n, L.key_a, L.idx_a);
+    timed("split_key", stream, [&] { split_key_kernel<<<tblocks, 256, 0, stream>>>(labels_in, n, L.key_a, L.idx_a); });
     FLC_LAUNCH_CHECK();
     idx_in = L.idx_a;
   }
@@ -435,8 +435,8 @@ int flc_split_clusters(const int32_t* labels_in, const double* precursor_mz, int
   FLC_CUDA(cub::DeviceRadixSort::SortPairs(L.cub_tmp, tmp, L.key_a, L.key_b, idx_in, perm, num, 0, 32, stream));
   count_launch(5);
   const uint32_t* key_sorted = L.key_b;
-  split_prepare_kernel<<<tblocks, 256, 0, stream>>>(key_sorted, perm, precursor_mz, n, L.vs, L.ghead,
-                                                    L.runhead);
+  timed("split_prepare", stream, [&] { split_prepare_kernel<<<tblocks, 256, 0, stream>>>(key_sorted, perm, precursor_mz, n, L.vs, L.ghead,
+                                                    L.runhead); });
   FLC_LAUNCH_CHECK();
   tmp = L.cub_bytes;
   FLC_CUDA(cub::DeviceSelect::Flagged(L.cub_tmp, tmp, cub::CountingInputIterator<int64_t>(0), L.ghead,
@@ -444,26 +444,26 @@ int flc_split_clusters(const int32_t* labels_in, const double* precursor_mz, int
   count_launch(2);
   // Upper bound on the number of groups is n: launch one warp per possible group.
   const unsigned gblocks = static_cast<unsigned>((n * 32 + 255) / 256);
-  split_group_kernel<<<gblocks, 256, 0, stream>>>(L.gstart, L.n_groups, key_sorted, L.vs, n, tol, tol_mode,
-                                                  L.list_a, L.list_b, L.runhead);
+  timed("split_group", stream, [&] { split_group_kernel<<<gblocks, 256, 0, stream>>>(L.gstart, L.n_groups, key_sorted, L.vs, n, tol, tol_mode,
+                                                  L.list_a, L.list_b, L.runhead); });
   FLC_LAUNCH_CHECK();
   tmp = L.cub_bytes;
   FLC_CUDA(cub::DeviceSelect::Flagged(L.cub_tmp, tmp, cub::CountingInputIterator<int64_t>(0), L.runhead,
                                       L.rstart, L.n_runs, num, stream));
   count_launch(2);
-  u8_to_i32_kernel<<<tblocks, 256, 0, stream>>>(L.runhead, n, L.run_i32);
+  timed("u8_to_i32", stream, [&] { u8_to_i32_kernel<<<tblocks, 256, 0, stream>>>(L.runhead, n, L.run_i32); });
   FLC_LAUNCH_CHECK();
   tmp = L.cub_bytes;
   FLC_CUDA(cub::DeviceScan::InclusiveSum(L.cub_tmp, tmp, L.run_i32, L.run_id, num, stream));
   count_launch(2);
-  split_keep_kernel<<<static_cast<unsigned>((n + 1 + 255) / 256), 256, 0, stream>>>(L.rstart, L.n_runs,
+  timed("split_keep", stream, [&] { split_keep_kernel<<<static_cast<unsigned>((n + 1 + 255) / 256), 256, 0, stream>>>(L.rstart, L.n_runs,
                                                                                    key_sorted, n, min_samples,
-                                                                                   L.kept);
+                                                                                   L.kept); });
   FLC_LAUNCH_CHECK();
   tmp = L.cub_bytes;
   FLC_CUDA(cub::DeviceScan::ExclusiveSum(L.cub_tmp, tmp, L.kept, L.new_id, num + 1, stream));
   count_launch(2);
-  split_label_kernel<<<tblocks, 256, 0, stream>>>(L.run_id, L.kept, L.new_id, perm, n, labels_out);
+  timed("split_label", stream, [&] { split_label_kernel<<<tblocks, 256, 0, stream>>>(L.run_id, L.kept, L.new_id, perm, n, labels_out); });
   FLC_LAUNCH_CHECK();
   int32_t total = 0;
   FLC_CUDA(cudaMemcpyAsync(&total, L.new_id + n, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));

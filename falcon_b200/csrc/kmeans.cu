@@ -300,8 +300,8 @@ int flc_ivf_plan(const int64_t* bucket_ptr, int64_t n_buckets, int32_t n_probe, 
   FLC_REQUIRE(n_probe >= 1, "n_probe must be >= 1");
   FLC_REQUIRE(total_centroids && max_nprobe, "null host outputs");
   cudaStream_t stream = as_stream(stream_);
-  ivf_plan_kernel<<<1, 1024, 0, stream>>>(bucket_ptr, n_buckets, n_probe, exhaustive, nlist, nprobe,
-                                          centroid_ptr);
+  timed("ivf_plan", stream, [&] { ivf_plan_kernel<<<1, 1024, 0, stream>>>(bucket_ptr, n_buckets, n_probe, exhaustive, nlist, nprobe,
+                                          centroid_ptr); });
   FLC_LAUNCH_CHECK();
   int64_t tail[2] = {0, 0};
   FLC_CUDA(cudaMemcpyAsync(tail, centroid_ptr + n_buckets, 2 * sizeof(int64_t), cudaMemcpyDeviceToHost, stream));
@@ -336,19 +336,19 @@ int flc_kmeans_train(const float* x, int64_t ld, int64_t n, uint32_t low_dim, co
     FLC_CUDA(cudaFuncSetAttribute(kmeans_assign_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   static_cast<int>(smem)));
   const unsigned cblocks = static_cast<unsigned>(total_centroids);
-  kmeans_init_kernel<<<cblocks, 128, 0, stream>>>(x, ld, low_dim, bucket_ptr, n_buckets, nlist, centroid_ptr,
-                                                  total_centroids, centroids);
+  timed("kmeans_init", stream, [&] { kmeans_init_kernel<<<cblocks, 128, 0, stream>>>(x, ld, low_dim, bucket_ptr, n_buckets, nlist, centroid_ptr,
+                                                  total_centroids, centroids); });
   FLC_LAUNCH_CHECK();
   for (int it = 0; it < niter; ++it) {
-    kmeans_assign_kernel<<<static_cast<unsigned>((n + 7) / 8), 256, smem, stream>>>(
-        x, ld, n, low_dim, bucket_ptr, n_buckets, nlist, centroid_ptr, centroids, L.assign);
+    timed("kmeans_assign", stream, [&] { kmeans_assign_kernel<<<static_cast<unsigned>((n + 7) / 8), 256, smem, stream>>>(
+        x, ld, n, low_dim, bucket_ptr, n_buckets, nlist, centroid_ptr, centroids, L.assign); });
     FLC_LAUNCH_CHECK();
-    kmeans_update_kernel<<<cblocks, 128, 0, stream>>>(x, ld, low_dim, bucket_ptr, n_buckets, centroid_ptr,
+    timed("kmeans_update", stream, [&] { kmeans_update_kernel<<<cblocks, 128, 0, stream>>>(x, ld, low_dim, bucket_ptr, n_buckets, centroid_ptr,
                                                       total_centroids, L.assign, centroids, L.new_centroids,
-                                                      L.counts);
+                                                      L.counts); });
     FLC_LAUNCH_CHECK();
-    kmeans_fix_kernel<<<static_cast<unsigned>(n_buckets), 128, 0, stream>>>(
-        low_dim, n_buckets, nlist, centroid_ptr, L.new_centroids, L.counts, centroids);
+    timed("kmeans_fix", stream, [&] { kmeans_fix_kernel<<<static_cast<unsigned>(n_buckets), 128, 0, stream>>>(
+        low_dim, n_buckets, nlist, centroid_ptr, L.new_centroids, L.counts, centroids); });
     FLC_LAUNCH_CHECK();
   }
   return FLC_OK;
@@ -369,9 +369,9 @@ int flc_ivf_assign(const float* x, int64_t ld, int64_t n, uint32_t low_dim, cons
   if (smem > 48 * 1024)
     FLC_CUDA(cudaFuncSetAttribute(ivf_assign_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   static_cast<int>(smem)));
-  ivf_assign_kernel<<<static_cast<unsigned>((n + 7) / 8), 256, smem, stream>>>(
+  timed("ivf_assign", stream, [&] { ivf_assign_kernel<<<static_cast<unsigned>((n + 7) / 8), 256, smem, stream>>>(
       x, ld, n, low_dim, bucket_ptr, n_buckets, nlist, nprobe, centroid_ptr, centroids, max_nprobe, list_id,
-      probes);
+      probes); });
   FLC_LAUNCH_CHECK();
   return FLC_OK;
 }

@@ -322,13 +322,13 @@ int flc_knn_csr(const uint64_t* pairs, const uint64_t* pair_count, uint64_t pair
   FLC_CUDA(cudaMemsetAsync(L.row_count, 0, sizeof(int32_t) * (n + 1), stream));
   const unsigned pair_blocks =
       static_cast<unsigned>(std::min<uint64_t>((total + 255) / 256 + 1, uint64_t(kNumSMs) * 32));
-  pair_hist_kernel<<<pair_blocks, 256, 0, stream>>>(pairs, pair_count, pair_capacity, n, L.cnt);
+  timed("pair_hist", stream, [&] { pair_hist_kernel<<<pair_blocks, 256, 0, stream>>>(pairs, pair_count, pair_capacity, n, L.cnt); });
   FLC_LAUNCH_CHECK();
   size_t tmp = L.cub_bytes;
   FLC_CUDA(cub::DeviceScan::ExclusiveSum(L.cub_tmp, tmp, L.cnt, L.off, static_cast<int>(n + 1), stream));
   count_launch(2);
-  pair_scatter_kernel<<<pair_blocks, 256, 0, stream>>>(pairs, pair_count, pair_capacity, n, L.off,
-                                                       L.cursor, L.grouped);
+  timed("pair_scatter", stream, [&] { pair_scatter_kernel<<<pair_blocks, 256, 0, stream>>>(pairs, pair_count, pair_capacity, n, L.off,
+                                                       L.cursor, L.grouped); });
   FLC_LAUNCH_CHECK();
 
   RefineParams P;
@@ -349,7 +349,7 @@ int flc_knn_csr(const uint64_t* pairs, const uint64_t* pair_count, uint64_t pair
     FLC_CUDA(cudaFuncSetAttribute(refine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   static_cast<int>(smem)));
   const unsigned rblocks = static_cast<unsigned>((n + kRefineWarps - 1) / kRefineWarps);
-  refine_kernel<<<rblocks, kRefineWarps * 32, smem, stream>>>(P, L.off, L.grouped, L.row_count);
+  timed("refine", stream, [&] { refine_kernel<<<rblocks, kRefineWarps * 32, smem, stream>>>(P, L.off, L.grouped, L.row_count); });
   FLC_LAUNCH_CHECK();
   tmp = L.cub_bytes;
   FLC_CUDA(cub::DeviceScan::ExclusiveSum(L.cub_tmp, tmp, L.row_count, indptr, static_cast<int>(n + 1), stream));
@@ -362,7 +362,7 @@ int flc_knn_csr(const uint64_t* pairs, const uint64_t* pair_count, uint64_t pair
     return set_error(FLC_ERR_CAPACITY, "CSR needs %lld entries, capacity %llu",
                      static_cast<long long>(total_nnz), static_cast<unsigned long long>(nnz_capacity));
   const unsigned cblocks = static_cast<unsigned>((n * 32 + 255) / 256);
-  csr_compact_kernel<<<cblocks, 256, 0, stream>>>(L.grouped, L.off, indptr, n, nnz_capacity, dist, indices);
+  timed("csr_compact", stream, [&] { csr_compact_kernel<<<cblocks, 256, 0, stream>>>(L.grouped, L.off, indptr, n, nnz_capacity, dist, indices); });
   FLC_LAUNCH_CHECK();
   return FLC_OK;
 }

@@ -112,9 +112,9 @@ int flc_scan_pairs(const uint16_t* x_bf16, int64_t ld_bf16, int64_t n, uint32_t 
     if (smem > 48 * 1024)
       FLC_CUDA(cudaFuncSetAttribute(scan_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     static_cast<int>(smem)));
-    scan_simt_kernel<<<static_cast<unsigned>((n + 3) / 4), 128, smem, stream>>>(
+    timed("scan_simt", stream, [&] { scan_simt_kernel<<<static_cast<unsigned>((n + 3) / 4), 128, smem, stream>>>(
         x_bf16, ld_bf16, n, low_dim, bucket_ptr, n_buckets, threshold, pairs, pair_capacity,
-        reinterpret_cast<unsigned long long*>(pair_count));
+        reinterpret_cast<unsigned long long*>(pair_count)); });
     FLC_LAUNCH_CHECK();
     return FLC_OK;
   }
@@ -122,8 +122,8 @@ int flc_scan_pairs(const uint16_t* x_bf16, int64_t ld_bf16, int64_t n, uint32_t 
   ScanLayout L;
   scan_layout(ws, n_buckets, L);
   if (!ws.ok) return set_error(FLC_ERR_WORKSPACE, "scan workspace too small: need %zu", ws.used);
-  tile_count_kernel<<<static_cast<unsigned>((n_buckets + 1 + 255) / 256), 256, 0, stream>>>(
-      bucket_ptr, n_buckets, L.tiles);
+  timed("tile_count", stream, [&] { tile_count_kernel<<<static_cast<unsigned>((n_buckets + 1 + 255) / 256), 256, 0, stream>>>(
+      bucket_ptr, n_buckets, L.tiles); });
   FLC_LAUNCH_CHECK();
   size_t tmp = L.cub_bytes;
   FLC_CUDA(cub::DeviceScan::ExclusiveSum(L.cub_tmp, tmp, L.tiles, L.tile_off,

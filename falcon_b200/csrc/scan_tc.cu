@@ -406,8 +406,8 @@ int launch_scan_tc(const uint16_t* x_bf16, int64_t ld_bf16, int64_t n, uint32_t 
     FLC_CUDA(cudaFuncSetAttribute(scan_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     attr_set = true;
   }
-  scan_tc_kernel<<<kNumSMs, kScanThreads, kSmemBytes, stream>>>(tmap, low_dim, bucket_ptr, n_buckets, tile_off,
-                                                               threshold, pairs, pair_capacity, pair_count);
+  timed("scan_tc", stream, [&] { scan_tc_kernel<<<kNumSMs, kScanThreads, kSmemBytes, stream>>>(tmap, low_dim, bucket_ptr, n_buckets, tile_off,
+                                                               threshold, pairs, pair_capacity, pair_count); });
   FLC_LAUNCH_CHECK();
   return FLC_OK;
 }

@@ -137,8 +137,8 @@ int flc_hash_table(uint32_t vec_len, uint32_t low_dim, uint32_t seed, uint32_t* 
   FLC_REQUIRE(low_dim > 0, "low_dim must be positive");
   FLC_REQUIRE(out != nullptr || vec_len == 0, "null output");
   if (vec_len == 0) return FLC_OK;
-  flc::hash_table_kernel<<<(vec_len + 255) / 256, 256, 0, flc::as_stream(stream)>>>(vec_len, low_dim,
-                                                                                  seed, out);
+  flc::timed("hash_table", stream, [&] { flc::hash_table_kernel<<<(vec_len + 255) / 256, 256, 0, flc::as_stream(stream)>>>(vec_len, low_dim,
+                                                                                  seed, out); });
   FLC_LAUNCH_CHECK();
   return FLC_OK;
 }
@@ -163,10 +163,10 @@ int flc_vectorize(const float* mz, const float* intensity, const int64_t* indptr
   int64_t blocks = (n + flc::kVecWarps - 1) / flc::kVecWarps;
   const int64_t max_blocks = static_cast<int64_t>(flc::kNumSMs) * 16;
   if (blocks > max_blocks) blocks = max_blocks;
-  flc::vectorize_kernel<<<static_cast<unsigned>(blocks), flc::kVecWarps * 32, smem,
+  flc::timed("vectorize", stream, [&] { flc::vectorize_kernel<<<static_cast<unsigned>(blocks), flc::kVecWarps * 32, smem,
                           flc::as_stream(stream)>>>(mz, intensity, indptr, order, n, min_mz, bin_size,
                                                     vec_len, low_dim, seed, norm, out_f32, ld_f32,
-                                                    out_bf16, ld_bf16, out_hash_idx);
+                                                    out_bf16, ld_bf16, out_hash_idx); });
   FLC_LAUNCH_CHECK();
   return FLC_OK;
 }

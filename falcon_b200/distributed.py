@@ -1,0 +1,60 @@
+"""Multi-GPU plumbing: precursor buckets are independent units, so
+each rank clusters its own buckets with no data-path communication; the only
+collective is the final gather of labels (and cluster counts for the label
+offsets), the same running-offset rule the reference applies per charge
+(/root/reference/falcon/falcon.py:189-193).
+
+Works with any ``torch.distributed`` backend: NCCL over NVLink on the B200
+box, gloo in the CPU tests.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def shard_buckets(bucket_sizes, world_size: int, exhaustive: bool = True) -> np.ndarray:
+    """Rank of every bucket: longest-processing-time bin packing by the scan
+    cost ``n_b^2`` (exhaustive) / ``n_b^2 * nprobe / nlist`` (IVF)."""
+    sizes = np.asarray(bucket_sizes, np.float64)
+    cost = sizes * sizes
+    if not exhaustive:
+        nlist = np.maximum(1.0, 2.0 ** np.floor(np.log2(np.maximum(sizes, 39.0) / 39.0)))
+        nlist[sizes < 100] = 1.0
+        cost = cost * np.maximum(1.0, np.minimum(np.ceil(nlist / 8), 32)) / nlist
+    cost = cost + sizes  # linear stages
+    owner = np.zeros(sizes.shape[0], np.int64)
+    load = np.zeros(world_size)
+    for b in np.argsort(-cost, kind="stable"):
+        r = int(np.argmin(load))
+        owner[b] = r
+        load[r] += cost[b]
+    return owner
+
+
+def gather_labels(labels: torch.Tensor, n_clusters: int, group=None):
+    """All ranks -> globally unique labels of every rank's spectra.
+
+    ``labels``: this rank's int32 labels (-1 = noise), any length.  Returns
+    ``(all_labels, counts)`` where ``all_labels`` is the concatenation over
+    ranks (rank order) with rank r's non-noise labels offset by the number of
+    clusters of ranks < r, and ``counts`` the per-rank lengths.
+    """
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    dev = labels.device
+    meta = torch.tensor([labels.shape[0], n_clusters], dtype=torch.int64, device=dev)
+    metas = [torch.empty_like(meta) for _ in range(world)]
+    dist.all_gather(metas, meta, group=group)
+    lens = [int(m[0]) for m in metas]
+    ncl = [int(m[1]) for m in metas]
+    offset = sum(ncl[:rank])
+    shifted = torch.where(labels >= 0, labels + offset, labels)
+    max_len = max(lens) if lens else 0
+    padded = torch.full((max_len,), -1, dtype=labels.dtype, device=dev)
+    padded[: labels.shape[0]] = shifted
+    out = torch.empty(world * max_len, dtype=labels.dtype, device=dev)
+    dist.all_gather_into_tensor(out, padded, group=group)
+    parts = [out[r * max_len: r * max_len + lens[r]] for r in range(world)]
+    return torch.cat(parts) if parts else out, lens

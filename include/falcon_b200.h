@@ -50,6 +50,13 @@ FLC_API int flc_version(void);
 /* Kernels launched by this library since load / last reset (all threads). */
 FLC_API uint64_t flc_launch_count(void);
 FLC_API void flc_reset_launch_count(void);
+/* Per-kernel device timing (CUDA events on the launching stream around every main
+ * kernel).  enable(1) ... run ... count()/get(i): summed milliseconds and launches
+ * per kernel name since the last reset.  count() synchronises the recorded events. */
+FLC_API void flc_profile_enable(int on);
+FLC_API void flc_profile_reset(void);
+FLC_API int flc_profile_count(void);
+FLC_API int flc_profile_get(int i, char* name, int name_bytes, double* total_ms, int* launches);
 /* Compute capability of `device` must be 10.x; returns FLC_ERR_UNSUPPORTED otherwise. */
 FLC_API int flc_check_device(int device);
 
@@ -110,7 +117,7 @@ FLC_API int flc_scatter32(const void* in, const int32_t* order, int64_t n, void*
  *  Synchronises the stream; returns the total number of centroids on the host. */
 FLC_API int flc_ivf_plan(const int64_t* bucket_ptr, int64_t n_buckets, int32_t n_probe,
                  int exhaustive, int32_t* nlist, int32_t* nprobe,
-                 int64_t* centroid_ptr /*[n_buckets+1]*/, int64_t* total_centroids /*host*/,
+                 int64_t* centroid_ptr /*[n_buckets+2]: scan, total, max nprobe*/, int64_t* total_centroids /*host*/,
                  int32_t* max_nprobe /*host*/, flc_stream_t stream);
 FLC_API size_t flc_kmeans_workspace_bytes(int64_t n, int64_t total_centroids, uint32_t low_dim);
 FLC_API int flc_kmeans_train(const float* x, int64_t ld, int64_t n, uint32_t low_dim,

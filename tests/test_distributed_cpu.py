@@ -1,0 +1,53 @@
+"""world_size-2 gloo test of the label gather and the bucket sharding rule."""
+import os
+import socket
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from falcon_b200 import distributed as fd
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    labels = [torch.tensor([0, -1, 1, 1, 0], dtype=torch.int32), torch.tensor([-1, 0, 0], dtype=torch.int32)][rank]
+    ncl = [2, 1][rank]
+    out, lens = fd.gather_labels(labels, ncl)
+    q.put((rank, out.tolist(), lens))
+    dist.destroy_process_group()
+
+
+def test_gather_labels_gloo_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    for _, out, lens in res:
+        assert out == [0, -1, 1, 1, 0, -1, 2, 2] and lens == [5, 3]
+
+
+def test_shard_buckets_balances_cost():
+    rng = np.random.default_rng(0)
+    sizes = rng.integers(10, 5000, 3000)
+    for world in (1, 2, 4, 8):
+        owner = fd.shard_buckets(sizes, world)
+        assert owner.min() >= 0 and owner.max() < world
+        cost = sizes.astype(np.float64) ** 2 + sizes
+        load = np.bincount(owner, weights=cost, minlength=world)
+        assert load.max() / load.mean() < 1.05
+    assert (fd.shard_buckets(sizes, 2, exhaustive=False) < 2).all()
