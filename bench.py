@@ -181,7 +181,8 @@ def kernel_rooflines(stats: dict, peaks: dict) -> dict:
     hbm = peaks["hbm_gbs"]
     work = {
         # bytes: peaks (m/z + intensity) + indptr + order + f32 row + bf16 row
-        "vectorize": ("hbm", p * 8 + (n + 1) * 8 + n * 4 + n * d * 4 + n * ldb * 2),
+        "vectorize": ("hbm", p * 8 + (n + 1) * 8 + n * 4 + n * d * 4 * stats.get("dense_f32", 1) + n * ldb * 2
+                      + n * stats.get("ell_width", 0) * 6),
         # HBM floor of the scan: every bf16 row read once, pairs written once
         "scan_tc": ("hbm", n * ldb * 2 + pairs * 8),
         # pairs in/out + exact re-score rows (L2-resident in practice) + m/z + row counts
@@ -193,6 +194,9 @@ def kernel_rooflines(stats: dict, peaks: dict) -> dict:
         "dbscan_propagate": ("hbm", nnz * 8 + (n + 1) * 8 + n * 9),
         "ivf_assign": ("hbm", n * d * 4 + n * 4 * (1 + stats.get("max_nprobe", 1))),
         "kmeans_assign": ("hbm", n * d * 4 + n * 4),
+        # fused trainer: every sparse row (6 bytes per ELL slot) read once, centroids written once
+        "kmeans_fused": ("hbm", stats.get("ivf_rows", 0) * stats.get("ell_width", 0) * 6
+                         + stats.get("total_centroids", 0) * d * 4),
         "kmeans_update": ("hbm", stats.get("ivf_rows", 0) * d * 4),
     }
     out = {}
@@ -324,7 +328,7 @@ def run_ours(args):
         idx = (b_of_row[:, None] * max_l + pr.clamp(min=0))
         required_pairs = float((lsize[idx] * valid).sum().item())
         nl = ivf.nlist[:-1].long()
-        stats_extra = {"max_nprobe": ivf.max_nprobe, "ivf_rows": int(sizes[nl > 0].sum().item()),
+        stats_extra = {"ell_width": keep["vectors"].ell_width, "max_nprobe": ivf.max_nprobe, "ivf_rows": int(sizes[nl > 0].sum().item()),
                        "total_centroids": ivf.total_centroids}
     stats = {"n": args.n, "n_peaks": sp.n_peaks, "low_dim": settings.low_dim, "ld_bf16": hp.ld_bf16,
              "n_pairs": keep["graph"].n_pairs, "nnz": keep["graph"].nnz, "kernels": kernels,
@@ -387,7 +391,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n", type=int, default=1_000_000, help="spectra per GPU")
     ap.add_argument("--exhaustive", action="store_true", help="n_probe = nlist (BASELINE configs[2])")
-    ap.add_argument("--cpu-sample", type=int, default=150_000)
+    ap.add_argument("--cpu-sample", type=int, default=1_000_000,
+                    help="spectra in the CPU-baseline sample (whole buckets; ~10 s of CPU work at 1M)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -116,10 +116,10 @@ def compute_pairwise_distances(
     z = up(spectra.precursor_charge, np.int32)
     rt = up(spectra.retention_time, np.float32)
     buckets = hp.bucket_sort(pmz, z, rt)
-    x, xb, _ = hp.vectorize(up(spectra.mz, np.float32), up(spectra.intensity, np.float32),
-                            up(spectra.indptr, np.int64), buckets.order)
-    ivf = None if exhaustive else hp.build_ivf(x, buckets)
-    g = hp.knn_graph(x, xb, buckets, ivf)
+    v = hp.vectorize(up(spectra.mz, np.float32), up(spectra.intensity, np.float32),
+                     up(spectra.indptr, np.int64), buckets.order)
+    ivf = None if exhaustive else hp.build_ivf(v, buckets)
+    g = hp.knn_graph(v, buckets, ivf)
     order = buckets.order.cpu().numpy()
     idx_dtype = np.int32 if n * n_neighbors < 2 ** 31 else np.int64
     mat = ss.csr_matrix((n, n), dtype=np.float32)

@@ -34,52 +34,44 @@ constexpr int32_t kInf = 0x7fffffff;
 constexpr uint32_t kNoiseKey = 0xffffffffu;
 
 // ---------------------------------------------------------------- DBSCAN
+// One thread per row: rows hold at most n_neighbors (64) entries, a handful on average.
 __global__ void dbscan_core_kernel(const float* __restrict__ dist, const int64_t* __restrict__ indptr,
                                    int64_t n, float eps, int32_t min_samples, int32_t* __restrict__ m,
                                    uint8_t* __restrict__ core) {
-  const int lane = threadIdx.x & 31;
-  const int64_t i = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const int64_t a = indptr[i], b = indptr[i + 1];
   int cnt = 0;
-  for (int64_t p = a + lane; p < b; p += 32) cnt += (dist[p] <= eps) ? 1 : 0;
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-  if (lane == 0) {
-    const bool c = cnt >= min_samples;
-    core[i] = c ? 1 : 0;
-    m[i] = c ? static_cast<int32_t>(i) : kInf;
-  }
+  for (int64_t p = a; p < b; ++p) cnt += (__ldg(dist + p) <= eps) ? 1 : 0;
+  const bool c = cnt >= min_samples;
+  core[i] = c ? 1 : 0;
+  m[i] = c ? static_cast<int32_t>(i) : kInf;
 }
 
 __global__ void dbscan_propagate_kernel(const float* __restrict__ dist, const int32_t* __restrict__ indices,
                                         const int64_t* __restrict__ indptr, int64_t n, float eps,
                                         const uint8_t* __restrict__ core, int32_t* m,
                                         int32_t* __restrict__ changed) {
-  const int lane = threadIdx.x & 31;
-  const int64_t u = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int64_t u = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (u >= n || !core[u]) return;
   // Shortcut: follow the chain of minimum ancestors to its current end.
-  int32_t mu = m[u];
-  if (lane == 0) {
-    int32_t r = mu;
-    while (true) {
-      const int32_t next = *reinterpret_cast<volatile int32_t*>(m + r);
-      if (next >= r) break;
-      r = next;
-    }
-    if (r < mu) {
-      atomicMin(m + u, r);
-      *changed = 1;
-      mu = r;
-    }
+  int32_t mu = *reinterpret_cast<volatile int32_t*>(m + u);
+  int32_t r = mu;
+  while (true) {
+    const int32_t next = *reinterpret_cast<volatile int32_t*>(m + r);
+    if (next >= r) break;
+    r = next;
   }
-  mu = __shfl_sync(0xffffffffu, mu, 0);
-  const int64_t a = indptr[u], b = indptr[u + 1];
   bool any = false;
-  for (int64_t p = a + lane; p < b; p += 32) {
-    if (dist[p] <= eps) {
-      const int32_t w = indices[p];
+  if (r < mu) {
+    atomicMin(m + u, r);
+    any = true;
+    mu = r;
+  }
+  const int64_t a = indptr[u], b = indptr[u + 1];
+  for (int64_t p = a; p < b; ++p) {
+    if (__ldg(dist + p) <= eps) {
+      const int32_t w = __ldg(indices + p);
       if (*reinterpret_cast<volatile int32_t*>(m + w) > mu) {
         const int32_t old = atomicMin(m + w, mu);
         any |= old > mu;
@@ -348,7 +340,7 @@ int flc_dbscan(const float* dist, const int32_t* indices, const int64_t* indptr,
   DbscanLayout L;
   dbscan_layout(ws, n, L);
   if (!ws.ok) return set_error(FLC_ERR_WORKSPACE, "dbscan workspace too small: need %zu", ws.used);
-  const unsigned wblocks = static_cast<unsigned>((n * 32 + 255) / 256);
+  const unsigned wblocks = static_cast<unsigned>((n + 255) / 256);
   const unsigned tblocks = static_cast<unsigned>((n + 1 + 255) / 256);
   timed("dbscan_core", stream, [&] { dbscan_core_kernel<<<wblocks, 256, 0, stream>>>(dist, indptr, n, eps, min_samples, L.m, L.core); });
   FLC_LAUNCH_CHECK();

@@ -32,6 +32,22 @@ __host__ __device__ inline int32_t nlist_rule(int64_t n) {
   return 1 << 20;
 }
 
+// Shared-memory budget of one bucket in the fused kernel: the ELL rows (uint16
+// column + float32 value per slot), the centroids (float32) and their float64
+// accumulators + counts.
+__host__ __device__ inline size_t fused_smem_bytes(int64_t nb, int32_t L, int32_t W, uint32_t low_dim) {
+  size_t b = static_cast<size_t>(nb) * W * 6;
+  b = (b + 15) & ~size_t(15);
+  b += static_cast<size_t>(L) * low_dim * 12 + static_cast<size_t>(L) * 8 + 64;
+  return b;
+}
+constexpr size_t kFusedSmemCap = 200 * 1024;
+
+__host__ __device__ inline bool bucket_is_fused(int64_t nb, int32_t L, int32_t W, uint32_t low_dim,
+                                                size_t smem_limit) {
+  return L > 0 && W > 0 && fused_smem_bytes(nb, L, W, low_dim) <= smem_limit;
+}
+
 // Single CTA: nlist / nprobe per bucket, exclusive scan -> centroid_ptr, max nprobe.
 __global__ void __launch_bounds__(1024)
 ivf_plan_kernel(const int64_t* __restrict__ bucket_ptr, int64_t n_buckets, int32_t n_probe, int exhaustive,
@@ -39,15 +55,20 @@ ivf_plan_kernel(const int64_t* __restrict__ bucket_ptr, int64_t n_buckets, int32
   __shared__ int64_t warp_sums[32];
   __shared__ int64_t carry_s;
   __shared__ int32_t max_s;
+  __shared__ unsigned long long max_nb_s;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (tid == 0) { carry_s = 0; max_s = 0; }
+  if (tid == 0) { carry_s = 0; max_s = 0; max_nb_s = 0; }
   __syncthreads();
   for (int64_t base = 0; base < n_buckets; base += 1024) {
     const int64_t b = base + tid;
     int32_t L = 0, P = 0;
     if (b < n_buckets) {
-      L = nlist_rule(bucket_ptr[b + 1] - bucket_ptr[b]);
-      if (L > 0) P = exhaustive ? L : max(1, min((L + 7) / 8, n_probe));
+      const int64_t nb = bucket_ptr[b + 1] - bucket_ptr[b];
+      L = nlist_rule(nb);
+      if (L > 0) {
+        P = exhaustive ? L : max(1, min((L + 7) / 8, n_probe));
+        atomicMax(&max_nb_s, static_cast<unsigned long long>(nb));
+      }
       nlist[b] = L;
       nprobe[b] = P;
     }
@@ -74,6 +95,7 @@ ivf_plan_kernel(const int64_t* __restrict__ bucket_ptr, int64_t n_buckets, int32
   if (tid == 0) {
     centroid_ptr[n_buckets] = carry_s;
     centroid_ptr[n_buckets + 1] = max_s;
+    centroid_ptr[n_buckets + 2] = static_cast<int64_t>(max_nb_s);
   }
 }
 
@@ -89,12 +111,14 @@ __device__ __forceinline__ int64_t find_segment(const int64_t* __restrict__ ptr,
 __global__ void kmeans_init_kernel(const float* __restrict__ x, int64_t ld, uint32_t low_dim,
                                    const int64_t* __restrict__ bucket_ptr, int64_t n_buckets,
                                    const int32_t* __restrict__ nlist, const int64_t* __restrict__ centroid_ptr,
-                                   int64_t total, float* __restrict__ centroids) {
+                                   int64_t total, int32_t W, size_t fused_limit,
+                                   float* __restrict__ centroids) {
   const int64_t gc = blockIdx.x;
   if (gc >= total) return;
   const int64_t b = find_segment(centroid_ptr, n_buckets, gc);
   const int64_t c = gc - centroid_ptr[b];
   const int64_t s = bucket_ptr[b], nb = bucket_ptr[b + 1] - s;
+  if (bucket_is_fused(nb, nlist[b], W, low_dim, fused_limit)) return;
   const int64_t row = s + (c * nb) / nlist[b];
   for (uint32_t i = threadIdx.x; i < low_dim; i += blockDim.x)
     centroids[gc * low_dim + i] = x[row * ld + i];
@@ -104,14 +128,15 @@ __global__ void __launch_bounds__(256)
 kmeans_assign_kernel(const float* __restrict__ x, int64_t ld, int64_t n, uint32_t low_dim,
                      const int64_t* __restrict__ bucket_ptr, int64_t n_buckets,
                      const int32_t* __restrict__ nlist, const int64_t* __restrict__ centroid_ptr,
-                     const float* __restrict__ centroids, int32_t* __restrict__ assign) {
+                     const float* __restrict__ centroids, int32_t W, size_t fused_limit,
+                     int32_t* __restrict__ assign) {
   extern __shared__ float smem_x[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t i = static_cast<int64_t>(blockIdx.x) * 8 + warp;
   if (i >= n) return;
   const int64_t b = find_segment(bucket_ptr, n_buckets, i);
   const int32_t L = nlist[b];
-  if (L == 0) {
+  if (L == 0 || bucket_is_fused(bucket_ptr[b + 1] - bucket_ptr[b], L, W, low_dim, fused_limit)) {
     if (lane == 0) assign[i] = 0;
     return;
   }
@@ -138,12 +163,14 @@ kmeans_update_kernel(const float* __restrict__ x, int64_t ld, uint32_t low_dim,
                      const int64_t* __restrict__ bucket_ptr, int64_t n_buckets,
                      const int64_t* __restrict__ centroid_ptr, int64_t total,
                      const int32_t* __restrict__ assign, const float* __restrict__ centroids,
+                     const int32_t* __restrict__ nlist, int32_t W, size_t fused_limit,
                      float* __restrict__ new_centroids, double* __restrict__ counts) {
   const int64_t gc = blockIdx.x;
   if (gc >= total) return;
   const int64_t b = find_segment(centroid_ptr, n_buckets, gc);
   const int32_t c = static_cast<int32_t>(gc - centroid_ptr[b]);
   const int64_t s = bucket_ptr[b], e = bucket_ptr[b + 1];
+  if (bucket_is_fused(e - s, nlist[b], W, low_dim, fused_limit)) return;
   constexpr int kMaxPerThread = 8;  // low_dim <= 128 * 8 handled in registers per pass
   for (uint32_t d0 = 0; d0 < low_dim; d0 += 128 * kMaxPerThread) {
     double acc[kMaxPerThread];
@@ -174,12 +201,13 @@ kmeans_update_kernel(const float* __restrict__ x, int64_t ld, uint32_t low_dim,
 // One CTA per bucket: split the largest list into every empty one, normalise.
 __global__ void __launch_bounds__(128)
 kmeans_fix_kernel(uint32_t low_dim, int64_t n_buckets, const int32_t* __restrict__ nlist,
-                  const int64_t* __restrict__ centroid_ptr, float* __restrict__ new_centroids,
+                  const int64_t* __restrict__ centroid_ptr, const int64_t* __restrict__ bucket_ptr, int32_t W,
+                  size_t fused_limit, float* __restrict__ new_centroids,
                   double* __restrict__ counts, float* __restrict__ centroids) {
   const int64_t b = blockIdx.x;
   if (b >= n_buckets) return;
   const int32_t L = nlist[b];
-  if (L == 0) return;
+  if (L == 0 || bucket_is_fused(bucket_ptr[b + 1] - bucket_ptr[b], L, W, low_dim, fused_limit)) return;
   const int64_t c0 = centroid_ptr[b];
   __shared__ int32_t cj_s;
   __shared__ double red[128];
@@ -237,7 +265,8 @@ ivf_assign_kernel(const float* __restrict__ x, int64_t ld, int64_t n, uint32_t l
                   const int64_t* __restrict__ bucket_ptr, int64_t n_buckets,
                   const int32_t* __restrict__ nlist, const int32_t* __restrict__ nprobe,
                   const int64_t* __restrict__ centroid_ptr, const float* __restrict__ centroids,
-                  int32_t max_nprobe, int32_t* __restrict__ list_id, int32_t* __restrict__ probes) {
+                  int32_t max_nprobe, const uint16_t* __restrict__ ell_idx, const float* __restrict__ ell_val,
+                  int32_t W, int32_t* __restrict__ list_id, int32_t* __restrict__ probes) {
   extern __shared__ float smem_x[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t i = static_cast<int64_t>(blockIdx.x) * 8 + warp;
@@ -251,16 +280,27 @@ ivf_assign_kernel(const float* __restrict__ x, int64_t ld, int64_t n, uint32_t l
   }
   const int32_t P = nprobe[b];
   float* xi = smem_x + static_cast<size_t>(warp) * low_dim;
-  for (uint32_t t = lane; t < low_dim; t += 32) xi[t] = x[i * ld + t];
-  __syncwarp();
+  if (ell_idx == nullptr) {
+    for (uint32_t t = lane; t < low_dim; t += 32) xi[t] = x[i * ld + t];
+    __syncwarp();
+  }
   const float* cent = centroids + centroid_ptr[b] * low_dim;
   double my_score = -INFINITY;
   int32_t my_id = -1;
   for (int32_t c = 0; c < L; ++c) {
     const float* cr = cent + static_cast<int64_t>(c) * low_dim;
     double acc = 0.0;
-    for (uint32_t t = lane; t < low_dim; t += 32)
-      acc = fma(static_cast<double>(xi[t]), static_cast<double>(__ldg(cr + t)), acc);
+    if (ell_idx != nullptr) {
+      // sparse row: only the non-zero columns contribute (zero products are exact)
+      for (int32_t j = lane; j < W; j += 32) {
+        const float v = __ldg(ell_val + i * W + j);
+        if (v != 0.f)
+          acc = fma(static_cast<double>(v), static_cast<double>(__ldg(cr + __ldg(ell_idx + i * W + j))), acc);
+      }
+    } else {
+      for (uint32_t t = lane; t < low_dim; t += 32)
+        acc = fma(static_cast<double>(xi[t]), static_cast<double>(__ldg(cr + t)), acc);
+    }
     acc = warp_sum_f64(acc);
     // entries ahead of the newcomer: strictly better, or equal (earlier id wins)
     const uint32_t ahead = __ballot_sync(0xffffffffu, my_id >= 0 && my_score >= acc);
@@ -274,6 +314,143 @@ ivf_assign_kernel(const float* __restrict__ x, int64_t ld, int64_t n, uint32_t l
   }
   if (lane < max_nprobe) probes[i * max_nprobe + lane] = lane < P ? my_id : -1;
   if (lane == 0) list_id[i] = my_id;
+}
+
+
+// ---------------------------------------------------------------- fused small-bucket trainer
+// One CTA per bucket (persistent over buckets): the bucket's sparse rows stay in
+// shared memory for all iterations, so HBM sees each row once.
+//   assign + update: one warp per row -- sparse dot products against the
+//     centroids in shared memory (float32), arg-max with ties to the lower id,
+//     then the row is scattered into the winner's float64 accumulator with
+//     shared-memory atomics (sums of float32 values in float64 are exact here, so
+//     the result does not depend on the order);
+//   fix: mean, empty-list re-seeding (+-1/1024), L2 normalisation.
+__global__ void __launch_bounds__(256)
+kmeans_fused_kernel(const uint16_t* __restrict__ ell_idx, const float* __restrict__ ell_val, int32_t W,
+                    uint32_t low_dim, const int64_t* __restrict__ bucket_ptr, int64_t n_buckets,
+                    const int32_t* __restrict__ nlist, const int64_t* __restrict__ centroid_ptr, int niter,
+                    size_t smem_limit, float* __restrict__ centroids) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ int32_t cj_s;
+  __shared__ double red_s[8];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int kWarps = 8;
+  const float eps = 1.0f / 1024.0f;
+
+  for (int64_t b = blockIdx.x; b < n_buckets; b += gridDim.x) {
+    const int32_t L = nlist[b];
+    const int64_t s = bucket_ptr[b];
+    const int32_t nb = static_cast<int32_t>(bucket_ptr[b + 1] - s);
+    if (!bucket_is_fused(nb, L, W, low_dim, smem_limit)) continue;
+    const int64_t c0 = centroid_ptr[b];
+    // carve shared memory
+    uint16_t* sidx = reinterpret_cast<uint16_t*>(smem_raw);
+    float* sval = reinterpret_cast<float*>(smem_raw + static_cast<size_t>(nb) * W * 2);
+    size_t off = (static_cast<size_t>(nb) * W * 6 + 15) & ~size_t(15);
+    double* acc = reinterpret_cast<double*>(smem_raw + off);
+    off += static_cast<size_t>(L) * low_dim * 8;
+    double* cnt = reinterpret_cast<double*>(smem_raw + off);
+    off += static_cast<size_t>(L) * 8;
+    float* C = reinterpret_cast<float*>(smem_raw + off);
+    __syncthreads();  // previous bucket fully written out
+    // load the bucket (coalesced)
+    {
+      const uint32_t* gi = reinterpret_cast<const uint32_t*>(ell_idx + s * W);
+      uint32_t* si = reinterpret_cast<uint32_t*>(sidx);
+      const int n32 = nb * W / 2;
+      if ((W & 1) == 0 && ((reinterpret_cast<uintptr_t>(gi) & 3) == 0)) {
+        for (int t = tid; t < n32; t += 256) si[t] = __ldg(gi + t);
+      } else {
+        for (int t = tid; t < nb * W; t += 256) sidx[t] = __ldg(ell_idx + s * W + t);
+      }
+      const float* gv = ell_val + s * W;
+      for (int t = tid; t < nb * W; t += 256) sval[t] = __ldg(gv + t);
+      for (int t = tid; t < L * static_cast<int>(low_dim); t += 256) C[t] = 0.f;
+    }
+    __syncthreads();
+    // init: centroid c = row (c * nb) / L
+    for (int t = tid; t < L * W; t += 256) {
+      const int c = t / W, j = t % W;
+      const int row = static_cast<int>((static_cast<int64_t>(c) * nb) / L);
+      const float v = sval[row * W + j];
+      if (v != 0.f) C[c * low_dim + sidx[row * W + j]] = v;
+    }
+    __syncthreads();
+    for (int it = 0; it < niter; ++it) {
+      for (int t = tid; t < L * static_cast<int>(low_dim); t += 256) acc[t] = 0.0;
+      if (tid < L) cnt[tid] = 0.0;
+      __syncthreads();
+      for (int r = warp; r < nb; r += kWarps) {
+        float best = -INFINITY;
+        int best_c = 0;
+        for (int c = 0; c < L; ++c) {
+          float a = 0.f;
+          for (int j = lane; j < W; j += 32) a = fmaf(sval[r * W + j], C[c * low_dim + sidx[r * W + j]], a);
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+          if (a > best) { best = a; best_c = c; }
+        }
+        for (int j = lane; j < W; j += 32) {
+          const float v = sval[r * W + j];
+          if (v != 0.f) atomicAdd(acc + best_c * low_dim + sidx[r * W + j], static_cast<double>(v));
+        }
+        if (lane == 0) atomicAdd(cnt + best_c, 1.0);
+      }
+      __syncthreads();
+      // mean (empty lists keep their centroid)
+      for (int t = tid; t < L * static_cast<int>(low_dim); t += 256) {
+        const double n_c = cnt[t / low_dim];
+        if (n_c > 0.0) C[t] = static_cast<float>(acc[t] / n_c);
+      }
+      __syncthreads();
+      // re-seed empty lists from the largest one
+      for (int ci = 0; ci < L; ++ci) {
+        if (cnt[ci] > 0.0) continue;  // uniform
+        if (tid == 0) {
+          int bestc = 0;
+          double bc = cnt[0];
+          for (int c = 1; c < L; ++c)
+            if (cnt[c] > bc) { bc = cnt[c]; bestc = c; }
+          cj_s = bestc;
+        }
+        __syncthreads();
+        const int cj = cj_s;
+        for (int t = tid; t < static_cast<int>(low_dim); t += 256) {
+          const float sign = (t % 2 == 0) ? 1.0f + eps : 1.0f - eps;
+          const float v = C[cj * low_dim + t];
+          C[ci * low_dim + t] = v * sign;
+          C[cj * low_dim + t] = v * (2.0f - sign);
+        }
+        __syncthreads();
+        if (tid == 0) {
+          const double half = cnt[cj] / 2.0;
+          cnt[ci] = half;
+          cnt[cj] -= half;
+        }
+        __syncthreads();
+      }
+      // normalise
+      for (int c = 0; c < L; ++c) {
+        double ss = 0.0;
+        for (int t = tid; t < static_cast<int>(low_dim); t += 256) {
+          const double v = static_cast<double>(C[c * low_dim + t]);
+          ss += v * v;
+        }
+        ss = warp_sum_f64(ss);
+        if (lane == 0) red_s[warp] = ss;
+        __syncthreads();
+        double tot = 0.0;
+#pragma unroll
+        for (int w = 0; w < kWarps; ++w) tot += red_s[w];
+        const double nrm = tot > 0.0 ? sqrt(tot) : 1.0;
+        for (int t = tid; t < static_cast<int>(low_dim); t += 256)
+          C[c * low_dim + t] = static_cast<float>(static_cast<double>(C[c * low_dim + t]) / nrm);
+        __syncthreads();
+      }
+    }
+    for (int t = tid; t < L * static_cast<int>(low_dim); t += 256) centroids[c0 * low_dim + t] = C[t];
+  }
 }
 
 struct KmeansLayout {
@@ -294,7 +471,7 @@ extern "C" {
 
 int flc_ivf_plan(const int64_t* bucket_ptr, int64_t n_buckets, int32_t n_probe, int exhaustive,
                  int32_t* nlist, int32_t* nprobe, int64_t* centroid_ptr, int64_t* total_centroids,
-                 int32_t* max_nprobe, flc_stream_t stream_) {
+                 int32_t* max_nprobe, int64_t* max_ivf_bucket, flc_stream_t stream_) {
   using namespace flc;
   FLC_REQUIRE(n_buckets >= 0, "n_buckets must be non-negative");
   FLC_REQUIRE(n_probe >= 1, "n_probe must be >= 1");
@@ -303,11 +480,12 @@ int flc_ivf_plan(const int64_t* bucket_ptr, int64_t n_buckets, int32_t n_probe, 
   timed("ivf_plan", stream, [&] { ivf_plan_kernel<<<1, 1024, 0, stream>>>(bucket_ptr, n_buckets, n_probe, exhaustive, nlist, nprobe,
                                           centroid_ptr); });
   FLC_LAUNCH_CHECK();
-  int64_t tail[2] = {0, 0};
-  FLC_CUDA(cudaMemcpyAsync(tail, centroid_ptr + n_buckets, 2 * sizeof(int64_t), cudaMemcpyDeviceToHost, stream));
+  int64_t tail[3] = {0, 0, 0};
+  FLC_CUDA(cudaMemcpyAsync(tail, centroid_ptr + n_buckets, 3 * sizeof(int64_t), cudaMemcpyDeviceToHost, stream));
   FLC_CUDA(cudaStreamSynchronize(stream));
   *total_centroids = tail[0];
   *max_nprobe = static_cast<int32_t>(tail[1] > 0 ? tail[1] : 1);
+  if (max_ivf_bucket) *max_ivf_bucket = tail[2];
   return FLC_OK;
 }
 
@@ -320,13 +498,40 @@ size_t flc_kmeans_workspace_bytes(int64_t n, int64_t total_centroids, uint32_t l
 
 int flc_kmeans_train(const float* x, int64_t ld, int64_t n, uint32_t low_dim, const int64_t* bucket_ptr,
                      int64_t n_buckets, const int32_t* nlist, const int64_t* centroid_ptr,
-                     int64_t total_centroids, int niter, float* centroids, void* workspace,
-                     size_t workspace_bytes, flc_stream_t stream_) {
+                     int64_t total_centroids, int64_t max_ivf_bucket, int niter,
+                     const uint16_t* ell_idx, const float* ell_val, int32_t ell_width, float* centroids,
+                     void* workspace, size_t workspace_bytes, flc_stream_t stream_) {
   using namespace flc;
   FLC_REQUIRE(n >= 0 && niter >= 0, "bad sizes");
   FLC_REQUIRE(low_dim > 0 && low_dim <= 8192, "low_dim must be in [1, 8192]");
+  FLC_REQUIRE((ell_idx == nullptr) == (ell_val == nullptr), "ell_idx and ell_val go together");
   if (n == 0 || total_centroids == 0) return FLC_OK;
   cudaStream_t stream = as_stream(stream_);
+  // Buckets whose sparse rows + centroids fit in shared memory train in the fused
+  // kernel; larger ones (and everything when no ELL copy is given) in the
+  // generic multi-kernel path on the dense rows.
+  const int32_t W = ell_idx ? ell_width : 0;
+  size_t fused_limit = 0;
+  bool any_generic = true;
+  if (W > 0) {
+    fused_limit = kFusedSmemCap;
+    // size the allocation for the largest bucket that will use the fused kernel
+    int64_t nb_max = max_ivf_bucket > 0 ? max_ivf_bucket : n;
+    size_t need = fused_smem_bytes(nb_max, nlist_rule(nb_max), W, low_dim);
+    if (need <= kFusedSmemCap) {
+      any_generic = false;  // every IVF bucket fits
+      fused_limit = need;
+    }
+    FLC_CUDA(cudaFuncSetAttribute(kmeans_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  static_cast<int>(fused_limit)));
+    const int64_t grid = n_buckets < 8 * kNumSMs ? n_buckets : 8 * kNumSMs;
+    timed("kmeans_fused", stream, [&] { kmeans_fused_kernel<<<static_cast<unsigned>(grid), 256, fused_limit, stream>>>(
+        ell_idx, ell_val, W, low_dim, bucket_ptr, n_buckets, nlist, centroid_ptr, niter, fused_limit,
+        centroids); });
+    FLC_LAUNCH_CHECK();
+  }
+  if (!any_generic) return FLC_OK;
+  FLC_REQUIRE(x != nullptr, "dense rows are needed for buckets too large for the fused trainer");
   Workspace ws(workspace, workspace_bytes);
   KmeansLayout L;
   kmeans_layout(ws, n, total_centroids, low_dim, L);
@@ -337,18 +542,19 @@ int flc_kmeans_train(const float* x, int64_t ld, int64_t n, uint32_t low_dim, co
                                   static_cast<int>(smem)));
   const unsigned cblocks = static_cast<unsigned>(total_centroids);
   timed("kmeans_init", stream, [&] { kmeans_init_kernel<<<cblocks, 128, 0, stream>>>(x, ld, low_dim, bucket_ptr, n_buckets, nlist, centroid_ptr,
-                                                  total_centroids, centroids); });
+                                                  total_centroids, W, fused_limit, centroids); });
   FLC_LAUNCH_CHECK();
   for (int it = 0; it < niter; ++it) {
     timed("kmeans_assign", stream, [&] { kmeans_assign_kernel<<<static_cast<unsigned>((n + 7) / 8), 256, smem, stream>>>(
-        x, ld, n, low_dim, bucket_ptr, n_buckets, nlist, centroid_ptr, centroids, L.assign); });
+        x, ld, n, low_dim, bucket_ptr, n_buckets, nlist, centroid_ptr, centroids, W, fused_limit, L.assign); });
     FLC_LAUNCH_CHECK();
     timed("kmeans_update", stream, [&] { kmeans_update_kernel<<<cblocks, 128, 0, stream>>>(x, ld, low_dim, bucket_ptr, n_buckets, centroid_ptr,
-                                                      total_centroids, L.assign, centroids, L.new_centroids,
-                                                      L.counts); });
+                                                      total_centroids, L.assign, centroids, nlist, W, fused_limit,
+                                                      L.new_centroids, L.counts); });
     FLC_LAUNCH_CHECK();
     timed("kmeans_fix", stream, [&] { kmeans_fix_kernel<<<static_cast<unsigned>(n_buckets), 128, 0, stream>>>(
-        low_dim, n_buckets, nlist, centroid_ptr, L.new_centroids, L.counts, centroids); });
+        low_dim, n_buckets, nlist, centroid_ptr, bucket_ptr, W, fused_limit, L.new_centroids, L.counts,
+        centroids); });
     FLC_LAUNCH_CHECK();
   }
   return FLC_OK;
@@ -357,10 +563,13 @@ int flc_kmeans_train(const float* x, int64_t ld, int64_t n, uint32_t low_dim, co
 int flc_ivf_assign(const float* x, int64_t ld, int64_t n, uint32_t low_dim, const int64_t* bucket_ptr,
                    int64_t n_buckets, const int32_t* nlist, const int32_t* nprobe,
                    const int64_t* centroid_ptr, const float* centroids, int32_t max_nprobe,
+                   const uint16_t* ell_idx, const float* ell_val, int32_t ell_width,
                    int32_t* list_id, int32_t* probes, flc_stream_t stream_) {
   using namespace flc;
   FLC_REQUIRE(n >= 0, "bad n");
   FLC_REQUIRE(max_nprobe >= 1, "max_nprobe must be >= 1");
+  FLC_REQUIRE((ell_idx == nullptr) == (ell_val == nullptr), "ell_idx and ell_val go together");
+  FLC_REQUIRE(ell_idx != nullptr || x != nullptr, "need dense or ELL rows");
   if (max_nprobe > 32)
     return set_error(FLC_ERR_UNSUPPORTED, "n_probe > 32 is not supported by the device probe selection");
   if (n == 0) return FLC_OK;
@@ -370,8 +579,8 @@ int flc_ivf_assign(const float* x, int64_t ld, int64_t n, uint32_t low_dim, cons
     FLC_CUDA(cudaFuncSetAttribute(ivf_assign_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   static_cast<int>(smem)));
   timed("ivf_assign", stream, [&] { ivf_assign_kernel<<<static_cast<unsigned>((n + 7) / 8), 256, smem, stream>>>(
-      x, ld, n, low_dim, bucket_ptr, n_buckets, nlist, nprobe, centroid_ptr, centroids, max_nprobe, list_id,
-      probes); });
+      x, ld, n, low_dim, bucket_ptr, n_buckets, nlist, nprobe, centroid_ptr, centroids, max_nprobe, ell_idx,
+      ell_val, ell_width, list_id, probes); });
   FLC_LAUNCH_CHECK();
   return FLC_OK;
 }

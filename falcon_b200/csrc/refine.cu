@@ -106,6 +106,9 @@ __device__ __forceinline__ void warp_sort_smem(uint64_t* buf, int len, int lane)
 }
 
 struct RefineParams {
+  const uint16_t* ell_idx;  // nullable sparse copy of the rows
+  const float* ell_val;
+  int32_t ell_width;
   const float* x;
   int64_t ld;
   int64_t n;
@@ -153,8 +156,17 @@ refine_kernel(RefineParams P, const int64_t* __restrict__ off, uint64_t* __restr
     if (lane == 0) row_count[q] = 0;
     return;
   }
-  const float* xrow = P.x + q * P.ld;
-  for (uint32_t i = lane; i < P.low_dim; i += 32) xq[i] = xrow[i];
+  if (P.x != nullptr) {
+    const float* xrow = P.x + q * P.ld;
+    for (uint32_t i = lane; i < P.low_dim; i += 32) xq[i] = xrow[i];
+  } else {  // densify the query row from its sparse copy
+    for (uint32_t i = lane; i < P.low_dim; i += 32) xq[i] = 0.f;
+    __syncwarp();
+    for (int32_t j = lane; j < P.ell_width; j += 32) {
+      const float v = P.ell_val[q * P.ell_width + j];
+      if (v != 0.f) xq[P.ell_idx[q * P.ell_width + j]] = v;
+    }
+  }
   __syncwarp();
   const double mq = P.mz[q];
   const float rq = P.rt ? P.rt[q] : 0.f;
@@ -171,10 +183,19 @@ refine_kernel(RefineParams P, const int64_t* __restrict__ off, uint64_t* __restr
     }
     uint64_t key = kKeyMax;
     if (member) {
-      const float* xc = P.x + static_cast<int64_t>(c) * P.ld;
       double acc = 0.0;
-      for (uint32_t i = lane; i < P.low_dim; i += 32)
-        acc = fma(static_cast<double>(xq[i]), static_cast<double>(__ldg(xc + i)), acc);
+      if (P.ell_idx != nullptr) {
+        // sparse candidate row against the dense query row (zero products are exact)
+        const int64_t rbase = static_cast<int64_t>(c) * P.ell_width;
+        for (int32_t j = lane; j < P.ell_width; j += 32) {
+          const float v = __ldg(P.ell_val + rbase + j);
+          if (v != 0.f) acc = fma(static_cast<double>(v), static_cast<double>(xq[__ldg(P.ell_idx + rbase + j)]), acc);
+        }
+      } else {
+        const float* xc = P.x + static_cast<int64_t>(c) * P.ld;
+        for (uint32_t i = lane; i < P.low_dim; i += 32)
+          acc = fma(static_cast<double>(xq[i]), static_cast<double>(__ldg(xc + i)), acc);
+      }
       acc = warp_sum_f64(acc);
       const float ip = static_cast<float>(acc);
       const float dist = fmaxf(1.0f - ip, 0.0f);
@@ -231,13 +252,12 @@ refine_kernel(RefineParams P, const int64_t* __restrict__ off, uint64_t* __restr
 __global__ void csr_compact_kernel(const uint64_t* __restrict__ grouped, const int64_t* __restrict__ off,
                                    const int64_t* __restrict__ indptr, int64_t n, uint64_t nnz_capacity,
                                    float* __restrict__ dist, int32_t* __restrict__ indices) {
-  const int lane = threadIdx.x & 31;
-  const int64_t q = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int64_t q = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (q >= n) return;
   const int64_t src = off[q];
   const int64_t dst = indptr[q];
   const int64_t cnt = indptr[q + 1] - dst;
-  for (int64_t t = lane; t < cnt; t += 32) {
+  for (int64_t t = 0; t < cnt; ++t) {
     if (static_cast<uint64_t>(dst + t) < nnz_capacity) {
       const uint64_t e = grouped[src + t];
       dist[dst + t] = __uint_as_float(static_cast<uint32_t>(e >> 32));
@@ -282,7 +302,8 @@ size_t flc_knn_csr_workspace_bytes(int64_t n, uint64_t n_pairs) {
 }
 
 int flc_knn_csr(const uint64_t* pairs, const uint64_t* pair_count, uint64_t pair_capacity,
-                const float* x, int64_t ld, int64_t n, uint32_t low_dim,
+                const float* x, int64_t ld, const uint16_t* ell_idx, const float* ell_val,
+                int32_t ell_width, int64_t n, uint32_t low_dim,
                 const double* precursor_mz, const float* rt, const int32_t* list_id,
                 const int32_t* probes, int32_t max_nprobe, double tol, int tol_mode, double rt_tol,
                 int32_t n_neighbors, int32_t n_neighbors_ann, float eps_cut, float* dist,
@@ -295,6 +316,8 @@ int flc_knn_csr(const uint64_t* pairs, const uint64_t* pair_count, uint64_t pair
               "n_neighbors_ann must be >= n_neighbors > 0");
   FLC_REQUIRE(n_neighbors_ann <= 1024, "n_neighbors_ann > 1024 not supported");
   FLC_REQUIRE((list_id == nullptr) == (probes == nullptr), "list_id and probes go together");
+  FLC_REQUIRE((ell_idx == nullptr) == (ell_val == nullptr), "ell_idx and ell_val go together");
+  FLC_REQUIRE(x != nullptr || ell_idx != nullptr, "need dense or ELL rows");
   FLC_REQUIRE(nnz != nullptr, "null nnz");
   cudaStream_t stream = as_stream(stream_);
   if (n == 0) {
@@ -332,6 +355,7 @@ int flc_knn_csr(const uint64_t* pairs, const uint64_t* pair_count, uint64_t pair
   FLC_LAUNCH_CHECK();
 
   RefineParams P;
+  P.ell_idx = ell_idx; P.ell_val = ell_val; P.ell_width = ell_width;
   P.x = x; P.ld = ld; P.n = n; P.low_dim = low_dim; P.mz = precursor_mz; P.rt = rt;
   P.list_id = list_id; P.probes = probes; P.max_nprobe = max_nprobe;
   P.tol = tol; P.tol_mode = tol_mode; P.rt_tol = rt_tol;
@@ -361,7 +385,7 @@ int flc_knn_csr(const uint64_t* pairs, const uint64_t* pair_count, uint64_t pair
   if (static_cast<uint64_t>(total_nnz) > nnz_capacity)
     return set_error(FLC_ERR_CAPACITY, "CSR needs %lld entries, capacity %llu",
                      static_cast<long long>(total_nnz), static_cast<unsigned long long>(nnz_capacity));
-  const unsigned cblocks = static_cast<unsigned>((n * 32 + 255) / 256);
+  const unsigned cblocks = static_cast<unsigned>((n + 255) / 256);
   timed("csr_compact", stream, [&] { csr_compact_kernel<<<cblocks, 256, 0, stream>>>(L.grouped, L.off, indptr, n, nnz_capacity, dist, indices); });
   FLC_LAUNCH_CHECK();
   return FLC_OK;

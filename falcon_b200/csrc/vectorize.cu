@@ -32,7 +32,9 @@ vectorize_kernel(const float* __restrict__ mz, const float* __restrict__ intensi
                  uint32_t low_dim, uint32_t seed, int norm,
                  float* __restrict__ out_f32, int64_t ld_f32,
                  uint16_t* __restrict__ out_bf16, int64_t ld_bf16,
-                 int32_t* __restrict__ out_hash_idx) {
+                 int32_t* __restrict__ out_hash_idx,
+                 uint16_t* __restrict__ ell_idx, float* __restrict__ ell_val, int32_t ell_width,
+                 int32_t* __restrict__ ell_overflow) {
   extern __shared__ float smem_rows[];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -84,21 +86,18 @@ vectorize_kernel(const float* __restrict__ mz, const float* __restrict__ intensi
       }
       ss = warp_sum_f64(ss);
       scale = ss > 0.0 ? 1.0 / sqrt(ss) : 1.0;
+      // normalise in place: every output below reads the final float32 value
+      for (uint32_t i = lane; i < low_dim; i += 32)
+        row[i] = static_cast<float>(static_cast<double>(row[i]) * scale);
+      __syncwarp();
     }
     if (out_f32) {
       float* dst = out_f32 + r * ld_f32;
       if (((low_dim | ld_f32) & 3) == 0) {
-        for (uint32_t i = lane * 4; i < low_dim; i += 128) {
-          float4 v;
-          v.x = static_cast<float>(static_cast<double>(row[i + 0]) * scale);
-          v.y = static_cast<float>(static_cast<double>(row[i + 1]) * scale);
-          v.z = static_cast<float>(static_cast<double>(row[i + 2]) * scale);
-          v.w = static_cast<float>(static_cast<double>(row[i + 3]) * scale);
-          *reinterpret_cast<float4*>(dst + i) = v;
-        }
+        for (uint32_t i = lane * 4; i < low_dim; i += 128)
+          *reinterpret_cast<float4*>(dst + i) = *reinterpret_cast<const float4*>(row + i);
       } else {
-        for (uint32_t i = lane; i < low_dim; i += 32)
-          dst[i] = static_cast<float>(static_cast<double>(row[i]) * scale);
+        for (uint32_t i = lane; i < low_dim; i += 32) dst[i] = row[i];
       }
     }
     if (out_bf16) {
@@ -109,8 +108,7 @@ vectorize_kernel(const float* __restrict__ mz, const float* __restrict__ intensi
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const int64_t c = i + j;
-            const float f = c < low_dim ? static_cast<float>(static_cast<double>(row[c]) * scale) : 0.f;
-            h[j] = f32_to_bf16_rne(f);
+            h[j] = f32_to_bf16_rne(c < low_dim ? row[c] : 0.f);
           }
           uint2 packed;
           packed.x = static_cast<uint32_t>(h[0]) | (static_cast<uint32_t>(h[1]) << 16);
@@ -118,11 +116,31 @@ vectorize_kernel(const float* __restrict__ mz, const float* __restrict__ intensi
           *reinterpret_cast<uint2*>(dst + i) = packed;
         }
       } else {
-        for (int64_t i = lane; i < ld_bf16; i += 32) {
-          const float f = i < low_dim ? static_cast<float>(static_cast<double>(row[i]) * scale) : 0.f;
-          dst[i] = f32_to_bf16_rne(f);
-        }
+        for (int64_t i = lane; i < ld_bf16; i += 32) dst[i] = f32_to_bf16_rne(i < low_dim ? row[i] : 0.f);
       }
+    }
+    if (ell_idx) {
+      // Sparse (ELL) copy: the non-zero columns in ascending order, zero padded.
+      uint16_t* di = ell_idx + r * ell_width;
+      float* dv = ell_val + r * ell_width;
+      int count = 0;
+      for (uint32_t base = 0; base < low_dim; base += 32) {
+        const uint32_t i = base + lane;
+        const float v = i < low_dim ? row[i] : 0.f;
+        const bool nz = v != 0.f;
+        const uint32_t ballot = __ballot_sync(0xffffffffu, nz);
+        const int pos = count + __popc(ballot & ((1u << lane) - 1u));
+        if (nz && pos < ell_width) {
+          di[pos] = static_cast<uint16_t>(i);
+          dv[pos] = v;
+        }
+        count += __popc(ballot);
+      }
+      for (int pos = count + lane; pos < ell_width; pos += 32) {
+        di[pos] = 0;
+        dv[pos] = 0.f;
+      }
+      if (count > ell_width && lane == 0) atomicMax(ell_overflow, count);
     }
     __syncwarp();
   }
@@ -147,6 +165,7 @@ int flc_vectorize(const float* mz, const float* intensity, const int64_t* indptr
                   const int32_t* order, int64_t n, double min_mz, double bin_size,
                   uint32_t vec_len, uint32_t low_dim, uint32_t seed, int norm, float* out_f32,
                   int64_t ld_f32, uint16_t* out_bf16, int64_t ld_bf16, int32_t* out_hash_idx,
+                  uint16_t* ell_idx, float* ell_val, int32_t ell_width, int32_t* ell_overflow,
                   flc_stream_t stream) {
   FLC_REQUIRE(n >= 0, "n must be non-negative");
   FLC_REQUIRE(low_dim > 0 && low_dim <= 8192, "low_dim must be in [1, 8192]");
@@ -154,6 +173,9 @@ int flc_vectorize(const float* mz, const float* intensity, const int64_t* indptr
   FLC_REQUIRE(vec_len > 0, "vec_len must be positive");
   FLC_REQUIRE(!out_f32 || ld_f32 >= low_dim, "ld_f32 < low_dim");
   FLC_REQUIRE(!out_bf16 || ld_bf16 >= low_dim, "ld_bf16 < low_dim");
+  FLC_REQUIRE((ell_idx == nullptr) == (ell_val == nullptr), "ell_idx and ell_val go together");
+  FLC_REQUIRE(!ell_idx || (ell_width > 0 && ell_overflow != nullptr && low_dim <= 65536),
+              "ELL output needs ell_width > 0, an overflow flag and low_dim <= 65536");
   if (n == 0) return FLC_OK;
   FLC_REQUIRE(indptr != nullptr, "null indptr");
   const size_t smem = static_cast<size_t>(flc::kVecWarps) * low_dim * sizeof(float);
@@ -166,7 +188,8 @@ int flc_vectorize(const float* mz, const float* intensity, const int64_t* indptr
   flc::timed("vectorize", stream, [&] { flc::vectorize_kernel<<<static_cast<unsigned>(blocks), flc::kVecWarps * 32, smem,
                           flc::as_stream(stream)>>>(mz, intensity, indptr, order, n, min_mz, bin_size,
                                                     vec_len, low_dim, seed, norm, out_f32, ld_f32,
-                                                    out_bf16, ld_bf16, out_hash_idx); });
+                                                    out_bf16, ld_bf16, out_hash_idx, ell_idx, ell_val,
+                                                    ell_width, ell_overflow); });
   FLC_LAUNCH_CHECK();
   return FLC_OK;
 }

@@ -50,6 +50,7 @@ class Settings:
     kmeans_iters: int = 10
     scan_impl: int = 0  # 0 = tcgen05, 1 = SIMT verification kernel
     eps_cut: bool = True  # keep only dist <= eps in the CSR (what generate_clusters reads)
+    dense_f32: bool = True  # also materialise the dense float32 rows (needed by the generic k-means path)
 
 
 def get_dim(min_mz: float, max_mz: float, bin_size: float):
@@ -106,6 +107,23 @@ class _TimerCtx:
             b = torch.cuda.Event(enable_timing=True)
             b.record()
             self.t.events.append((self.name, self.a, b))
+
+
+@dataclasses.dataclass
+class Vectors:
+    """Hashed vectors of the spectra (rows in bucket order when ``order`` was given)."""
+
+    x: Optional[torch.Tensor]  # float32 [n, low_dim]
+    xb: Optional[torch.Tensor]  # bfloat16 [n, ld_bf16] (tcgen05 scan operand)
+    hash_idx: Optional[torch.Tensor]  # int32 [n_peaks]
+    ell_idx: Optional[torch.Tensor]  # int16 storage of uint16 [n, ell_width]
+    ell_val: Optional[torch.Tensor]  # float32 [n, ell_width]
+    ell_width: int
+    n: int
+    low_dim: int
+
+    def __iter__(self):  # x, xb, hash_idx = hp.vectorize(...)
+        return iter((self.x, self.xb, self.hash_idx))
 
 
 @dataclasses.dataclass
@@ -183,17 +201,28 @@ class HotPath:
     # ------------------------------------------------------------------ a2-a4
     def vectorize(self, mz: torch.Tensor, intensity: torch.Tensor, indptr: torch.Tensor,
                   order: Optional[torch.Tensor] = None, want_bf16: bool = True,
-                  want_hash_idx: bool = False, norm: bool = True):
+                  want_hash_idx: bool = False, norm: bool = True, want_f32: bool = True,
+                  want_ell: bool = True, max_peaks: Optional[int] = None) -> Vectors:
         n = indptr.shape[0] - 1
         d = self.s.low_dim
-        x = torch.empty((n, d), dtype=torch.float32, device=self.device)
+        x = torch.empty((n, d), dtype=torch.float32, device=self.device) if want_f32 else None
         xb = torch.empty((n, self.ld_bf16), dtype=torch.bfloat16, device=self.device) if want_bf16 else None
         hidx = self._empty(mz.shape[0], torch.int32) if want_hash_idx else None
+        ell_idx = ell_val = overflow = None
+        width = 0
+        if want_ell and n > 0:
+            if max_peaks is None:  # a row has at most as many non-zeros as the spectrum has peaks
+                max_peaks = int((indptr[1:] - indptr[:-1]).max().item())
+            width = max(8, (min(max_peaks, d) + 7) // 8 * 8)
+            ell_idx = torch.empty((n, width), dtype=torch.int16, device=self.device)
+            ell_val = torch.empty((n, width), dtype=torch.float32, device=self.device)
+            overflow = torch.zeros(1, dtype=torch.int32, device=self.device)
         with self.timer("vectorize"):
             check(lib.flc_vectorize(ptr(mz), ptr(intensity), ptr(indptr), ptr(order), n,
                                     self.min_mz, self.s.fragment_tol, self.vec_len, d, self.s.hash_seed,
-                                    1 if norm else 0, ptr(x), d, ptr(xb), self.ld_bf16, ptr(hidx), _stream()))
-        return x, xb, hidx
+                                    1 if norm else 0, ptr(x), d, ptr(xb), self.ld_bf16, ptr(hidx),
+                                    ptr(ell_idx), ptr(ell_val), width, ptr(overflow), _stream()))
+        return Vectors(x, xb, hidx, ell_idx, ell_val, width, n, d)
 
     def hash_table(self) -> torch.Tensor:
         out = self._empty(self.vec_len, torch.int32)
@@ -205,30 +234,34 @@ class HotPath:
         nb = buckets.n_buckets
         nlist = self._empty(nb + 1, torch.int32)
         nprobe = self._empty(nb + 1, torch.int32)
-        cptr = self._empty(nb + 2, torch.int64)
-        total, maxp = C.c_int64(0), C.c_int32(0)
+        cptr = self._empty(nb + 3, torch.int64)
+        total, maxp, maxb = C.c_int64(0), C.c_int32(0), C.c_int64(0)
         check(lib.flc_ivf_plan(ptr(buckets.bucket_ptr), nb, self.s.n_probe, 0, ptr(nlist), ptr(nprobe),
-                               ptr(cptr), C.byref(total), C.byref(maxp), _stream()))
-        return nlist, nprobe, cptr, int(total.value), int(maxp.value)
+                               ptr(cptr), C.byref(total), C.byref(maxp), C.byref(maxb), _stream()))
+        return nlist, nprobe, cptr, int(total.value), int(maxp.value), int(maxb.value)
 
-    def build_ivf(self, x: torch.Tensor, buckets: Buckets,
+    def build_ivf(self, v: Vectors, buckets: Buckets,
                   centroids: Optional[torch.Tensor] = None) -> IvfIndex:
-        n, d = x.shape
+        n, d = v.n, v.low_dim
+        x = v.x
+        ld = x.stride(0) if x is not None else d
         with self.timer("ivf_train"):
-            nlist, nprobe, cptr, total, maxp = self.ivf_plan(buckets)
+            nlist, nprobe, cptr, total, maxp, maxb = self.ivf_plan(buckets)
             if centroids is None:
                 centroids = torch.empty((max(total, 1), d), dtype=torch.float32, device=self.device)
-                ws = self._ws(lib.flc_kmeans_workspace_bytes(n, total, d))
-                check(lib.flc_kmeans_train(ptr(x), x.stride(0), n, d, ptr(buckets.bucket_ptr),
-                                           buckets.n_buckets, ptr(nlist), ptr(cptr), total,
-                                           self.s.kmeans_iters, ptr(centroids), ptr(ws), ws.numel(), _stream()))
+                ws = self._ws(lib.flc_kmeans_workspace_bytes(n, total, d) if x is not None else 0)
+                check(lib.flc_kmeans_train(ptr(x), ld, n, d, ptr(buckets.bucket_ptr),
+                                           buckets.n_buckets, ptr(nlist), ptr(cptr), total, maxb,
+                                           self.s.kmeans_iters, ptr(v.ell_idx), ptr(v.ell_val), v.ell_width,
+                                           ptr(centroids), ptr(ws), ws.numel(), _stream()))
             elif centroids.shape[0] < total:
                 raise ValueError("centroids array too small for the bucket plan")
         with self.timer("ivf_assign"):
             list_id = self._empty(n, torch.int32)
             probes = torch.empty((n, maxp), dtype=torch.int32, device=self.device)
-            check(lib.flc_ivf_assign(ptr(x), x.stride(0), n, d, ptr(buckets.bucket_ptr), buckets.n_buckets,
+            check(lib.flc_ivf_assign(ptr(x), ld, n, d, ptr(buckets.bucket_ptr), buckets.n_buckets,
                                      ptr(nlist), ptr(nprobe), ptr(cptr), ptr(centroids), maxp,
+                                     ptr(v.ell_idx), ptr(v.ell_val), v.ell_width,
                                      ptr(list_id), ptr(probes), _stream()))
         return IvfIndex(nlist, nprobe, cptr, centroids, list_id, probes, maxp, total)
 
@@ -238,9 +271,10 @@ class HotPath:
             return -math.inf
         return float(np.float32(1.0) - np.float32(self.s.eps) - np.float32(SCAN_MARGIN))
 
-    def knn_graph(self, x: torch.Tensor, xb: torch.Tensor, buckets: Buckets,
+    def knn_graph(self, v: Vectors, buckets: Buckets,
                   ivf: Optional[IvfIndex] = None, pair_capacity: Optional[int] = None) -> KnnGraph:
-        n, d = x.shape
+        n, d = v.n, v.low_dim
+        x, xb = v.x, v.xb
         s = self.s
         thr = self.scan_threshold()
         if pair_capacity is None:
@@ -270,7 +304,9 @@ class HotPath:
         nnz = C.c_int64(0)
         with self.timer("knn_csr"):
             ws2 = self._ws(lib.flc_knn_csr_workspace_bytes(n, n_pairs))
-            check(lib.flc_knn_csr(ptr(pairs), ptr(pair_count), pair_capacity, ptr(x), x.stride(0), n, d,
+            check(lib.flc_knn_csr(ptr(pairs), ptr(pair_count), pair_capacity,
+                                  ptr(x), x.stride(0) if x is not None else d,
+                                  ptr(v.ell_idx), ptr(v.ell_val), v.ell_width, n, d,
                                   ptr(buckets.mz), ptr(buckets.rt) if s.rt_tol is not None else None,
                                   ptr(ivf.list_id) if ivf else None, ptr(ivf.probes) if ivf else None,
                                   ivf.max_nprobe if ivf else 0,
@@ -317,16 +353,16 @@ class HotPath:
             empty = self._empty(0, torch.int32)
             return (empty, 0, {}) if keep else (empty, 0)
         buckets = self.bucket_sort(precursor_mz, charge, rt if self.s.rt_tol is not None else None)
-        x, xb, _ = self.vectorize(mz, intensity, indptr, buckets.order)
-        ivf = None if self.s.exhaustive else self.build_ivf(x, buckets)
-        graph = self.knn_graph(x, xb, buckets, ivf)
+        v = self.vectorize(mz, intensity, indptr, buckets.order, want_f32=keep or self.s.dense_f32)
+        ivf = None if self.s.exhaustive else self.build_ivf(v, buckets)
+        graph = self.knn_graph(v, buckets, ivf)
         db_labels, _ = self.dbscan(graph, n)
         sorted_labels, n_clusters = self.split(db_labels, buckets.mz, values_sorted=True)
         labels = self._empty(n, torch.int32)
         with self.timer("scatter"):
             check(lib.flc_scatter32(ptr(sorted_labels), ptr(buckets.order), n, ptr(labels), _stream()))
         if keep:
-            return labels, n_clusters, dict(buckets=buckets, x=x, xb=xb, ivf=ivf, graph=graph,
+            return labels, n_clusters, dict(buckets=buckets, x=v.x, xb=v.xb, vectors=v, ivf=ivf, graph=graph,
                                             db_labels=db_labels, sorted_labels=sorted_labels)
         return labels, n_clusters
 

@@ -78,14 +78,20 @@ FLC_API int flc_hash_table(uint32_t vec_len, uint32_t low_dim, uint32_t seed,
  *   out_f32   [n, ld_f32]  float32 (nullable)
  *   out_bf16  [n, ld_bf16] bfloat16 bits, columns >= low_dim zeroed (nullable)
  *   out_hash_idx [n_peaks] hashed column of every peak in input peak order,
- *                -1 for peaks outside [0, vec_len) (nullable; parity checks) */
+ *                -1 for peaks outside [0, vec_len) (nullable; parity checks)
+ *   ell_idx / ell_val [n, ell_width] sparse (ELL) copy of the rows: non-zero
+ *                columns ascending (uint16) and their float32 values, zero padded
+ *                (nullable); *ell_overflow (device int32, caller zeroes it) receives
+ *                the largest row population if one exceeds ell_width */
 FLC_API int flc_vectorize(const float* mz, const float* intensity, const int64_t* indptr,
                   const int32_t* order, int64_t n,
                   double min_mz, double bin_size, uint32_t vec_len,
                   uint32_t low_dim, uint32_t seed, int norm,
                   float* out_f32, int64_t ld_f32,
                   uint16_t* out_bf16, int64_t ld_bf16,
-                  int32_t* out_hash_idx, flc_stream_t stream);
+                  int32_t* out_hash_idx,
+                  uint16_t* ell_idx, float* ell_val, int32_t ell_width, int32_t* ell_overflow,
+                  flc_stream_t stream);
 
 /* ------------------------------------------------------------------ a5: buckets
  * A.2 bucket rule: round(((mz - 1.00794) * max(|z|,1)) / 1.0005079) // mz_interval,
@@ -111,19 +117,24 @@ FLC_API int flc_scatter32(const void* in, const int32_t* order, int64_t n, void*
 /* ------------------------------------------------------------------ a6: IVF train / assign
  * A.2 (faiss IndexIVFFlat over IndexFlatIP): per bucket
  * n_list = 0 (flat) if n < 100 else 2^floor(log2(n/39)) (..., see flc_ivf_plan),
- * spherical k-means (niter iterations), assignment = arg-max inner product. */
+ * spherical k-means (niter iterations), assignment = arg-max inner product.
+ * With the ELL copy from flc_vectorize, buckets whose sparse rows fit in shared
+ * memory train in one fused kernel (x may then be NULL); others use dense x. */
 /*  nlist[b], nprobe[b] (int32) and centroid_ptr[b] (int64 exclusive scan of nlist)
  *  for every bucket; exhaustive != 0 lifts the nprobe cap (nprobe = nlist).
  *  Synchronises the stream; returns the total number of centroids on the host. */
 FLC_API int flc_ivf_plan(const int64_t* bucket_ptr, int64_t n_buckets, int32_t n_probe,
                  int exhaustive, int32_t* nlist, int32_t* nprobe,
-                 int64_t* centroid_ptr /*[n_buckets+2]: scan, total, max nprobe*/, int64_t* total_centroids /*host*/,
-                 int32_t* max_nprobe /*host*/, flc_stream_t stream);
+                 int64_t* centroid_ptr /*[n_buckets+3]: scan, total, max nprobe, max IVF bucket*/,
+                 int64_t* total_centroids /*host*/, int32_t* max_nprobe /*host*/,
+                 int64_t* max_ivf_bucket /*host, nullable*/, flc_stream_t stream);
 FLC_API size_t flc_kmeans_workspace_bytes(int64_t n, int64_t total_centroids, uint32_t low_dim);
 FLC_API int flc_kmeans_train(const float* x, int64_t ld, int64_t n, uint32_t low_dim,
                      const int64_t* bucket_ptr, int64_t n_buckets,
                      const int32_t* nlist, const int64_t* centroid_ptr,
-                     int64_t total_centroids, int niter,
+                     int64_t total_centroids, int64_t max_ivf_bucket /*from flc_ivf_plan, 0 = unknown*/,
+                     int niter,
+                     const uint16_t* ell_idx, const float* ell_val, int32_t ell_width /*nullable ELL copy*/,
                      float* centroids /*[total_centroids, low_dim]*/,
                      void* workspace, size_t workspace_bytes, flc_stream_t stream);
 /*  list_id[i] (int32, bucket-local list of row i, 0 for flat buckets) and
@@ -133,7 +144,9 @@ FLC_API int flc_ivf_assign(const float* x, int64_t ld, int64_t n, uint32_t low_d
                    const int64_t* bucket_ptr, int64_t n_buckets,
                    const int32_t* nlist, const int32_t* nprobe,
                    const int64_t* centroid_ptr, const float* centroids,
-                   int32_t max_nprobe, int32_t* list_id, int32_t* probes,
+                   int32_t max_nprobe,
+                   const uint16_t* ell_idx, const float* ell_val, int32_t ell_width /*nullable ELL copy*/,
+                   int32_t* list_id, int32_t* probes,
                    flc_stream_t stream);
 
 /* ------------------------------------------------------------------ a7: inverted-list scan
@@ -165,7 +178,9 @@ FLC_API int flc_scan_pairs(const uint16_t* x_bf16, int64_t ld_bf16, int64_t n, u
  * Synchronises the stream; returns nnz on the host. */
 FLC_API size_t flc_knn_csr_workspace_bytes(int64_t n, uint64_t n_pairs);
 FLC_API int flc_knn_csr(const uint64_t* pairs, const uint64_t* pair_count, uint64_t pair_capacity,
-                const float* x, int64_t ld, int64_t n, uint32_t low_dim,
+                const float* x, int64_t ld /*dense rows, nullable if ELL given*/,
+                const uint16_t* ell_idx, const float* ell_val, int32_t ell_width /*nullable ELL copy*/,
+                int64_t n, uint32_t low_dim,
                 const double* precursor_mz, const float* rt,
                 const int32_t* list_id, const int32_t* probes, int32_t max_nprobe,
                 double tol, int tol_mode, double rt_tol,

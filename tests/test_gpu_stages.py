@@ -49,9 +49,21 @@ def test_vectorize_synthetic(low_dim):
     h = pipeline.HotPath(pipeline.Settings(low_dim=low_dim))
     sp = helpers.dataset(5000, 1)
     d = helpers.to_device(sp, h.device)
-    x, xb, hidx = h.vectorize(d["mz"], d["intensity"], d["indptr"], want_hash_idx=True)
+    v = h.vectorize(d["mz"], d["intensity"], d["indptr"], want_hash_idx=True)
+    x, xb, hidx = v
     ref, ref_idx = helpers.oracle_vectors(sp, low_dim, return_hash_idx=True)
     assert np.array_equal(_cpu(hidx), ref_idx)
+    # sparse (ELL) copy: ascending non-zero columns + values, zero padded
+    ei, ev = _cpu(v.ell_idx).view(np.uint16), _cpu(v.ell_val)
+    assert v.ell_width % 8 == 0 and v.ell_width >= np.diff(sp.indptr).max()
+    dense = np.zeros_like(_cpu(x))
+    rows = np.repeat(np.arange(len(sp)), v.ell_width).reshape(ei.shape)
+    np.add.at(dense, (rows, ei), ev)
+    assert np.array_equal(dense, _cpu(x))
+    nnz = (ev != 0).sum(axis=1)
+    assert np.array_equal(nnz, (_cpu(x) != 0).sum(axis=1))
+    for r in range(0, len(sp), 500):
+        assert (np.diff(ei[r, : nnz[r]].astype(np.int64)) > 0).all() and (ev[r, nnz[r]:] == 0).all()
     np.testing.assert_allclose(_cpu(x), ref, rtol=0, atol=1e-6)
     xb_bits = _cpu(xb.view(torch.int16)).view(np.uint16)
     assert np.array_equal(xb_bits[:, :low_dim], ovec.to_bf16_bits(_cpu(x)))
@@ -123,7 +135,8 @@ def test_scan_pairs_tc_and_simt(n, lo, hi, low_dim):
     sp = helpers.dataset(n, 9, lo, hi)
     d = helpers.to_device(sp, h.device)
     b = h.bucket_sort(d["precursor_mz"], d["charge"])
-    x, xb, _ = h.vectorize(d["mz"], d["intensity"], d["indptr"], b.order)
+    v = h.vectorize(d["mz"], d["intensity"], d["indptr"], b.order)
+    x, xb = v.x, v.xb
     thr = h.scan_threshold()
     xf = _cpu(xb.float())[:, :low_dim].astype(np.float64)
     xe = _cpu(x).astype(np.float64)
@@ -151,8 +164,9 @@ def test_knn_csr_exhaustive_exact(n, lo, hi, scan_impl):
     sp = helpers.dataset(n, 13, lo, hi)
     d = helpers.to_device(sp, h.device)
     b = h.bucket_sort(d["precursor_mz"], d["charge"])
-    x, xb, _ = h.vectorize(d["mz"], d["intensity"], d["indptr"], b.order)
-    g = h.knn_graph(x, xb, b)
+    v = h.vectorize(d["mz"], d["intensity"], d["indptr"], b.order)
+    x, xb = v.x, v.xb
+    g = h.knn_graph(v, b)
     o = helpers.oracle_pipeline(sp, exhaustive=True, vectors=_cpu(x))
     ref = o["csr_cut"]
     assert np.array_equal(_cpu(g.indptr), ref.indptr)
@@ -166,8 +180,9 @@ def test_knn_csr_without_eps_cut_matches_full_reference_matrix():
     sp = helpers.dataset(3000, 17)
     d = helpers.to_device(sp, h.device)
     b = h.bucket_sort(d["precursor_mz"], d["charge"])
-    x, xb, _ = h.vectorize(d["mz"], d["intensity"], d["indptr"], b.order)
-    g = h.knn_graph(x, xb, b)
+    v = h.vectorize(d["mz"], d["intensity"], d["indptr"], b.order)
+    x, xb = v.x, v.xb
+    g = h.knn_graph(v, b)
     ref = helpers.oracle_pipeline(sp, exhaustive=True, vectors=_cpu(x))["csr"]
     assert np.array_equal(_cpu(g.indptr), ref.indptr)
     assert np.array_equal(_cpu(g.indices), ref.indices)
@@ -181,8 +196,9 @@ def test_knn_csr_da_mode_and_small_k():
     sp = helpers.dataset(4000, 19, 1000.0, 1004.0)
     d = helpers.to_device(sp, h.device)
     b = h.bucket_sort(d["precursor_mz"], d["charge"])
-    x, xb, _ = h.vectorize(d["mz"], d["intensity"], d["indptr"], b.order)
-    g = h.knn_graph(x, xb, b)
+    v = h.vectorize(d["mz"], d["intensity"], d["indptr"], b.order)
+    x, xb = v.x, v.xb
+    g = h.knn_graph(v, b)
     order, bptr, _ = oivf.bucket_sort(sp.precursor_mz, sp.precursor_charge)
     mat, _ = oivf.compute_pairwise_distances(_cpu(x), sp.precursor_mz[order], None, bptr, 0.01, "Da", None,
                                              3, 5, 32, True)
@@ -192,15 +208,26 @@ def test_knn_csr_da_mode_and_small_k():
 
 
 # ------------------------------------------------------------------ IVF
-def test_ivf_shared_centroids_exact_and_recall():
+def _drop_ell(v):
+    import dataclasses
+
+    return dataclasses.replace(v, ell_idx=None, ell_val=None, ell_width=0)
+
+
+@pytest.mark.parametrize("sparse", [True, False])
+def test_ivf_shared_centroids_exact_and_recall(sparse):
     """Default n_probe with centroids shared between the CUDA path and the oracle:
-    neighbour sets identical (north_star asks recall >= 0.99)."""
+    neighbour sets identical (north_star asks recall >= 0.99).  sparse=True uses the
+    ELL rows (fused trainer), sparse=False the dense generic kernels."""
     h = pipeline.HotPath(pipeline.Settings(exhaustive=False))
     sp = helpers.dataset(8000, 23, 1000.0, 1008.0)
     d = helpers.to_device(sp, h.device)
     b = h.bucket_sort(d["precursor_mz"], d["charge"])
-    x, xb, _ = h.vectorize(d["mz"], d["intensity"], d["indptr"], b.order)
-    ivf = h.build_ivf(x, b)
+    v = h.vectorize(d["mz"], d["intensity"], d["indptr"], b.order)
+    if not sparse:
+        v = _drop_ell(v)
+    x, xb = v.x, v.xb
+    ivf = h.build_ivf(v, b)
     assert ivf.total_centroids > 0
     nlist, cptr = _cpu(ivf.nlist), _cpu(ivf.centroid_ptr)
     bptr = _cpu(b.bucket_ptr)
@@ -217,7 +244,7 @@ def test_ivf_shared_centroids_exact_and_recall():
             p = oivf.n_probe_rule(int(nlist[i]), 32)
             assert np.array_equal(probes[s:e, :p], oivf.probe_lists(xs[s:e], shared[i], p))
             assert (probes[s:e, p:] == -1).all()
-    g = h.knn_graph(x, xb, b, ivf)
+    g = h.knn_graph(v, b, ivf)
     o = helpers.oracle_pipeline(sp, exhaustive=False, centroids=shared, vectors=xs)
     ref = o["csr_cut"]
     gi, gp = _cpu(g.indices), _cpu(g.indptr)
@@ -227,13 +254,19 @@ def test_ivf_shared_centroids_exact_and_recall():
     assert np.array_equal(gp, ref.indptr) and np.array_equal(gi, ref.indices)
 
 
-def test_kmeans_quality_close_to_oracle():
+@pytest.mark.parametrize("sparse,n,hi", [(True, 6000, 1003.0), (False, 6000, 1003.0), (True, 30000, 1002.0)])
+def test_kmeans_quality_close_to_oracle(sparse, n, hi):
+    """n = 30000 over 2 Da makes buckets of ~7500 rows: too large for the fused
+    trainer, so the ELL run exercises the fused/generic split as well."""
     h = pipeline.HotPath(pipeline.Settings(exhaustive=False))
-    sp = helpers.dataset(6000, 29, 1000.0, 1003.0)
+    sp = helpers.dataset(n, 29, 1000.0, hi)
     d = helpers.to_device(sp, h.device)
     b = h.bucket_sort(d["precursor_mz"], d["charge"])
-    x, _, _ = h.vectorize(d["mz"], d["intensity"], d["indptr"], b.order, want_bf16=False)
-    ivf = h.build_ivf(x, b)
+    v = h.vectorize(d["mz"], d["intensity"], d["indptr"], b.order, want_bf16=False)
+    if not sparse:
+        v = _drop_ell(v)
+    x = v.x
+    ivf = h.build_ivf(v, b)
     xs, bptr, nlist, cptr = _cpu(x), _cpu(b.bucket_ptr), _cpu(ivf.nlist), _cpu(ivf.centroid_ptr)
     cents = _cpu(ivf.centroids)
     checked = 0
