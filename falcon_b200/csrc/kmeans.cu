@@ -16,6 +16,8 @@
 //             centroid is L2-normalised (spherical k-means for the IP metric).
 // The final assignment / probe selection (flc_ivf_assign) uses float64 inner
 // products so that it agrees with the oracle wherever there is no exact tie.
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace flc {
@@ -32,16 +34,21 @@ __host__ __device__ inline int32_t nlist_rule(int64_t n) {
   return 1 << 20;
 }
 
-// Shared-memory budget of one bucket in the fused kernel: the ELL rows (uint16
-// column + float32 value per slot), the centroids (float32) and their float64
-// accumulators + counts.
+// Shared-memory budget of one bucket in the fused kernel: the ELL rows (float32
+// values with an odd pitch, uint16 columns), the centroids ([column][list]
+// float32), their float64 accumulators ([list][column]), counts, assignments.
 __host__ __device__ inline size_t fused_smem_bytes(int64_t nb, int32_t L, int32_t W, uint32_t low_dim) {
-  size_t b = static_cast<size_t>(nb) * W * 6;
+  const size_t lp = static_cast<size_t>((L + 3) & ~3);
+  size_t b = static_cast<size_t>(nb) * (W + 1) * 4;       // values
+  b += static_cast<size_t>(nb) * (W + 2) * 2;             // columns
   b = (b + 15) & ~size_t(15);
-  b += static_cast<size_t>(L) * low_dim * 12 + static_cast<size_t>(L) * 8 + 64;
+  b += static_cast<size_t>(L) * low_dim * 8;              // accumulators
+  b += static_cast<size_t>(low_dim) * lp * 4;             // centroids
+  b += static_cast<size_t>(L) * 8 + ((static_cast<size_t>(nb) + 15) & ~size_t(15)) + 64;
   return b;
 }
-constexpr size_t kFusedSmemCap = 200 * 1024;
+constexpr size_t kFusedSmemCap = 200 * 1024;   // largest bucket the fused trainer takes
+constexpr size_t kFusedSmemSmall = 100 * 1024; // buckets below this run two CTAs per SM
 
 __host__ __device__ inline bool bucket_is_fused(int64_t nb, int32_t L, int32_t W, uint32_t low_dim,
                                                 size_t smem_limit) {
@@ -320,91 +327,117 @@ ivf_assign_kernel(const float* __restrict__ x, int64_t ld, int64_t n, uint32_t l
 // ---------------------------------------------------------------- fused small-bucket trainer
 // One CTA per bucket (persistent over buckets): the bucket's sparse rows stay in
 // shared memory for all iterations, so HBM sees each row once.
-//   assign + update: one warp per row -- sparse dot products against the
-//     centroids in shared memory (float32), arg-max with ties to the lower id,
-//     then the row is scattered into the winner's float64 accumulator with
-//     shared-memory atomics (sums of float32 values in float64 are exact here, so
-//     the result does not depend on the order);
+//   assign: one THREAD per row -- sparse dot products against the centroids in
+//     shared memory ([column][list] so one 16-byte load serves four lists),
+//     float32, arg-max with ties to the lower id; no shuffles, no idle lanes;
+//   update: one WARP per list walks the list's rows in row order; a row's
+//     non-zero columns are distinct, so the lanes add them into the float64
+//     accumulator without atomics (shared-memory float atomics are CAS loops on
+//     sm_100) and in exactly the oracle's summation order;
 //   fix: mean, empty-list re-seeding (+-1/1024), L2 normalisation.
+// Launched per size class [need_lo, need_hi) so that small buckets run two CTAs per SM.
 __global__ void __launch_bounds__(256)
 kmeans_fused_kernel(const uint16_t* __restrict__ ell_idx, const float* __restrict__ ell_val, int32_t W,
                     uint32_t low_dim, const int64_t* __restrict__ bucket_ptr, int64_t n_buckets,
                     const int32_t* __restrict__ nlist, const int64_t* __restrict__ centroid_ptr, int niter,
-                    size_t smem_limit, float* __restrict__ centroids) {
+                    size_t need_lo, size_t need_hi, float* __restrict__ centroids) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ int32_t cj_s;
   __shared__ double red_s[8];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int kWarps = 8;
   const float eps = 1.0f / 1024.0f;
+  const int d = static_cast<int>(low_dim);
+  const int vp = W + 1;  // value pitch (odd: thread-per-row reads are conflict free)
+  const int ip = W + 2;  // column pitch ((W + 2) / 2 is odd for W % 8 == 0)
 
   for (int64_t b = blockIdx.x; b < n_buckets; b += gridDim.x) {
     const int32_t L = nlist[b];
     const int64_t s = bucket_ptr[b];
     const int32_t nb = static_cast<int32_t>(bucket_ptr[b + 1] - s);
-    if (!bucket_is_fused(nb, L, W, low_dim, smem_limit)) continue;
+    if (L <= 0) continue;
+    const size_t need = fused_smem_bytes(nb, L, W, low_dim);
+    if (need < need_lo || need >= need_hi) continue;
     const int64_t c0 = centroid_ptr[b];
+    const int lp = (L + 3) & ~3;
     // carve shared memory
-    uint16_t* sidx = reinterpret_cast<uint16_t*>(smem_raw);
-    float* sval = reinterpret_cast<float*>(smem_raw + static_cast<size_t>(nb) * W * 2);
-    size_t off = (static_cast<size_t>(nb) * W * 6 + 15) & ~size_t(15);
+    float* sval = reinterpret_cast<float*>(smem_raw);
+    uint16_t* sidx = reinterpret_cast<uint16_t*>(smem_raw + static_cast<size_t>(nb) * vp * 4);
+    size_t off = (static_cast<size_t>(nb) * vp * 4 + static_cast<size_t>(nb) * ip * 2 + 15) & ~size_t(15);
     double* acc = reinterpret_cast<double*>(smem_raw + off);
-    off += static_cast<size_t>(L) * low_dim * 8;
+    off += static_cast<size_t>(L) * d * 8;
+    float* C = reinterpret_cast<float*>(smem_raw + off);
+    off += static_cast<size_t>(d) * lp * 4;
     double* cnt = reinterpret_cast<double*>(smem_raw + off);
     off += static_cast<size_t>(L) * 8;
-    float* C = reinterpret_cast<float*>(smem_raw + off);
+    uint8_t* assign = smem_raw + off;
     __syncthreads();  // previous bucket fully written out
-    // load the bucket (coalesced)
-    {
-      const uint32_t* gi = reinterpret_cast<const uint32_t*>(ell_idx + s * W);
-      uint32_t* si = reinterpret_cast<uint32_t*>(sidx);
-      const int n32 = nb * W / 2;
-      if ((W & 1) == 0 && ((reinterpret_cast<uintptr_t>(gi) & 3) == 0)) {
-        for (int t = tid; t < n32; t += 256) si[t] = __ldg(gi + t);
-      } else {
-        for (int t = tid; t < nb * W; t += 256) sidx[t] = __ldg(ell_idx + s * W + t);
-      }
-      const float* gv = ell_val + s * W;
-      for (int t = tid; t < nb * W; t += 256) sval[t] = __ldg(gv + t);
-      for (int t = tid; t < L * static_cast<int>(low_dim); t += 256) C[t] = 0.f;
+    for (int t = tid; t < nb * W; t += 256) {
+      const int r = t / W, j = t - r * W;
+      sval[r * vp + j] = __ldg(ell_val + s * W + t);
+      sidx[r * ip + j] = __ldg(ell_idx + s * W + t);
     }
+    for (int t = tid; t < d * lp; t += 256) C[t] = 0.f;
     __syncthreads();
     // init: centroid c = row (c * nb) / L
     for (int t = tid; t < L * W; t += 256) {
-      const int c = t / W, j = t % W;
+      const int c = t / W, j = t - c * W;
       const int row = static_cast<int>((static_cast<int64_t>(c) * nb) / L);
-      const float v = sval[row * W + j];
-      if (v != 0.f) C[c * low_dim + sidx[row * W + j]] = v;
+      const float v = sval[row * vp + j];
+      if (v != 0.f) C[sidx[row * ip + j] * lp + c] = v;
     }
     __syncthreads();
     for (int it = 0; it < niter; ++it) {
-      for (int t = tid; t < L * static_cast<int>(low_dim); t += 256) acc[t] = 0.0;
-      if (tid < L) cnt[tid] = 0.0;
-      __syncthreads();
-      for (int r = warp; r < nb; r += kWarps) {
+      // ---- assign (thread per row)
+      for (int r = tid; r < nb; r += 256) {
         float best = -INFINITY;
         int best_c = 0;
-        for (int c = 0; c < L; ++c) {
-          float a = 0.f;
-          for (int j = lane; j < W; j += 32) a = fmaf(sval[r * W + j], C[c * low_dim + sidx[r * W + j]], a);
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-          if (a > best) { best = a; best_c = c; }
+        const float* rv = sval + r * vp;
+        const uint16_t* ri = sidx + r * ip;
+        for (int cb = 0; cb < lp; cb += 4) {
+          float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll 8
+          for (int j = 0; j < W; ++j) {
+            const float v = rv[j];
+            const float4 cv = *reinterpret_cast<const float4*>(C + ri[j] * lp + cb);
+            a0 = fmaf(v, cv.x, a0);
+            a1 = fmaf(v, cv.y, a1);
+            a2 = fmaf(v, cv.z, a2);
+            a3 = fmaf(v, cv.w, a3);
+          }
+          if (cb + 0 < L && a0 > best) { best = a0; best_c = cb + 0; }
+          if (cb + 1 < L && a1 > best) { best = a1; best_c = cb + 1; }
+          if (cb + 2 < L && a2 > best) { best = a2; best_c = cb + 2; }
+          if (cb + 3 < L && a3 > best) { best = a3; best_c = cb + 3; }
         }
-        for (int j = lane; j < W; j += 32) {
-          const float v = sval[r * W + j];
-          if (v != 0.f) atomicAdd(acc + best_c * low_dim + sidx[r * W + j], static_cast<double>(v));
+        assign[r] = static_cast<uint8_t>(best_c);
+      }
+      for (int t = tid; t < L * d; t += 256) acc[t] = 0.0;
+      __syncthreads();
+      // ---- update (warp per list, rows in order)
+      for (int c = warp; c < L; c += kWarps) {
+        double* ac = acc + c * d;
+        int n_c = 0;
+        for (int r = 0; r < nb; ++r) {
+          if (assign[r] != c) continue;  // warp uniform
+          ++n_c;
+          for (int j = lane; j < W; j += 32) {
+            const float v = sval[r * vp + j];
+            if (v != 0.f) ac[sidx[r * ip + j]] += static_cast<double>(v);
+          }
+          __syncwarp();
         }
-        if (lane == 0) atomicAdd(cnt + best_c, 1.0);
+        if (lane == 0) cnt[c] = static_cast<double>(n_c);
       }
       __syncthreads();
-      // mean (empty lists keep their centroid)
-      for (int t = tid; t < L * static_cast<int>(low_dim); t += 256) {
-        const double n_c = cnt[t / low_dim];
-        if (n_c > 0.0) C[t] = static_cast<float>(acc[t] / n_c);
+      // ---- mean (empty lists keep their centroid)
+      for (int t = tid; t < L * d; t += 256) {
+        const int c = t / d, k = t - c * d;
+        const double n_c = cnt[c];
+        if (n_c > 0.0) C[k * lp + c] = static_cast<float>(acc[t] / n_c);
       }
       __syncthreads();
-      // re-seed empty lists from the largest one
+      // ---- re-seed empty lists from the largest one
       for (int ci = 0; ci < L; ++ci) {
         if (cnt[ci] > 0.0) continue;  // uniform
         if (tid == 0) {
@@ -416,11 +449,11 @@ kmeans_fused_kernel(const uint16_t* __restrict__ ell_idx, const float* __restric
         }
         __syncthreads();
         const int cj = cj_s;
-        for (int t = tid; t < static_cast<int>(low_dim); t += 256) {
-          const float sign = (t % 2 == 0) ? 1.0f + eps : 1.0f - eps;
-          const float v = C[cj * low_dim + t];
-          C[ci * low_dim + t] = v * sign;
-          C[cj * low_dim + t] = v * (2.0f - sign);
+        for (int k = tid; k < d; k += 256) {
+          const float sign = (k % 2 == 0) ? 1.0f + eps : 1.0f - eps;
+          const float v = C[k * lp + cj];
+          C[k * lp + ci] = v * sign;
+          C[k * lp + cj] = v * (2.0f - sign);
         }
         __syncthreads();
         if (tid == 0) {
@@ -430,11 +463,11 @@ kmeans_fused_kernel(const uint16_t* __restrict__ ell_idx, const float* __restric
         }
         __syncthreads();
       }
-      // normalise
+      // ---- normalise
       for (int c = 0; c < L; ++c) {
         double ss = 0.0;
-        for (int t = tid; t < static_cast<int>(low_dim); t += 256) {
-          const double v = static_cast<double>(C[c * low_dim + t]);
+        for (int k = tid; k < d; k += 256) {
+          const double v = static_cast<double>(C[k * lp + c]);
           ss += v * v;
         }
         ss = warp_sum_f64(ss);
@@ -444,12 +477,15 @@ kmeans_fused_kernel(const uint16_t* __restrict__ ell_idx, const float* __restric
 #pragma unroll
         for (int w = 0; w < kWarps; ++w) tot += red_s[w];
         const double nrm = tot > 0.0 ? sqrt(tot) : 1.0;
-        for (int t = tid; t < static_cast<int>(low_dim); t += 256)
-          C[c * low_dim + t] = static_cast<float>(static_cast<double>(C[c * low_dim + t]) / nrm);
+        for (int k = tid; k < d; k += 256)
+          C[k * lp + c] = static_cast<float>(static_cast<double>(C[k * lp + c]) / nrm);
         __syncthreads();
       }
     }
-    for (int t = tid; t < L * static_cast<int>(low_dim); t += 256) centroids[c0 * low_dim + t] = C[t];
+    for (int t = tid; t < L * d; t += 256) {
+      const int c = t / d, k = t - c * d;
+      centroids[c0 * low_dim + t] = C[k * lp + c];
+    }
   }
 }
 
@@ -514,21 +550,26 @@ int flc_kmeans_train(const float* x, int64_t ld, int64_t n, uint32_t low_dim, co
   size_t fused_limit = 0;
   bool any_generic = true;
   if (W > 0) {
+    FLC_REQUIRE((W % 8) == 0, "ell_width must be a multiple of 8");
     fused_limit = kFusedSmemCap;
-    // size the allocation for the largest bucket that will use the fused kernel
-    int64_t nb_max = max_ivf_bucket > 0 ? max_ivf_bucket : n;
-    size_t need = fused_smem_bytes(nb_max, nlist_rule(nb_max), W, low_dim);
-    if (need <= kFusedSmemCap) {
-      any_generic = false;  // every IVF bucket fits
-      fused_limit = need;
+    const int64_t nb_max = max_ivf_bucket > 0 ? max_ivf_bucket : n;
+    const size_t need_max = fused_smem_bytes(nb_max, nlist_rule(nb_max), W, low_dim);
+    if (need_max <= kFusedSmemCap) any_generic = false;  // every IVF bucket fits
+    const size_t hi_bytes = need_max < kFusedSmemCap ? need_max + 16 : kFusedSmemCap + 16;
+    // two size classes: [0, small) at two CTAs per SM, [small, cap] at one
+    const size_t bounds[3] = {0, std::min(kFusedSmemSmall, hi_bytes), hi_bytes};
+    for (int cls = 0; cls < 2; ++cls) {
+      if (bounds[cls] >= bounds[cls + 1]) continue;
+      const size_t smem = bounds[cls + 1];
+      FLC_CUDA(cudaFuncSetAttribute(kmeans_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    static_cast<int>(smem)));
+      const int64_t cap = static_cast<int64_t>(kNumSMs) * (cls == 0 ? 2 : 1);
+      const int64_t grid = n_buckets < cap ? n_buckets : cap;
+      timed("kmeans_fused", stream, [&] { kmeans_fused_kernel<<<static_cast<unsigned>(grid), 256, smem, stream>>>(
+          ell_idx, ell_val, W, low_dim, bucket_ptr, n_buckets, nlist, centroid_ptr, niter, bounds[cls],
+          bounds[cls + 1], centroids); });
+      FLC_LAUNCH_CHECK();
     }
-    FLC_CUDA(cudaFuncSetAttribute(kmeans_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  static_cast<int>(fused_limit)));
-    const int64_t grid = n_buckets < 8 * kNumSMs ? n_buckets : 8 * kNumSMs;
-    timed("kmeans_fused", stream, [&] { kmeans_fused_kernel<<<static_cast<unsigned>(grid), 256, fused_limit, stream>>>(
-        ell_idx, ell_val, W, low_dim, bucket_ptr, n_buckets, nlist, centroid_ptr, niter, fused_limit,
-        centroids); });
-    FLC_LAUNCH_CHECK();
   }
   if (!any_generic) return FLC_OK;
   FLC_REQUIRE(x != nullptr, "dense rows are needed for buckets too large for the fused trainer");
