@@ -63,7 +63,7 @@ SIGNATURES = {
                                C.POINTER(_i64), _p]),
     "flc_kmeans_workspace_bytes": (_sz, [_i64, _i64, _u32]),
     "flc_kmeans_train": (C.c_int, [_p, _i64, _i64, _u32, _p, _i64, _p, _p, _i64, _i64, C.c_int,
-                                   _p, _p, _i32, _p, _p, _sz, _p]),
+                                   _p, _p, _i32, _p, _p, _i32, _p, _p, C.POINTER(_i32), _p, _sz, _p]),
     "flc_ivf_assign": (C.c_int, [_p, _i64, _i64, _u32, _p, _i64, _p, _p, _p, _p, _i32,
                                  _p, _p, _i32, _p, _p, _p]),
     "flc_scan_workspace_bytes": (_sz, [_i64, _i64]),

@@ -330,17 +330,26 @@ ivf_assign_kernel(const float* __restrict__ x, int64_t ld, int64_t n, uint32_t l
 //   assign: one THREAD per row -- sparse dot products against the centroids in
 //     shared memory ([column][list] so one 16-byte load serves four lists),
 //     float32, arg-max with ties to the lower id; no shuffles, no idle lanes;
-//   update: one WARP per list walks the list's rows in row order; a row's
-//     non-zero columns are distinct, so the lanes add them into the float64
-//     accumulator without atomics (shared-memory float atomics are CAS loops on
-//     sm_100) and in exactly the oracle's summation order;
-//   fix: mean, empty-list re-seeding (+-1/1024), L2 normalisation.
+//   update: 8 / L warps per list (each owning an interleaved share of the
+//     columns) walk the list's rows in row order; a row's non-zero columns are
+//     distinct, so lanes add them into the float64 accumulator without atomics
+//     (shared-memory float atomics are CAS loops on sm_100) and in exactly the
+//     oracle's summation order;
+//   mean + L2 normalisation: one warp per list, no block-wide reductions;
+//     empty lists (rare) take a slow path that re-seeds them from the largest
+//     list with the +-1/1024 perturbation faiss uses;
+//   after the last iteration the final assignment / probe list (float64 inner
+//     products, ties to the lower id) is produced from the same shared memory.
 // Launched per size class [need_lo, need_hi) so that small buckets run two CTAs per SM.
+constexpr int kFusedMaxProbe = 4;
+
 __global__ void __launch_bounds__(256)
 kmeans_fused_kernel(const uint16_t* __restrict__ ell_idx, const float* __restrict__ ell_val, int32_t W,
                     uint32_t low_dim, const int64_t* __restrict__ bucket_ptr, int64_t n_buckets,
                     const int32_t* __restrict__ nlist, const int64_t* __restrict__ centroid_ptr, int niter,
-                    size_t need_lo, size_t need_hi, float* __restrict__ centroids) {
+                    size_t need_lo, size_t need_hi, float* __restrict__ centroids,
+                    const int32_t* __restrict__ nprobe, int32_t max_nprobe, int32_t* __restrict__ list_id,
+                    int32_t* __restrict__ probes) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ int32_t cj_s;
   __shared__ double red_s[8];
@@ -355,7 +364,15 @@ kmeans_fused_kernel(const uint16_t* __restrict__ ell_idx, const float* __restric
     const int32_t L = nlist[b];
     const int64_t s = bucket_ptr[b];
     const int32_t nb = static_cast<int32_t>(bucket_ptr[b + 1] - s);
-    if (L <= 0) continue;
+    if (L <= 0) {
+      // flat bucket: a single implicit list (written once, by the first size class)
+      if (list_id != nullptr && need_lo == 0) {
+        for (int t = tid; t < nb; t += 256) list_id[s + t] = 0;
+        for (int t = tid; t < nb * max_nprobe; t += 256)
+          probes[s * max_nprobe + t] = (t % max_nprobe) == 0 ? 0 : -1;
+      }
+      continue;
+    }
     const size_t need = fused_smem_bytes(nb, L, W, low_dim);
     if (need < need_lo || need >= need_hi) continue;
     const int64_t c0 = centroid_ptr[b];
@@ -387,6 +404,7 @@ kmeans_fused_kernel(const uint16_t* __restrict__ ell_idx, const float* __restric
       if (v != 0.f) C[sidx[row * ip + j] * lp + c] = v;
     }
     __syncthreads();
+    const int wpc = L >= kWarps ? 1 : kWarps / L;  // warps per list in the update (L is a power of two)
     for (int it = 0; it < niter; ++it) {
       // ---- assign (thread per row)
       for (int r = tid; r < nb; r += 256) {
@@ -414,77 +432,150 @@ kmeans_fused_kernel(const uint16_t* __restrict__ ell_idx, const float* __restric
       }
       for (int t = tid; t < L * d; t += 256) acc[t] = 0.0;
       __syncthreads();
-      // ---- update (warp per list, rows in order)
-      for (int c = warp; c < L; c += kWarps) {
+      // ---- update: warp (c, h) adds the columns with idx % wpc == h of list c's rows, in row order
+      for (int cw = warp; cw < L * wpc; cw += kWarps) {
+        const int c = cw / wpc, h = cw - c * wpc;
         double* ac = acc + c * d;
         int n_c = 0;
-        for (int r = 0; r < nb; ++r) {
-          if (assign[r] != c) continue;  // warp uniform
-          ++n_c;
-          for (int j = lane; j < W; j += 32) {
-            const float v = sval[r * vp + j];
-            if (v != 0.f) ac[sidx[r * ip + j]] += static_cast<double>(v);
+        for (int r0 = 0; r0 < nb; r0 += 32) {
+          const int rr = r0 + lane;
+          uint32_t mine = __ballot_sync(0xffffffffu, rr < nb && assign[rr] == c);
+          n_c += __popc(mine);
+          while (mine) {
+            const int r = r0 + __ffs(mine) - 1;
+            mine &= mine - 1;
+            for (int j = lane; j < W; j += 32) {
+              const float v = sval[r * vp + j];
+              const int k = sidx[r * ip + j];
+              if (v != 0.f && (k & (wpc - 1)) == h) ac[k] += static_cast<double>(v);
+            }
+            __syncwarp();
           }
-          __syncwarp();
         }
-        if (lane == 0) cnt[c] = static_cast<double>(n_c);
+        if (lane == 0 && h == 0) cnt[c] = static_cast<double>(n_c);
       }
       __syncthreads();
-      // ---- mean (empty lists keep their centroid)
-      for (int t = tid; t < L * d; t += 256) {
-        const int c = t / d, k = t - c * d;
-        const double n_c = cnt[c];
-        if (n_c > 0.0) C[k * lp + c] = static_cast<float>(acc[t] / n_c);
-      }
-      __syncthreads();
-      // ---- re-seed empty lists from the largest one
-      for (int ci = 0; ci < L; ++ci) {
-        if (cnt[ci] > 0.0) continue;  // uniform
-        if (tid == 0) {
-          int bestc = 0;
-          double bc = cnt[0];
-          for (int c = 1; c < L; ++c)
-            if (cnt[c] > bc) { bc = cnt[c]; bestc = c; }
-          cj_s = bestc;
+      bool any_empty = false;
+      for (int c = 0; c < L; ++c) any_empty |= !(cnt[c] > 0.0);
+      if (!any_empty) {
+        // ---- fast path: mean + normalise, one warp per list
+        for (int c = warp; c < L; c += kWarps) {
+          const double inv_n = 1.0 / cnt[c];
+          double ss = 0.0;
+          for (int k = lane; k < d; k += 32) {
+            const float m = static_cast<float>(acc[c * d + k] * inv_n);
+            ss = fma(static_cast<double>(m), static_cast<double>(m), ss);
+          }
+          ss = warp_sum_f64(ss);
+          const double inv_nrm = ss > 0.0 ? 1.0 / sqrt(ss) : 1.0;
+          for (int k = lane; k < d; k += 32) {
+            const float m = static_cast<float>(acc[c * d + k] * inv_n);
+            C[k * lp + c] = static_cast<float>(static_cast<double>(m) * inv_nrm);
+          }
         }
         __syncthreads();
-        const int cj = cj_s;
-        for (int k = tid; k < d; k += 256) {
-          const float sign = (k % 2 == 0) ? 1.0f + eps : 1.0f - eps;
-          const float v = C[k * lp + cj];
-          C[k * lp + ci] = v * sign;
-          C[k * lp + cj] = v * (2.0f - sign);
+      } else {
+        // ---- slow path: mean (empty lists keep their centroid), re-seed, normalise
+        for (int t = tid; t < L * d; t += 256) {
+          const int c = t / d, k = t - c * d;
+          const double n_c = cnt[c];
+          if (n_c > 0.0) C[k * lp + c] = static_cast<float>(acc[t] * (1.0 / n_c));
         }
         __syncthreads();
-        if (tid == 0) {
-          const double half = cnt[cj] / 2.0;
-          cnt[ci] = half;
-          cnt[cj] -= half;
+        for (int ci = 0; ci < L; ++ci) {
+          if (cnt[ci] > 0.0) continue;  // uniform
+          if (tid == 0) {
+            int bestc = 0;
+            double bc = cnt[0];
+            for (int c = 1; c < L; ++c)
+              if (cnt[c] > bc) { bc = cnt[c]; bestc = c; }
+            cj_s = bestc;
+          }
+          __syncthreads();
+          const int cj = cj_s;
+          for (int k = tid; k < d; k += 256) {
+            const float sign = (k % 2 == 0) ? 1.0f + eps : 1.0f - eps;
+            const float v = C[k * lp + cj];
+            C[k * lp + ci] = v * sign;
+            C[k * lp + cj] = v * (2.0f - sign);
+          }
+          __syncthreads();
+          if (tid == 0) {
+            const double half = cnt[cj] / 2.0;
+            cnt[ci] = half;
+            cnt[cj] -= half;
+          }
+          __syncthreads();
         }
-        __syncthreads();
-      }
-      // ---- normalise
-      for (int c = 0; c < L; ++c) {
-        double ss = 0.0;
-        for (int k = tid; k < d; k += 256) {
-          const double v = static_cast<double>(C[k * lp + c]);
-          ss += v * v;
-        }
-        ss = warp_sum_f64(ss);
-        if (lane == 0) red_s[warp] = ss;
-        __syncthreads();
-        double tot = 0.0;
+        for (int c = 0; c < L; ++c) {
+          double ss = 0.0;
+          for (int k = tid; k < d; k += 256) {
+            const double v = static_cast<double>(C[k * lp + c]);
+            ss += v * v;
+          }
+          ss = warp_sum_f64(ss);
+          if (lane == 0) red_s[warp] = ss;
+          __syncthreads();
+          double tot = 0.0;
 #pragma unroll
-        for (int w = 0; w < kWarps; ++w) tot += red_s[w];
-        const double nrm = tot > 0.0 ? sqrt(tot) : 1.0;
-        for (int k = tid; k < d; k += 256)
-          C[k * lp + c] = static_cast<float>(static_cast<double>(C[k * lp + c]) / nrm);
-        __syncthreads();
+          for (int w = 0; w < kWarps; ++w) tot += red_s[w];
+          const double inv_nrm = tot > 0.0 ? 1.0 / sqrt(tot) : 1.0;
+          for (int k = tid; k < d; k += 256)
+            C[k * lp + c] = static_cast<float>(static_cast<double>(C[k * lp + c]) * inv_nrm);
+          __syncthreads();
+        }
       }
     }
     for (int t = tid; t < L * d; t += 256) {
       const int c = t / d, k = t - c * d;
       centroids[c0 * low_dim + t] = C[k * lp + c];
+    }
+    // ---- final assignment + probe list (thread per row, float64)
+    if (list_id != nullptr) {
+      const int P = nprobe[b];
+      for (int r = tid; r < nb; r += 256) {
+        double ps[kFusedMaxProbe];
+        int pi[kFusedMaxProbe];
+#pragma unroll
+        for (int t = 0; t < kFusedMaxProbe; ++t) { ps[t] = -INFINITY; pi[t] = -1; }
+        const float* rv = sval + r * vp;
+        const uint16_t* ri = sidx + r * ip;
+        for (int cb = 0; cb < lp; cb += 4) {
+          double a[4] = {0.0, 0.0, 0.0, 0.0};
+          for (int j = 0; j < W; ++j) {
+            const float v = rv[j];
+            if (v != 0.f) {
+              const float4 cv = *reinterpret_cast<const float4*>(C + ri[j] * lp + cb);
+              const double dv = static_cast<double>(v);
+              a[0] = fma(dv, static_cast<double>(cv.x), a[0]);
+              a[1] = fma(dv, static_cast<double>(cv.y), a[1]);
+              a[2] = fma(dv, static_cast<double>(cv.z), a[2]);
+              a[3] = fma(dv, static_cast<double>(cv.w), a[3]);
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int c = cb + u;
+            if (c < L) {
+              // insert behind every entry that is better or equal (earlier id wins ties)
+              const double sc = a[u];
+              int pos = P;
+#pragma unroll
+              for (int t = 0; t < kFusedMaxProbe; ++t)
+                if (t < P && pos == P && (pi[t] < 0 || sc > ps[t])) pos = t;
+#pragma unroll
+              for (int t = kFusedMaxProbe - 1; t >= 1; --t)
+                if (t < P && t > pos) { ps[t] = ps[t - 1]; pi[t] = pi[t - 1]; }
+#pragma unroll
+              for (int t = 0; t < kFusedMaxProbe; ++t)
+                if (t == pos) { ps[t] = sc; pi[t] = c; }
+            }
+          }
+        }
+        list_id[s + r] = pi[0];
+        for (int t = 0; t < max_nprobe; ++t)
+          probes[(s + r) * max_nprobe + t] = (t < P && t < kFusedMaxProbe) ? pi[t] : -1;
+      }
     }
   }
 }
@@ -536,11 +627,13 @@ int flc_kmeans_train(const float* x, int64_t ld, int64_t n, uint32_t low_dim, co
                      int64_t n_buckets, const int32_t* nlist, const int64_t* centroid_ptr,
                      int64_t total_centroids, int64_t max_ivf_bucket, int niter,
                      const uint16_t* ell_idx, const float* ell_val, int32_t ell_width, float* centroids,
-                     void* workspace, size_t workspace_bytes, flc_stream_t stream_) {
+                     const int32_t* nprobe, int32_t max_nprobe, int32_t* list_id, int32_t* probes,
+                     int32_t* assigned, void* workspace, size_t workspace_bytes, flc_stream_t stream_) {
   using namespace flc;
   FLC_REQUIRE(n >= 0 && niter >= 0, "bad sizes");
   FLC_REQUIRE(low_dim > 0 && low_dim <= 8192, "low_dim must be in [1, 8192]");
   FLC_REQUIRE((ell_idx == nullptr) == (ell_val == nullptr), "ell_idx and ell_val go together");
+  if (assigned) *assigned = 0;
   if (n == 0 || total_centroids == 0) return FLC_OK;
   cudaStream_t stream = as_stream(stream_);
   // Buckets whose sparse rows + centroids fit in shared memory train in the fused
@@ -555,6 +648,11 @@ int flc_kmeans_train(const float* x, int64_t ld, int64_t n, uint32_t low_dim, co
     const int64_t nb_max = max_ivf_bucket > 0 ? max_ivf_bucket : n;
     const size_t need_max = fused_smem_bytes(nb_max, nlist_rule(nb_max), W, low_dim);
     if (need_max <= kFusedSmemCap) any_generic = false;  // every IVF bucket fits
+    // The fused trainer also emits the final assignment when it covers every bucket
+    // and the probe lists are short.
+    const bool emit = !any_generic && list_id != nullptr && probes != nullptr && nprobe != nullptr &&
+                      max_nprobe >= 1 && max_nprobe <= kFusedMaxProbe;
+    if (assigned) *assigned = emit ? 1 : 0;
     const size_t hi_bytes = need_max < kFusedSmemCap ? need_max + 16 : kFusedSmemCap + 16;
     // two size classes: [0, small) at two CTAs per SM, [small, cap] at one
     const size_t bounds[3] = {0, std::min(kFusedSmemSmall, hi_bytes), hi_bytes};
@@ -567,7 +665,7 @@ int flc_kmeans_train(const float* x, int64_t ld, int64_t n, uint32_t low_dim, co
       const int64_t grid = n_buckets < cap ? n_buckets : cap;
       timed("kmeans_fused", stream, [&] { kmeans_fused_kernel<<<static_cast<unsigned>(grid), 256, smem, stream>>>(
           ell_idx, ell_val, W, low_dim, bucket_ptr, n_buckets, nlist, centroid_ptr, niter, bounds[cls],
-          bounds[cls + 1], centroids); });
+          bounds[cls + 1], centroids, nprobe, max_nprobe, emit ? list_id : nullptr, emit ? probes : nullptr); });
       FLC_LAUNCH_CHECK();
     }
   }

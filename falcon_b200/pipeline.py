@@ -245,24 +245,27 @@ class HotPath:
         n, d = v.n, v.low_dim
         x = v.x
         ld = x.stride(0) if x is not None else d
+        assigned = C.c_int32(0)
         with self.timer("ivf_train"):
             nlist, nprobe, cptr, total, maxp, maxb = self.ivf_plan(buckets)
+            list_id = self._empty(n, torch.int32)
+            probes = torch.empty((n, maxp), dtype=torch.int32, device=self.device)
             if centroids is None:
                 centroids = torch.empty((max(total, 1), d), dtype=torch.float32, device=self.device)
                 ws = self._ws(lib.flc_kmeans_workspace_bytes(n, total, d) if x is not None else 0)
                 check(lib.flc_kmeans_train(ptr(x), ld, n, d, ptr(buckets.bucket_ptr),
                                            buckets.n_buckets, ptr(nlist), ptr(cptr), total, maxb,
                                            self.s.kmeans_iters, ptr(v.ell_idx), ptr(v.ell_val), v.ell_width,
-                                           ptr(centroids), ptr(ws), ws.numel(), _stream()))
+                                           ptr(centroids), ptr(nprobe), maxp, ptr(list_id), ptr(probes),
+                                           C.byref(assigned), ptr(ws), ws.numel(), _stream()))
             elif centroids.shape[0] < total:
                 raise ValueError("centroids array too small for the bucket plan")
-        with self.timer("ivf_assign"):
-            list_id = self._empty(n, torch.int32)
-            probes = torch.empty((n, maxp), dtype=torch.int32, device=self.device)
-            check(lib.flc_ivf_assign(ptr(x), ld, n, d, ptr(buckets.bucket_ptr), buckets.n_buckets,
-                                     ptr(nlist), ptr(nprobe), ptr(cptr), ptr(centroids), maxp,
-                                     ptr(v.ell_idx), ptr(v.ell_val), v.ell_width,
-                                     ptr(list_id), ptr(probes), _stream()))
+        if not assigned.value:
+            with self.timer("ivf_assign"):
+                check(lib.flc_ivf_assign(ptr(x), ld, n, d, ptr(buckets.bucket_ptr), buckets.n_buckets,
+                                         ptr(nlist), ptr(nprobe), ptr(cptr), ptr(centroids), maxp,
+                                         ptr(v.ell_idx), ptr(v.ell_val), v.ell_width,
+                                         ptr(list_id), ptr(probes), _stream()))
         return IvfIndex(nlist, nprobe, cptr, centroids, list_id, probes, maxp, total)
 
     # ------------------------------------------------------------------ a7-a9

@@ -136,6 +136,9 @@ FLC_API int flc_kmeans_train(const float* x, int64_t ld, int64_t n, uint32_t low
                      int niter,
                      const uint16_t* ell_idx, const float* ell_val, int32_t ell_width /*nullable ELL copy*/,
                      float* centroids /*[total_centroids, low_dim]*/,
+                     /* optional fused final assignment (same outputs as flc_ivf_assign): */
+                     const int32_t* nprobe, int32_t max_nprobe, int32_t* list_id, int32_t* probes,
+                     int32_t* assigned /*host, nullable: 1 if list_id/probes were written for every row*/,
                      void* workspace, size_t workspace_bytes, flc_stream_t stream);
 /*  list_id[i] (int32, bucket-local list of row i, 0 for flat buckets) and
  *  probes[i * max_nprobe + j] (int32 list ids best first, -1 padded), both from
