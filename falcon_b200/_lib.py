@@ -54,16 +54,16 @@ SIGNATURES = {
     "flc_get_dim": (C.c_int, [_f32, _f32, _f32, C.POINTER(_u32), C.POINTER(_f32), C.POINTER(_f32)]),
     "flc_hash_table": (C.c_int, [_u32, _u32, _u32, _p, _p]),
     "flc_vectorize": (C.c_int, [_p, _p, _p, _p, _i64, _f64, _f64, _u32, _u32, _u32, C.c_int,
-                                _p, _i64, _p, _i64, _p, _p, _p, _i32, _p, _p]),
+                                _p, _i64, _p, _i64, _p, _p, _p, _p, _i32, _p, _p]),
     "flc_bucket_sort_workspace_bytes": (_sz, [_i64]),
     "flc_bucket_sort": (C.c_int, [_p, _p, _i64, _i32, _p, _p, _p, _p, C.POINTER(_i64), _p, _sz, _p]),
     "flc_gather": (C.c_int, [_p, _p, _i64, C.c_int, _p, _p]),
     "flc_scatter32": (C.c_int, [_p, _p, _i64, _p, _p]),
     "flc_ivf_plan": (C.c_int, [_p, _i64, _i32, C.c_int, _p, _p, _p, C.POINTER(_i64), C.POINTER(_i32),
                                C.POINTER(_i64), _p]),
-    "flc_kmeans_workspace_bytes": (_sz, [_i64, _i64, _u32]),
-    "flc_kmeans_train": (C.c_int, [_p, _i64, _i64, _u32, _p, _i64, _p, _p, _i64, _i64, C.c_int,
-                                   _p, _p, _i32, _p, _p, _i32, _p, _p, C.POINTER(_i32), _p, _sz, _p]),
+    "flc_kmeans_workspace_bytes": (_sz, [_i64, _i64, _i64, _i64, _i32, _u32]),
+    "flc_kmeans_train": (C.c_int, [_p, _p, _p, _i32, _i64, _u32, _p, _i64, _p, _p, _i64, _i64, C.c_int,
+                                   _p, _p, _i32, _p, _p, _p, _sz, _p]),
     "flc_ivf_assign": (C.c_int, [_p, _i64, _i64, _u32, _p, _i64, _p, _p, _p, _p, _i32,
                                  _p, _p, _i32, _p, _p, _p]),
     "flc_scan_workspace_bytes": (_sz, [_i64, _i64]),

@@ -2,21 +2,29 @@
 // coarse assignment and probe selection (faiss IndexIVFFlat over an
 // IndexFlatIP quantiser, METRIC_INNER_PRODUCT).
 //
-// All buckets are trained together ("batched"): rows find their bucket by
-// binary search in bucket_ptr, centroids find theirs in centroid_ptr, so one
-// launch covers thousands of small buckets and a 100k-row bucket alike.
-//   assign  : one warp per row, float32 inner products against the bucket's
-//             centroids (L2 resident), arg-max with ties to the lower id.
-//   update  : one CTA per centroid, threads own dimensions and walk the
-//             bucket's rows in index order accumulating in float64 --
-//             deterministic (no float atomics) and identical to the oracle's
-//             sequential float64 sum.
-//   fix     : one CTA per bucket: empty lists are re-seeded from the largest
-//             list with the +-1/1024 perturbation faiss uses, then every
-//             centroid is L2-normalised (spherical k-means for the IP metric).
-// The final assignment / probe selection (flc_ivf_assign) uses float64 inner
-// products so that it agrees with the oracle wherever there is no exact tie.
+// Training works on the sparse (ELL) rows flc_vectorize emits (~35 of 400 columns
+// are populated).  One definition of the arithmetic, two schedules:
+//   * fused (kmeans_fused_kernel): one CTA per bucket, the bucket's rows resident
+//     in shared memory for all iterations -- HBM sees every row once.  Covers
+//     buckets of up to ~600 rows / 8 lists (all of them at 1 M spectra).
+//   * tiled (kmeans_tiled_*): larger buckets; rows stream from HBM/L2 once per
+//     iteration, list sums are accumulated with 64-bit integer atomics.
+// Arithmetic (oracle/ivf.py:kmeans_train follows the same):
+//   - assignment during training: float32 inner products, arg-max, ties to the
+//     lower list id;
+//   - list sums in 2^-40 fixed point (int64): sum_r rint(x[r][k] * 2^40).  Integer
+//     addition is associative, so the result does not depend on the schedule or
+//     on the order atomics land in -- both paths and every run give the same bits;
+//   - mean = float32(double(sum) * (2^-40 / count)); empty lists keep their
+//     centroid and are then re-seeded from the largest list with the +-1/1024
+//     perturbation faiss uses; every centroid is L2-normalised (spherical k-means
+//     for the IP metric): float32(double(c) * (1 / sqrt(sum c^2)));
+//   - iterations stop early at a fixed point (assignments unchanged, no empty
+//     list): further iterations would reproduce the same centroids bit for bit.
+// The final assignment / probe selection uses float64 inner products so that it
+// agrees with the oracle wherever there is no exact tie.
 #include <algorithm>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -34,28 +42,41 @@ __host__ __device__ inline int32_t nlist_rule(int64_t n) {
   return 1 << 20;
 }
 
-// Shared-memory budget of one bucket in the fused kernel: the ELL rows (float32
-// values with an odd pitch, uint16 columns), the centroids ([column][list]
-// float32), their float64 accumulators ([list][column]), counts, assignments.
-__host__ __device__ inline size_t fused_smem_bytes(int64_t nb, int32_t L, int32_t W, uint32_t low_dim) {
-  const size_t lp = static_cast<size_t>((L + 3) & ~3);
-  size_t b = static_cast<size_t>(nb) * (W + 1) * 4;       // values
-  b += static_cast<size_t>(nb) * (W + 2) * 2;             // columns
-  b = (b + 15) & ~size_t(15);
-  b += static_cast<size_t>(L) * low_dim * 8;              // accumulators
-  b += static_cast<size_t>(low_dim) * lp * 4;             // centroids
-  b += static_cast<size_t>(L) * 8 + ((static_cast<size_t>(nb) + 15) & ~size_t(15)) + 64;
-  return b;
-}
-constexpr size_t kFusedSmemCap = 200 * 1024;   // largest bucket the fused trainer takes
-constexpr size_t kFusedSmemSmall = 100 * 1024; // buckets below this run two CTAs per SM
+constexpr float kFixScaleF = 1099511627776.0f;     // 2^40
+constexpr double kFixInv = 1.0 / 1099511627776.0;  // 2^-40
+constexpr int kFusedMaxL = 8;                      // lists per bucket the fused trainer handles
+constexpr uint8_t kClsTiled = 2, kClsFlat = 3;
 
-__host__ __device__ inline bool bucket_is_fused(int64_t nb, int32_t L, int32_t W, uint32_t low_dim,
-                                                size_t smem_limit) {
-  return L > 0 && W > 0 && fused_smem_bytes(nb, L, W, low_dim) <= smem_limit;
+// Fused classes: 0 = two CTAs of 256 threads per SM, 1 = one CTA of 512 threads.
+__host__ __device__ constexpr size_t fused_smem_limit(int cls) { return cls == 0 ? 110 * 1024 : 222 * 1024; }
+__host__ __device__ constexpr int fused_threads(int cls) { return cls == 0 ? 256 : 512; }
+
+// Shared-memory plan of one bucket in the fused trainer.  What only depends on
+// (nb, L) comes first, so it can be placed before the row pitch is known.
+struct FusedPlan {
+  uint32_t rnnz, split, rowlist, assign, C, acc, val, idx, total;
+  int lp, h;
+};
+__host__ __device__ inline FusedPlan fused_plan(int nb, int pitch, int L, int d, int warps) {
+  FusedPlan p;
+  p.lp = L <= 4 ? 4 : 8;                          // centroid row length in shared memory
+  const int lc = L <= 2 ? 2 : (L <= 4 ? 4 : 8);
+  p.h = warps / lc;                               // column ranges per list in the update
+  uint32_t o = 0;
+  p.rnnz = o;    o += 2u * nb;
+  p.split = o;   o += 2u * nb * (p.h - 1);
+  p.rowlist = o; o += 2u * nb * L;
+  p.assign = o;  o += nb;
+  o = (o + 15u) & ~15u;
+  p.C = o;       o += 4u * d * p.lp;
+  p.acc = o;     o += 8u * d * L;
+  p.val = o;     o += 4u * nb * pitch;
+  p.idx = o;     o += 2u * nb * pitch;
+  p.total = (o + 15u) & ~15u;
+  return p;
 }
 
-// Single CTA: nlist / nprobe per bucket, exclusive scan -> centroid_ptr, max nprobe.
+// Single CTA: nlist / nprobe per bucket, exclusive scan -> centroid_ptr, max nprobe, max IVF bucket.
 __global__ void __launch_bounds__(1024)
 ivf_plan_kernel(const int64_t* __restrict__ bucket_ptr, int64_t n_buckets, int32_t n_probe, int exhaustive,
                 int32_t* __restrict__ nlist, int32_t* __restrict__ nprobe, int64_t* __restrict__ centroid_ptr) {
@@ -115,170 +136,23 @@ __device__ __forceinline__ int64_t find_segment(const int64_t* __restrict__ ptr,
   return lo;
 }
 
-__global__ void kmeans_init_kernel(const float* __restrict__ x, int64_t ld, uint32_t low_dim,
-                                   const int64_t* __restrict__ bucket_ptr, int64_t n_buckets,
-                                   const int32_t* __restrict__ nlist, const int64_t* __restrict__ centroid_ptr,
-                                   int64_t total, int32_t W, size_t fused_limit,
-                                   float* __restrict__ centroids) {
-  const int64_t gc = blockIdx.x;
-  if (gc >= total) return;
-  const int64_t b = find_segment(centroid_ptr, n_buckets, gc);
-  const int64_t c = gc - centroid_ptr[b];
-  const int64_t s = bucket_ptr[b], nb = bucket_ptr[b + 1] - s;
-  if (bucket_is_fused(nb, nlist[b], W, low_dim, fused_limit)) return;
-  const int64_t row = s + (c * nb) / nlist[b];
-  for (uint32_t i = threadIdx.x; i < low_dim; i += blockDim.x)
-    centroids[gc * low_dim + i] = x[row * ld + i];
-}
-
-__global__ void __launch_bounds__(256)
-kmeans_assign_kernel(const float* __restrict__ x, int64_t ld, int64_t n, uint32_t low_dim,
-                     const int64_t* __restrict__ bucket_ptr, int64_t n_buckets,
-                     const int32_t* __restrict__ nlist, const int64_t* __restrict__ centroid_ptr,
-                     const float* __restrict__ centroids, int32_t W, size_t fused_limit,
-                     int32_t* __restrict__ assign) {
-  extern __shared__ float smem_x[];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int64_t i = static_cast<int64_t>(blockIdx.x) * 8 + warp;
-  if (i >= n) return;
-  const int64_t b = find_segment(bucket_ptr, n_buckets, i);
-  const int32_t L = nlist[b];
-  if (L == 0 || bucket_is_fused(bucket_ptr[b + 1] - bucket_ptr[b], L, W, low_dim, fused_limit)) {
-    if (lane == 0) assign[i] = 0;
-    return;
-  }
-  float* xi = smem_x + static_cast<size_t>(warp) * low_dim;
-  for (uint32_t t = lane; t < low_dim; t += 32) xi[t] = x[i * ld + t];
-  __syncwarp();
-  const float* cent = centroids + centroid_ptr[b] * low_dim;
-  float best = -INFINITY;
-  int32_t best_c = 0;
-  for (int32_t c = 0; c < L; ++c) {
-    const float* cr = cent + static_cast<int64_t>(c) * low_dim;
-    float acc = 0.f;
-    for (uint32_t t = lane; t < low_dim; t += 32) acc = fmaf(xi[t], __ldg(cr + t), acc);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if (acc > best) { best = acc; best_c = c; }
-  }
-  if (lane == 0) assign[i] = best_c;
-}
-
-// One CTA per centroid: float64 sum of the rows assigned to it, in row order.
-__global__ void __launch_bounds__(128)
-kmeans_update_kernel(const float* __restrict__ x, int64_t ld, uint32_t low_dim,
-                     const int64_t* __restrict__ bucket_ptr, int64_t n_buckets,
-                     const int64_t* __restrict__ centroid_ptr, int64_t total,
-                     const int32_t* __restrict__ assign, const float* __restrict__ centroids,
-                     const int32_t* __restrict__ nlist, int32_t W, size_t fused_limit,
-                     float* __restrict__ new_centroids, double* __restrict__ counts) {
-  const int64_t gc = blockIdx.x;
-  if (gc >= total) return;
-  const int64_t b = find_segment(centroid_ptr, n_buckets, gc);
-  const int32_t c = static_cast<int32_t>(gc - centroid_ptr[b]);
-  const int64_t s = bucket_ptr[b], e = bucket_ptr[b + 1];
-  if (bucket_is_fused(e - s, nlist[b], W, low_dim, fused_limit)) return;
-  constexpr int kMaxPerThread = 8;  // low_dim <= 128 * 8 handled in registers per pass
-  for (uint32_t d0 = 0; d0 < low_dim; d0 += 128 * kMaxPerThread) {
-    double acc[kMaxPerThread];
-#pragma unroll
-    for (int k = 0; k < kMaxPerThread; ++k) acc[k] = 0.0;
-    int64_t cnt = 0;
-    for (int64_t i = s; i < e; ++i) {
-      if (__ldg(assign + i) == c) {
-        ++cnt;
-#pragma unroll
-        for (int k = 0; k < kMaxPerThread; ++k) {
-          const uint32_t t = d0 + threadIdx.x + 128 * k;
-          if (t < low_dim) acc[k] += static_cast<double>(__ldg(x + i * ld + t));
-        }
-      }
-    }
-#pragma unroll
-    for (int k = 0; k < kMaxPerThread; ++k) {
-      const uint32_t t = d0 + threadIdx.x + 128 * k;
-      if (t < low_dim)
-        new_centroids[gc * low_dim + t] =
-            cnt > 0 ? static_cast<float>(acc[k] / static_cast<double>(cnt)) : centroids[gc * low_dim + t];
-    }
-    if (threadIdx.x == 0 && d0 == 0) counts[gc] = static_cast<double>(cnt);
-  }
-}
-
-// One CTA per bucket: split the largest list into every empty one, normalise.
-__global__ void __launch_bounds__(128)
-kmeans_fix_kernel(uint32_t low_dim, int64_t n_buckets, const int32_t* __restrict__ nlist,
-                  const int64_t* __restrict__ centroid_ptr, const int64_t* __restrict__ bucket_ptr, int32_t W,
-                  size_t fused_limit, float* __restrict__ new_centroids,
-                  double* __restrict__ counts, float* __restrict__ centroids) {
-  const int64_t b = blockIdx.x;
-  if (b >= n_buckets) return;
-  const int32_t L = nlist[b];
-  if (L == 0 || bucket_is_fused(bucket_ptr[b + 1] - bucket_ptr[b], L, W, low_dim, fused_limit)) return;
-  const int64_t c0 = centroid_ptr[b];
-  __shared__ int32_t cj_s;
-  __shared__ double red[128];
-  const float eps = 1.0f / 1024.0f;
-  for (int32_t ci = 0; ci < L; ++ci) {
-    if (counts[c0 + ci] > 0.0) continue;  // uniform: all threads read the same value
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      int32_t best = 0;
-      double bc = counts[c0];
-      for (int32_t c = 1; c < L; ++c)
-        if (counts[c0 + c] > bc) { bc = counts[c0 + c]; best = c; }
-      cj_s = best;
-    }
-    __syncthreads();
-    const int32_t cj = cj_s;
-    for (uint32_t t = threadIdx.x; t < low_dim; t += blockDim.x) {
-      const float sign = (t % 2 == 0) ? 1.0f + eps : 1.0f - eps;
-      const float v = new_centroids[(c0 + cj) * low_dim + t];
-      new_centroids[(c0 + ci) * low_dim + t] = v * sign;
-      new_centroids[(c0 + cj) * low_dim + t] = v * (2.0f - sign);
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      const double half = counts[c0 + cj] / 2.0;
-      counts[c0 + ci] = half;
-      counts[c0 + cj] -= half;
-    }
-    __syncthreads();
-  }
-  for (int32_t c = 0; c < L; ++c) {
-    double ss = 0.0;
-    for (uint32_t t = threadIdx.x; t < low_dim; t += blockDim.x) {
-      const double v = static_cast<double>(new_centroids[(c0 + c) * low_dim + t]);
-      ss += v * v;
-    }
-    red[threadIdx.x] = ss;
-    __syncthreads();
-    for (int o = 64; o > 0; o >>= 1) {
-      if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
-      __syncthreads();
-    }
-    const double nrm = red[0] > 0.0 ? sqrt(red[0]) : 1.0;
-    __syncthreads();
-    for (uint32_t t = threadIdx.x; t < low_dim; t += blockDim.x)
-      centroids[(c0 + c) * low_dim + t] =
-          static_cast<float>(static_cast<double>(new_centroids[(c0 + c) * low_dim + t]) / nrm);
-  }
-}
-
-// Final assignment + probe list: float64 inner products, best-first insertion
-// into a warp-resident list (lane j holds the j-th best so far).
+// Final assignment + probe list: one warp per row, float64 inner products,
+// best-first insertion into a warp-resident list (lane j holds the j-th best so
+// far).  With `bclass` only rows of tiled buckets are handled.
 __global__ void __launch_bounds__(256)
 ivf_assign_kernel(const float* __restrict__ x, int64_t ld, int64_t n, uint32_t low_dim,
                   const int64_t* __restrict__ bucket_ptr, int64_t n_buckets,
                   const int32_t* __restrict__ nlist, const int32_t* __restrict__ nprobe,
                   const int64_t* __restrict__ centroid_ptr, const float* __restrict__ centroids,
                   int32_t max_nprobe, const uint16_t* __restrict__ ell_idx, const float* __restrict__ ell_val,
-                  int32_t W, int32_t* __restrict__ list_id, int32_t* __restrict__ probes) {
+                  int32_t W, const uint8_t* __restrict__ bclass, int32_t* __restrict__ list_id,
+                  int32_t* __restrict__ probes) {
   extern __shared__ float smem_x[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t i = static_cast<int64_t>(blockIdx.x) * 8 + warp;
   if (i >= n) return;
   const int64_t b = find_segment(bucket_ptr, n_buckets, i);
+  if (bclass != nullptr && bclass[b] != kClsTiled) return;
   const int32_t L = nlist[b];
   if (L == 0) {
     if (lane == 0) list_id[i] = 0;
@@ -323,273 +197,673 @@ ivf_assign_kernel(const float* __restrict__ x, int64_t ld, int64_t n, uint32_t l
   if (lane == 0) list_id[i] = my_id;
 }
 
-
-// ---------------------------------------------------------------- fused small-bucket trainer
-// One CTA per bucket (persistent over buckets): the bucket's sparse rows stay in
-// shared memory for all iterations, so HBM sees each row once.
-//   assign: one THREAD per row -- sparse dot products against the centroids in
-//     shared memory ([column][list] so one 16-byte load serves four lists),
-//     float32, arg-max with ties to the lower id; no shuffles, no idle lanes;
-//   update: 8 / L warps per list (each owning an interleaved share of the
-//     columns) walk the list's rows in row order; a row's non-zero columns are
-//     distinct, so lanes add them into the float64 accumulator without atomics
-//     (shared-memory float atomics are CAS loops on sm_100) and in exactly the
-//     oracle's summation order;
-//   mean + L2 normalisation: one warp per list, no block-wide reductions;
-//     empty lists (rare) take a slow path that re-seeds them from the largest
-//     list with the +-1/1024 perturbation faiss uses;
-//   after the last iteration the final assignment / probe list (float64 inner
-//     products, ties to the lower id) is produced from the same shared memory.
-// Launched per size class [need_lo, need_hi) so that small buckets run two CTAs per SM.
-constexpr int kFusedMaxProbe = 4;
+// ---------------------------------------------------------------- classification
+// One warp per bucket: which trainer takes it (by the shared memory its rows
+// need), appended to that class's work queue.  Flat buckets (no IVF) get their
+// trivial list_id / probes here.
+struct TrainQueues {
+  int32_t* ctr;     // [4] pull counters
+  int32_t* cnt;     // [4] queue lengths
+  int32_t* queue;   // [3][n_buckets]
+  uint8_t* bclass;  // [n_buckets]
+};
 
 __global__ void __launch_bounds__(256)
-kmeans_fused_kernel(const uint16_t* __restrict__ ell_idx, const float* __restrict__ ell_val, int32_t W,
-                    uint32_t low_dim, const int64_t* __restrict__ bucket_ptr, int64_t n_buckets,
-                    const int32_t* __restrict__ nlist, const int64_t* __restrict__ centroid_ptr, int niter,
-                    size_t need_lo, size_t need_hi, float* __restrict__ centroids,
-                    const int32_t* __restrict__ nprobe, int32_t max_nprobe, int32_t* __restrict__ list_id,
-                    int32_t* __restrict__ probes) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  __shared__ int32_t cj_s;
-  __shared__ double red_s[8];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  constexpr int kWarps = 8;
-  const float eps = 1.0f / 1024.0f;
-  const int d = static_cast<int>(low_dim);
-  const int vp = W + 1;  // value pitch (odd: thread-per-row reads are conflict free)
-  const int ip = W + 2;  // column pitch ((W + 2) / 2 is odd for W % 8 == 0)
-
-  for (int64_t b = blockIdx.x; b < n_buckets; b += gridDim.x) {
-    const int32_t L = nlist[b];
-    const int64_t s = bucket_ptr[b];
-    const int32_t nb = static_cast<int32_t>(bucket_ptr[b + 1] - s);
-    if (L <= 0) {
-      // flat bucket: a single implicit list (written once, by the first size class)
-      if (list_id != nullptr && need_lo == 0) {
-        for (int t = tid; t < nb; t += 256) list_id[s + t] = 0;
-        for (int t = tid; t < nb * max_nprobe; t += 256)
-          probes[s * max_nprobe + t] = (t % max_nprobe) == 0 ? 0 : -1;
-      }
-      continue;
-    }
-    const size_t need = fused_smem_bytes(nb, L, W, low_dim);
-    if (need < need_lo || need >= need_hi) continue;
-    const int64_t c0 = centroid_ptr[b];
-    const int lp = (L + 3) & ~3;
-    // carve shared memory
-    float* sval = reinterpret_cast<float*>(smem_raw);
-    uint16_t* sidx = reinterpret_cast<uint16_t*>(smem_raw + static_cast<size_t>(nb) * vp * 4);
-    size_t off = (static_cast<size_t>(nb) * vp * 4 + static_cast<size_t>(nb) * ip * 2 + 15) & ~size_t(15);
-    double* acc = reinterpret_cast<double*>(smem_raw + off);
-    off += static_cast<size_t>(L) * d * 8;
-    float* C = reinterpret_cast<float*>(smem_raw + off);
-    off += static_cast<size_t>(d) * lp * 4;
-    double* cnt = reinterpret_cast<double*>(smem_raw + off);
-    off += static_cast<size_t>(L) * 8;
-    uint8_t* assign = smem_raw + off;
-    __syncthreads();  // previous bucket fully written out
-    for (int t = tid; t < nb * W; t += 256) {
-      const int r = t / W, j = t - r * W;
-      sval[r * vp + j] = __ldg(ell_val + s * W + t);
-      sidx[r * ip + j] = __ldg(ell_idx + s * W + t);
-    }
-    for (int t = tid; t < d * lp; t += 256) C[t] = 0.f;
-    __syncthreads();
-    // init: centroid c = row (c * nb) / L
-    for (int t = tid; t < L * W; t += 256) {
-      const int c = t / W, j = t - c * W;
-      const int row = static_cast<int>((static_cast<int64_t>(c) * nb) / L);
-      const float v = sval[row * vp + j];
-      if (v != 0.f) C[sidx[row * ip + j] * lp + c] = v;
-    }
-    __syncthreads();
-    const int wpc = L >= kWarps ? 1 : kWarps / L;  // warps per list in the update (L is a power of two)
-    for (int it = 0; it < niter; ++it) {
-      // ---- assign (thread per row)
-      for (int r = tid; r < nb; r += 256) {
-        float best = -INFINITY;
-        int best_c = 0;
-        const float* rv = sval + r * vp;
-        const uint16_t* ri = sidx + r * ip;
-        for (int cb = 0; cb < lp; cb += 4) {
-          float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-#pragma unroll 8
-          for (int j = 0; j < W; ++j) {
-            const float v = rv[j];
-            const float4 cv = *reinterpret_cast<const float4*>(C + ri[j] * lp + cb);
-            a0 = fmaf(v, cv.x, a0);
-            a1 = fmaf(v, cv.y, a1);
-            a2 = fmaf(v, cv.z, a2);
-            a3 = fmaf(v, cv.w, a3);
-          }
-          if (cb + 0 < L && a0 > best) { best = a0; best_c = cb + 0; }
-          if (cb + 1 < L && a1 > best) { best = a1; best_c = cb + 1; }
-          if (cb + 2 < L && a2 > best) { best = a2; best_c = cb + 2; }
-          if (cb + 3 < L && a3 > best) { best = a3; best_c = cb + 3; }
-        }
-        assign[r] = static_cast<uint8_t>(best_c);
-      }
-      for (int t = tid; t < L * d; t += 256) acc[t] = 0.0;
-      __syncthreads();
-      // ---- update: warp (c, h) adds the columns with idx % wpc == h of list c's rows, in row order
-      for (int cw = warp; cw < L * wpc; cw += kWarps) {
-        const int c = cw / wpc, h = cw - c * wpc;
-        double* ac = acc + c * d;
-        int n_c = 0;
-        for (int r0 = 0; r0 < nb; r0 += 32) {
-          const int rr = r0 + lane;
-          uint32_t mine = __ballot_sync(0xffffffffu, rr < nb && assign[rr] == c);
-          n_c += __popc(mine);
-          while (mine) {
-            const int r = r0 + __ffs(mine) - 1;
-            mine &= mine - 1;
-            for (int j = lane; j < W; j += 32) {
-              const float v = sval[r * vp + j];
-              const int k = sidx[r * ip + j];
-              if (v != 0.f && (k & (wpc - 1)) == h) ac[k] += static_cast<double>(v);
-            }
-            __syncwarp();
-          }
-        }
-        if (lane == 0 && h == 0) cnt[c] = static_cast<double>(n_c);
-      }
-      __syncthreads();
-      bool any_empty = false;
-      for (int c = 0; c < L; ++c) any_empty |= !(cnt[c] > 0.0);
-      if (!any_empty) {
-        // ---- fast path: mean + normalise, one warp per list
-        for (int c = warp; c < L; c += kWarps) {
-          const double inv_n = 1.0 / cnt[c];
-          double ss = 0.0;
-          for (int k = lane; k < d; k += 32) {
-            const float m = static_cast<float>(acc[c * d + k] * inv_n);
-            ss = fma(static_cast<double>(m), static_cast<double>(m), ss);
-          }
-          ss = warp_sum_f64(ss);
-          const double inv_nrm = ss > 0.0 ? 1.0 / sqrt(ss) : 1.0;
-          for (int k = lane; k < d; k += 32) {
-            const float m = static_cast<float>(acc[c * d + k] * inv_n);
-            C[k * lp + c] = static_cast<float>(static_cast<double>(m) * inv_nrm);
-          }
-        }
-        __syncthreads();
-      } else {
-        // ---- slow path: mean (empty lists keep their centroid), re-seed, normalise
-        for (int t = tid; t < L * d; t += 256) {
-          const int c = t / d, k = t - c * d;
-          const double n_c = cnt[c];
-          if (n_c > 0.0) C[k * lp + c] = static_cast<float>(acc[t] * (1.0 / n_c));
-        }
-        __syncthreads();
-        for (int ci = 0; ci < L; ++ci) {
-          if (cnt[ci] > 0.0) continue;  // uniform
-          if (tid == 0) {
-            int bestc = 0;
-            double bc = cnt[0];
-            for (int c = 1; c < L; ++c)
-              if (cnt[c] > bc) { bc = cnt[c]; bestc = c; }
-            cj_s = bestc;
-          }
-          __syncthreads();
-          const int cj = cj_s;
-          for (int k = tid; k < d; k += 256) {
-            const float sign = (k % 2 == 0) ? 1.0f + eps : 1.0f - eps;
-            const float v = C[k * lp + cj];
-            C[k * lp + ci] = v * sign;
-            C[k * lp + cj] = v * (2.0f - sign);
-          }
-          __syncthreads();
-          if (tid == 0) {
-            const double half = cnt[cj] / 2.0;
-            cnt[ci] = half;
-            cnt[cj] -= half;
-          }
-          __syncthreads();
-        }
-        for (int c = 0; c < L; ++c) {
-          double ss = 0.0;
-          for (int k = tid; k < d; k += 256) {
-            const double v = static_cast<double>(C[k * lp + c]);
-            ss += v * v;
-          }
-          ss = warp_sum_f64(ss);
-          if (lane == 0) red_s[warp] = ss;
-          __syncthreads();
-          double tot = 0.0;
-#pragma unroll
-          for (int w = 0; w < kWarps; ++w) tot += red_s[w];
-          const double inv_nrm = tot > 0.0 ? 1.0 / sqrt(tot) : 1.0;
-          for (int k = tid; k < d; k += 256)
-            C[k * lp + c] = static_cast<float>(static_cast<double>(C[k * lp + c]) * inv_nrm);
-          __syncthreads();
-        }
-      }
-    }
-    for (int t = tid; t < L * d; t += 256) {
-      const int c = t / d, k = t - c * d;
-      centroids[c0 * low_dim + t] = C[k * lp + c];
-    }
-    // ---- final assignment + probe list (thread per row, float64)
+kmeans_classify_kernel(const uint16_t* __restrict__ ell_nnz, uint32_t low_dim,
+                       const int64_t* __restrict__ bucket_ptr, int64_t n_buckets,
+                       const int32_t* __restrict__ nlist, TrainQueues q, int force_tiled, int32_t max_nprobe,
+                       int32_t* __restrict__ list_id, int32_t* __restrict__ probes) {
+  const int lane = threadIdx.x & 31;
+  const int64_t b = static_cast<int64_t>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  if (b >= n_buckets) return;
+  const int32_t L = nlist[b];
+  const int64_t s = bucket_ptr[b];
+  const int64_t nb = bucket_ptr[b + 1] - s;
+  if (L <= 0) {
+    if (lane == 0) q.bclass[b] = kClsFlat;
     if (list_id != nullptr) {
-      const int P = nprobe[b];
-      for (int r = tid; r < nb; r += 256) {
-        double ps[kFusedMaxProbe];
-        int pi[kFusedMaxProbe];
+      for (int64_t t = lane; t < nb; t += 32) list_id[s + t] = 0;
+      for (int64_t t = lane; t < nb * max_nprobe; t += 32)
+        probes[s * max_nprobe + t] = (t % max_nprobe) == 0 ? 0 : -1;
+    }
+    return;
+  }
+  int wb = 1;
+  for (int64_t t = lane; t < nb; t += 32) wb = max(wb, static_cast<int>(__ldg(ell_nnz + s + t)));
 #pragma unroll
-        for (int t = 0; t < kFusedMaxProbe; ++t) { ps[t] = -INFINITY; pi[t] = -1; }
-        const float* rv = sval + r * vp;
-        const uint16_t* ri = sidx + r * ip;
-        for (int cb = 0; cb < lp; cb += 4) {
-          double a[4] = {0.0, 0.0, 0.0, 0.0};
-          for (int j = 0; j < W; ++j) {
-            const float v = rv[j];
-            if (v != 0.f) {
-              const float4 cv = *reinterpret_cast<const float4*>(C + ri[j] * lp + cb);
-              const double dv = static_cast<double>(v);
-              a[0] = fma(dv, static_cast<double>(cv.x), a[0]);
-              a[1] = fma(dv, static_cast<double>(cv.y), a[1]);
-              a[2] = fma(dv, static_cast<double>(cv.z), a[2]);
-              a[3] = fma(dv, static_cast<double>(cv.w), a[3]);
-            }
-          }
+  for (int o = 16; o > 0; o >>= 1) wb = max(wb, __shfl_xor_sync(0xffffffffu, wb, o));
+  int cls = kClsTiled;
+  if (L <= kFusedMaxL && nb <= 65535 && !force_tiled) {
+    for (int c = 1; c >= 0; --c)
+      if (fused_plan(static_cast<int>(nb), wb | 1, L, static_cast<int>(low_dim), fused_threads(c) / 32).total <=
+          fused_smem_limit(c))
+        cls = c;
+  }
+  if (lane == 0) {
+    q.bclass[b] = static_cast<uint8_t>(cls);
+    const int32_t pos = atomicAdd(q.cnt + cls, 1);
+    q.queue[static_cast<int64_t>(cls) * n_buckets + pos] = static_cast<int32_t>(b);
+  }
+}
+
+// ---------------------------------------------------------------- fused trainer
+template <int LP, typename T>
+__device__ __forceinline__ void row_scores(const float* __restrict__ vr, const uint16_t* __restrict__ ir, int m,
+                                           const float* __restrict__ C, T (&a)[LP]) {
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int c = cb + u;
-            if (c < L) {
-              // insert behind every entry that is better or equal (earlier id wins ties)
-              const double sc = a[u];
-              int pos = P;
+  for (int u = 0; u < LP; ++u) a[u] = T(0);
+#pragma unroll 4
+  for (int j = 0; j < m; ++j) {
+    const T v = static_cast<T>(vr[j]);
+    const float* cr = C + static_cast<int>(ir[j]) * LP;
 #pragma unroll
-              for (int t = 0; t < kFusedMaxProbe; ++t)
-                if (t < P && pos == P && (pi[t] < 0 || sc > ps[t])) pos = t;
-#pragma unroll
-              for (int t = kFusedMaxProbe - 1; t >= 1; --t)
-                if (t < P && t > pos) { ps[t] = ps[t - 1]; pi[t] = pi[t - 1]; }
-#pragma unroll
-              for (int t = 0; t < kFusedMaxProbe; ++t)
-                if (t == pos) { ps[t] = sc; pi[t] = c; }
-            }
-          }
-        }
-        list_id[s + r] = pi[0];
-        for (int t = 0; t < max_nprobe; ++t)
-          probes[(s + r) * max_nprobe + t] = (t < P && t < kFusedMaxProbe) ? pi[t] : -1;
-      }
+    for (int u = 0; u < LP; u += 4) {
+      const float4 c4 = *reinterpret_cast<const float4*>(cr + u);
+      a[u] = fma(v, static_cast<T>(c4.x), a[u]);
+      a[u + 1] = fma(v, static_cast<T>(c4.y), a[u + 1]);
+      a[u + 2] = fma(v, static_cast<T>(c4.z), a[u + 2]);
+      a[u + 3] = fma(v, static_cast<T>(c4.w), a[u + 3]);
     }
   }
 }
 
-struct KmeansLayout {
-  int32_t* assign;
-  float* new_centroids;
-  double* counts;
+struct FusedArgs {
+  const uint16_t* ell_idx;
+  const float* ell_val;
+  const uint16_t* ell_nnz;
+  int32_t W;
+  uint32_t low_dim;
+  const int64_t* bucket_ptr;
+  int64_t n_buckets;
+  const int32_t* nlist;
+  const int64_t* centroid_ptr;
+  int niter;
+  TrainQueues q;
+  float* centroids;
+  const int32_t* nprobe;
+  int32_t max_nprobe;
+  int32_t* list_id;
+  int32_t* probes;
 };
 
-static void kmeans_layout(Workspace& ws, int64_t n, int64_t total, uint32_t low_dim, KmeansLayout& L) {
-  L.assign = ws.take<int32_t>(n);
-  L.new_centroids = ws.take<float>(static_cast<size_t>(total) * low_dim);
-  L.counts = ws.take<double>(total);
+struct FusedStatic {  // static shared memory of the fused kernel
+  int32_t cnt[8];
+  double scale[8];
+  double cntd[8];
+  double red[16 * 8];
+  int32_t wmax[16];
+  int32_t pick;
+  int32_t qi;
+};
+
+// Everything one bucket needs once its rows are in shared memory.  LP = centroid
+// row length in shared memory (4 or 8 lists), NT = threads of the CTA.
+template <int LP, int NT>
+__device__ void fused_train_bucket(const FusedArgs& A, const FusedPlan& pl, unsigned char* smem, FusedStatic& S,
+                                   int nb, int L, int pitch, int64_t s, int64_t c0, int P) {
+  constexpr int kWarps = NT / 32;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int d = static_cast<int>(A.low_dim);
+  const uint16_t* rnnz = reinterpret_cast<const uint16_t*>(smem + pl.rnnz);
+  const uint16_t* split = reinterpret_cast<const uint16_t*>(smem + pl.split);
+  uint16_t* rowlist = reinterpret_cast<uint16_t*>(smem + pl.rowlist);
+  uint8_t* assign = smem + pl.assign;
+  float* C = reinterpret_cast<float*>(smem + pl.C);
+  long long* acc = reinterpret_cast<long long*>(smem + pl.acc);
+  const float* val = reinterpret_cast<const float*>(smem + pl.val);
+  const uint16_t* idx = reinterpret_cast<const uint16_t*>(smem + pl.idx);
+  const float eps = 1.0f / 1024.0f;
+  const int H = pl.h;
+
+  for (int it = 0; it < A.niter; ++it) {
+    // ---- assign: one thread per row
+    int changed = 0;
+    for (int r0 = warp * 32; r0 < nb; r0 += NT) {
+      const int r = r0 + lane;
+      const bool active = r < nb;
+      int best_c = -1;
+      if (active) {
+        float a[LP];
+        row_scores<LP, float>(val + r * pitch, idx + r * pitch, rnnz[r], C, a);
+        float best = -INFINITY;
+        best_c = 0;
+#pragma unroll
+        for (int u = 0; u < LP; ++u)
+          if (u < L && a[u] > best) { best = a[u]; best_c = u; }
+        changed |= (assign[r] != best_c) ? 1 : 0;
+        assign[r] = static_cast<uint8_t>(best_c);
+      }
+      // per-list row lists (their order is irrelevant: the sums are integers)
+#pragma unroll
+      for (int u = 0; u < LP; ++u) {
+        if (u < L) {
+          const uint32_t mask = __ballot_sync(0xffffffffu, best_c == u);
+          if (mask != 0u) {
+            int base = 0;
+            if (lane == 0) base = atomicAdd(S.cnt + u, __popc(mask));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (best_c == u) rowlist[u * nb + base + __popc(mask & ((1u << lane) - 1u))] = static_cast<uint16_t>(r);
+          }
+        }
+      }
+    }
+    changed = __syncthreads_or(changed);
+    bool any_empty = false;
+#pragma unroll
+    for (int u = 0; u < LP; ++u) any_empty |= (u < L && S.cnt[u] == 0);
+    if (it > 0 && !changed && !any_empty) break;  // fixed point
+    if (tid < L) S.scale[tid] = S.cnt[tid] > 0 ? kFixInv / static_cast<double>(S.cnt[tid]) : 0.0;
+    // ---- update: warp (list c, column range h) adds its rows into acc[c][.]
+    {
+      const int c = warp / H, h = warp - c * H;
+      if (c < L) {
+        long long* acc_c = acc + c * d;
+        const uint16_t* rl = rowlist + c * nb;
+        const int n_c = S.cnt[c];
+        int r = 0, j0 = 0, j1 = 0, k = 0;
+        float v = 0.f;
+        auto fetch = [&](int i) {
+          r = rl[i];
+          j0 = h == 0 ? 0 : static_cast<int>(split[(h - 1) * nb + r]);
+          j1 = h == H - 1 ? static_cast<int>(rnnz[r]) : static_cast<int>(split[h * nb + r]);
+          if (j0 + lane < j1) {
+            k = idx[r * pitch + j0 + lane];
+            v = val[r * pitch + j0 + lane];
+          }
+        };
+        if (n_c > 0) fetch(0);
+        for (int i = 0; i < n_c; ++i) {
+          const int cr = r, cj0 = j0, cj1 = j1, ck = k;
+          const float cv = v;
+          if (i + 1 < n_c) fetch(i + 1);  // next row's operands are in flight during this row's RMW
+          if (cj0 + lane < cj1) acc_c[ck] += __float2ll_rn(cv * kFixScaleF);
+          for (int j = cj0 + 32 + lane; j < cj1; j += 32)  // rows wider than a warp (rare)
+            acc_c[idx[cr * pitch + j]] += __float2ll_rn(val[cr * pitch + j] * kFixScaleF);
+          __syncwarp();  // two rows may share a column: keep their read-modify-writes apart
+        }
+      }
+    }
+    __syncthreads();
+    // ---- means (one thread per column), partial square norms, reset of the sums
+    {
+      double ssq[LP];
+#pragma unroll
+      for (int u = 0; u < LP; ++u) ssq[u] = 0.0;
+      for (int k = tid; k < d; k += NT) {
+        float m[LP];
+#pragma unroll
+        for (int u = 0; u < LP; u += 4) {
+          const float4 t = *reinterpret_cast<const float4*>(C + k * LP + u);
+          m[u] = t.x; m[u + 1] = t.y; m[u + 2] = t.z; m[u + 3] = t.w;
+        }
+#pragma unroll
+        for (int u = 0; u < LP; ++u) {
+          if (u < L) {
+            const long long sum = acc[u * d + k];
+            acc[u * d + k] = 0;
+            if (S.cnt[u] > 0) m[u] = static_cast<float>(__ll2double_rn(sum) * S.scale[u]);
+            ssq[u] = fma(static_cast<double>(m[u]), static_cast<double>(m[u]), ssq[u]);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < LP; u += 4)
+          *reinterpret_cast<float4*>(C + k * LP + u) = make_float4(m[u], m[u + 1], m[u + 2], m[u + 3]);
+      }
+#pragma unroll
+      for (int u = 0; u < LP; ++u) {
+        const double t = warp_sum_f64(ssq[u]);
+        if (lane == 0) S.red[warp * 8 + u] = t;
+      }
+    }
+    __syncthreads();
+    if (any_empty) {
+      // ---- slow path: re-seed every empty list from the (currently) largest one
+      if (tid < L) S.cntd[tid] = static_cast<double>(S.cnt[tid]);
+      __syncthreads();
+      for (int ci = 0; ci < L; ++ci) {
+        if (S.cntd[ci] > 0.0) continue;  // uniform
+        if (tid == 0) {
+          int bestc = 0;
+          double bc = S.cntd[0];
+          for (int c = 1; c < L; ++c)
+            if (S.cntd[c] > bc) { bc = S.cntd[c]; bestc = c; }
+          S.pick = bestc;
+        }
+        __syncthreads();
+        const int cj = S.pick;
+        for (int k = tid; k < d; k += NT) {
+          const float sign = (k % 2 == 0) ? 1.0f + eps : 1.0f - eps;
+          const float v = C[k * LP + cj];
+          C[k * LP + ci] = v * sign;
+          C[k * LP + cj] = v * (2.0f - sign);
+        }
+        __syncthreads();
+        if (tid == 0) {
+          const double half = S.cntd[cj] / 2.0;
+          S.cntd[ci] = half;
+          S.cntd[cj] -= half;
+        }
+        __syncthreads();
+      }
+      // square norms again (the re-seeded lists changed)
+      double ssq[LP];
+#pragma unroll
+      for (int u = 0; u < LP; ++u) ssq[u] = 0.0;
+      for (int k = tid; k < d; k += NT) {
+#pragma unroll
+        for (int u = 0; u < LP; ++u) {
+          const double v = static_cast<double>(C[k * LP + u]);
+          ssq[u] = fma(v, v, ssq[u]);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < LP; ++u) {
+        const double t = warp_sum_f64(ssq[u]);
+        if (lane == 0) S.red[warp * 8 + u] = t;
+      }
+      __syncthreads();
+    }
+    if (tid < 8) {
+      double tot = 0.0;
+#pragma unroll
+      for (int w = 0; w < kWarps; ++w) tot += S.red[w * 8 + tid];
+      S.scale[tid] = (tid < L && tot > 0.0) ? 1.0 / sqrt(tot) : 1.0;
+      S.cnt[tid] = 0;
+    }
+    __syncthreads();
+    for (int k = tid; k < d; k += NT) {
+#pragma unroll
+      for (int u = 0; u < LP; u += 4) {
+        float4 t = *reinterpret_cast<const float4*>(C + k * LP + u);
+        t.x = static_cast<float>(static_cast<double>(t.x) * S.scale[u]);
+        t.y = static_cast<float>(static_cast<double>(t.y) * S.scale[u + 1]);
+        t.z = static_cast<float>(static_cast<double>(t.z) * S.scale[u + 2]);
+        t.w = static_cast<float>(static_cast<double>(t.w) * S.scale[u + 3]);
+        *reinterpret_cast<float4*>(C + k * LP + u) = t;
+      }
+    }
+    __syncthreads();
+  }
+  // ---- centroids out: [list][column]
+  for (int t = tid; t < L * d; t += NT) {
+    const int c = t / d, k = t - c * d;
+    A.centroids[c0 * A.low_dim + t] = C[k * LP + c];
+  }
+  // ---- final assignment + probe list (one thread per row, float64, ties to the lower id)
+  if (A.list_id != nullptr) {
+    for (int r = tid; r < nb; r += NT) {
+      double a[LP];
+      row_scores<LP, double>(val + r * pitch, idx + r * pitch, rnnz[r], C, a);
+      uint32_t used = 0;
+      int32_t* pr = A.probes + (s + r) * A.max_nprobe;
+      for (int t = 0; t < P; ++t) {
+        double best = -INFINITY;
+        int best_c = -1;
+#pragma unroll
+        for (int u = 0; u < LP; ++u)
+          if (u < L && !((used >> u) & 1u) && (best_c < 0 || a[u] > best)) { best = a[u]; best_c = u; }
+        used |= 1u << best_c;
+        pr[t] = best_c;
+        if (t == 0) A.list_id[s + r] = best_c;
+      }
+      for (int t = P; t < A.max_nprobe; ++t) pr[t] = -1;
+    }
+  }
+}
+
+template <int NT>
+__global__ void __launch_bounds__(NT)
+kmeans_fused_kernel(FusedArgs A, int cls) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  __shared__ FusedStatic S;
+  constexpr int kWarps = NT / 32;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int d = static_cast<int>(A.low_dim);
+  const int W = A.W;
+  const int n_queued = A.q.cnt[cls];
+  const int32_t* queue = A.q.queue + static_cast<int64_t>(cls) * A.n_buckets;
+
+  for (;;) {
+    __syncthreads();  // the previous bucket is done with shared memory
+    if (tid == 0) S.qi = atomicAdd(A.q.ctr + cls, 1);
+    __syncthreads();
+    const int qi = S.qi;
+    if (qi >= n_queued) break;
+    const int64_t b = queue[qi];
+    const int L = A.nlist[b];
+    const int64_t s = A.bucket_ptr[b];
+    const int nb = static_cast<int>(A.bucket_ptr[b + 1] - s);
+    const int64_t c0 = A.centroid_ptr[b];
+    // ---- row populations, widest row -> pitch
+    FusedPlan pl = fused_plan(nb, 1, L, d, kWarps);
+    uint16_t* rnnz = reinterpret_cast<uint16_t*>(smem + pl.rnnz);
+    int wb = 1;
+    for (int t = tid; t < nb; t += NT) {
+      const int m = min(static_cast<int>(__ldg(A.ell_nnz + s + t)), W);
+      rnnz[t] = static_cast<uint16_t>(m);
+      wb = max(wb, m);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) wb = max(wb, __shfl_xor_sync(0xffffffffu, wb, o));
+    if (lane == 0) S.wmax[warp] = wb;
+    if (tid < 8) S.cnt[tid] = 0;
+    __syncthreads();
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) wb = max(wb, S.wmax[w]);
+    const int pitch = wb | 1;  // odd: one thread per row reads without bank conflicts
+    pl = fused_plan(nb, pitch, L, d, kWarps);
+    float* val = reinterpret_cast<float*>(smem + pl.val);
+    uint16_t* idx = reinterpret_cast<uint16_t*>(smem + pl.idx);
+    float* C = reinterpret_cast<float*>(smem + pl.C);
+    long long* acc = reinterpret_cast<long long*>(smem + pl.acc);
+    uint8_t* assign = smem + pl.assign;
+    // ---- rows: coalesced 16-byte loads of 8 slots, scattered into the odd-pitch layout
+    {
+      const int cpr = W >> 3;
+      const int items = nb * cpr;
+#pragma unroll 2
+      for (int i = tid; i < items; i += NT) {
+        const int r = i / cpr, j0 = (i - r * cpr) << 3;
+        const int m = rnnz[r];
+        if (j0 < m) {
+          const int64_t g = (s + r) * W + j0;
+          const uint4 ki = __ldg(reinterpret_cast<const uint4*>(A.ell_idx + g));
+          const float4 v0 = __ldg(reinterpret_cast<const float4*>(A.ell_val + g));
+          const float4 v1 = __ldg(reinterpret_cast<const float4*>(A.ell_val + g + 4));
+          const float vv[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+          const uint32_t kk[4] = {ki.x, ki.y, ki.z, ki.w};
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            if (j0 + u < m) {
+              val[r * pitch + j0 + u] = vv[u];
+              idx[r * pitch + j0 + u] = static_cast<uint16_t>((kk[u >> 1] >> ((u & 1) * 16)) & 0xffffu);
+            }
+          }
+        }
+      }
+    }
+    for (int t = tid; t < d * pl.lp; t += NT) C[t] = 0.f;
+    for (int t = tid; t < d * L; t += NT) acc[t] = 0;
+    for (int t = tid; t < nb; t += NT) assign[t] = 0xff;
+    __syncthreads();
+    // ---- column-range split points of every row (update phase), initial centroids
+    if (pl.h > 1) {
+      uint16_t* split = reinterpret_cast<uint16_t*>(smem + pl.split);
+      for (int r = tid; r < nb; r += NT) {
+        const int m = rnnz[r];
+        for (int h = 1; h < pl.h; ++h) {
+          const int bound = (d * h) / pl.h;
+          int lo = 0, hi = m;  // first j with idx >= bound
+          while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (idx[r * pitch + mid] < bound) lo = mid + 1; else hi = mid;
+          }
+          split[(h - 1) * nb + r] = static_cast<uint16_t>(lo);
+        }
+      }
+    }
+    for (int t = tid; t < L * wb; t += NT) {
+      const int c = t / wb, j = t - c * wb;
+      const int row = static_cast<int>((static_cast<int64_t>(c) * nb) / L);
+      if (j < rnnz[row]) C[idx[row * pitch + j] * pl.lp + c] = val[row * pitch + j];
+    }
+    __syncthreads();
+    const int P = A.list_id != nullptr ? min(A.nprobe[b], L) : 0;
+    if (pl.lp == 4)
+      fused_train_bucket<4, NT>(A, pl, smem, S, nb, L, pitch, s, c0, P);
+    else
+      fused_train_bucket<8, NT>(A, pl, smem, S, nb, L, pitch, s, c0, P);
+  }
+}
+
+// ---------------------------------------------------------------- tiled trainer (large buckets)
+// Rows stream from global memory once per iteration; the bucket's centroids are
+// staged in shared memory 32 lists at a time ([column][32], from the transposed
+// training copy `ct`); sums go to global int64 accumulators with atomics.
+struct TiledArgs {
+  const uint16_t* ell_idx;
+  const float* ell_val;
+  const uint16_t* ell_nnz;
+  int32_t W;
+  uint32_t low_dim;
+  int64_t n;
+  const int64_t* bucket_ptr;
+  int64_t n_buckets;
+  const int32_t* nlist;
+  const int64_t* centroid_ptr;
+  TrainQueues q;
+  float* centroids;  // [total][d] final layout
+  float* ct;         // per bucket [d][L]: training copy
+  long long* gsum;   // [total][d]
+  int32_t* gcnt;     // [total]
+  double* gcntd;     // [total] (re-seeding of empty lists)
+  int32_t* gassign;  // [n] previous assignment
+  int32_t* bstate;   // [n_buckets][2]: changed flag, converged flag
+};
+
+__global__ void __launch_bounds__(128)
+kmeans_tiled_init_kernel(TiledArgs A, int64_t total) {
+  const int64_t gc = blockIdx.x;
+  if (gc >= total) return;
+  const int64_t b = find_segment(A.centroid_ptr, A.n_buckets, gc);
+  if (A.q.bclass[b] != kClsTiled) return;
+  const int64_t c0 = A.centroid_ptr[b];
+  const int64_t c = gc - c0;
+  const int32_t L = A.nlist[b];
+  const int64_t s = A.bucket_ptr[b], nb = A.bucket_ptr[b + 1] - s;
+  const int64_t row = s + (c * nb) / L;
+  const uint32_t d = A.low_dim;
+  float* cr = A.centroids + gc * d;
+  float* ctb = A.ct + c0 * d;
+  for (uint32_t k = threadIdx.x; k < d; k += blockDim.x) {
+    cr[k] = 0.f;
+    ctb[static_cast<int64_t>(k) * L + c] = 0.f;
+  }
+  __syncthreads();
+  const int m = min(static_cast<int>(A.ell_nnz[row]), A.W);
+  for (int j = threadIdx.x; j < m; j += blockDim.x) {
+    const uint32_t k = A.ell_idx[row * A.W + j];
+    const float v = A.ell_val[row * A.W + j];
+    cr[k] = v;
+    ctb[static_cast<int64_t>(k) * L + c] = v;
+  }
+}
+
+constexpr int kTiledRows = 256;  // rows (threads) per CTA
+constexpr int kTiledG = 32;      // lists staged per pass
+
+__global__ void __launch_bounds__(kTiledRows)
+kmeans_tiled_assign_kernel(TiledArgs A) {
+  extern __shared__ __align__(16) float Cs[];  // [d][kTiledG]
+  const int tid = threadIdx.x;
+  const int64_t i0 = static_cast<int64_t>(blockIdx.x) * kTiledRows;
+  const int64_t i1 = min(i0 + kTiledRows, A.n);
+  const int d = static_cast<int>(A.low_dim);
+  int64_t b = find_segment(A.bucket_ptr, A.n_buckets, i0);
+  for (; b < A.n_buckets && A.bucket_ptr[b] < i1; ++b) {
+    if (A.q.bclass[b] != kClsTiled || A.bstate[2 * b + 1] != 0) continue;  // uniform
+    const int64_t s = max(A.bucket_ptr[b], i0), e = min(A.bucket_ptr[b + 1], i1);
+    const int32_t L = A.nlist[b];
+    const int64_t c0 = A.centroid_ptr[b];
+    const float* ctb = A.ct + c0 * d;
+    const int64_t i = s + tid;
+    const bool active = i < e;
+    const int m = active ? min(static_cast<int>(A.ell_nnz[i]), A.W) : 0;
+    const uint16_t* ir = A.ell_idx + i * A.W;
+    const float* vr = A.ell_val + i * A.W;
+    float best = -INFINITY;
+    int best_c = 0;
+    for (int g0 = 0; g0 < L; g0 += kTiledG) {
+      const int G = min(kTiledG, L - g0);
+      __syncthreads();
+      for (int t = tid; t < d * kTiledG; t += kTiledRows) {
+        const int k = t / kTiledG, g = t - k * kTiledG;
+        Cs[t] = g < G ? __ldg(ctb + static_cast<int64_t>(k) * L + g0 + g) : 0.f;
+      }
+      __syncthreads();
+      if (active) {
+        float a[kTiledG];
+#pragma unroll
+        for (int u = 0; u < kTiledG; ++u) a[u] = 0.f;
+        for (int j = 0; j < m; ++j) {
+          const float v = __ldg(vr + j);
+          const float* cr = Cs + static_cast<int>(__ldg(ir + j)) * kTiledG;
+#pragma unroll
+          for (int u = 0; u < kTiledG; u += 4) {
+            if (u < G) {  // uniform across the CTA
+              const float4 c4 = *reinterpret_cast<const float4*>(cr + u);
+              a[u] = fmaf(v, c4.x, a[u]);
+              a[u + 1] = fmaf(v, c4.y, a[u + 1]);
+              a[u + 2] = fmaf(v, c4.z, a[u + 2]);
+              a[u + 3] = fmaf(v, c4.w, a[u + 3]);
+            }
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < kTiledG; ++u)
+          if (u < G && a[u] > best) { best = a[u]; best_c = g0 + u; }
+      }
+    }
+    if (active) {
+      if (A.gassign[i] != best_c) {
+        A.gassign[i] = best_c;
+        A.bstate[2 * b] = 1;  // benign race: every writer stores 1
+      }
+      atomicAdd(A.gcnt + c0 + best_c, 1);
+      unsigned long long* dst = reinterpret_cast<unsigned long long*>(A.gsum + (c0 + best_c) * d);
+      for (int j = 0; j < m; ++j)
+        atomicAdd(dst + __ldg(ir + j), static_cast<unsigned long long>(__float2ll_rn(__ldg(vr + j) * kFixScaleF)));
+    }
+  }
+}
+
+// One CTA per tiled bucket: means, re-seeding of empty lists, normalisation; writes
+// both centroid layouts, clears the accumulators, records convergence.
+__global__ void __launch_bounds__(256)
+kmeans_tiled_update_kernel(TiledArgs A) {
+  __shared__ int32_t cj_s;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int d = static_cast<int>(A.low_dim);
+  const float eps = 1.0f / 1024.0f;
+  const int32_t n_queued = A.q.cnt[kClsTiled];
+  const int32_t* queue = A.q.queue + static_cast<int64_t>(kClsTiled) * A.n_buckets;
+  for (int32_t qi = blockIdx.x; qi < n_queued; qi += gridDim.x) {
+    const int64_t b = queue[qi];
+    if (A.bstate[2 * b + 1] != 0) continue;  // converged earlier
+    const int32_t L = A.nlist[b];
+    const int64_t c0 = A.centroid_ptr[b];
+    float* cent = A.centroids + c0 * d;
+    float* ctb = A.ct + c0 * d;
+    long long* gs = A.gsum + c0 * d;
+    bool any_empty = false;
+    for (int32_t c = 0; c < L; ++c) {
+      const int32_t n_c = A.gcnt[c0 + c];
+      if (n_c > 0) {
+        const double scale = kFixInv / static_cast<double>(n_c);
+        for (int k = tid; k < d; k += 256) {
+          cent[static_cast<int64_t>(c) * d + k] =
+              static_cast<float>(__ll2double_rn(gs[static_cast<int64_t>(c) * d + k]) * scale);
+          gs[static_cast<int64_t>(c) * d + k] = 0;
+        }
+      } else {
+        any_empty = true;
+      }
+    }
+    __syncthreads();
+    if (any_empty) {
+      for (int32_t c = tid; c < L; c += 256) A.gcntd[c0 + c] = static_cast<double>(A.gcnt[c0 + c]);
+      __syncthreads();
+      for (int32_t ci = 0; ci < L; ++ci) {
+        if (A.gcntd[c0 + ci] > 0.0) continue;  // uniform
+        if (tid == 0) {
+          int32_t best = 0;
+          double bc = A.gcntd[c0];
+          for (int32_t c = 1; c < L; ++c)
+            if (A.gcntd[c0 + c] > bc) { bc = A.gcntd[c0 + c]; best = c; }
+          cj_s = best;
+        }
+        __syncthreads();
+        const int32_t cj = cj_s;
+        for (int k = tid; k < d; k += 256) {
+          const float sign = (k % 2 == 0) ? 1.0f + eps : 1.0f - eps;
+          const float v = cent[static_cast<int64_t>(cj) * d + k];
+          cent[static_cast<int64_t>(ci) * d + k] = v * sign;
+          cent[static_cast<int64_t>(cj) * d + k] = v * (2.0f - sign);
+        }
+        __syncthreads();
+        if (tid == 0) {
+          const double half = A.gcntd[c0 + cj] / 2.0;
+          A.gcntd[c0 + ci] = half;
+          A.gcntd[c0 + cj] -= half;
+        }
+        __syncthreads();
+      }
+    }
+    // normalise: one warp per list
+    for (int32_t c = warp; c < L; c += 8) {
+      float* cr = cent + static_cast<int64_t>(c) * d;
+      double ss = 0.0;
+      for (int k = lane; k < d; k += 32) {
+        const double v = static_cast<double>(cr[k]);
+        ss = fma(v, v, ss);
+      }
+      ss = warp_sum_f64(ss);
+      const double inv = ss > 0.0 ? 1.0 / sqrt(ss) : 1.0;
+      for (int k = lane; k < d; k += 32) {
+        const float v = static_cast<float>(static_cast<double>(cr[k]) * inv);
+        cr[k] = v;
+        ctb[static_cast<int64_t>(k) * L + c] = v;
+      }
+    }
+    for (int32_t c = tid; c < L; c += 256) A.gcnt[c0 + c] = 0;
+    if (tid == 0) {
+      if (A.bstate[2 * b] == 0 && !any_empty) A.bstate[2 * b + 1] = 1;
+      A.bstate[2 * b] = 0;
+    }
+    __syncthreads();
+  }
+}
+
+struct KmeansLayout {
+  int32_t* qctr;  // [8]: pull counters, queue lengths
+  int32_t* queue;
+  uint8_t* bclass;
+  // tiled only
+  float* ct;
+  long long* gsum;
+  int32_t* gcnt;
+  double* gcntd;
+  int32_t* gassign;
+  int32_t* bstate;
+};
+
+static void kmeans_layout(Workspace& ws, int64_t n, int64_t n_buckets, int64_t total, uint32_t low_dim,
+                          bool tiled, KmeansLayout& L) {
+  const size_t nbk = static_cast<size_t>(n_buckets > 0 ? n_buckets : 1);
+  L.qctr = ws.take<int32_t>(8);
+  L.queue = ws.take<int32_t>(3 * nbk);
+  L.bclass = ws.take<uint8_t>(nbk);
+  L.ct = nullptr; L.gsum = nullptr; L.gcnt = nullptr; L.gcntd = nullptr; L.gassign = nullptr; L.bstate = nullptr;
+  if (tiled) {
+    const size_t t = static_cast<size_t>(total > 0 ? total : 1);
+    L.ct = ws.take<float>(t * low_dim);
+    L.gsum = ws.take<long long>(t * low_dim);
+    L.gcnt = ws.take<int32_t>(t);
+    L.gcntd = ws.take<double>(t);
+    L.gassign = ws.take<int32_t>(static_cast<size_t>(n > 0 ? n : 1));
+    L.bstate = ws.take<int32_t>(2 * nbk);
+  }
+}
+
+// Can any bucket be too large for the fused trainer?  Upper bound: every ELL slot
+// of the largest IVF bucket populated.
+static bool kmeans_needs_tiled(int64_t n, int64_t max_ivf_bucket, int32_t W, uint32_t low_dim) {
+  const int64_t nb = max_ivf_bucket > 0 ? max_ivf_bucket : n;
+  if (nb > 65535) return true;
+  const int32_t L = nlist_rule(nb);
+  if (L > kFusedMaxL) return true;
+  return fused_plan(static_cast<int>(nb), W | 1, L, static_cast<int>(low_dim), fused_threads(1) / 32).total >
+         fused_smem_limit(1);
 }
 
 }  // namespace flc
@@ -604,8 +878,8 @@ int flc_ivf_plan(const int64_t* bucket_ptr, int64_t n_buckets, int32_t n_probe, 
   FLC_REQUIRE(n_probe >= 1, "n_probe must be >= 1");
   FLC_REQUIRE(total_centroids && max_nprobe, "null host outputs");
   cudaStream_t stream = as_stream(stream_);
-  timed("ivf_plan", stream, [&] { ivf_plan_kernel<<<1, 1024, 0, stream>>>(bucket_ptr, n_buckets, n_probe, exhaustive, nlist, nprobe,
-                                          centroid_ptr); });
+  timed("ivf_plan", stream, [&] { ivf_plan_kernel<<<1, 1024, 0, stream>>>(
+      bucket_ptr, n_buckets, n_probe, exhaustive, nlist, nprobe, centroid_ptr); });
   FLC_LAUNCH_CHECK();
   int64_t tail[3] = {0, 0, 0};
   FLC_CUDA(cudaMemcpyAsync(tail, centroid_ptr + n_buckets, 3 * sizeof(int64_t), cudaMemcpyDeviceToHost, stream));
@@ -616,84 +890,102 @@ int flc_ivf_plan(const int64_t* bucket_ptr, int64_t n_buckets, int32_t n_probe, 
   return FLC_OK;
 }
 
-size_t flc_kmeans_workspace_bytes(int64_t n, int64_t total_centroids, uint32_t low_dim) {
+size_t flc_kmeans_workspace_bytes(int64_t n, int64_t n_buckets, int64_t total_centroids,
+                                  int64_t max_ivf_bucket, int32_t ell_width, uint32_t low_dim) {
   flc::Workspace ws(nullptr, 0);
   flc::KmeansLayout L;
-  flc::kmeans_layout(ws, n > 0 ? n : 1, total_centroids > 0 ? total_centroids : 1, low_dim, L);
+  const char* force_env = getenv("FLC_KMEANS_FORCE_TILED");
+  const bool force_tiled = force_env != nullptr && force_env[0] == '1';
+  flc::kmeans_layout(ws, n, n_buckets, total_centroids, low_dim,
+                     force_tiled || flc::kmeans_needs_tiled(n, max_ivf_bucket, ell_width, low_dim), L);
   return ws.used + 256;
 }
 
-int flc_kmeans_train(const float* x, int64_t ld, int64_t n, uint32_t low_dim, const int64_t* bucket_ptr,
-                     int64_t n_buckets, const int32_t* nlist, const int64_t* centroid_ptr,
-                     int64_t total_centroids, int64_t max_ivf_bucket, int niter,
-                     const uint16_t* ell_idx, const float* ell_val, int32_t ell_width, float* centroids,
-                     const int32_t* nprobe, int32_t max_nprobe, int32_t* list_id, int32_t* probes,
-                     int32_t* assigned, void* workspace, size_t workspace_bytes, flc_stream_t stream_) {
+int flc_kmeans_train(const uint16_t* ell_idx, const float* ell_val, const uint16_t* ell_nnz, int32_t ell_width,
+                     int64_t n, uint32_t low_dim, const int64_t* bucket_ptr, int64_t n_buckets,
+                     const int32_t* nlist, const int64_t* centroid_ptr, int64_t total_centroids,
+                     int64_t max_ivf_bucket, int niter, float* centroids, const int32_t* nprobe,
+                     int32_t max_nprobe, int32_t* list_id, int32_t* probes, void* workspace,
+                     size_t workspace_bytes, flc_stream_t stream_) {
   using namespace flc;
-  FLC_REQUIRE(n >= 0 && niter >= 0, "bad sizes");
+  FLC_REQUIRE(n >= 0 && niter >= 0 && n_buckets >= 0, "bad sizes");
   FLC_REQUIRE(low_dim > 0 && low_dim <= 8192, "low_dim must be in [1, 8192]");
-  FLC_REQUIRE((ell_idx == nullptr) == (ell_val == nullptr), "ell_idx and ell_val go together");
-  if (assigned) *assigned = 0;
-  if (n == 0 || total_centroids == 0) return FLC_OK;
+  FLC_REQUIRE(ell_idx && ell_val && ell_nnz, "k-means trains on the sparse rows of flc_vectorize");
+  FLC_REQUIRE(ell_width > 0 && (ell_width % 8) == 0, "ell_width must be a positive multiple of 8");
+  FLC_REQUIRE((reinterpret_cast<uintptr_t>(ell_idx) % 16) == 0 && (reinterpret_cast<uintptr_t>(ell_val) % 16) == 0,
+              "ELL arrays must be 16-byte aligned");
+  FLC_REQUIRE((list_id == nullptr) == (probes == nullptr), "list_id and probes go together");
+  FLC_REQUIRE(list_id == nullptr || (nprobe != nullptr && max_nprobe >= 1), "probe outputs need nprobe / max_nprobe");
+  if (n == 0 || n_buckets == 0) return FLC_OK;
   cudaStream_t stream = as_stream(stream_);
-  // Buckets whose sparse rows + centroids fit in shared memory train in the fused
-  // kernel; larger ones (and everything when no ELL copy is given) in the
-  // generic multi-kernel path on the dense rows.
-  const int32_t W = ell_idx ? ell_width : 0;
-  size_t fused_limit = 0;
-  bool any_generic = true;
-  if (W > 0) {
-    FLC_REQUIRE((W % 8) == 0, "ell_width must be a multiple of 8");
-    fused_limit = kFusedSmemCap;
-    const int64_t nb_max = max_ivf_bucket > 0 ? max_ivf_bucket : n;
-    const size_t need_max = fused_smem_bytes(nb_max, nlist_rule(nb_max), W, low_dim);
-    if (need_max <= kFusedSmemCap) any_generic = false;  // every IVF bucket fits
-    // The fused trainer also emits the final assignment when it covers every bucket
-    // and the probe lists are short.
-    const bool emit = !any_generic && list_id != nullptr && probes != nullptr && nprobe != nullptr &&
-                      max_nprobe >= 1 && max_nprobe <= kFusedMaxProbe;
-    if (assigned) *assigned = emit ? 1 : 0;
-    const size_t hi_bytes = need_max < kFusedSmemCap ? need_max + 16 : kFusedSmemCap + 16;
-    // two size classes: [0, small) at two CTAs per SM, [small, cap] at one
-    const size_t bounds[3] = {0, std::min(kFusedSmemSmall, hi_bytes), hi_bytes};
-    for (int cls = 0; cls < 2; ++cls) {
-      if (bounds[cls] >= bounds[cls + 1]) continue;
-      const size_t smem = bounds[cls + 1];
-      FLC_CUDA(cudaFuncSetAttribute(kmeans_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    static_cast<int>(smem)));
-      const int64_t cap = static_cast<int64_t>(kNumSMs) * (cls == 0 ? 2 : 1);
-      const int64_t grid = n_buckets < cap ? n_buckets : cap;
-      timed("kmeans_fused", stream, [&] { kmeans_fused_kernel<<<static_cast<unsigned>(grid), 256, smem, stream>>>(
-          ell_idx, ell_val, W, low_dim, bucket_ptr, n_buckets, nlist, centroid_ptr, niter, bounds[cls],
-          bounds[cls + 1], centroids, nprobe, max_nprobe, emit ? list_id : nullptr, emit ? probes : nullptr); });
-      FLC_LAUNCH_CHECK();
-    }
-  }
-  if (!any_generic) return FLC_OK;
-  FLC_REQUIRE(x != nullptr, "dense rows are needed for buckets too large for the fused trainer");
+  const int32_t W = ell_width;
+  // FLC_KMEANS_FORCE_TILED=1 sends every bucket through the tiled trainer (tests
+  // use it to check that the two schedules agree bit for bit).
+  const char* force_env = getenv("FLC_KMEANS_FORCE_TILED");
+  const int force_tiled = (force_env != nullptr && force_env[0] == '1') ? 1 : 0;
+  const bool tiled = force_tiled || kmeans_needs_tiled(n, max_ivf_bucket, W, low_dim);
+  if (tiled && list_id != nullptr && max_nprobe > 32)
+    return set_error(FLC_ERR_UNSUPPORTED, "n_probe > 32 is not supported by the device probe selection");
   Workspace ws(workspace, workspace_bytes);
-  KmeansLayout L;
-  kmeans_layout(ws, n, total_centroids, low_dim, L);
+  KmeansLayout K;
+  kmeans_layout(ws, n, n_buckets, total_centroids, low_dim, tiled, K);
   if (!ws.ok) return set_error(FLC_ERR_WORKSPACE, "kmeans workspace too small: need %zu", ws.used);
-  const size_t smem = static_cast<size_t>(8) * low_dim * sizeof(float);
-  if (smem > 48 * 1024)
-    FLC_CUDA(cudaFuncSetAttribute(kmeans_assign_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  static_cast<int>(smem)));
-  const unsigned cblocks = static_cast<unsigned>(total_centroids);
-  timed("kmeans_init", stream, [&] { kmeans_init_kernel<<<cblocks, 128, 0, stream>>>(x, ld, low_dim, bucket_ptr, n_buckets, nlist, centroid_ptr,
-                                                  total_centroids, W, fused_limit, centroids); });
+  TrainQueues q{K.qctr, K.qctr + 4, K.queue, K.bclass};
+  FLC_CUDA(cudaMemsetAsync(K.qctr, 0, 8 * sizeof(int32_t), stream));
+  timed("kmeans_classify", stream, [&] {
+    kmeans_classify_kernel<<<static_cast<unsigned>((n_buckets + 7) / 8), 256, 0, stream>>>(
+        ell_nnz, low_dim, bucket_ptr, n_buckets, nlist, q, force_tiled, max_nprobe, list_id, probes); });
   FLC_LAUNCH_CHECK();
+  if (total_centroids == 0) return FLC_OK;
+  // ---- fused classes
+  FusedArgs A{ell_idx, ell_val, ell_nnz, W, low_dim, bucket_ptr, n_buckets, nlist, centroid_ptr, niter, q,
+              centroids, nprobe, max_nprobe, list_id, probes};
+  {
+    FLC_CUDA(cudaFuncSetAttribute(kmeans_fused_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  static_cast<int>(fused_smem_limit(0))));
+    const int64_t grid0 = std::min<int64_t>(n_buckets, 2 * kNumSMs);
+    timed("kmeans_fused", stream, [&] {
+      kmeans_fused_kernel<256><<<static_cast<unsigned>(grid0), 256, fused_smem_limit(0), stream>>>(A, 0); });
+    FLC_LAUNCH_CHECK();
+    FLC_CUDA(cudaFuncSetAttribute(kmeans_fused_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  static_cast<int>(fused_smem_limit(1))));
+    const int64_t grid1 = std::min<int64_t>(n_buckets, kNumSMs);
+    timed("kmeans_fused_large", stream, [&] {
+      kmeans_fused_kernel<512><<<static_cast<unsigned>(grid1), 512, fused_smem_limit(1), stream>>>(A, 1); });
+    FLC_LAUNCH_CHECK();
+  }
+  if (!tiled) return FLC_OK;
+  // ---- tiled trainer for what is left
+  TiledArgs T{ell_idx, ell_val, ell_nnz, W, low_dim, n, bucket_ptr, n_buckets, nlist, centroid_ptr, q,
+              centroids, K.ct, K.gsum, K.gcnt, K.gcntd, K.gassign, K.bstate};
+  FLC_CUDA(cudaMemsetAsync(K.gsum, 0, static_cast<size_t>(total_centroids) * low_dim * sizeof(long long), stream));
+  FLC_CUDA(cudaMemsetAsync(K.gcnt, 0, static_cast<size_t>(total_centroids) * sizeof(int32_t), stream));
+  FLC_CUDA(cudaMemsetAsync(K.gassign, 0xff, static_cast<size_t>(n) * sizeof(int32_t), stream));
+  FLC_CUDA(cudaMemsetAsync(K.bstate, 0, static_cast<size_t>(n_buckets) * 2 * sizeof(int32_t), stream));
+  timed("kmeans_tiled_init", stream, [&] {
+    kmeans_tiled_init_kernel<<<static_cast<unsigned>(total_centroids), 128, 0, stream>>>(T, total_centroids); });
+  FLC_LAUNCH_CHECK();
+  const size_t smem = static_cast<size_t>(low_dim) * kTiledG * sizeof(float);
+  FLC_REQUIRE(smem <= 200 * 1024, "low_dim too large for the tiled trainer");
+  FLC_CUDA(cudaFuncSetAttribute(kmeans_tiled_assign_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                static_cast<int>(smem)));
+  const unsigned row_blocks = static_cast<unsigned>((n + kTiledRows - 1) / kTiledRows);
+  const unsigned upd_blocks = static_cast<unsigned>(std::min<int64_t>(n_buckets, 4 * kNumSMs));
   for (int it = 0; it < niter; ++it) {
-    timed("kmeans_assign", stream, [&] { kmeans_assign_kernel<<<static_cast<unsigned>((n + 7) / 8), 256, smem, stream>>>(
-        x, ld, n, low_dim, bucket_ptr, n_buckets, nlist, centroid_ptr, centroids, W, fused_limit, L.assign); });
+    timed("kmeans_tiled_assign", stream, [&] {
+      kmeans_tiled_assign_kernel<<<row_blocks, kTiledRows, smem, stream>>>(T); });
     FLC_LAUNCH_CHECK();
-    timed("kmeans_update", stream, [&] { kmeans_update_kernel<<<cblocks, 128, 0, stream>>>(x, ld, low_dim, bucket_ptr, n_buckets, centroid_ptr,
-                                                      total_centroids, L.assign, centroids, nlist, W, fused_limit,
-                                                      L.new_centroids, L.counts); });
+    timed("kmeans_tiled_update", stream, [&] { kmeans_tiled_update_kernel<<<upd_blocks, 256, 0, stream>>>(T); });
     FLC_LAUNCH_CHECK();
-    timed("kmeans_fix", stream, [&] { kmeans_fix_kernel<<<static_cast<unsigned>(n_buckets), 128, 0, stream>>>(
-        low_dim, n_buckets, nlist, centroid_ptr, bucket_ptr, W, fused_limit, L.new_centroids, L.counts,
-        centroids); });
+  }
+  if (list_id != nullptr) {
+    const size_t smem_a = static_cast<size_t>(8) * low_dim * sizeof(float);
+    if (smem_a > 48 * 1024)
+      FLC_CUDA(cudaFuncSetAttribute(ivf_assign_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    static_cast<int>(smem_a)));
+    timed("ivf_assign", stream, [&] { ivf_assign_kernel<<<static_cast<unsigned>((n + 7) / 8), 256, smem_a, stream>>>(
+        nullptr, 0, n, low_dim, bucket_ptr, n_buckets, nlist, nprobe, centroid_ptr, centroids, max_nprobe, ell_idx,
+        ell_val, W, K.bclass, list_id, probes); });
     FLC_LAUNCH_CHECK();
   }
   return FLC_OK;
@@ -719,7 +1011,7 @@ int flc_ivf_assign(const float* x, int64_t ld, int64_t n, uint32_t low_dim, cons
                                   static_cast<int>(smem)));
   timed("ivf_assign", stream, [&] { ivf_assign_kernel<<<static_cast<unsigned>((n + 7) / 8), 256, smem, stream>>>(
       x, ld, n, low_dim, bucket_ptr, n_buckets, nlist, nprobe, centroid_ptr, centroids, max_nprobe, ell_idx,
-      ell_val, ell_width, list_id, probes); });
+      ell_val, ell_width, nullptr, list_id, probes); });
   FLC_LAUNCH_CHECK();
   return FLC_OK;
 }

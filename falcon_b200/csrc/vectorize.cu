@@ -33,8 +33,8 @@ vectorize_kernel(const float* __restrict__ mz, const float* __restrict__ intensi
                  float* __restrict__ out_f32, int64_t ld_f32,
                  uint16_t* __restrict__ out_bf16, int64_t ld_bf16,
                  int32_t* __restrict__ out_hash_idx,
-                 uint16_t* __restrict__ ell_idx, float* __restrict__ ell_val, int32_t ell_width,
-                 int32_t* __restrict__ ell_overflow) {
+                 uint16_t* __restrict__ ell_idx, float* __restrict__ ell_val, uint16_t* __restrict__ ell_nnz,
+                 int32_t ell_width, int32_t* __restrict__ ell_overflow) {
   extern __shared__ float smem_rows[];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -140,6 +140,7 @@ vectorize_kernel(const float* __restrict__ mz, const float* __restrict__ intensi
         di[pos] = 0;
         dv[pos] = 0.f;
       }
+      if (ell_nnz && lane == 0) ell_nnz[r] = static_cast<uint16_t>(min(count, ell_width));
       if (count > ell_width && lane == 0) atomicMax(ell_overflow, count);
     }
     __syncwarp();
@@ -165,8 +166,8 @@ int flc_vectorize(const float* mz, const float* intensity, const int64_t* indptr
                   const int32_t* order, int64_t n, double min_mz, double bin_size,
                   uint32_t vec_len, uint32_t low_dim, uint32_t seed, int norm, float* out_f32,
                   int64_t ld_f32, uint16_t* out_bf16, int64_t ld_bf16, int32_t* out_hash_idx,
-                  uint16_t* ell_idx, float* ell_val, int32_t ell_width, int32_t* ell_overflow,
-                  flc_stream_t stream) {
+                  uint16_t* ell_idx, float* ell_val, uint16_t* ell_nnz, int32_t ell_width,
+                  int32_t* ell_overflow, flc_stream_t stream) {
   FLC_REQUIRE(n >= 0, "n must be non-negative");
   FLC_REQUIRE(low_dim > 0 && low_dim <= 8192, "low_dim must be in [1, 8192]");
   FLC_REQUIRE(bin_size > 0.0, "bin_size must be positive");
@@ -174,8 +175,9 @@ int flc_vectorize(const float* mz, const float* intensity, const int64_t* indptr
   FLC_REQUIRE(!out_f32 || ld_f32 >= low_dim, "ld_f32 < low_dim");
   FLC_REQUIRE(!out_bf16 || ld_bf16 >= low_dim, "ld_bf16 < low_dim");
   FLC_REQUIRE((ell_idx == nullptr) == (ell_val == nullptr), "ell_idx and ell_val go together");
-  FLC_REQUIRE(!ell_idx || (ell_width > 0 && ell_overflow != nullptr && low_dim <= 65536),
-              "ELL output needs ell_width > 0, an overflow flag and low_dim <= 65536");
+  FLC_REQUIRE(!ell_idx || (ell_width > 0 && ell_width <= 65535 && ell_overflow != nullptr && low_dim <= 65536),
+              "ELL output needs 0 < ell_width < 65536, an overflow flag and low_dim <= 65536");
+  FLC_REQUIRE(!ell_nnz || ell_idx, "ell_nnz needs the ELL arrays");
   if (n == 0) return FLC_OK;
   FLC_REQUIRE(indptr != nullptr, "null indptr");
   const size_t smem = static_cast<size_t>(flc::kVecWarps) * low_dim * sizeof(float);
@@ -189,7 +191,7 @@ int flc_vectorize(const float* mz, const float* intensity, const int64_t* indptr
                           flc::as_stream(stream)>>>(mz, intensity, indptr, order, n, min_mz, bin_size,
                                                     vec_len, low_dim, seed, norm, out_f32, ld_f32,
                                                     out_bf16, ld_bf16, out_hash_idx, ell_idx, ell_val,
-                                                    ell_width, ell_overflow); });
+                                                    ell_nnz, ell_width, ell_overflow); });
   FLC_LAUNCH_CHECK();
   return FLC_OK;
 }

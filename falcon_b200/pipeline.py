@@ -118,6 +118,7 @@ class Vectors:
     hash_idx: Optional[torch.Tensor]  # int32 [n_peaks]
     ell_idx: Optional[torch.Tensor]  # int16 storage of uint16 [n, ell_width]
     ell_val: Optional[torch.Tensor]  # float32 [n, ell_width]
+    ell_nnz: Optional[torch.Tensor]  # int16 storage of uint16 [n]: populated slots per row
     ell_width: int
     n: int
     low_dim: int
@@ -208,7 +209,7 @@ class HotPath:
         x = torch.empty((n, d), dtype=torch.float32, device=self.device) if want_f32 else None
         xb = torch.empty((n, self.ld_bf16), dtype=torch.bfloat16, device=self.device) if want_bf16 else None
         hidx = self._empty(mz.shape[0], torch.int32) if want_hash_idx else None
-        ell_idx = ell_val = overflow = None
+        ell_idx = ell_val = ell_nnz = overflow = None
         width = 0
         if want_ell and n > 0:
             if max_peaks is None:  # a row has at most as many non-zeros as the spectrum has peaks
@@ -216,13 +217,14 @@ class HotPath:
             width = max(8, (min(max_peaks, d) + 7) // 8 * 8)
             ell_idx = torch.empty((n, width), dtype=torch.int16, device=self.device)
             ell_val = torch.empty((n, width), dtype=torch.float32, device=self.device)
+            ell_nnz = self._empty(n, torch.int16)
             overflow = torch.zeros(1, dtype=torch.int32, device=self.device)
         with self.timer("vectorize"):
             check(lib.flc_vectorize(ptr(mz), ptr(intensity), ptr(indptr), ptr(order), n,
                                     self.min_mz, self.s.fragment_tol, self.vec_len, d, self.s.hash_seed,
                                     1 if norm else 0, ptr(x), d, ptr(xb), self.ld_bf16, ptr(hidx),
-                                    ptr(ell_idx), ptr(ell_val), width, ptr(overflow), _stream()))
-        return Vectors(x, xb, hidx, ell_idx, ell_val, width, n, d)
+                                    ptr(ell_idx), ptr(ell_val), ptr(ell_nnz), width, ptr(overflow), _stream()))
+        return Vectors(x, xb, hidx, ell_idx, ell_val, ell_nnz, width, n, d)
 
     def hash_table(self) -> torch.Tensor:
         out = self._empty(self.vec_len, torch.int32)
@@ -242,30 +244,32 @@ class HotPath:
 
     def build_ivf(self, v: Vectors, buckets: Buckets,
                   centroids: Optional[torch.Tensor] = None) -> IvfIndex:
+        """IVF index of every bucket: trained here (sparse rows needed), or coarse
+        assignment against the given ``centroids`` (dense or sparse rows)."""
         n, d = v.n, v.low_dim
         x = v.x
         ld = x.stride(0) if x is not None else d
-        assigned = C.c_int32(0)
         with self.timer("ivf_train"):
             nlist, nprobe, cptr, total, maxp, maxb = self.ivf_plan(buckets)
             list_id = self._empty(n, torch.int32)
             probes = torch.empty((n, maxp), dtype=torch.int32, device=self.device)
             if centroids is None:
+                if v.ell_idx is None:
+                    raise ValueError("k-means trains on the sparse rows: vectorize(..., want_ell=True)")
                 centroids = torch.empty((max(total, 1), d), dtype=torch.float32, device=self.device)
-                ws = self._ws(lib.flc_kmeans_workspace_bytes(n, total, d) if x is not None else 0)
-                check(lib.flc_kmeans_train(ptr(x), ld, n, d, ptr(buckets.bucket_ptr),
-                                           buckets.n_buckets, ptr(nlist), ptr(cptr), total, maxb,
-                                           self.s.kmeans_iters, ptr(v.ell_idx), ptr(v.ell_val), v.ell_width,
-                                           ptr(centroids), ptr(nprobe), maxp, ptr(list_id), ptr(probes),
-                                           C.byref(assigned), ptr(ws), ws.numel(), _stream()))
-            elif centroids.shape[0] < total:
+                ws = self._ws(lib.flc_kmeans_workspace_bytes(n, buckets.n_buckets, total, maxb, v.ell_width, d))
+                check(lib.flc_kmeans_train(ptr(v.ell_idx), ptr(v.ell_val), ptr(v.ell_nnz), v.ell_width, n, d,
+                                           ptr(buckets.bucket_ptr), buckets.n_buckets, ptr(nlist), ptr(cptr),
+                                           total, maxb, self.s.kmeans_iters, ptr(centroids), ptr(nprobe), maxp,
+                                           ptr(list_id), ptr(probes), ptr(ws), ws.numel(), _stream()))
+                return IvfIndex(nlist, nprobe, cptr, centroids, list_id, probes, maxp, total)
+            if centroids.shape[0] < total:
                 raise ValueError("centroids array too small for the bucket plan")
-        if not assigned.value:
-            with self.timer("ivf_assign"):
-                check(lib.flc_ivf_assign(ptr(x), ld, n, d, ptr(buckets.bucket_ptr), buckets.n_buckets,
-                                         ptr(nlist), ptr(nprobe), ptr(cptr), ptr(centroids), maxp,
-                                         ptr(v.ell_idx), ptr(v.ell_val), v.ell_width,
-                                         ptr(list_id), ptr(probes), _stream()))
+        with self.timer("ivf_assign"):
+            check(lib.flc_ivf_assign(ptr(x), ld, n, d, ptr(buckets.bucket_ptr), buckets.n_buckets,
+                                     ptr(nlist), ptr(nprobe), ptr(cptr), ptr(centroids), maxp,
+                                     ptr(v.ell_idx), ptr(v.ell_val), v.ell_width,
+                                     ptr(list_id), ptr(probes), _stream()))
         return IvfIndex(nlist, nprobe, cptr, centroids, list_id, probes, maxp, total)
 
     # ------------------------------------------------------------------ a7-a9

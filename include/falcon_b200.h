@@ -81,6 +81,7 @@ FLC_API int flc_hash_table(uint32_t vec_len, uint32_t low_dim, uint32_t seed,
  *                -1 for peaks outside [0, vec_len) (nullable; parity checks)
  *   ell_idx / ell_val [n, ell_width] sparse (ELL) copy of the rows: non-zero
  *                columns ascending (uint16) and their float32 values, zero padded
+ *                (nullable); ell_nnz [n] uint16 = populated slots of every row
  *                (nullable); *ell_overflow (device int32, caller zeroes it) receives
  *                the largest row population if one exceeds ell_width */
 FLC_API int flc_vectorize(const float* mz, const float* intensity, const int64_t* indptr,
@@ -90,8 +91,8 @@ FLC_API int flc_vectorize(const float* mz, const float* intensity, const int64_t
                   float* out_f32, int64_t ld_f32,
                   uint16_t* out_bf16, int64_t ld_bf16,
                   int32_t* out_hash_idx,
-                  uint16_t* ell_idx, float* ell_val, int32_t ell_width, int32_t* ell_overflow,
-                  flc_stream_t stream);
+                  uint16_t* ell_idx, float* ell_val, uint16_t* ell_nnz, int32_t ell_width,
+                  int32_t* ell_overflow, flc_stream_t stream);
 
 /* ------------------------------------------------------------------ a5: buckets
  * A.2 bucket rule: round(((mz - 1.00794) * max(|z|,1)) / 1.0005079) // mz_interval,
@@ -117,9 +118,11 @@ FLC_API int flc_scatter32(const void* in, const int32_t* order, int64_t n, void*
 /* ------------------------------------------------------------------ a6: IVF train / assign
  * A.2 (faiss IndexIVFFlat over IndexFlatIP): per bucket
  * n_list = 0 (flat) if n < 100 else 2^floor(log2(n/39)) (..., see flc_ivf_plan),
- * spherical k-means (niter iterations), assignment = arg-max inner product.
- * With the ELL copy from flc_vectorize, buckets whose sparse rows fit in shared
- * memory train in one fused kernel (x may then be NULL); others use dense x. */
+ * spherical k-means (niter iterations, stops early at a fixed point), assignment
+ * = arg-max inner product.  Training reads the sparse (ELL) rows of flc_vectorize:
+ * buckets whose rows fit in shared memory train in one fused kernel, larger ones
+ * in a tiled multi-launch path; list sums are 2^-40 fixed point (int64), so both
+ * give the same bits (csrc/kmeans.cu). */
 /*  nlist[b], nprobe[b] (int32) and centroid_ptr[b] (int64 exclusive scan of nlist)
  *  for every bucket; exhaustive != 0 lifts the nprobe cap (nprobe = nlist).
  *  Synchronises the stream; returns the total number of centroids on the host. */
@@ -128,17 +131,17 @@ FLC_API int flc_ivf_plan(const int64_t* bucket_ptr, int64_t n_buckets, int32_t n
                  int64_t* centroid_ptr /*[n_buckets+3]: scan, total, max nprobe, max IVF bucket*/,
                  int64_t* total_centroids /*host*/, int32_t* max_nprobe /*host*/,
                  int64_t* max_ivf_bucket /*host, nullable*/, flc_stream_t stream);
-FLC_API size_t flc_kmeans_workspace_bytes(int64_t n, int64_t total_centroids, uint32_t low_dim);
-FLC_API int flc_kmeans_train(const float* x, int64_t ld, int64_t n, uint32_t low_dim,
+FLC_API size_t flc_kmeans_workspace_bytes(int64_t n, int64_t n_buckets, int64_t total_centroids,
+                                  int64_t max_ivf_bucket, int32_t ell_width, uint32_t low_dim);
+FLC_API int flc_kmeans_train(const uint16_t* ell_idx, const float* ell_val, const uint16_t* ell_nnz,
+                     int32_t ell_width, int64_t n, uint32_t low_dim,
                      const int64_t* bucket_ptr, int64_t n_buckets,
                      const int32_t* nlist, const int64_t* centroid_ptr,
                      int64_t total_centroids, int64_t max_ivf_bucket /*from flc_ivf_plan, 0 = unknown*/,
                      int niter,
-                     const uint16_t* ell_idx, const float* ell_val, int32_t ell_width /*nullable ELL copy*/,
                      float* centroids /*[total_centroids, low_dim]*/,
-                     /* optional fused final assignment (same outputs as flc_ivf_assign): */
+                     /* optional final assignment (same outputs as flc_ivf_assign; both or neither): */
                      const int32_t* nprobe, int32_t max_nprobe, int32_t* list_id, int32_t* probes,
-                     int32_t* assigned /*host, nullable: 1 if list_id/probes were written for every row*/,
                      void* workspace, size_t workspace_bytes, flc_stream_t stream);
 /*  list_id[i] (int32, bucket-local list of row i, 0 for flat buckets) and
  *  probes[i * max_nprobe + j] (int32 list ids best first, -1 padded), both from

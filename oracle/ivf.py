@@ -88,22 +88,31 @@ def kmeans_train(x: np.ndarray, n_list: int, n_iter: int = 10) -> np.ndarray:
     (niter = 10, centroids re-normalised every iteration, empty
     clusters split off the largest one with a +-1/1024 perturbation).
 
-    Initialisation: rows ``(c * n) // n_list``.  Assignment during training is
-    float32 argmax of the inner product (ties -> lower id).
+    Conventions shared with the CUDA trainers (csrc/kmeans.cu): initialisation
+    from rows ``(c * n) // n_list``; float32 argmax assignment (ties -> lower
+    id); list sums in 2^-40 fixed point (``sum rint(x * 2^40)`` as int64, exact
+    and order independent); mean = float32(sum * (2^-40 / count)); unit norm by
+    float32(c * (1 / sqrt(sum c^2))); iterations stop at a fixed point.
     """
     n, d = x.shape
-    cent = x[(np.arange(n_list, dtype=np.int64) * n) // n_list].astype(np.float32).copy()
+    x = np.ascontiguousarray(x, np.float32)
+    cent = x[(np.arange(n_list, dtype=np.int64) * n) // n_list].copy()
+    xq = np.rint(x.astype(np.float64) * 2.0 ** 40).astype(np.int64)
     eps = np.float32(1.0 / 1024.0)
+    prev = None
     for _ in range(n_iter):
         ip = x @ cent.T
         assign = np.argmax(ip, axis=1)
         counts = np.bincount(assign, minlength=n_list).astype(np.int64)
-        sums = np.zeros((n_list, d), np.float64)
-        np.add.at(sums, assign, x.astype(np.float64))
-        new = cent.astype(np.float64)
         nz = counts > 0
-        new[nz] = sums[nz] / counts[nz, None]
-        new = new.astype(np.float32)
+        if prev is not None and nz.all() and np.array_equal(assign, prev):
+            break
+        prev = assign
+        sums = np.zeros((n_list, d), np.int64)
+        np.add.at(sums, assign, xq)
+        new = cent.copy()
+        scale = (2.0 ** -40) / counts[nz].astype(np.float64)
+        new[nz] = (sums[nz].astype(np.float64) * scale[:, None]).astype(np.float32)
         # Split the largest cluster into every empty one.
         cnt = counts.astype(np.float64)
         sign = np.where(np.arange(d) % 2 == 0, np.float32(1) + eps, np.float32(1) - eps)
@@ -113,9 +122,9 @@ def kmeans_train(x: np.ndarray, n_list: int, n_iter: int = 10) -> np.ndarray:
             new[cj] = new[cj] * (np.float32(2) - sign)
             cnt[ci] = cnt[cj] / 2
             cnt[cj] -= cnt[ci]
-        nrm = np.sqrt((new.astype(np.float64) ** 2).sum(axis=1, keepdims=True))
-        nrm[nrm == 0] = 1.0
-        cent = (new.astype(np.float64) / nrm).astype(np.float32)
+        ssq = (new.astype(np.float64) ** 2).sum(axis=1, keepdims=True)
+        inv = np.where(ssq > 0, 1.0 / np.sqrt(np.where(ssq > 0, ssq, 1.0)), 1.0)
+        cent = (new.astype(np.float64) * inv).astype(np.float32)
     return cent
 
 

@@ -211,23 +211,27 @@ def test_knn_csr_da_mode_and_small_k():
 def _drop_ell(v):
     import dataclasses
 
-    return dataclasses.replace(v, ell_idx=None, ell_val=None, ell_width=0)
+    return dataclasses.replace(v, ell_idx=None, ell_val=None, ell_nnz=None, ell_width=0)
 
 
 @pytest.mark.parametrize("sparse", [True, False])
 def test_ivf_shared_centroids_exact_and_recall(sparse):
     """Default n_probe with centroids shared between the CUDA path and the oracle:
     neighbour sets identical (north_star asks recall >= 0.99).  sparse=True uses the
-    ELL rows (fused trainer), sparse=False the dense generic kernels."""
+    ELL rows (final assignment fused into the trainer), sparse=False re-assigns the
+    dense rows to the trained centroids with flc_ivf_assign."""
     h = pipeline.HotPath(pipeline.Settings(exhaustive=False))
     sp = helpers.dataset(8000, 23, 1000.0, 1008.0)
     d = helpers.to_device(sp, h.device)
     b = h.bucket_sort(d["precursor_mz"], d["charge"])
     v = h.vectorize(d["mz"], d["intensity"], d["indptr"], b.order)
-    if not sparse:
-        v = _drop_ell(v)
     x, xb = v.x, v.xb
     ivf = h.build_ivf(v, b)
+    if not sparse:
+        with pytest.raises(ValueError):
+            h.build_ivf(_drop_ell(v), b)
+        v = _drop_ell(v)
+        ivf = h.build_ivf(v, b, centroids=ivf.centroids)
     assert ivf.total_centroids > 0
     nlist, cptr = _cpu(ivf.nlist), _cpu(ivf.centroid_ptr)
     bptr = _cpu(b.bucket_ptr)
@@ -254,21 +258,30 @@ def test_ivf_shared_centroids_exact_and_recall(sparse):
     assert np.array_equal(gp, ref.indptr) and np.array_equal(gi, ref.indices)
 
 
-@pytest.mark.parametrize("sparse,n,hi", [(True, 6000, 1003.0), (False, 6000, 1003.0), (True, 30000, 1002.0)])
-def test_kmeans_quality_close_to_oracle(sparse, n, hi):
-    """n = 30000 over 2 Da makes buckets of ~7500 rows: too large for the fused
-    trainer, so the ELL run exercises the fused/generic split as well."""
+def _train(n, seed, lo, hi, force_tiled=False, monkeypatch=None):
+    if monkeypatch is not None:
+        if force_tiled:
+            monkeypatch.setenv("FLC_KMEANS_FORCE_TILED", "1")
+        else:
+            monkeypatch.delenv("FLC_KMEANS_FORCE_TILED", raising=False)
     h = pipeline.HotPath(pipeline.Settings(exhaustive=False))
-    sp = helpers.dataset(n, 29, 1000.0, hi)
+    sp = helpers.dataset(n, seed, lo, hi)
     d = helpers.to_device(sp, h.device)
     b = h.bucket_sort(d["precursor_mz"], d["charge"])
     v = h.vectorize(d["mz"], d["intensity"], d["indptr"], b.order, want_bf16=False)
-    if not sparse:
-        v = _drop_ell(v)
-    x = v.x
-    ivf = h.build_ivf(v, b)
-    xs, bptr, nlist, cptr = _cpu(x), _cpu(b.bucket_ptr), _cpu(ivf.nlist), _cpu(ivf.centroid_ptr)
+    return h, b, v, h.build_ivf(v, b)
+
+
+@pytest.mark.parametrize("n,hi", [(6000, 1003.0), (30000, 1002.0), (12000, 1012.0)])
+def test_kmeans_quality_close_to_oracle(n, hi):
+    """n = 30000 over 2 Da makes buckets of ~7500 rows: too large for the fused
+    trainer, so that run exercises the tiled trainer; the other two are fused
+    (two size classes).  Same arithmetic conventions as the oracle, so the
+    objective is the same up to float32 arg-max near-ties."""
+    h, b, v, ivf = _train(n, 29, 1000.0, hi)
+    xs, bptr, nlist, cptr = _cpu(v.x), _cpu(b.bucket_ptr), _cpu(ivf.nlist), _cpu(ivf.centroid_ptr)
     cents = _cpu(ivf.centroids)
+    lid = _cpu(ivf.list_id)
     checked = 0
     for i in range(b.n_buckets):
         if nlist[i] and checked < 3:
@@ -279,8 +292,24 @@ def test_kmeans_quality_close_to_oracle(sparse, n, hi):
             obj_gpu = (xb_ @ c_gpu.T).max(axis=1).sum()
             obj_cpu = (xb_ @ c_cpu.T).max(axis=1).sum()
             assert obj_gpu >= 0.98 * obj_cpu
+            # the final assignment belongs to the trained centroids
+            assert np.array_equal(lid[bptr[i]: bptr[i + 1]], oivf.assign_lists(xb_, c_gpu))
             checked += 1
     assert checked > 0
+
+
+def test_kmeans_fused_and_tiled_give_the_same_bits(monkeypatch):
+    """List sums are fixed point, so the schedule (fused shared-memory trainer vs
+    tiled multi-launch trainer with atomics) cannot change a single bit, and
+    neither can a re-run."""
+    _, b, _, fused = _train(9000, 31, 1000.0, 1010.0, False, monkeypatch)
+    _, _, _, tiled = _train(9000, 31, 1000.0, 1010.0, True, monkeypatch)
+    _, _, _, again = _train(9000, 31, 1000.0, 1010.0, True, monkeypatch)
+    assert fused.total_centroids > 0
+    for other in (tiled, again):
+        assert torch.equal(fused.centroids, other.centroids)
+        assert torch.equal(fused.list_id, other.list_id)
+        assert torch.equal(fused.probes, other.probes)
 
 
 # ------------------------------------------------------------------ DBSCAN + split
