@@ -54,24 +54,21 @@ __host__ __device__ constexpr int fused_threads(int cls) { return cls == 0 ? 256
 // Shared-memory plan of one bucket in the fused trainer.  What only depends on
 // (nb, L) comes first, so it can be placed before the row pitch is known.
 struct FusedPlan {
-  uint32_t rnnz, split, rowlist, assign, C, acc, val, idx, total;
-  int lp, h;
+  uint32_t rnnz, dlist, assign, C, acc, val, idx, total;
+  int lp;
 };
-__host__ __device__ inline FusedPlan fused_plan(int nb, int pitch, int L, int d, int warps) {
+__host__ __device__ inline FusedPlan fused_plan(int nb, int pitch, int L, int d) {
   FusedPlan p;
-  p.lp = L <= 4 ? 4 : 8;                          // centroid row length in shared memory
-  const int lc = L <= 2 ? 2 : (L <= 4 ? 4 : 8);
-  p.h = warps / lc;                               // column ranges per list in the update
+  p.lp = L <= 4 ? 4 : 8;  // centroid row length in shared memory
   uint32_t o = 0;
-  p.rnnz = o;    o += 2u * nb;
-  p.split = o;   o += 2u * nb * (p.h - 1);
-  p.rowlist = o; o += 2u * nb * L;
-  p.assign = o;  o += nb;
+  p.dlist = o;  o += 4u * nb * L;  // per list: rows that entered / left it this iteration
+  p.rnnz = o;   o += 2u * nb;
+  p.assign = o; o += nb;
   o = (o + 15u) & ~15u;
-  p.C = o;       o += 4u * d * p.lp;
-  p.acc = o;     o += 8u * d * L;
-  p.val = o;     o += 4u * nb * pitch;
-  p.idx = o;     o += 2u * nb * pitch;
+  p.C = o;      o += 4u * d * p.lp;
+  p.acc = o;    o += 8u * d * L;
+  p.val = o;    o += 4u * nb * pitch;
+  p.idx = o;    o += 2u * nb * pitch;
   p.total = (o + 15u) & ~15u;
   return p;
 }
@@ -233,11 +230,9 @@ kmeans_classify_kernel(const uint16_t* __restrict__ ell_nnz, uint32_t low_dim,
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) wb = max(wb, __shfl_xor_sync(0xffffffffu, wb, o));
   int cls = kClsTiled;
-  if (L <= kFusedMaxL && nb <= 65535 && !force_tiled) {
+  if (L <= kFusedMaxL && nb <= 32767 && !force_tiled) {
     for (int c = 1; c >= 0; --c)
-      if (fused_plan(static_cast<int>(nb), wb | 1, L, static_cast<int>(low_dim), fused_threads(c) / 32).total <=
-          fused_smem_limit(c))
-        cls = c;
+      if (fused_plan(static_cast<int>(nb), wb | 1, L, static_cast<int>(low_dim)).total <= fused_smem_limit(c)) cls = c;
   }
   if (lane == 0) {
     q.bclass[b] = static_cast<uint8_t>(cls);
@@ -287,7 +282,8 @@ struct FusedArgs {
 };
 
 struct FusedStatic {  // static shared memory of the fused kernel
-  int32_t cnt[8];
+  int32_t cnt[8];  // rows per list
+  int32_t dn[8];   // entries in each list's delta list
   double scale[8];
   double cntd[8];
   double red[16 * 8];
@@ -305,44 +301,58 @@ __device__ void fused_train_bucket(const FusedArgs& A, const FusedPlan& pl, unsi
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int d = static_cast<int>(A.low_dim);
   const uint16_t* rnnz = reinterpret_cast<const uint16_t*>(smem + pl.rnnz);
-  const uint16_t* split = reinterpret_cast<const uint16_t*>(smem + pl.split);
-  uint16_t* rowlist = reinterpret_cast<uint16_t*>(smem + pl.rowlist);
+  uint32_t* dlist = reinterpret_cast<uint32_t*>(smem + pl.dlist);
   uint8_t* assign = smem + pl.assign;
   float* C = reinterpret_cast<float*>(smem + pl.C);
   long long* acc = reinterpret_cast<long long*>(smem + pl.acc);
   const float* val = reinterpret_cast<const float*>(smem + pl.val);
   const uint16_t* idx = reinterpret_cast<const uint16_t*>(smem + pl.idx);
   const float eps = 1.0f / 1024.0f;
-  const int H = pl.h;
 
   for (int it = 0; it < A.niter; ++it) {
-    // ---- assign: one thread per row
+    // ---- assign: one thread per row.  A row that moves from list a to list b is
+    // queued as "+row" on b's delta list and "-row" on a's: the sums are integers,
+    // so they can be maintained incrementally and the order of the queue is irrelevant.
     int changed = 0;
     for (int r0 = warp * 32; r0 < nb; r0 += NT) {
       const int r = r0 + lane;
-      const bool active = r < nb;
-      int best_c = -1;
-      if (active) {
+      int old_c = -1, new_c = -1, m = 0;
+      if (r < nb) {
         float a[LP];
-        row_scores<LP, float>(val + r * pitch, idx + r * pitch, rnnz[r], C, a);
+        m = rnnz[r];
+        row_scores<LP, float>(val + r * pitch, idx + r * pitch, m, C, a);
         float best = -INFINITY;
-        best_c = 0;
+        int best_c = 0;
 #pragma unroll
         for (int u = 0; u < LP; ++u)
           if (u < L && a[u] > best) { best = a[u]; best_c = u; }
-        changed |= (assign[r] != best_c) ? 1 : 0;
-        assign[r] = static_cast<uint8_t>(best_c);
+        const int prev = assign[r];
+        if (prev != best_c) {
+          old_c = prev == 0xff ? -1 : prev;
+          new_c = best_c;
+          assign[r] = static_cast<uint8_t>(best_c);
+          changed = 1;
+        }
       }
-      // per-list row lists (their order is irrelevant: the sums are integers)
+      if (__any_sync(0xffffffffu, new_c >= 0)) {
+        const uint32_t below = (1u << lane) - 1u;
 #pragma unroll
-      for (int u = 0; u < LP; ++u) {
-        if (u < L) {
-          const uint32_t mask = __ballot_sync(0xffffffffu, best_c == u);
-          if (mask != 0u) {
-            int base = 0;
-            if (lane == 0) base = atomicAdd(S.cnt + u, __popc(mask));
-            base = __shfl_sync(0xffffffffu, base, 0);
-            if (best_c == u) rowlist[u * nb + base + __popc(mask & ((1u << lane) - 1u))] = static_cast<uint16_t>(r);
+        for (int u = 0; u < LP; ++u) {
+          if (u < L) {
+            const uint32_t enter = __ballot_sync(0xffffffffu, new_c == u);
+            const uint32_t leave = __ballot_sync(0xffffffffu, old_c == u);
+            if ((enter | leave) != 0u) {
+              const int ne = __popc(enter);
+              int base = 0;
+              if (lane == 0) {
+                base = atomicAdd(S.dn + u, ne + __popc(leave));
+                atomicAdd(S.cnt + u, ne - __popc(leave));
+              }
+              base = __shfl_sync(0xffffffffu, base, 0);
+              const uint32_t e = static_cast<uint32_t>(r) | (static_cast<uint32_t>(m) << 16);
+              if (new_c == u) dlist[u * nb + base + __popc(enter & below)] = e;
+              if (old_c == u) dlist[u * nb + base + ne + __popc(leave & below)] = e | 0x8000u;
+            }
           }
         }
       }
@@ -353,38 +363,51 @@ __device__ void fused_train_bucket(const FusedArgs& A, const FusedPlan& pl, unsi
     for (int u = 0; u < LP; ++u) any_empty |= (u < L && S.cnt[u] == 0);
     if (it > 0 && !changed && !any_empty) break;  // fixed point
     if (tid < L) S.scale[tid] = S.cnt[tid] > 0 ? kFixInv / static_cast<double>(S.cnt[tid]) : 0.0;
-    // ---- update: warp (list c, column range h) adds its rows into acc[c][.]
-    {
-      const int c = warp / H, h = warp - c * H;
-      if (c < L) {
-        long long* acc_c = acc + c * d;
-        const uint16_t* rl = rowlist + c * nb;
-        const int n_c = S.cnt[c];
-        int r = 0, j0 = 0, j1 = 0, k = 0;
-        float v = 0.f;
-        auto fetch = [&](int i) {
-          r = rl[i];
-          j0 = h == 0 ? 0 : static_cast<int>(split[(h - 1) * nb + r]);
-          j1 = h == H - 1 ? static_cast<int>(rnnz[r]) : static_cast<int>(split[h * nb + r]);
-          if (j0 + lane < j1) {
-            k = idx[r * pitch + j0 + lane];
-            v = val[r * pitch + j0 + lane];
-          }
-        };
-        if (n_c > 0) fetch(0);
-        for (int i = 0; i < n_c; ++i) {
-          const int cr = r, cj0 = j0, cj1 = j1, ck = k;
-          const float cv = v;
-          if (i + 1 < n_c) fetch(i + 1);  // next row's operands are in flight during this row's RMW
-          if (cj0 + lane < cj1) acc_c[ck] += __float2ll_rn(cv * kFixScaleF);
-          for (int j = cj0 + 32 + lane; j < cj1; j += 32)  // rows wider than a warp (rare)
-            acc_c[idx[cr * pitch + j]] += __float2ll_rn(val[cr * pitch + j] * kFixScaleF);
-          __syncwarp();  // two rows may share a column: keep their read-modify-writes apart
+    // ---- update: warp c walks list c's delta list; lanes take the row's columns
+    // (distinct within a row, so no conflicts inside a step).
+    if (warp < L) {
+      long long* acc_c = acc + warp * d;
+      const uint32_t* dl = dlist + warp * nb;
+      const int n_c = S.dn[warp];
+      uint32_t e_next = n_c > 1 ? dl[1] : 0u;
+      uint32_t e = n_c > 0 ? dl[0] : 0u;
+      int k = 0;
+      float v = 0.f;
+      if (n_c > 0 && lane < static_cast<int>(e >> 16)) {
+        const int o = static_cast<int>(e & 0x7fffu) * pitch + lane;
+        k = idx[o];
+        v = val[o];
+      }
+      for (int i = 0; i < n_c; ++i) {
+        const uint32_t ce = e;
+        const int ck = k;
+        const float cv = v;
+        // operands of the next two rows are in flight during this row's read-modify-write
+        e = e_next;
+        e_next = i + 2 < n_c ? dl[i + 2] : 0u;
+        if (i + 1 < n_c && lane < static_cast<int>(e >> 16)) {
+          const int o = static_cast<int>(e & 0x7fffu) * pitch + lane;
+          k = idx[o];
+          v = val[o];
         }
+        const int m = static_cast<int>(ce >> 16);
+        const bool neg = (ce & 0x8000u) != 0u;
+        if (lane < m) {
+          const long long q = __float2ll_rn(cv * kFixScaleF);
+          acc_c[ck] += neg ? -q : q;
+        }
+        if (m > 32) {  // uniform
+          const int o = static_cast<int>(ce & 0x7fffu) * pitch;
+          for (int j = 32 + lane; j < m; j += 32) {
+            const long long q = __float2ll_rn(val[o + j] * kFixScaleF);
+            acc_c[idx[o + j]] += neg ? -q : q;
+          }
+        }
+        __syncwarp();  // two rows may share a column: keep their read-modify-writes apart
       }
     }
     __syncthreads();
-    // ---- means (one thread per column), partial square norms, reset of the sums
+    // ---- means (one thread per column), partial square norms
     {
       double ssq[LP];
 #pragma unroll
@@ -400,7 +423,6 @@ __device__ void fused_train_bucket(const FusedArgs& A, const FusedPlan& pl, unsi
         for (int u = 0; u < LP; ++u) {
           if (u < L) {
             const long long sum = acc[u * d + k];
-            acc[u * d + k] = 0;
             if (S.cnt[u] > 0) m[u] = static_cast<float>(__ll2double_rn(sum) * S.scale[u]);
             ssq[u] = fma(static_cast<double>(m[u]), static_cast<double>(m[u]), ssq[u]);
           }
@@ -468,7 +490,7 @@ __device__ void fused_train_bucket(const FusedArgs& A, const FusedPlan& pl, unsi
 #pragma unroll
       for (int w = 0; w < kWarps; ++w) tot += S.red[w * 8 + tid];
       S.scale[tid] = (tid < L && tot > 0.0) ? 1.0 / sqrt(tot) : 1.0;
-      S.cnt[tid] = 0;
+      S.dn[tid] = 0;  // every warp is past its delta list
     }
     __syncthreads();
     for (int k = tid; k < d; k += NT) {
@@ -535,7 +557,7 @@ kmeans_fused_kernel(FusedArgs A, int cls) {
     const int nb = static_cast<int>(A.bucket_ptr[b + 1] - s);
     const int64_t c0 = A.centroid_ptr[b];
     // ---- row populations, widest row -> pitch
-    FusedPlan pl = fused_plan(nb, 1, L, d, kWarps);
+    FusedPlan pl = fused_plan(nb, 1, L, d);
     uint16_t* rnnz = reinterpret_cast<uint16_t*>(smem + pl.rnnz);
     int wb = 1;
     for (int t = tid; t < nb; t += NT) {
@@ -546,12 +568,12 @@ kmeans_fused_kernel(FusedArgs A, int cls) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) wb = max(wb, __shfl_xor_sync(0xffffffffu, wb, o));
     if (lane == 0) S.wmax[warp] = wb;
-    if (tid < 8) S.cnt[tid] = 0;
+    if (tid < 8) { S.cnt[tid] = 0; S.dn[tid] = 0; }
     __syncthreads();
 #pragma unroll
     for (int w = 0; w < kWarps; ++w) wb = max(wb, S.wmax[w]);
     const int pitch = wb | 1;  // odd: one thread per row reads without bank conflicts
-    pl = fused_plan(nb, pitch, L, d, kWarps);
+    pl = fused_plan(nb, pitch, L, d);
     float* val = reinterpret_cast<float*>(smem + pl.val);
     uint16_t* idx = reinterpret_cast<uint16_t*>(smem + pl.idx);
     float* C = reinterpret_cast<float*>(smem + pl.C);
@@ -586,22 +608,7 @@ kmeans_fused_kernel(FusedArgs A, int cls) {
     for (int t = tid; t < d * L; t += NT) acc[t] = 0;
     for (int t = tid; t < nb; t += NT) assign[t] = 0xff;
     __syncthreads();
-    // ---- column-range split points of every row (update phase), initial centroids
-    if (pl.h > 1) {
-      uint16_t* split = reinterpret_cast<uint16_t*>(smem + pl.split);
-      for (int r = tid; r < nb; r += NT) {
-        const int m = rnnz[r];
-        for (int h = 1; h < pl.h; ++h) {
-          const int bound = (d * h) / pl.h;
-          int lo = 0, hi = m;  // first j with idx >= bound
-          while (lo < hi) {
-            const int mid = (lo + hi) >> 1;
-            if (idx[r * pitch + mid] < bound) lo = mid + 1; else hi = mid;
-          }
-          split[(h - 1) * nb + r] = static_cast<uint16_t>(lo);
-        }
-      }
-    }
+    // ---- initial centroids: evenly strided rows
     for (int t = tid; t < L * wb; t += NT) {
       const int c = t / wb, j = t - c * wb;
       const int row = static_cast<int>((static_cast<int64_t>(c) * nb) / L);
@@ -859,11 +866,10 @@ static void kmeans_layout(Workspace& ws, int64_t n, int64_t n_buckets, int64_t t
 // of the largest IVF bucket populated.
 static bool kmeans_needs_tiled(int64_t n, int64_t max_ivf_bucket, int32_t W, uint32_t low_dim) {
   const int64_t nb = max_ivf_bucket > 0 ? max_ivf_bucket : n;
-  if (nb > 65535) return true;
+  if (nb > 32767) return true;
   const int32_t L = nlist_rule(nb);
   if (L > kFusedMaxL) return true;
-  return fused_plan(static_cast<int>(nb), W | 1, L, static_cast<int>(low_dim), fused_threads(1) / 32).total >
-         fused_smem_limit(1);
+  return fused_plan(static_cast<int>(nb), W | 1, L, static_cast<int>(low_dim)).total > fused_smem_limit(1);
 }
 
 }  // namespace flc
