@@ -182,11 +182,12 @@ def kernel_rooflines(stats: dict, peaks: dict) -> dict:
     work = {
         # bytes: peaks (m/z + intensity) + indptr + order + f32 row + bf16 row
         "vectorize": ("hbm", p * 8 + (n + 1) * 8 + n * 4 + n * d * 4 * stats.get("dense_f32", 1) + n * ldb * 2
-                      + n * stats.get("ell_width", 0) * 6),
+                      + n * (stats.get("ell_width", 0) * 6 + 2)),
         # HBM floor of the scan: every bf16 row read once, pairs written once
         "scan_tc": ("hbm", n * ldb * 2 + pairs * 8),
         # pairs in/out + exact re-score rows (L2-resident in practice) + m/z + row counts
-        "refine": ("hbm", pairs * 16 + pairs * d * 4 + n * (d * 4 + 8 + 8 + 4)),
+        "refine": ("hbm", pairs * 16 + pairs * stats.get("ell_width", 0) * 6
+                   + n * (stats.get("ell_width", 0) * 6 + 8 + 8 + 4)),
         "pair_hist": ("hbm", pairs * 8 + pairs * 4),
         "pair_scatter": ("hbm", pairs * 16 + pairs * 12),
         "csr_compact": ("hbm", nnz * 16 + (n + 1) * 24),
@@ -341,6 +342,7 @@ def run_ours(args):
                        "ivf_rows": int(sizes[nl > 0].sum().item()), "ivf_nnz": int(ell_nnz[row_in_ivf].sum().item()),
                        "total_centroids": ivf.total_centroids}
     stats = {"n": args.n, "n_peaks": sp.n_peaks, "low_dim": settings.low_dim, "ld_bf16": hp.ld_bf16,
+             "dense_f32": 1 if settings.dense_f32 else 0, "ell_width": keep["vectors"].ell_width,
              "n_pairs": keep["graph"].n_pairs, "nnz": keep["graph"].nnz, "kernels": kernels,
              "steps": args.steps, "required_pairs": required_pairs, "computed_pairs": computed_pairs,
              **stats_extra}

@@ -23,7 +23,7 @@
 
 namespace flc {
 
-constexpr int kRefineWarps = 4;
+constexpr int kRefineWarps = 8;
 constexpr uint64_t kKeyMax = ~uint64_t(0);
 
 __global__ void pair_hist_kernel(const uint64_t* __restrict__ pairs, const uint64_t* __restrict__ pair_count,
@@ -128,125 +128,178 @@ struct RefineParams {
   int use_eps;
 };
 
-__device__ __forceinline__ bool tolerance_ok(const RefineParams& P, double mq, float rq, uint32_t c) {
-  const double mc = P.mz[c];
+__device__ __forceinline__ bool tolerance_ok(const RefineParams& P, double mq, float rq, double mc, float rc) {
   const double dm = fabs(mq - mc);
   bool ok = P.tol_mode == FLC_TOL_DA ? (dm < P.tol) : (dm / mc * 1000000.0 < P.tol);
   if (ok && P.rt != nullptr && P.rt_tol >= 0.0)
-    ok = fabs(static_cast<double>(rq) - static_cast<double>(P.rt[c])) < P.rt_tol;
+    ok = fabs(static_cast<double>(rq) - static_cast<double>(rc)) < P.rt_tol;
   return ok;
 }
 
+// Exact inner product of candidate row c with the query row held densely in
+// shared memory (xq): float32 inputs, float64 accumulate, rounded once.  Sparse
+// rows: every lane takes two ELL slots (zero padding multiplies to an exact zero).
+__device__ __forceinline__ float exact_ip(const RefineParams& P, const float* xq, uint32_t c, int lane) {
+  double acc = 0.0;
+  if (P.ell_idx != nullptr) {
+    const int64_t rbase = static_cast<int64_t>(c) * P.ell_width;
+    for (int32_t j = 2 * lane; j < P.ell_width; j += 64) {
+      const uint32_t kk = __ldg(reinterpret_cast<const uint32_t*>(P.ell_idx + rbase + j));
+      const float2 vv = __ldg(reinterpret_cast<const float2*>(P.ell_val + rbase + j));
+      acc = fma(static_cast<double>(vv.x), static_cast<double>(xq[kk & 0xffffu]), acc);
+      acc = fma(static_cast<double>(vv.y), static_cast<double>(xq[kk >> 16]), acc);
+    }
+  } else {
+    const float* xc = P.x + static_cast<int64_t>(c) * P.ld;
+    for (uint32_t i = lane; i < P.low_dim; i += 32)
+      acc = fma(static_cast<double>(xq[i]), static_cast<double>(__ldg(xc + i)), acc);
+  }
+  return static_cast<float>(warp_sum_f64(acc));
+}
+
+// One warp per query (grid-stride).  The query row sits densely in shared memory:
+// scattered in from its sparse copy and scattered back out to zero afterwards.
 __global__ void __launch_bounds__(kRefineWarps * 32)
 refine_kernel(RefineParams P, const int64_t* __restrict__ off, uint64_t* __restrict__ grouped,
               int32_t* __restrict__ row_count) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
+  const uint32_t below = (1u << lane) - 1u;
   const size_t per_warp = static_cast<size_t>(2) * P.ka_pow2 * sizeof(uint64_t) +
                           ((static_cast<size_t>(P.low_dim) * sizeof(float) + 15) & ~size_t(15));
   uint64_t* buf = reinterpret_cast<uint64_t*>(smem_raw + warp * per_warp);
   float* xq = reinterpret_cast<float*>(buf + 2 * P.ka_pow2);
-
-  const int64_t q = static_cast<int64_t>(blockIdx.x) * kRefineWarps + warp;
-  if (q >= P.n) return;
-  const int64_t base = off[q];
-  const int64_t m = off[q + 1] - base;
-  if (m == 0) {
-    if (lane == 0) row_count[q] = 0;
-    return;
-  }
-  if (P.x != nullptr) {
-    const float* xrow = P.x + q * P.ld;
-    for (uint32_t i = lane; i < P.low_dim; i += 32) xq[i] = xrow[i];
-  } else {  // densify the query row from its sparse copy
+  const bool sparse = P.ell_idx != nullptr;
+  if (sparse) {
     for (uint32_t i = lane; i < P.low_dim; i += 32) xq[i] = 0.f;
     __syncwarp();
-    for (int32_t j = lane; j < P.ell_width; j += 32) {
-      const float v = P.ell_val[q * P.ell_width + j];
-      if (v != 0.f) xq[P.ell_idx[q * P.ell_width + j]] = v;
-    }
   }
-  __syncwarp();
-  const double mq = P.mz[q];
-  const float rq = P.rt ? P.rt[q] : 0.f;
-
-  // Phase A: exact score of every candidate -> sort key (in place).
-  for (int64_t j = 0; j < m; ++j) {
-    const uint32_t c = static_cast<uint32_t>(grouped[base + j]);
-    bool member = true;
-    if (P.list_id != nullptr) {
-      const int32_t lc = P.list_id[c];
-      bool hit = false;
-      for (int32_t t = lane; t < P.max_nprobe; t += 32) hit |= (P.probes[q * P.max_nprobe + t] == lc);
-      member = __any_sync(0xffffffffu, hit);
+  const int64_t warps_total = static_cast<int64_t>(gridDim.x) * kRefineWarps;
+  for (int64_t q = static_cast<int64_t>(blockIdx.x) * kRefineWarps + warp; q < P.n; q += warps_total) {
+    const int64_t base = off[q];
+    const int64_t m = off[q + 1] - base;
+    if (m == 0) {
+      if (lane == 0) row_count[q] = 0;
+      continue;
     }
-    uint64_t key = kKeyMax;
-    if (member) {
-      double acc = 0.0;
-      if (P.ell_idx != nullptr) {
-        // sparse candidate row against the dense query row (zero products are exact)
-        const int64_t rbase = static_cast<int64_t>(c) * P.ell_width;
-        for (int32_t j = lane; j < P.ell_width; j += 32) {
-          const float v = __ldg(P.ell_val + rbase + j);
-          if (v != 0.f) acc = fma(static_cast<double>(v), static_cast<double>(xq[__ldg(P.ell_idx + rbase + j)]), acc);
+    // ---- query row -> dense
+    if (sparse) {
+      const int64_t qb = q * P.ell_width;
+      for (int32_t j = 2 * lane; j < P.ell_width; j += 64) {
+        const uint32_t kk = __ldg(reinterpret_cast<const uint32_t*>(P.ell_idx + qb + j));
+        const float2 vv = __ldg(reinterpret_cast<const float2*>(P.ell_val + qb + j));
+        if (vv.x != 0.f) xq[kk & 0xffffu] = vv.x;
+        if (vv.y != 0.f) xq[kk >> 16] = vv.y;
+      }
+    } else {
+      const float* xrow = P.x + q * P.ld;
+      for (uint32_t i = lane; i < P.low_dim; i += 32) xq[i] = xrow[i];
+    }
+    __syncwarp();
+    const double mq = P.mz[q];
+    const float rq = P.rt ? P.rt[q] : 0.f;
+    int32_t kept = 0;
+
+    if (m <= 32) {
+      // ---- every candidate in its own lane: ids, membership, tolerance operands up front
+      const bool have = lane < m;
+      const uint32_t c = have ? static_cast<uint32_t>(grouped[base + lane]) : 0u;
+      bool member = have;
+      if (have && P.list_id != nullptr) {
+        const int32_t lc = P.list_id[c];
+        bool hit = false;
+        for (int32_t t = 0; t < P.max_nprobe; ++t) hit |= (__ldg(P.probes + q * P.max_nprobe + t) == lc);
+        member = hit;
+      }
+      const double mc = have ? P.mz[c] : 1.0;
+      const float rc = (have && P.rt) ? P.rt[c] : 0.f;
+      const uint32_t members = __ballot_sync(0xffffffffu, member);
+      float ip = 0.f;
+      for (uint32_t rest = members; rest != 0u; rest &= rest - 1u) {
+        const int j = __ffs(rest) - 1;
+        const float v = exact_ip(P, xq, __shfl_sync(0xffffffffu, c, j), lane);
+        if (lane == j) ip = v;
+      }
+      const float dist = fmaxf(1.0f - ip, 0.0f);
+      const bool valid = member && (!P.use_eps || dist <= P.eps);
+      const uint64_t key = valid ? ((static_cast<uint64_t>(ip_key_desc(ip)) << 32) | c) : kKeyMax;
+      const bool ok = valid && tolerance_ok(P, mq, rq, mc, rc);
+      // ---- rank by counting: lanes with a smaller (ip desc, id asc) key
+      uint32_t lt = 0;
+      for (int i = 0; i < m; ++i) {
+        const uint64_t ki = (static_cast<uint64_t>(__shfl_sync(0xffffffffu, static_cast<uint32_t>(key >> 32), i)) << 32) |
+                            __shfl_sync(0xffffffffu, static_cast<uint32_t>(key), i);
+        lt |= (ki < key ? 1u : 0u) << i;
+      }
+      const uint32_t ann = __ballot_sync(0xffffffffu, valid && __popc(lt) < P.k_ann);
+      const uint32_t okm = __ballot_sync(0xffffffffu, ok) & ann;
+      const int prank = __popc(lt & okm);
+      if (ok && ((ann >> lane) & 1u) && prank < P.k)
+        grouped[base + prank] = (static_cast<uint64_t>(__float_as_uint(dist)) << 32) | c;
+      kept = min(__popc(okm), P.k);
+    } else {
+      // ---- Phase A: exact score of every candidate -> sort key (in place)
+      for (int64_t j0 = 0; j0 < m; j0 += 32) {
+        const bool have = j0 + lane < m;
+        const uint32_t c = have ? static_cast<uint32_t>(grouped[base + j0 + lane]) : 0u;
+        bool member = have;
+        if (have && P.list_id != nullptr) {
+          const int32_t lc = P.list_id[c];
+          bool hit = false;
+          for (int32_t t = 0; t < P.max_nprobe; ++t) hit |= (__ldg(P.probes + q * P.max_nprobe + t) == lc);
+          member = hit;
         }
-      } else {
-        const float* xc = P.x + static_cast<int64_t>(c) * P.ld;
-        for (uint32_t i = lane; i < P.low_dim; i += 32)
-          acc = fma(static_cast<double>(xq[i]), static_cast<double>(__ldg(xc + i)), acc);
-      }
-      acc = warp_sum_f64(acc);
-      const float ip = static_cast<float>(acc);
-      const float dist = fmaxf(1.0f - ip, 0.0f);
-      if (!P.use_eps || dist <= P.eps) key = (static_cast<uint64_t>(ip_key_desc(ip)) << 32) | c;
-    }
-    if (lane == 0) grouped[base + j] = key;
-  }
-  __syncwarp();
-
-  int32_t kept = 0;
-  if (m <= 32) {
-    uint64_t key = lane < m ? grouped[base + lane] : kKeyMax;
-    key = warp_sort32(key, lane);
-    const bool valid = key != kKeyMax && lane < P.k_ann;
-    const uint32_t c = static_cast<uint32_t>(key);
-    const bool pass = valid && tolerance_ok(P, mq, rq, c);
-    const uint32_t ballot = __ballot_sync(0xffffffffu, pass);
-    const int rank = __popc(ballot & ((1u << lane) - 1u));
-    if (pass && rank < P.k) {
-      const float ip = ip_from_key(static_cast<uint32_t>(key >> 32));
-      const float dist = fmaxf(1.0f - ip, 0.0f);
-      grouped[base + rank] = (static_cast<uint64_t>(__float_as_uint(dist)) << 32) | c;
-    }
-    kept = min(__popc(ballot), P.k);
-  } else {
-    const int KA = P.ka_pow2;
-    for (int t = lane; t < KA; t += 32) buf[t] = kKeyMax;
-    for (int64_t blk = 0; blk < m; blk += KA) {
-      for (int t = lane; t < KA; t += 32) buf[KA + t] = (blk + t < m) ? grouped[base + blk + t] : kKeyMax;
-      __syncwarp();
-      warp_sort_smem(buf, 2 * KA, lane);
-    }
-    // Phase C: tolerance filter in similarity order.
-    for (int s = 0; s < P.k_ann && kept < P.k; s += 32) {
-      const int t = s + lane;
-      const uint64_t key = (t < P.k_ann && t < KA) ? buf[t] : kKeyMax;
-      const bool valid = key != kKeyMax;
-      const uint32_t c = static_cast<uint32_t>(key);
-      const bool pass = valid && tolerance_ok(P, mq, rq, c);
-      const uint32_t ballot = __ballot_sync(0xffffffffu, pass);
-      const int rank = kept + __popc(ballot & ((1u << lane) - 1u));
-      if (pass && rank < P.k) {
-        const float ip = ip_from_key(static_cast<uint32_t>(key >> 32));
+        float ip = 0.f;
+        for (uint32_t rest = __ballot_sync(0xffffffffu, member); rest != 0u; rest &= rest - 1u) {
+          const int j = __ffs(rest) - 1;
+          const float v = exact_ip(P, xq, __shfl_sync(0xffffffffu, c, j), lane);
+          if (lane == j) ip = v;
+        }
         const float dist = fmaxf(1.0f - ip, 0.0f);
-        grouped[base + rank] = (static_cast<uint64_t>(__float_as_uint(dist)) << 32) | c;
+        const bool valid = member && (!P.use_eps || dist <= P.eps);
+        if (have) grouped[base + j0 + lane] = valid ? ((static_cast<uint64_t>(ip_key_desc(ip)) << 32) | c) : kKeyMax;
       }
-      kept = min(kept + __popc(ballot), P.k);
-      if (__ballot_sync(0xffffffffu, valid) != 0xffffffffu) break;
+      __syncwarp();
+      // ---- Phase B: running top-k_ann by bitonic merges in shared memory
+      const int KA = P.ka_pow2;
+      for (int t = lane; t < KA; t += 32) buf[t] = kKeyMax;
+      for (int64_t blk = 0; blk < m; blk += KA) {
+        for (int t = lane; t < KA; t += 32) buf[KA + t] = (blk + t < m) ? grouped[base + blk + t] : kKeyMax;
+        __syncwarp();
+        warp_sort_smem(buf, 2 * KA, lane);
+      }
+      // ---- Phase C: tolerance filter in similarity order
+      for (int s = 0; s < P.k_ann && kept < P.k; s += 32) {
+        const int t = s + lane;
+        const uint64_t key = (t < P.k_ann && t < KA) ? buf[t] : kKeyMax;
+        const bool valid = key != kKeyMax;
+        const uint32_t c = static_cast<uint32_t>(key);
+        const bool pass = valid && tolerance_ok(P, mq, rq, P.mz[c], P.rt ? P.rt[c] : 0.f);
+        const uint32_t ballot = __ballot_sync(0xffffffffu, pass);
+        const int rank = kept + __popc(ballot & below);
+        if (pass && rank < P.k) {
+          const float ip = ip_from_key(static_cast<uint32_t>(key >> 32));
+          const float dist = fmaxf(1.0f - ip, 0.0f);
+          grouped[base + rank] = (static_cast<uint64_t>(__float_as_uint(dist)) << 32) | c;
+        }
+        kept = min(kept + __popc(ballot), P.k);
+        if (__ballot_sync(0xffffffffu, valid) != 0xffffffffu) break;
+      }
     }
+    if (lane == 0) row_count[q] = kept;
+    // ---- query row back to zero
+    if (sparse) {
+      __syncwarp();
+      const int64_t qb = q * P.ell_width;
+      for (int32_t j = 2 * lane; j < P.ell_width; j += 64) {
+        const uint32_t kk = __ldg(reinterpret_cast<const uint32_t*>(P.ell_idx + qb + j));
+        xq[kk & 0xffffu] = 0.f;
+        xq[kk >> 16] = 0.f;
+      }
+    }
+    __syncwarp();
   }
-  if (lane == 0) row_count[q] = kept;
 }
 
 __global__ void csr_compact_kernel(const uint64_t* __restrict__ grouped, const int64_t* __restrict__ off,
@@ -372,7 +425,11 @@ int flc_knn_csr(const uint64_t* pairs, const uint64_t* pair_count, uint64_t pair
   if (smem > 48 * 1024)
     FLC_CUDA(cudaFuncSetAttribute(refine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   static_cast<int>(smem)));
-  const unsigned rblocks = static_cast<unsigned>((n + kRefineWarps - 1) / kRefineWarps);
+  FLC_REQUIRE(ell_idx == nullptr || ((ell_width % 2) == 0 && (reinterpret_cast<uintptr_t>(ell_idx) % 4) == 0 &&
+                                     (reinterpret_cast<uintptr_t>(ell_val) % 8) == 0),
+              "ELL arrays must be even-width and 4/8-byte aligned");
+  const unsigned rblocks = static_cast<unsigned>(
+      std::min<int64_t>((n + kRefineWarps - 1) / kRefineWarps, static_cast<int64_t>(kNumSMs) * 16));
   timed("refine", stream, [&] { refine_kernel<<<rblocks, kRefineWarps * 32, smem, stream>>>(P, L.off, L.grouped, L.row_count); });
   FLC_LAUNCH_CHECK();
   tmp = L.cub_bytes;

@@ -8,11 +8,15 @@
 // Peaks that collide on a hashed column are added in peak order
 // (__match_any_sync gives every lane its rank among same-column lanes) so the
 // float32 sum is bit-identical to the sequential reference loop (A.1).  The
-// squared norm is reduced in float64 with warp shuffles; the row leaves as
-// float32 (exact re-scoring, k-means) and bfloat16 (tcgen05 scan operand).
+// squared norm is reduced in float64 with warp shuffles; one sweep over the row
+// then emits every output: float32 (optional), bfloat16 (tcgen05 scan operand)
+// and the sparse ELL copy (columns ascending) that k-means and the exact
+// re-scoring read, and leaves the row zeroed for the next spectrum.
 //
-// HBM-bound: algorithmic bytes per spectrum = 8 * peaks + 16 (indptr) +
-// 4 * low_dim (+ 2 * ld_bf16 for the bf16 copy).
+// HBM-bound: algorithmic bytes per spectrum = 8 * peaks + 16 (indptr) + 4 (order)
+// + 4 * low_dim [f32] + 2 * ld_bf16 [bf16] + 6 * ell_width + 2 [ELL].
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
 namespace flc {
@@ -25,123 +29,152 @@ __global__ void hash_table_kernel(uint32_t vec_len, uint32_t low_dim, uint32_t s
   if (i < vec_len) out[i] = murmur3_int32(i, seed) % low_dim;
 }
 
+struct VecParams {
+  const float* mz;
+  const float* intensity;
+  const int64_t* indptr;
+  const int32_t* order;
+  int64_t n;
+  double min_mz, bin_size, inv_bin;
+  uint32_t vec_len, low_dim, mod_magic, seed;
+  int norm;
+  uint32_t row_len;  // low_dim rounded up to 64
+  float* out_f32;
+  int64_t ld_f32;
+  uint16_t* out_bf16;
+  int64_t ld_bf16;
+  int32_t* out_hash_idx;
+  uint16_t* ell_idx;
+  float* ell_val;
+  uint16_t* ell_nnz;
+  int32_t ell_width;
+  int32_t* ell_overflow;
+};
+
 __global__ void __launch_bounds__(kVecWarps * 32)
-vectorize_kernel(const float* __restrict__ mz, const float* __restrict__ intensity,
-                 const int64_t* __restrict__ indptr, const int32_t* __restrict__ order,
-                 int64_t n, double min_mz, double bin_size, uint32_t vec_len,
-                 uint32_t low_dim, uint32_t seed, int norm,
-                 float* __restrict__ out_f32, int64_t ld_f32,
-                 uint16_t* __restrict__ out_bf16, int64_t ld_bf16,
-                 int32_t* __restrict__ out_hash_idx,
-                 uint16_t* __restrict__ ell_idx, float* __restrict__ ell_val, uint16_t* __restrict__ ell_nnz,
-                 int32_t ell_width, int32_t* __restrict__ ell_overflow) {
-  extern __shared__ float smem_rows[];
+vectorize_kernel(const VecParams P) {
+  extern __shared__ __align__(16) float smem_rows[];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
-  float* row = smem_rows + static_cast<size_t>(warp) * low_dim;
+  float* row = smem_rows + static_cast<size_t>(warp) * P.row_len;
   const int64_t warps_total = static_cast<int64_t>(gridDim.x) * kVecWarps;
+  const uint32_t below = (1u << lane) - 1u;
+  const double vec_len_d = static_cast<double>(P.vec_len);
 
-  for (int64_t r = static_cast<int64_t>(blockIdx.x) * kVecWarps + warp; r < n; r += warps_total) {
-    const int64_t src = order ? static_cast<int64_t>(order[r]) : r;
-    const int64_t p0 = indptr[src];
-    const int64_t p1 = indptr[src + 1];
-    for (uint32_t i = lane; i < low_dim; i += 32) row[i] = 0.f;
-    __syncwarp();
+  for (uint32_t i = lane; i < P.row_len; i += 32) row[i] = 0.f;  // invariant: zero between spectra
+  __syncwarp();
+
+  for (int64_t r = static_cast<int64_t>(blockIdx.x) * kVecWarps + warp; r < P.n; r += warps_total) {
+    const int64_t src = P.order ? static_cast<int64_t>(__ldg(P.order + r)) : r;
+    const int64_t p0 = __ldg(P.indptr + src);
+    const int64_t p1 = __ldg(P.indptr + src + 1);
 
     for (int64_t base = p0; base < p1; base += 32) {
       const int64_t p = base + lane;
-      const bool in_range = p < p1;
       float x = 0.f;
       uint32_t col = 0;
       bool valid = false;
-      if (in_range) {
-        const float m = __ldg(mz + p);
-        x = __ldg(intensity + p);
-        const double b = floor((static_cast<double>(m) - min_mz) / bin_size);
-        if (b >= 0.0 && b < static_cast<double>(vec_len)) {
-          col = murmur3_int32(static_cast<uint32_t>(static_cast<int32_t>(b)), seed) % low_dim;
+      if (p < p1) {
+        const float m = __ldg(P.mz + p);
+        x = __ldg(P.intensity + p);
+        // floor((m - min_mz) / bin_size) in float64.  The quotient is first taken as a
+        // product with 1 / bin_size (relative error < 2^-51); only when that lands within
+        // 1e-4 of an integer is the exact division needed to get the reference's floor.
+        const double t = static_cast<double>(m) - P.min_mz;
+        const double q = t * P.inv_bin;
+        double b = floor(q);
+        const double frac = q - b;
+        if (frac < 1e-4 || frac > 1.0 - 1e-4) b = floor(t / P.bin_size);
+        if (b >= 0.0 && b < vec_len_d) {
+          const uint32_t h = murmur3_int32(static_cast<uint32_t>(static_cast<int32_t>(b)), P.seed);
+          // h % low_dim with a precomputed reciprocal: the estimate is short by at most one
+          col = h - __umulhi(h, P.mod_magic) * P.low_dim;
+          if (col >= P.low_dim) col -= P.low_dim;
           valid = true;
         }
-        if (out_hash_idx) out_hash_idx[p] = valid ? static_cast<int32_t>(col) : -1;
+        if (P.out_hash_idx) P.out_hash_idx[p] = valid ? static_cast<int32_t>(col) : -1;
       }
       // Rank of this lane among the lanes that hit the same column (peak order).
       const uint32_t key = valid ? col : (0x80000000u | lane);
       const uint32_t same = __match_any_sync(0xffffffffu, key);
-      const int rank = __popc(same & ((1u << lane) - 1u));
-      int rounds = __popc(same);
+      if (__all_sync(0xffffffffu, (same & (same - 1u)) == 0u)) {
+        if (valid) row[col] += x;  // no two lanes share a column
+      } else {
+        const int rank = __popc(same & below);
+        int rounds = __popc(same);
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) rounds = max(rounds, __shfl_xor_sync(0xffffffffu, rounds, o));
-      for (int t = 0; t < rounds; ++t) {
-        if (valid && rank == t) row[col] += x;
-        __syncwarp();
+        for (int o = 16; o > 0; o >>= 1) rounds = max(rounds, __shfl_xor_sync(0xffffffffu, rounds, o));
+        for (int t = 0; t < rounds; ++t) {
+          if (valid && rank == t) row[col] += x;
+          __syncwarp();
+        }
       }
+      __syncwarp();
     }
 
     double scale = 1.0;
-    if (norm) {
+    if (P.norm) {
       double ss = 0.0;
-      for (uint32_t i = lane; i < low_dim; i += 32) {
-        const double v = static_cast<double>(row[i]);
-        ss = fma(v, v, ss);
+      for (uint32_t i = 2 * lane; i < P.row_len; i += 64) {
+        const float2 v = *reinterpret_cast<const float2*>(row + i);
+        ss = fma(static_cast<double>(v.x), static_cast<double>(v.x), ss);
+        ss = fma(static_cast<double>(v.y), static_cast<double>(v.y), ss);
       }
       ss = warp_sum_f64(ss);
       scale = ss > 0.0 ? 1.0 / sqrt(ss) : 1.0;
-      // normalise in place: every output below reads the final float32 value
-      for (uint32_t i = lane; i < low_dim; i += 32)
-        row[i] = static_cast<float>(static_cast<double>(row[i]) * scale);
-      __syncwarp();
     }
-    if (out_f32) {
-      float* dst = out_f32 + r * ld_f32;
-      if (((low_dim | ld_f32) & 3) == 0) {
-        for (uint32_t i = lane * 4; i < low_dim; i += 128)
-          *reinterpret_cast<float4*>(dst + i) = *reinterpret_cast<const float4*>(row + i);
-      } else {
-        for (uint32_t i = lane; i < low_dim; i += 32) dst[i] = row[i];
-      }
-    }
-    if (out_bf16) {
-      uint16_t* dst = out_bf16 + r * ld_bf16;
-      if ((ld_bf16 & 3) == 0) {
-        for (int64_t i = lane * 4; i < ld_bf16; i += 128) {
-          uint16_t h[4];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int64_t c = i + j;
-            h[j] = f32_to_bf16_rne(c < low_dim ? row[c] : 0.f);
-          }
-          uint2 packed;
-          packed.x = static_cast<uint32_t>(h[0]) | (static_cast<uint32_t>(h[1]) << 16);
-          packed.y = static_cast<uint32_t>(h[2]) | (static_cast<uint32_t>(h[3]) << 16);
-          *reinterpret_cast<uint2*>(dst + i) = packed;
+    // One sweep: scale, emit every output, zero the row.  Lane l owns columns 2l, 2l+1 (+64 per step).
+    float* dst_f = P.out_f32 ? P.out_f32 + r * P.ld_f32 : nullptr;
+    uint16_t* dst_b = P.out_bf16 ? P.out_bf16 + r * P.ld_bf16 : nullptr;
+    uint16_t* di = P.ell_idx ? P.ell_idx + r * P.ell_width : nullptr;
+    float* dv = P.ell_idx ? P.ell_val + r * P.ell_width : nullptr;
+    const bool vec_f = ((P.ld_f32 | P.low_dim) & 1) == 0;
+    const bool vec_b = (P.ld_bf16 & 1) == 0;
+    int count = 0;
+    for (uint32_t i = 2 * lane; i < P.row_len; i += 64) {
+      const float2 v = *reinterpret_cast<const float2*>(row + i);
+      *reinterpret_cast<float2*>(row + i) = make_float2(0.f, 0.f);
+      const float s0 = static_cast<float>(static_cast<double>(v.x) * scale);
+      const float s1 = static_cast<float>(static_cast<double>(v.y) * scale);
+      if (dst_f) {
+        if (vec_f) {
+          if (i < P.low_dim) *reinterpret_cast<float2*>(dst_f + i) = make_float2(s0, s1);
+        } else {
+          if (i < P.low_dim) dst_f[i] = s0;
+          if (i + 1 < P.low_dim) dst_f[i + 1] = s1;
         }
-      } else {
-        for (int64_t i = lane; i < ld_bf16; i += 32) dst[i] = f32_to_bf16_rne(i < low_dim ? row[i] : 0.f);
+      }
+      if (dst_b) {
+        const __nv_bfloat162 h = __floats2bfloat162_rn(s0, s1);
+        if (vec_b) {
+          if (static_cast<int64_t>(i) < P.ld_bf16) *reinterpret_cast<__nv_bfloat162*>(dst_b + i) = h;
+        } else {
+          if (static_cast<int64_t>(i) < P.ld_bf16) dst_b[i] = __bfloat16_as_ushort(h.x);
+          if (static_cast<int64_t>(i) + 1 < P.ld_bf16) dst_b[i + 1] = __bfloat16_as_ushort(h.y);
+        }
+      }
+      if (di) {
+        const bool nz0 = s0 != 0.f, nz1 = s1 != 0.f;
+        const uint32_t b0 = __ballot_sync(0xffffffffu, nz0);
+        const uint32_t b1 = __ballot_sync(0xffffffffu, nz1);
+        int pos = count + __popc(b0 & below) + __popc(b1 & below);
+        if (nz0) {
+          if (pos < P.ell_width) { di[pos] = static_cast<uint16_t>(i); dv[pos] = s0; }
+          ++pos;
+        }
+        if (nz1 && pos < P.ell_width) { di[pos] = static_cast<uint16_t>(i + 1); dv[pos] = s1; }
+        count += __popc(b0) + __popc(b1);
       }
     }
-    if (ell_idx) {
-      // Sparse (ELL) copy: the non-zero columns in ascending order, zero padded.
-      uint16_t* di = ell_idx + r * ell_width;
-      float* dv = ell_val + r * ell_width;
-      int count = 0;
-      for (uint32_t base = 0; base < low_dim; base += 32) {
-        const uint32_t i = base + lane;
-        const float v = i < low_dim ? row[i] : 0.f;
-        const bool nz = v != 0.f;
-        const uint32_t ballot = __ballot_sync(0xffffffffu, nz);
-        const int pos = count + __popc(ballot & ((1u << lane) - 1u));
-        if (nz && pos < ell_width) {
-          di[pos] = static_cast<uint16_t>(i);
-          dv[pos] = v;
-        }
-        count += __popc(ballot);
-      }
-      for (int pos = count + lane; pos < ell_width; pos += 32) {
+    if (di) {
+      for (int pos = count + lane; pos < P.ell_width; pos += 32) {  // zero padding
         di[pos] = 0;
         dv[pos] = 0.f;
       }
-      if (ell_nnz && lane == 0) ell_nnz[r] = static_cast<uint16_t>(min(count, ell_width));
-      if (count > ell_width && lane == 0) atomicMax(ell_overflow, count);
+      if (lane == 0) {
+        if (P.ell_nnz) P.ell_nnz[r] = static_cast<uint16_t>(min(count, P.ell_width));
+        if (count > P.ell_width) atomicMax(P.ell_overflow, count);
+      }
     }
     __syncwarp();
   }
@@ -180,18 +213,28 @@ int flc_vectorize(const float* mz, const float* intensity, const int64_t* indptr
   FLC_REQUIRE(!ell_nnz || ell_idx, "ell_nnz needs the ELL arrays");
   if (n == 0) return FLC_OK;
   FLC_REQUIRE(indptr != nullptr, "null indptr");
-  const size_t smem = static_cast<size_t>(flc::kVecWarps) * low_dim * sizeof(float);
+  flc::VecParams P;
+  P.mz = mz; P.intensity = intensity; P.indptr = indptr; P.order = order; P.n = n;
+  P.min_mz = min_mz; P.bin_size = bin_size; P.inv_bin = 1.0 / bin_size;
+  P.vec_len = vec_len; P.low_dim = low_dim; P.seed = seed; P.norm = norm;
+  // floor((2^32 - 1) / low_dim): the quotient estimate __umulhi(h, magic) is short by at most one
+  P.mod_magic = static_cast<uint32_t>(0xffffffffull / low_dim);
+  P.row_len = (low_dim + 63u) & ~63u;
+  P.out_f32 = out_f32; P.ld_f32 = ld_f32; P.out_bf16 = out_bf16; P.ld_bf16 = ld_bf16;
+  P.out_hash_idx = out_hash_idx;
+  P.ell_idx = ell_idx; P.ell_val = ell_val; P.ell_nnz = ell_nnz; P.ell_width = ell_width;
+  P.ell_overflow = ell_overflow;
+  FLC_REQUIRE(!out_bf16 || ld_bf16 <= static_cast<int64_t>(P.row_len), "ld_bf16 exceeds low_dim rounded up to 64");
+  const size_t smem = static_cast<size_t>(flc::kVecWarps) * P.row_len * sizeof(float);
+  FLC_REQUIRE(smem <= 200 * 1024, "low_dim too large");
   if (smem > 48 * 1024)
     FLC_CUDA(cudaFuncSetAttribute(flc::vectorize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   static_cast<int>(smem)));
   int64_t blocks = (n + flc::kVecWarps - 1) / flc::kVecWarps;
-  const int64_t max_blocks = static_cast<int64_t>(flc::kNumSMs) * 16;
+  const int64_t max_blocks = static_cast<int64_t>(flc::kNumSMs) * 8;
   if (blocks > max_blocks) blocks = max_blocks;
-  flc::timed("vectorize", stream, [&] { flc::vectorize_kernel<<<static_cast<unsigned>(blocks), flc::kVecWarps * 32, smem,
-                          flc::as_stream(stream)>>>(mz, intensity, indptr, order, n, min_mz, bin_size,
-                                                    vec_len, low_dim, seed, norm, out_f32, ld_f32,
-                                                    out_bf16, ld_bf16, out_hash_idx, ell_idx, ell_val,
-                                                    ell_nnz, ell_width, ell_overflow); });
+  flc::timed("vectorize", stream, [&] {
+    flc::vectorize_kernel<<<static_cast<unsigned>(blocks), flc::kVecWarps * 32, smem, flc::as_stream(stream)>>>(P); });
   FLC_LAUNCH_CHECK();
   return FLC_OK;
 }

@@ -50,7 +50,7 @@ class Settings:
     kmeans_iters: int = 10
     scan_impl: int = 0  # 0 = tcgen05, 1 = SIMT verification kernel
     eps_cut: bool = True  # keep only dist <= eps in the CSR (what generate_clusters reads)
-    dense_f32: bool = True  # also materialise the dense float32 rows (needed by the generic k-means path)
+    dense_f32: bool = False  # also materialise the dense float32 rows (no stage needs them: all read the sparse copy)
 
 
 def get_dim(min_mz: float, max_mz: float, bin_size: float):
