@@ -8,10 +8,12 @@
 // Peaks that collide on a hashed column are added in peak order
 // (__match_any_sync gives every lane its rank among same-column lanes) so the
 // float32 sum is bit-identical to the sequential reference loop (A.1).  The
-// squared norm is reduced in float64 with warp shuffles; one sweep over the row
-// then emits every output: float32 (optional), bfloat16 (tcgen05 scan operand)
-// and the sparse ELL copy (columns ascending) that k-means and the exact
-// re-scoring read, and leaves the row zeroed for the next spectrum.
+// squared norm is reduced in float64 with warp shuffles.  Spectra of up to 64
+// peaks (falcon keeps at most 50) never sweep the dense row: the first lane of
+// every distinct column owns it and emits its value to the float32 row
+// (optional), the bfloat16 row (tcgen05 scan operand, staged in shared memory
+// and copied out 16 bytes per lane) and the sparse ELL copy that k-means and
+// the exact re-scoring read (distinct columns, peak order, zero padded).
 //
 // HBM-bound: algorithmic bytes per spectrum = 8 * peaks + 16 (indptr) + 4 (order)
 // + 4 * low_dim [f32] + 2 * ld_bf16 [bf16] + 6 * ell_width + 2 [ELL].
@@ -51,119 +53,180 @@ struct VecParams {
   int32_t* ell_overflow;
 };
 
+struct Peak {
+  uint32_t col;
+  float x;
+  bool valid;
+};
+
+// Bin + hash of peak p (invalid beyond p1 or outside [0, vec_len)).
+__device__ __forceinline__ Peak load_peak(const VecParams& P, int64_t p, int64_t p1, double vec_len_d) {
+  Peak k{0u, 0.f, false};
+  if (p < p1) {
+    const float m = __ldg(P.mz + p);
+    k.x = __ldg(P.intensity + p);
+    // floor((m - min_mz) / bin_size) in float64.  The quotient is first taken as a
+    // product with 1 / bin_size (relative error < 2^-51); only when that lands within
+    // 1e-4 of an integer is the exact division needed to get the reference's floor.
+    const double t = static_cast<double>(m) - P.min_mz;
+    const double q = t * P.inv_bin;
+    double b = floor(q);
+    const double frac = q - b;
+    if (frac < 1e-4 || frac > 1.0 - 1e-4) b = floor(t / P.bin_size);
+    if (b >= 0.0 && b < vec_len_d) {
+      const uint32_t h = murmur3_int32(static_cast<uint32_t>(static_cast<int32_t>(b)), P.seed);
+      // h % low_dim with a precomputed reciprocal: the quotient estimate is short by at most one
+      k.col = h - __umulhi(h, P.mod_magic) * P.low_dim;
+      if (k.col >= P.low_dim) k.col -= P.low_dim;
+      k.valid = true;
+    }
+    if (P.out_hash_idx) P.out_hash_idx[p] = k.valid ? static_cast<int32_t>(k.col) : -1;
+  }
+  return k;
+}
+
+// row[col] += x for the 32 peaks of one pass, colliding lanes in peak order.
+// Returns true for the first lane of every distinct (valid) column.
+__device__ __forceinline__ bool accumulate_pass(float* row, const Peak& k, int lane, uint32_t below) {
+  const uint32_t key = k.valid ? k.col : (0x80000000u | lane);
+  const uint32_t same = __match_any_sync(0xffffffffu, key);
+  const int rank = __popc(same & below);
+  if (__all_sync(0xffffffffu, (same & (same - 1u)) == 0u)) {
+    if (k.valid) row[k.col] += k.x;  // no two lanes share a column
+  } else {
+    int rounds = __popc(same);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) rounds = max(rounds, __shfl_xor_sync(0xffffffffu, rounds, o));
+    for (int t = 0; t < rounds; ++t) {
+      if (k.valid && rank == t) row[k.col] += k.x;
+      __syncwarp();
+    }
+  }
+  __syncwarp();
+  return k.valid && rank == 0;
+}
+
+// One warp per spectrum.  Per-warp shared memory: the float32 accumulation row,
+// a bfloat16 staging row (both all-zero between spectra) and a stamp row that
+// tells which columns an earlier pass of the same spectrum already owns.
 __global__ void __launch_bounds__(kVecWarps * 32)
 vectorize_kernel(const VecParams P) {
-  extern __shared__ __align__(16) float smem_rows[];
+  extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
-  float* row = smem_rows + static_cast<size_t>(warp) * P.row_len;
+  const size_t per_warp = static_cast<size_t>(P.row_len) * 8;
+  float* row = reinterpret_cast<float*>(smem_raw + warp * per_warp);
+  uint16_t* brow = reinterpret_cast<uint16_t*>(row + P.row_len);
+  uint16_t* stamp = brow + P.row_len;
   const int64_t warps_total = static_cast<int64_t>(gridDim.x) * kVecWarps;
   const uint32_t below = (1u << lane) - 1u;
   const double vec_len_d = static_cast<double>(P.vec_len);
+  const bool bf16_vec = P.out_bf16 != nullptr && (P.ld_bf16 & 7) == 0 && (reinterpret_cast<uintptr_t>(P.out_bf16) & 15) == 0;
 
-  for (uint32_t i = lane; i < P.row_len; i += 32) row[i] = 0.f;  // invariant: zero between spectra
+  for (uint32_t i = lane; i < P.row_len; i += 32) {
+    row[i] = 0.f;
+    brow[i] = 0;
+    stamp[i] = 0;
+  }
   __syncwarp();
+  uint32_t serial = 0;
 
   for (int64_t r = static_cast<int64_t>(blockIdx.x) * kVecWarps + warp; r < P.n; r += warps_total) {
     const int64_t src = P.order ? static_cast<int64_t>(__ldg(P.order + r)) : r;
     const int64_t p0 = __ldg(P.indptr + src);
     const int64_t p1 = __ldg(P.indptr + src + 1);
-
-    for (int64_t base = p0; base < p1; base += 32) {
-      const int64_t p = base + lane;
-      float x = 0.f;
-      uint32_t col = 0;
-      bool valid = false;
-      if (p < p1) {
-        const float m = __ldg(P.mz + p);
-        x = __ldg(P.intensity + p);
-        // floor((m - min_mz) / bin_size) in float64.  The quotient is first taken as a
-        // product with 1 / bin_size (relative error < 2^-51); only when that lands within
-        // 1e-4 of an integer is the exact division needed to get the reference's floor.
-        const double t = static_cast<double>(m) - P.min_mz;
-        const double q = t * P.inv_bin;
-        double b = floor(q);
-        const double frac = q - b;
-        if (frac < 1e-4 || frac > 1.0 - 1e-4) b = floor(t / P.bin_size);
-        if (b >= 0.0 && b < vec_len_d) {
-          const uint32_t h = murmur3_int32(static_cast<uint32_t>(static_cast<int32_t>(b)), P.seed);
-          // h % low_dim with a precomputed reciprocal: the estimate is short by at most one
-          col = h - __umulhi(h, P.mod_magic) * P.low_dim;
-          if (col >= P.low_dim) col -= P.low_dim;
-          valid = true;
-        }
-        if (P.out_hash_idx) P.out_hash_idx[p] = valid ? static_cast<int32_t>(col) : -1;
-      }
-      // Rank of this lane among the lanes that hit the same column (peak order).
-      const uint32_t key = valid ? col : (0x80000000u | lane);
-      const uint32_t same = __match_any_sync(0xffffffffu, key);
-      if (__all_sync(0xffffffffu, (same & (same - 1u)) == 0u)) {
-        if (valid) row[col] += x;  // no two lanes share a column
-      } else {
-        const int rank = __popc(same & below);
-        int rounds = __popc(same);
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) rounds = max(rounds, __shfl_xor_sync(0xffffffffu, rounds, o));
-        for (int t = 0; t < rounds; ++t) {
-          if (valid && rank == t) row[col] += x;
-          __syncwarp();
-        }
-      }
-      __syncwarp();
-    }
-
-    double scale = 1.0;
-    if (P.norm) {
-      double ss = 0.0;
-      for (uint32_t i = 2 * lane; i < P.row_len; i += 64) {
-        const float2 v = *reinterpret_cast<const float2*>(row + i);
-        ss = fma(static_cast<double>(v.x), static_cast<double>(v.x), ss);
-        ss = fma(static_cast<double>(v.y), static_cast<double>(v.y), ss);
-      }
-      ss = warp_sum_f64(ss);
-      scale = ss > 0.0 ? 1.0 / sqrt(ss) : 1.0;
-    }
-    // One sweep: scale, emit every output, zero the row.  Lane l owns columns 2l, 2l+1 (+64 per step).
     float* dst_f = P.out_f32 ? P.out_f32 + r * P.ld_f32 : nullptr;
     uint16_t* dst_b = P.out_bf16 ? P.out_bf16 + r * P.ld_bf16 : nullptr;
     uint16_t* di = P.ell_idx ? P.ell_idx + r * P.ell_width : nullptr;
     float* dv = P.ell_idx ? P.ell_val + r * P.ell_width : nullptr;
-    const bool vec_f = ((P.ld_f32 | P.low_dim) & 1) == 0;
-    const bool vec_b = (P.ld_bf16 & 1) == 0;
     int count = 0;
-    for (uint32_t i = 2 * lane; i < P.row_len; i += 64) {
-      const float2 v = *reinterpret_cast<const float2*>(row + i);
-      *reinterpret_cast<float2*>(row + i) = make_float2(0.f, 0.f);
-      const float s0 = static_cast<float>(static_cast<double>(v.x) * scale);
-      const float s1 = static_cast<float>(static_cast<double>(v.y) * scale);
-      if (dst_f) {
-        if (vec_f) {
-          if (i < P.low_dim) *reinterpret_cast<float2*>(dst_f + i) = make_float2(s0, s1);
-        } else {
-          if (i < P.low_dim) dst_f[i] = s0;
-          if (i + 1 < P.low_dim) dst_f[i + 1] = s1;
-        }
+
+    if (p1 - p0 <= 64) {
+      // ---- fast path: both passes stay in registers; no sweep over the dense row
+      if (++serial == 0x10000u) {  // stamps are 16 bit: start over before a tag could repeat
+        for (uint32_t i = lane; i < P.row_len; i += 32) stamp[i] = 0;
+        serial = 1;
+        __syncwarp();
+      }
+      const uint16_t tag = static_cast<uint16_t>(serial);
+      const Peak a = load_peak(P, p0 + lane, p1, vec_len_d);
+      const Peak b = load_peak(P, p0 + 32 + lane, p1, vec_len_d);
+      const bool own0 = accumulate_pass(row, a, lane, below);
+      bool own1 = false;
+      if (p1 - p0 > 32) {
+        if (own0) stamp[a.col] = tag;
+        __syncwarp();
+        own1 = accumulate_pass(row, b, lane, below);
+        own1 = own1 && stamp[b.col] != tag;
+      }
+      const float v0 = own0 ? row[a.col] : 0.f;
+      const float v1 = own1 ? row[b.col] : 0.f;
+      double scale = 1.0;
+      if (P.norm) {
+        double ss = static_cast<double>(v0) * static_cast<double>(v0);
+        ss = fma(static_cast<double>(v1), static_cast<double>(v1), ss);
+        ss = warp_sum_f64(ss);
+        scale = ss > 0.0 ? 1.0 / sqrt(ss) : 1.0;
+      }
+      const float s0 = static_cast<float>(static_cast<double>(v0) * scale);
+      const float s1 = static_cast<float>(static_cast<double>(v1) * scale);
+      if (own0) row[a.col] = 0.f;
+      if (own1) row[b.col] = 0.f;
+      if (dst_f) {  // dense float32 row: zero fill, then the owners scatter
+        for (uint32_t i = lane; i < P.low_dim; i += 32) dst_f[i] = 0.f;
+        __syncwarp();
+        if (own0) dst_f[a.col] = s0;
+        if (own1) dst_f[b.col] = s1;
       }
       if (dst_b) {
-        const __nv_bfloat162 h = __floats2bfloat162_rn(s0, s1);
-        if (vec_b) {
-          if (static_cast<int64_t>(i) < P.ld_bf16) *reinterpret_cast<__nv_bfloat162*>(dst_b + i) = h;
+        if (own0) brow[a.col] = __bfloat16_as_ushort(__float2bfloat16_rn(s0));
+        if (own1) brow[b.col] = __bfloat16_as_ushort(__float2bfloat16_rn(s1));
+        __syncwarp();
+        if (bf16_vec) {
+          for (int64_t i = 8 * lane; i < P.ld_bf16; i += 256) {
+            *reinterpret_cast<uint4*>(dst_b + i) = *reinterpret_cast<const uint4*>(brow + i);
+            *reinterpret_cast<uint4*>(brow + i) = make_uint4(0u, 0u, 0u, 0u);
+          }
         } else {
-          if (static_cast<int64_t>(i) < P.ld_bf16) dst_b[i] = __bfloat16_as_ushort(h.x);
-          if (static_cast<int64_t>(i) + 1 < P.ld_bf16) dst_b[i + 1] = __bfloat16_as_ushort(h.y);
+          for (int64_t i = lane; i < P.ld_bf16; i += 32) {
+            dst_b[i] = brow[i];
+            brow[i] = 0;
+          }
         }
       }
-      if (di) {
-        const bool nz0 = s0 != 0.f, nz1 = s1 != 0.f;
+      if (di) {  // sparse copy: the owners' non-zero values, in peak order
+        const bool nz0 = own0 && s0 != 0.f, nz1 = own1 && s1 != 0.f;
         const uint32_t b0 = __ballot_sync(0xffffffffu, nz0);
         const uint32_t b1 = __ballot_sync(0xffffffffu, nz1);
-        int pos = count + __popc(b0 & below) + __popc(b1 & below);
-        if (nz0) {
-          if (pos < P.ell_width) { di[pos] = static_cast<uint16_t>(i); dv[pos] = s0; }
-          ++pos;
+        const int pos0 = __popc(b0 & below), pos1 = __popc(b0) + __popc(b1 & below);
+        if (nz0 && pos0 < P.ell_width) { di[pos0] = static_cast<uint16_t>(a.col); dv[pos0] = s0; }
+        if (nz1 && pos1 < P.ell_width) { di[pos1] = static_cast<uint16_t>(b.col); dv[pos1] = s1; }
+        count = __popc(b0) + __popc(b1);
+      }
+    } else {
+      // ---- general path (more than 64 peaks): accumulate pass by pass, then sweep the dense row
+      for (int64_t base = p0; base < p1; base += 32)
+        accumulate_pass(row, load_peak(P, base + lane, p1, vec_len_d), lane, below);
+      double scale = 1.0;
+      if (P.norm) {
+        double ss = 0.0;
+        for (uint32_t i = lane; i < P.low_dim; i += 32) ss = fma(static_cast<double>(row[i]), static_cast<double>(row[i]), ss);
+        ss = warp_sum_f64(ss);
+        scale = ss > 0.0 ? 1.0 / sqrt(ss) : 1.0;
+      }
+      for (uint32_t base = 0; base < P.row_len; base += 32) {
+        const uint32_t i = base + lane;
+        const float sv = static_cast<float>(static_cast<double>(row[i]) * scale);
+        row[i] = 0.f;
+        if (dst_f && i < P.low_dim) dst_f[i] = sv;
+        if (dst_b && static_cast<int64_t>(i) < P.ld_bf16) dst_b[i] = __bfloat16_as_ushort(__float2bfloat16_rn(sv));
+        if (di) {
+          const bool nz = sv != 0.f;
+          const uint32_t bal = __ballot_sync(0xffffffffu, nz);
+          const int pos = count + __popc(bal & below);
+          if (nz && pos < P.ell_width) { di[pos] = static_cast<uint16_t>(i); dv[pos] = sv; }
+          count += __popc(bal);
         }
-        if (nz1 && pos < P.ell_width) { di[pos] = static_cast<uint16_t>(i + 1); dv[pos] = s1; }
-        count += __popc(b0) + __popc(b1);
       }
     }
     if (di) {
@@ -225,7 +288,7 @@ int flc_vectorize(const float* mz, const float* intensity, const int64_t* indptr
   P.ell_idx = ell_idx; P.ell_val = ell_val; P.ell_nnz = ell_nnz; P.ell_width = ell_width;
   P.ell_overflow = ell_overflow;
   FLC_REQUIRE(!out_bf16 || ld_bf16 <= static_cast<int64_t>(P.row_len), "ld_bf16 exceeds low_dim rounded up to 64");
-  const size_t smem = static_cast<size_t>(flc::kVecWarps) * P.row_len * sizeof(float);
+  const size_t smem = static_cast<size_t>(flc::kVecWarps) * P.row_len * 8;  // f32 row + bf16 row + stamps
   FLC_REQUIRE(smem <= 200 * 1024, "low_dim too large");
   if (smem > 48 * 1024)
     FLC_CUDA(cudaFuncSetAttribute(flc::vectorize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -53,7 +53,7 @@ def test_vectorize_synthetic(low_dim):
     x, xb, hidx = v
     ref, ref_idx = helpers.oracle_vectors(sp, low_dim, return_hash_idx=True)
     assert np.array_equal(_cpu(hidx), ref_idx)
-    # sparse (ELL) copy: ascending non-zero columns + values, zero padded
+    # sparse (ELL) copy: distinct non-zero columns + values, zero padded, population in ell_nnz
     ei, ev = _cpu(v.ell_idx).view(np.uint16), _cpu(v.ell_val)
     assert v.ell_width % 8 == 0 and v.ell_width >= np.diff(sp.indptr).max()
     dense = np.zeros_like(_cpu(x))
@@ -62,8 +62,9 @@ def test_vectorize_synthetic(low_dim):
     assert np.array_equal(dense, _cpu(x))
     nnz = (ev != 0).sum(axis=1)
     assert np.array_equal(nnz, (_cpu(x) != 0).sum(axis=1))
+    assert np.array_equal(nnz, _cpu(v.ell_nnz).view(np.uint16))
     for r in range(0, len(sp), 500):
-        assert (np.diff(ei[r, : nnz[r]].astype(np.int64)) > 0).all() and (ev[r, nnz[r]:] == 0).all()
+        assert len(set(ei[r, : nnz[r]].tolist())) == nnz[r] and (ev[r, nnz[r]:] == 0).all()
     np.testing.assert_allclose(_cpu(x), ref, rtol=0, atol=1e-6)
     xb_bits = _cpu(xb.view(torch.int16)).view(np.uint16)
     assert np.array_equal(xb_bits[:, :low_dim], ovec.to_bf16_bits(_cpu(x)))
