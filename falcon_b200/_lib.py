@@ -53,7 +53,7 @@ SIGNATURES = {
     "flc_profile_get": (C.c_int, [C.c_int, C.c_char_p, C.c_int, C.POINTER(_f64), C.POINTER(C.c_int)]),
     "flc_get_dim": (C.c_int, [_f32, _f32, _f32, C.POINTER(_u32), C.POINTER(_f32), C.POINTER(_f32)]),
     "flc_hash_table": (C.c_int, [_u32, _u32, _u32, _p, _p]),
-    "flc_vectorize": (C.c_int, [_p, _p, _p, _p, _i64, _f64, _f64, _u32, _u32, _u32, C.c_int,
+    "flc_vectorize": (C.c_int, [_p, _p, _p, _p, _p, _i64, _f64, _f64, _u32, _u32, _u32, C.c_int,
                                 _p, _i64, _p, _i64, _p, _p, _p, _p, _i32, _p, _p]),
     "flc_bucket_sort_workspace_bytes": (_sz, [_i64]),
     "flc_bucket_sort": (C.c_int, [_p, _p, _i64, _i32, _p, _p, _p, _p, C.POINTER(_i64), _p, _sz, _p]),

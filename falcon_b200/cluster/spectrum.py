@@ -84,7 +84,7 @@ def to_vector_parallel(
     inten = torch.from_numpy(ss.intensity).to(dev)
     indptr = torch.from_numpy(ss.indptr).to(dev)
     out = torch.empty((n, dim), dtype=torch.float32, device=dev)
-    check(lib.flc_vectorize(ptr(mz), ptr(inten), ptr(indptr), None, n, float(min_mz), float(bin_size),
+    check(lib.flc_vectorize(ptr(mz), ptr(inten), ptr(indptr), None, None, n, float(min_mz), float(bin_size),
                             vec_len, dim, seed, 1 if norm else 0, ptr(out), dim, None, 0, None,
                             None, None, None, 0, None, pipeline._stream()))
     return out.cpu().numpy()

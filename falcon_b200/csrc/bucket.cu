@@ -40,7 +40,7 @@ __global__ void gather_kernel(const T* __restrict__ in, const int32_t* __restric
 __global__ void scatter32_kernel(const uint32_t* __restrict__ in, const int32_t* __restrict__ order,
                                  int64_t n, uint32_t* __restrict__ out) {
   const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i < n) out[order[i]] = in[i];
+  if (i < n) out[order[i]] = in ? in[i] : static_cast<uint32_t>(i);  // in == NULL: inverse permutation
 }
 
 __global__ void bucket_head_kernel(const uint32_t* __restrict__ key, int64_t n,

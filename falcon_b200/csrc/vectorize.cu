@@ -36,6 +36,7 @@ struct VecParams {
   const float* intensity;
   const int64_t* indptr;
   const int32_t* order;
+  const int32_t* dest;
   int64_t n;
   double min_mz, bin_size, inv_bin;
   uint32_t vec_len, low_dim, mod_magic, seed;
@@ -131,8 +132,9 @@ vectorize_kernel(const VecParams P) {
   __syncwarp();
   uint32_t serial = 0;
 
-  for (int64_t r = static_cast<int64_t>(blockIdx.x) * kVecWarps + warp; r < P.n; r += warps_total) {
-    const int64_t src = P.order ? static_cast<int64_t>(__ldg(P.order + r)) : r;
+  for (int64_t rr = static_cast<int64_t>(blockIdx.x) * kVecWarps + warp; rr < P.n; rr += warps_total) {
+    const int64_t src = P.order ? static_cast<int64_t>(__ldg(P.order + rr)) : rr;
+    const int64_t r = P.dest ? static_cast<int64_t>(__ldg(P.dest + rr)) : rr;
     const int64_t p0 = __ldg(P.indptr + src);
     const int64_t p1 = __ldg(P.indptr + src + 1);
     float* dst_f = P.out_f32 ? P.out_f32 + r * P.ld_f32 : nullptr;
@@ -259,7 +261,7 @@ int flc_hash_table(uint32_t vec_len, uint32_t low_dim, uint32_t seed, uint32_t* 
 }
 
 int flc_vectorize(const float* mz, const float* intensity, const int64_t* indptr,
-                  const int32_t* order, int64_t n, double min_mz, double bin_size,
+                  const int32_t* order, const int32_t* dest, int64_t n, double min_mz, double bin_size,
                   uint32_t vec_len, uint32_t low_dim, uint32_t seed, int norm, float* out_f32,
                   int64_t ld_f32, uint16_t* out_bf16, int64_t ld_bf16, int32_t* out_hash_idx,
                   uint16_t* ell_idx, float* ell_val, uint16_t* ell_nnz, int32_t ell_width,
@@ -277,7 +279,7 @@ int flc_vectorize(const float* mz, const float* intensity, const int64_t* indptr
   if (n == 0) return FLC_OK;
   FLC_REQUIRE(indptr != nullptr, "null indptr");
   flc::VecParams P;
-  P.mz = mz; P.intensity = intensity; P.indptr = indptr; P.order = order; P.n = n;
+  P.mz = mz; P.intensity = intensity; P.indptr = indptr; P.order = order; P.dest = dest; P.n = n;
   P.min_mz = min_mz; P.bin_size = bin_size; P.inv_bin = 1.0 / bin_size;
   P.vec_len = vec_len; P.low_dim = low_dim; P.seed = seed; P.norm = norm;
   // floor((2^32 - 1) / low_dim): the quotient estimate __umulhi(h, magic) is short by at most one

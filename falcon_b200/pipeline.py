@@ -122,6 +122,7 @@ class Vectors:
     ell_width: int
     n: int
     low_dim: int
+    overflow: Optional[torch.Tensor] = None  # int32 [1]: widest row if it exceeded ell_width (else 0)
 
     def __iter__(self):  # x, xb, hash_idx = hp.vectorize(...)
         return iter((self.x, self.xb, self.hash_idx))
@@ -200,31 +201,48 @@ class HotPath:
         return Buckets(order, key, mz_sorted, rt_sorted, bucket_ptr[: nb.value + 1], int(nb.value))
 
     # ------------------------------------------------------------------ a2-a4
+    def _ell_width(self, indptr: torch.Tensor, max_peaks: Optional[int]) -> int:
+        if max_peaks is None:  # a row has at most as many non-zeros as the spectrum has peaks
+            max_peaks = int((indptr[1:] - indptr[:-1]).max().item()) if indptr.shape[0] > 1 else 0
+        return max(8, (min(max_peaks, self.s.low_dim) + 7) // 8 * 8)
+
+    def alloc_vectors(self, n: int, width: int, want_bf16=True, want_f32=False, want_ell=True) -> Vectors:
+        d = self.s.low_dim
+        x = torch.empty((n, d), dtype=torch.float32, device=self.device) if want_f32 else None
+        xb = torch.empty((n, self.ld_bf16), dtype=torch.bfloat16, device=self.device) if want_bf16 else None
+        ell_idx = ell_val = ell_nnz = None
+        if want_ell and n > 0:
+            ell_idx = torch.empty((n, width), dtype=torch.int16, device=self.device)
+            ell_val = torch.empty((n, width), dtype=torch.float32, device=self.device)
+            ell_nnz = self._empty(n, torch.int16)
+        return Vectors(x, xb, None, ell_idx, ell_val, ell_nnz, width if ell_idx is not None else 0, n, d)
+
+    def vectorize_into(self, v: Vectors, mz: torch.Tensor, intensity: torch.Tensor, indptr: torch.Tensor,
+                       n: int, order: Optional[torch.Tensor] = None, dest: Optional[torch.Tensor] = None,
+                       overflow: Optional[torch.Tensor] = None, hash_idx: Optional[torch.Tensor] = None,
+                       norm: bool = True) -> None:
+        """Vectorise ``n`` spectra (``indptr`` has n + 1 absolute peak offsets) into the
+        rows of ``v``: row r <- spectrum order[r], or spectrum r -> row dest[r]."""
+        with self.timer("vectorize"):
+            check(lib.flc_vectorize(ptr(mz), ptr(intensity), ptr(indptr), ptr(order), ptr(dest), n,
+                                    self.min_mz, self.s.fragment_tol, self.vec_len, v.low_dim, self.s.hash_seed,
+                                    1 if norm else 0, ptr(v.x), v.low_dim, ptr(v.xb), self.ld_bf16, ptr(hash_idx),
+                                    ptr(v.ell_idx), ptr(v.ell_val), ptr(v.ell_nnz), v.ell_width, ptr(overflow),
+                                    _stream()))
+
     def vectorize(self, mz: torch.Tensor, intensity: torch.Tensor, indptr: torch.Tensor,
                   order: Optional[torch.Tensor] = None, want_bf16: bool = True,
                   want_hash_idx: bool = False, norm: bool = True, want_f32: bool = True,
                   want_ell: bool = True, max_peaks: Optional[int] = None) -> Vectors:
         n = indptr.shape[0] - 1
-        d = self.s.low_dim
-        x = torch.empty((n, d), dtype=torch.float32, device=self.device) if want_f32 else None
-        xb = torch.empty((n, self.ld_bf16), dtype=torch.bfloat16, device=self.device) if want_bf16 else None
-        hidx = self._empty(mz.shape[0], torch.int32) if want_hash_idx else None
-        ell_idx = ell_val = ell_nnz = overflow = None
-        width = 0
-        if want_ell and n > 0:
-            if max_peaks is None:  # a row has at most as many non-zeros as the spectrum has peaks
-                max_peaks = int((indptr[1:] - indptr[:-1]).max().item())
-            width = max(8, (min(max_peaks, d) + 7) // 8 * 8)
-            ell_idx = torch.empty((n, width), dtype=torch.int16, device=self.device)
-            ell_val = torch.empty((n, width), dtype=torch.float32, device=self.device)
-            ell_nnz = self._empty(n, torch.int16)
-            overflow = torch.zeros(1, dtype=torch.int32, device=self.device)
-        with self.timer("vectorize"):
-            check(lib.flc_vectorize(ptr(mz), ptr(intensity), ptr(indptr), ptr(order), n,
-                                    self.min_mz, self.s.fragment_tol, self.vec_len, d, self.s.hash_seed,
-                                    1 if norm else 0, ptr(x), d, ptr(xb), self.ld_bf16, ptr(hidx),
-                                    ptr(ell_idx), ptr(ell_val), ptr(ell_nnz), width, ptr(overflow), _stream()))
-        return Vectors(x, xb, hidx, ell_idx, ell_val, ell_nnz, width, n, d)
+        width = self._ell_width(indptr, max_peaks) if (want_ell and n > 0) else 0
+        v = self.alloc_vectors(n, width, want_bf16, want_f32, want_ell)
+        v.hash_idx = self._empty(mz.shape[0], torch.int32) if want_hash_idx else None
+        overflow = torch.zeros(1, dtype=torch.int32, device=self.device) if v.ell_idx is not None else None
+        self.vectorize_into(v, mz, intensity, indptr, n, order=order, overflow=overflow, hash_idx=v.hash_idx,
+                            norm=norm)
+        v.overflow = overflow
+        return v
 
     def hash_table(self) -> torch.Tensor:
         out = self._empty(self.vec_len, torch.int32)
@@ -351,18 +369,12 @@ class HotPath:
         return out, int(nc.value)
 
     # ------------------------------------------------------------------ whole path
-    def run(self, mz, intensity, indptr, precursor_mz, charge, rt=None, keep=False):
-        """All stages on device tensors; returns labels in INPUT order (int32,
-        -1 = noise) and the number of clusters.  ``keep`` also returns the
-        intermediates (bucket order) for parity checks."""
-        n = precursor_mz.shape[0]
-        if n == 0:
-            empty = self._empty(0, torch.int32)
-            return (empty, 0, {}) if keep else (empty, 0)
-        buckets = self.bucket_sort(precursor_mz, charge, rt if self.s.rt_tol is not None else None)
-        v = self.vectorize(mz, intensity, indptr, buckets.order, want_f32=keep or self.s.dense_f32)
+    def _cluster_vectors(self, v: Vectors, buckets: Buckets, n: int, keep: bool):
         ivf = None if self.s.exhaustive else self.build_ivf(v, buckets)
         graph = self.knn_graph(v, buckets, ivf)
+        if v.overflow is not None and int(v.overflow.item()) > 0:  # the stream was just synchronised
+            raise RuntimeError(f"a spectrum hashed to {int(v.overflow.item())} distinct columns but the sparse rows "
+                               f"hold {v.ell_width}: pass the true max_peaks")
         db_labels, _ = self.dbscan(graph, n)
         sorted_labels, n_clusters = self.split(db_labels, buckets.mz, values_sorted=True)
         labels = self._empty(n, torch.int32)
@@ -373,22 +385,95 @@ class HotPath:
                                             db_labels=db_labels, sorted_labels=sorted_labels)
         return labels, n_clusters
 
+    def run(self, mz, intensity, indptr, precursor_mz, charge, rt=None, keep=False, max_peaks=None):
+        """All stages on device tensors; returns labels in INPUT order (int32,
+        -1 = noise) and the number of clusters.  ``keep`` also returns the
+        intermediates (bucket order) for parity checks."""
+        n = precursor_mz.shape[0]
+        if n == 0:
+            empty = self._empty(0, torch.int32)
+            return (empty, 0, {}) if keep else (empty, 0)
+        buckets = self.bucket_sort(precursor_mz, charge, rt if self.s.rt_tol is not None else None)
+        v = self.vectorize(mz, intensity, indptr, buckets.order, want_f32=keep or self.s.dense_f32,
+                           max_peaks=max_peaks)
+        return self._cluster_vectors(v, buckets, n, keep)
+
+    def run_host(self, mz, intensity, indptr, precursor_mz, charge, rt=None, labels_out=None,
+                 max_peaks: Optional[int] = None, n_chunks: int = 8):
+        """The same path from HOST tensors (pinned memory for real overlap): the
+        precursor columns go first so that bucketing runs while the peak arrays
+        are still crossing PCIe; peaks arrive in chunks on a copy stream and every
+        chunk is vectorised -- scattered straight into bucket order -- as soon as
+        it lands.  Returns (labels, n_clusters); labels are copied into
+        ``labels_out`` (host) when given."""
+        n = int(precursor_mz.shape[0])
+        if n == 0:
+            return self._empty(0, torch.int32), 0
+        dev = self.device
+        compute = torch.cuda.current_stream()
+        if getattr(self, "_copy_stream", None) is None:
+            self._copy_stream = torch.cuda.Stream(device=dev)
+        copy = self._copy_stream
+        copy.wait_stream(compute)
+        use_rt = rt is not None and self.s.rt_tol is not None
+        n_peaks = int(mz.shape[0])
+        n_chunks = max(1, min(n_chunks, n))
+        bounds = [n * c // n_chunks for c in range(n_chunks + 1)]
+        peak_bounds = [int(indptr[b]) for b in bounds]
+        if max_peaks is None:
+            max_peaks = int((indptr[1:] - indptr[:-1]).max())
+        with torch.cuda.stream(copy):
+            pmz_d = precursor_mz.to(dev, non_blocking=True)
+            z_d = charge.to(dev, non_blocking=True)
+            rt_d = rt.to(dev, non_blocking=True) if use_rt else None
+            ev_meta = torch.cuda.Event()
+            ev_meta.record(copy)
+            indptr_d = indptr.to(dev, non_blocking=True)
+            mz_d = torch.empty(n_peaks, dtype=torch.float32, device=dev)
+            in_d = torch.empty(n_peaks, dtype=torch.float32, device=dev)
+            events = []
+            for c in range(n_chunks):
+                a, b = peak_bounds[c], peak_bounds[c + 1]
+                mz_d[a:b].copy_(mz[a:b], non_blocking=True)
+                in_d[a:b].copy_(intensity[a:b], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(copy)
+                events.append(ev)
+        for t in (pmz_d, z_d, rt_d, indptr_d, mz_d, in_d):
+            if t is not None:
+                t.record_stream(compute)
+        compute.wait_event(ev_meta)
+        buckets = self.bucket_sort(pmz_d, z_d, rt_d)
+        rank = self._empty(n, torch.int32)  # input position -> bucket-order row
+        check(lib.flc_scatter32(None, ptr(buckets.order), n, ptr(rank), _stream()))
+        v = self.alloc_vectors(n, self._ell_width(indptr, max_peaks), want_f32=self.s.dense_f32)
+        overflow = torch.zeros(1, dtype=torch.int32, device=dev)
+        for c in range(n_chunks):
+            compute.wait_event(events[c])
+            i0, i1 = bounds[c], bounds[c + 1]
+            self.vectorize_into(v, mz_d, in_d, indptr_d[i0:], i1 - i0, dest=rank[i0:], overflow=overflow)
+        v.overflow = overflow
+        labels, n_clusters = self._cluster_vectors(v, buckets, n, False)
+        if labels_out is not None:
+            labels_out.copy_(labels, non_blocking=True)
+        return labels, n_clusters
+
 
 def cluster_host(spectra, settings: Settings | None = None, device=None, profile=False):
-    """End-to-end on HOST arrays (a ``synth.SpectrumSet``-like object): H2D copy,
-    all stages, D2H of the labels.  This is the call ``bench.py`` times as e2e."""
+    """End-to-end on HOST arrays (a ``synth.SpectrumSet``-like object): chunked H2D
+    copy overlapped with vectorisation, all stages, D2H of the labels.  Returns
+    (labels int32 numpy in input order, n_clusters, per-stage ms)."""
     hp = HotPath(settings, device, profile)
-    dev = hp.device
 
-    def up(a, dtype):
+    def pin(a, dtype):
         t = torch.from_numpy(np.ascontiguousarray(a, dtype=dtype))
-        return t.to(dev, non_blocking=True)
+        return t.pin_memory() if t.numel() else t
 
-    mz = up(spectra.mz, np.float32)
-    inten = up(spectra.intensity, np.float32)
-    indptr = up(spectra.indptr, np.int64)
-    pmz = up(spectra.precursor_mz, np.float64)
-    z = up(spectra.precursor_charge, np.int32)
-    rt = up(spectra.retention_time, np.float32) if hp.s.rt_tol is not None else None
-    labels, n_clusters = hp.run(mz, inten, indptr, pmz, z, rt)
-    return labels.cpu().numpy(), n_clusters, hp.timer.result()
+    n = len(spectra.precursor_mz)
+    out = torch.empty(n, dtype=torch.int32).pin_memory() if n else torch.empty(0, dtype=torch.int32)
+    rt = pin(spectra.retention_time, np.float32) if hp.s.rt_tol is not None else None
+    _, n_clusters = hp.run_host(pin(spectra.mz, np.float32), pin(spectra.intensity, np.float32),
+                                pin(spectra.indptr, np.int64), pin(spectra.precursor_mz, np.float64),
+                                pin(spectra.precursor_charge, np.int32), rt, labels_out=out)
+    torch.cuda.current_stream().synchronize()
+    return out.numpy().copy(), n_clusters, hp.timer.result()

@@ -74,7 +74,9 @@ FLC_API int flc_hash_table(uint32_t vec_len, uint32_t low_dim, uint32_t seed,
 /* ------------------------------------------------------------------ a2 + a4: vectorise
  * Binning (falcon/cluster/spectrum.py:250-296, expression :291 in float64),
  * feature hashing + L2 norm (A.1; snapshot sibling spectrum.py:202-247).
- * Row r of the outputs is spectrum order[r] (order == NULL: identity).
+ * Row r of the outputs is spectrum order[r] (order == NULL: identity).  With
+ * dest != NULL the spectrum handled as r is written to row dest[r] instead (a
+ * scatter: lets a chunk of the input, in input order, land in bucket order).
  *   out_f32   [n, ld_f32]  float32 (nullable)
  *   out_bf16  [n, ld_bf16] bfloat16 bits, columns >= low_dim zeroed (nullable)
  *   out_hash_idx [n_peaks] hashed column of every peak in input peak order,
@@ -85,7 +87,7 @@ FLC_API int flc_hash_table(uint32_t vec_len, uint32_t low_dim, uint32_t seed,
  *                (nullable); *ell_overflow (device int32, caller zeroes it) receives
  *                the largest row population if one exceeds ell_width */
 FLC_API int flc_vectorize(const float* mz, const float* intensity, const int64_t* indptr,
-                  const int32_t* order, int64_t n,
+                  const int32_t* order, const int32_t* dest, int64_t n,
                   double min_mz, double bin_size, uint32_t vec_len,
                   uint32_t low_dim, uint32_t seed, int norm,
                   float* out_f32, int64_t ld_f32,
@@ -111,7 +113,8 @@ FLC_API int flc_bucket_sort(const double* precursor_mz, const int32_t* charge, i
 /* out[i] = in[order[i]] for 4- or 8-byte elements. */
 FLC_API int flc_gather(const void* in, const int32_t* order, int64_t n, int elem_bytes,
                void* out, flc_stream_t stream);
-/* out[order[i]] = in[i] for 4-byte elements. */
+/* out[order[i]] = in[i] for 4-byte elements; in == NULL scatters i itself
+ * (out = inverse permutation of order). */
 FLC_API int flc_scatter32(const void* in, const int32_t* order, int64_t n, void* out,
                   flc_stream_t stream);
 
