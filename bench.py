@@ -276,6 +276,22 @@ def run_ours(args):
         torch.cuda.current_stream().synchronize()
         return out, nc
 
+    def run_e2e_pipelined(steps):
+        """K batches through the host API, software-pipelined two deep: batch i + 1 is staged
+        (its H2D copies enqueued on the copy stream) before batch i's kernels run.  Every
+        batch's H2D, kernels and D2H are inside the caller's timed region."""
+        out = None
+        staged = hp.stage_host(host["mz"], host["intensity"], host["indptr"], host["precursor_mz"],
+                               host["charge"], max_peaks=max_peaks)
+        for i in range(steps):
+            nxt = hp.stage_host(host["mz"], host["intensity"], host["indptr"], host["precursor_mz"],
+                                host["charge"], max_peaks=max_peaks) if i + 1 < steps else None
+            labels, nc = hp.run_staged(staged, labels_out=labels_host)
+            out = (gather(labels, nc), nc)
+            staged = nxt
+        torch.cuda.current_stream().synchronize()
+        return out
+
     def barrier():
         if world > 1:
             dist.barrier()
@@ -318,6 +334,9 @@ def run_ours(args):
         small = kernels.get("kmeans_fused", (0.0, big[1]))
         kernels["kmeans_fused"] = (small[0] + big[0], small[1])
     ms_e2e, _, _, _ = timed(step_e2e, args.steps, max(1, args.warmup - 1))
+    # the same K batches, software-pipelined two deep (one call = K steps)
+    ms_pipe, _, _, _ = timed(lambda: run_e2e_pipelined(args.steps), 1, 1)
+    ms_pipe /= args.steps
     total = args.n * world
 
     # one instrumented pass for the roofline statistics (outside the timed regions)
@@ -381,8 +400,11 @@ def run_ours(args):
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16 scan / f32 vectors / f64 re-score", "data": "synthetic",
             "config": workload_config(args),
-            "e2e": {"value": total / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
-                    "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": args.n * 4},
+            "e2e": {"value": total / (ms_pipe * 1e-3), "unit": UNIT, "ms_per_step": ms_pipe,
+                    "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": args.n * 4,
+                    "mode": "host API, batches software-pipelined two deep (stage_host of batch i+1 before "
+                            "run_staged of batch i); all K batches' H2D + kernels + D2H inside the timed region",
+                    "unpipelined": {"value": total / (ms_e2e * 1e-3), "ms_per_step": ms_e2e}},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
             "n_clusters": int(n_clusters),
             "stage_ms": stage_ms,

@@ -398,39 +398,55 @@ class HotPath:
                            max_peaks=max_peaks)
         return self._cluster_vectors(v, buckets, n, keep)
 
-    def run_host(self, mz, intensity, indptr, precursor_mz, charge, rt=None, labels_out=None,
-                 max_peaks: Optional[int] = None, n_chunks: int = 8):
-        """The same path from HOST tensors (pinned memory for real overlap): the
-        precursor columns go first so that bucketing runs while the peak arrays
-        are still crossing PCIe; peaks arrive in chunks on a copy stream and every
-        chunk is vectorised -- scattered straight into bucket order -- as soon as
-        it lands.  Returns (labels, n_clusters); labels are copied into
-        ``labels_out`` (host) when given."""
+    def stage_host(self, mz, intensity, indptr, precursor_mz, charge, rt=None,
+                   max_peaks: Optional[int] = None, n_chunks: int = 8) -> Optional[dict]:
+        """Enqueue the H2D copies of one batch of HOST tensors (pinned memory for real
+        overlap) on the copy stream and return at once.  The precursor columns go
+        first so that bucketing can start while the peak arrays are still crossing
+        PCIe; the peaks follow in chunks, one event each."""
         n = int(precursor_mz.shape[0])
         if n == 0:
-            return self._empty(0, torch.int32), 0
+            return None
         dev = self.device
-        compute = torch.cuda.current_stream()
         if getattr(self, "_copy_stream", None) is None:
             self._copy_stream = torch.cuda.Stream(device=dev)
+            self._slots = [dict(cap_n=0, cap_p=0, free=None) for _ in range(2)]
+            self._staged = 0
         copy = self._copy_stream
-        copy.wait_stream(compute)
+        slot = self._slots[self._staged % 2]  # two persistent device-side input slots, used alternately
+        if slot.get("pending"):
+            raise RuntimeError("stage_host: both input slots hold batches that have not been run yet")
+        self._staged += 1
+        slot["pending"] = True
         use_rt = rt is not None and self.s.rt_tol is not None
         n_peaks = int(mz.shape[0])
+        if slot["cap_n"] < n or slot["cap_p"] < n_peaks or (use_rt and slot.get("rt") is None):
+            cap_n, cap_p = max(n, slot["cap_n"]), max(n_peaks, slot["cap_p"])
+            torch.cuda.synchronize(dev)  # growing a slot: nothing may still be reading or filling the old buffers
+            slot.update(cap_n=cap_n, cap_p=cap_p,
+                        pmz=self._empty(cap_n, torch.float64), z=self._empty(cap_n, torch.int32),
+                        rt=self._empty(cap_n, torch.float32) if use_rt else None,
+                        indptr=self._empty(cap_n + 1, torch.int64),
+                        mz=self._empty(cap_p, torch.float32), intensity=self._empty(cap_p, torch.float32))
+            copy.wait_stream(torch.cuda.current_stream())
         n_chunks = max(1, min(n_chunks, n))
         bounds = [n * c // n_chunks for c in range(n_chunks + 1)]
         peak_bounds = [int(indptr[b]) for b in bounds]
         if max_peaks is None:
             max_peaks = int((indptr[1:] - indptr[:-1]).max())
         with torch.cuda.stream(copy):
-            pmz_d = precursor_mz.to(dev, non_blocking=True)
-            z_d = charge.to(dev, non_blocking=True)
-            rt_d = rt.to(dev, non_blocking=True) if use_rt else None
+            if slot["free"] is not None:
+                copy.wait_event(slot["free"])  # the batch that used this slot last has read its inputs
+            pmz_d, z_d, indptr_d = slot["pmz"][:n], slot["z"][:n], slot["indptr"][: n + 1]
+            mz_d, in_d = slot["mz"][:n_peaks], slot["intensity"][:n_peaks]
+            rt_d = slot["rt"][:n] if use_rt else None
+            pmz_d.copy_(precursor_mz, non_blocking=True)
+            z_d.copy_(charge, non_blocking=True)
+            if use_rt:
+                rt_d.copy_(rt, non_blocking=True)
             ev_meta = torch.cuda.Event()
             ev_meta.record(copy)
-            indptr_d = indptr.to(dev, non_blocking=True)
-            mz_d = torch.empty(n_peaks, dtype=torch.float32, device=dev)
-            in_d = torch.empty(n_peaks, dtype=torch.float32, device=dev)
+            indptr_d.copy_(indptr, non_blocking=True)
             events = []
             for c in range(n_chunks):
                 a, b = peak_bounds[c], peak_bounds[c + 1]
@@ -439,24 +455,46 @@ class HotPath:
                 ev = torch.cuda.Event()
                 ev.record(copy)
                 events.append(ev)
-        for t in (pmz_d, z_d, rt_d, indptr_d, mz_d, in_d):
-            if t is not None:
-                t.record_stream(compute)
-        compute.wait_event(ev_meta)
-        buckets = self.bucket_sort(pmz_d, z_d, rt_d)
+        return dict(n=n, pmz=pmz_d, z=z_d, rt=rt_d, indptr=indptr_d, mz=mz_d, intensity=in_d, ev_meta=ev_meta,
+                    events=events, bounds=bounds, width=self._ell_width(indptr, max_peaks), slot=slot)
+
+    def run_staged(self, st: Optional[dict], labels_out=None):
+        """The compute stages of a batch staged with ``stage_host``: every chunk is
+        vectorised -- scattered straight into bucket order -- as soon as it has
+        landed.  Returns (labels, n_clusters); labels are also copied to
+        ``labels_out`` (host) when given."""
+        if st is None:
+            return self._empty(0, torch.int32), 0
+        n = st["n"]
+        compute = torch.cuda.current_stream()
+        compute.wait_event(st["ev_meta"])
+        buckets = self.bucket_sort(st["pmz"], st["z"], st["rt"])
         rank = self._empty(n, torch.int32)  # input position -> bucket-order row
         check(lib.flc_scatter32(None, ptr(buckets.order), n, ptr(rank), _stream()))
-        v = self.alloc_vectors(n, self._ell_width(indptr, max_peaks), want_f32=self.s.dense_f32)
-        overflow = torch.zeros(1, dtype=torch.int32, device=dev)
-        for c in range(n_chunks):
-            compute.wait_event(events[c])
+        v = self.alloc_vectors(n, st["width"], want_f32=self.s.dense_f32)
+        overflow = torch.zeros(1, dtype=torch.int32, device=self.device)
+        bounds = st["bounds"]
+        for c, ev in enumerate(st["events"]):
+            compute.wait_event(ev)
             i0, i1 = bounds[c], bounds[c + 1]
-            self.vectorize_into(v, mz_d, in_d, indptr_d[i0:], i1 - i0, dest=rank[i0:], overflow=overflow)
+            self.vectorize_into(v, st["mz"], st["intensity"], st["indptr"][i0:], i1 - i0, dest=rank[i0:],
+                                overflow=overflow)
         v.overflow = overflow
+        st["slot"]["free"] = torch.cuda.Event()  # the staged inputs are not read past this point
+        st["slot"]["free"].record(compute)
+        st["slot"]["pending"] = False
         labels, n_clusters = self._cluster_vectors(v, buckets, n, False)
         if labels_out is not None:
             labels_out.copy_(labels, non_blocking=True)
         return labels, n_clusters
+
+    def run_host(self, mz, intensity, indptr, precursor_mz, charge, rt=None, labels_out=None,
+                 max_peaks: Optional[int] = None, n_chunks: int = 8):
+        """The whole path from HOST tensors: ``stage_host`` + ``run_staged``.  Batches
+        can be software-pipelined by staging batch i + 1 before running batch i
+        (the copies then hide behind the previous batch's kernels)."""
+        return self.run_staged(self.stage_host(mz, intensity, indptr, precursor_mz, charge, rt, max_peaks, n_chunks),
+                               labels_out)
 
 
 def cluster_host(spectra, settings: Settings | None = None, device=None, profile=False):
