@@ -66,6 +66,8 @@ SIGNATURES = {
                                    _p, _p, _i32, _p, _p, _p, _sz, _p]),
     "flc_ivf_assign": (C.c_int, [_p, _i64, _i64, _u32, _p, _i64, _p, _p, _p, _p, _i32,
                                  _p, _p, _i32, _p, _p, _p]),
+    "flc_medoids_workspace_bytes": (_sz, [_i64]),
+    "flc_medoids": (C.c_int, [_p, _p, _p, _i64, _p, _i64, _p, _p, _sz, _p]),
     "flc_scan_workspace_bytes": (_sz, [_i64, _i64]),
     "flc_scan_pairs": (C.c_int, [_p, _i64, _i64, _u32, _p, _i64, _p, _p, _i32, _p, _f32, C.c_int,
                                  _p, _u64, _p, _p, _sz, _p]),

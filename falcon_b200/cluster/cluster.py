@@ -170,3 +170,35 @@ def generate_clusters(
     logger.info("%d spectra grouped in %d clusters, %d spectra remain as singletons",
                 int((out != -1).sum()), n_clusters, int((out == -1).sum()))
     return out
+
+
+def get_cluster_representatives(
+    clusters: np.ndarray,
+    pairwise_indptr: np.ndarray,
+    pairwise_indices: np.ndarray,
+    pairwise_data: np.ndarray,
+) -> Optional[np.ndarray]:
+    """Indexes of the cluster representative spectra (medoids) -- published falcon
+    ``get_cluster_representatives`` (the snapshot's dense descendant is
+    /root/reference/falcon/cluster/cluster.py:512-553).
+
+    ``clusters``: label of every row of the pairwise distance matrix (-1 = noise).
+    Returns, for every distinct non-noise label in ascending order, the row whose
+    mean distance to the cluster members present in its sparse row is smallest;
+    ``None`` if there is no cluster.
+    """
+    clusters = np.asarray(clusters)
+    n = clusters.shape[0]
+    if len(pairwise_indptr) != n + 1:
+        raise ValueError("clusters does not match the distance matrix")
+    uniq, dense = np.unique(clusters[clusters >= 0], return_inverse=True)
+    if uniq.size == 0:
+        return None
+    lab = np.full(n, -1, np.int32)
+    lab[clusters >= 0] = dense.astype(np.int32)
+    hp = pipeline.HotPath(pipeline.Settings())
+    dev = hp.device
+    up = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a, dtype=dt)).to(dev)  # noqa: E731
+    g = pipeline.KnnGraph(up(pairwise_data, np.float32), up(pairwise_indices, np.int32),
+                          up(pairwise_indptr, np.int64), int(len(pairwise_data)), 0)
+    return hp.medoids(g, up(lab, np.int32), int(uniq.size)).cpu().numpy()

@@ -1,8 +1,8 @@
 """Multi-GPU plumbing: precursor buckets are independent units, so
 each rank clusters its own buckets with no data-path communication; the only
-collective is the final gather of labels (and cluster counts for the label
-offsets), the same running-offset rule the reference applies per charge
-(/root/reference/falcon/falcon.py:189-193).
+collective is the final gather of labels and cluster representatives (with the
+cluster counts for the label offsets), the same running-offset rule the
+reference applies per charge (/root/reference/falcon/falcon.py:189-193).
 
 Works with any ``torch.distributed`` backend: NCCL over NVLink on the B200
 box, gloo in the CPU tests.
@@ -58,3 +58,24 @@ def gather_labels(labels: torch.Tensor, n_clusters: int, group=None):
     dist.all_gather_into_tensor(out, padded, group=group)
     parts = [out[r * max_len: r * max_len + lens[r]] for r in range(world)]
     return torch.cat(parts) if parts else out, lens
+
+
+def gather_representatives(representatives: torch.Tensor, n_spectra: int, group=None) -> torch.Tensor:
+    """All ranks -> the representatives (medoid spectrum indices) of every cluster,
+    in the global label order of ``gather_labels``: rank r's indices are offset by
+    the number of spectra of ranks < r, i.e. they index the concatenated labels."""
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    dev = representatives.device
+    meta = torch.tensor([representatives.shape[0], n_spectra], dtype=torch.int64, device=dev)
+    metas = [torch.empty_like(meta) for _ in range(world)]
+    dist.all_gather(metas, meta, group=group)
+    lens = [int(m[0]) for m in metas]
+    offset = sum(int(m[1]) for m in metas[:rank])
+    max_len = max(lens) if lens else 0
+    padded = torch.full((max_len,), -1, dtype=torch.int64, device=dev)
+    padded[: representatives.shape[0]] = representatives.to(torch.int64) + offset
+    out = torch.empty(world * max_len, dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(out, padded, group=group)
+    parts = [out[r * max_len: r * max_len + lens[r]] for r in range(world)]
+    return torch.cat(parts) if parts else out

@@ -50,6 +50,7 @@ class Settings:
     kmeans_iters: int = 10
     scan_impl: int = 0  # 0 = tcgen05, 1 = SIMT verification kernel
     eps_cut: bool = True  # keep only dist <= eps in the CSR (what generate_clusters reads)
+    representatives: bool = False  # also pick every cluster's medoid (HotPath.representatives, input indices)
     dense_f32: bool = False  # also materialise the dense float32 rows (no stage needs them: all read the sparse copy)
 
 
@@ -368,6 +369,16 @@ class HotPath:
                                          C.byref(nc), ptr(ws), ws.numel(), _stream()))
         return out, int(nc.value)
 
+    # ------------------------------------------------------------------ a16
+    def medoids(self, g: KnnGraph, labels: torch.Tensor, n_clusters: int) -> torch.Tensor:
+        """Row index (in the matrix' row order) of the representative of every cluster."""
+        out = self._empty(n_clusters, torch.int32)
+        with self.timer("medoids"):
+            ws = self._ws(lib.flc_medoids_workspace_bytes(n_clusters))
+            check(lib.flc_medoids(ptr(g.dist), ptr(g.indices), ptr(g.indptr), labels.shape[0], ptr(labels),
+                                  n_clusters, ptr(out), ptr(ws), ws.numel(), _stream()))
+        return out
+
     # ------------------------------------------------------------------ whole path
     def _cluster_vectors(self, v: Vectors, buckets: Buckets, n: int, keep: bool):
         ivf = None if self.s.exhaustive else self.build_ivf(v, buckets)
@@ -380,9 +391,15 @@ class HotPath:
         labels = self._empty(n, torch.int32)
         with self.timer("scatter"):
             check(lib.flc_scatter32(ptr(sorted_labels), ptr(buckets.order), n, ptr(labels), _stream()))
+        self.representatives = None
+        if self.s.representatives:  # input index of every cluster's medoid
+            rows = self.medoids(graph, sorted_labels, n_clusters)
+            self.representatives = self._empty(n_clusters, torch.int32)
+            check(lib.flc_gather(ptr(buckets.order), ptr(rows), n_clusters, 4, ptr(self.representatives), _stream()))
         if keep:
             return labels, n_clusters, dict(buckets=buckets, x=v.x, xb=v.xb, vectors=v, ivf=ivf, graph=graph,
-                                            db_labels=db_labels, sorted_labels=sorted_labels)
+                                            db_labels=db_labels, sorted_labels=sorted_labels,
+                                            representatives=self.representatives)
         return labels, n_clusters
 
     def run(self, mz, intensity, indptr, precursor_mz, charge, rt=None, keep=False, max_peaks=None):

@@ -223,6 +223,18 @@ FLC_API int flc_split_clusters(const int32_t* labels_in, const double* precursor
                        int values_sorted, int32_t* labels_out, int64_t* n_clusters /*host*/,
                        void* workspace, size_t workspace_bytes, flc_stream_t stream);
 
+/* ------------------------------------------------------------------ a16: representatives
+ * Published falcon get_cluster_representatives (dense descendant at
+ * falcon/cluster/cluster.py:512-553): per cluster the member with the smallest
+ * mean distance to the members present in its sparse row (rows holding no more
+ * than a quarter of the cluster are not eligible; <= 2 members, ties and "no
+ * eligible row" give the first member).  labels[i] in [0, n_clusters) or -1 (noise),
+ * in the row order of the matrix; medoids[l] = row index (-1 for an unused label). */
+FLC_API size_t flc_medoids_workspace_bytes(int64_t n_clusters);
+FLC_API int flc_medoids(const float* dist, const int32_t* indices, const int64_t* indptr, int64_t n,
+                const int32_t* labels, int64_t n_clusters, int32_t* medoids,
+                void* workspace, size_t workspace_bytes, flc_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -22,7 +22,9 @@ def _worker(rank, world, port, q):
     labels = [torch.tensor([0, -1, 1, 1, 0], dtype=torch.int32), torch.tensor([-1, 0, 0], dtype=torch.int32)][rank]
     ncl = [2, 1][rank]
     out, lens = fd.gather_labels(labels, ncl)
-    q.put((rank, out.tolist(), lens))
+    reps = [torch.tensor([0, 2], dtype=torch.int32), torch.tensor([1], dtype=torch.int32)][rank]
+    rep_all = fd.gather_representatives(reps, labels.shape[0])
+    q.put((rank, out.tolist(), lens, rep_all.tolist()))
     dist.destroy_process_group()
 
 
@@ -37,8 +39,10 @@ def test_gather_labels_gloo_world2():
     for p in procs:
         p.join(60)
         assert p.exitcode == 0
-    for _, out, lens in res:
+    for _, out, lens, reps in res:
         assert out == [0, -1, 1, 1, 0, -1, 2, 2] and lens == [5, 3]
+        # cluster c's representative carries label c in the gathered labels
+        assert reps == [0, 2, 6] and [out[i] for i in reps] == [0, 1, 2]
 
 
 def test_shard_buckets_balances_cost():

@@ -336,6 +336,44 @@ def test_dbscan_random_directed_graphs(hp, n, max_deg, seed):
     assert nc == ref.max() + 1
 
 
+def test_medoids_match_oracle(hp):
+    """a16: representatives from the sparse matrix; random graphs with random
+    labels exercise the quarter-of-the-cluster rule, ties and tiny clusters."""
+    from oracle import medoids as omed
+
+    for seed, n, max_deg, n_lab in [(0, 1, 1, 1), (1, 400, 6, 40), (2, 5000, 8, 300), (3, 3000, 12, 5)]:
+        rng = np.random.default_rng(seed)
+        data, indices, indptr = _random_graph(rng, n, max_deg)
+        labels = rng.integers(-1, n_lab, n).astype(np.int32)
+        nc = int(labels.max()) + 1
+        dev = hp.device
+        g = pipeline.KnnGraph(torch.from_numpy(data).to(dev), torch.from_numpy(indices).to(dev),
+                              torch.from_numpy(indptr).to(dev), data.shape[0], 0)
+        got = _cpu(hp.medoids(g, torch.from_numpy(labels).to(dev), nc)) if nc > 0 else np.zeros(0, np.int32)
+        assert np.array_equal(got, omed.cluster_medoids(data, indices, indptr, labels))
+
+
+def test_representatives_end_to_end():
+    from falcon_b200.cluster import cluster as fcluster
+    from oracle import medoids as omed
+
+    h = pipeline.HotPath(pipeline.Settings(exhaustive=True, representatives=True))
+    sp = helpers.dataset(6000, 41, 1000.0, 1010.0)
+    d = helpers.to_device(sp, h.device)
+    labels, nc, keep = h.run(d["mz"], d["intensity"], d["indptr"], d["precursor_mz"], d["charge"], keep=True)
+    reps = _cpu(keep["representatives"])
+    assert reps.shape == (nc,) and np.array_equal(_cpu(labels)[reps], np.arange(nc))
+    g = keep["graph"]
+    ref_rows = omed.cluster_medoids(_cpu(g.dist), _cpu(g.indices), _cpu(g.indptr), _cpu(keep["sorted_labels"]))
+    assert np.array_equal(reps, _cpu(keep["buckets"].order)[ref_rows])
+    # the facade with the published signature gives the same rows
+    rows = fcluster.get_cluster_representatives(_cpu(keep["sorted_labels"]), _cpu(g.indptr), _cpu(g.indices),
+                                                _cpu(g.dist))
+    assert np.array_equal(rows, ref_rows)
+    assert fcluster.get_cluster_representatives(np.full(3, -1), np.zeros(4, np.int64), np.zeros(0, np.int32),
+                                                np.zeros(0, np.float32)) is None
+
+
 def test_dbscan_long_chain(hp):
     """A 30k-long one-way chain: pointer jumping must converge and give one cluster."""
     n = 30000

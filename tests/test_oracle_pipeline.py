@@ -88,3 +88,34 @@ def test_oracle_clusters_are_pure_on_synthetic_data():
     assert lab.max() > 300
     for l in np.unique(lab[lab >= 0])[:200]:
         assert np.unique(tmpl[lab == l]).shape[0] == 1
+
+
+def test_medoid_oracle_hand_example():
+    """SURVEY A.5 on a 5-member cluster + a pair + noise: eligibility needs more than
+    a quarter of the cluster in the row; first minimum wins; pairs give the first member."""
+    import scipy.sparse as ss
+
+    from oracle import medoids as omed
+
+    labels = np.array([0, 0, 0, 0, 0, 1, 1, -1], np.int32)
+    rows = {
+        0: {0: 0.0, 1: 0.4, 2: 0.4},          # mean 0.2667 over 3 members
+        1: {1: 0.0, 0: 0.1, 2: 0.1, 3: 0.1},  # mean 0.075 -> the medoid
+        2: {2: 0.0, 7: 0.01},                 # only itself present: 1 <= 5 / 4 -> not eligible
+        3: {3: 0.0, 1: 0.15, 5: 0.0},         # other cluster's member ignored: mean 0.075, ties lose to row 1
+        4: {4: 0.0, 0: 0.3},                  # mean 0.15
+        5: {5: 0.0, 6: 0.05},
+        6: {6: 0.0, 5: 0.05},
+        7: {7: 0.0},
+    }
+    m = ss.lil_matrix((8, 8), dtype=np.float32)
+    data, indices, indptr = [], [], [0]
+    for r in range(8):
+        for c, v in rows[r].items():
+            indices.append(c)
+            data.append(v)
+        indptr.append(len(indices))
+    got = omed.cluster_medoids(np.float32(data), np.int32(indices), np.int64(indptr), labels)
+    assert got.tolist() == [1, 5]
+    assert omed.cluster_medoids(np.zeros(0, np.float32), np.zeros(0, np.int32), np.zeros(1, np.int64),
+                                np.zeros(0, np.int32)).shape == (0,)
