@@ -54,29 +54,34 @@ __global__ void dbscan_propagate_kernel(const float* __restrict__ dist, const in
                                         int32_t* __restrict__ changed) {
   const int64_t u = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (u >= n || !core[u]) return;
-  // Shortcut: follow the chain of minimum ancestors to its current end.
-  int32_t mu = *reinterpret_cast<volatile int32_t*>(m + u);
-  int32_t r = mu;
-  while (true) {
-    const int32_t next = *reinterpret_cast<volatile int32_t*>(m + r);
-    if (next >= r) break;
-    r = next;
-  }
-  bool any = false;
-  if (r < mu) {
-    atomicMin(m + u, r);
-    any = true;
-    mu = r;
-  }
   const int64_t a = indptr[u], b = indptr[u + 1];
-  for (int64_t p = a; p < b; ++p) {
-    if (__ldg(dist + p) <= eps) {
-      const int32_t w = __ldg(indices + p);
-      if (*reinterpret_cast<volatile int32_t*>(m + w) > mu) {
-        const int32_t old = atomicMin(m + w, mu);
-        any |= old > mu;
+  bool any = false;
+  // Push until this row's own value stops improving under us: neighbours run the
+  // same loop concurrently, so small components settle within a single sweep.
+  for (int round = 0; round < 64; ++round) {
+    // Shortcut: follow the chain of minimum ancestors to its current end.
+    int32_t mu = *reinterpret_cast<volatile int32_t*>(m + u);
+    int32_t r = mu;
+    while (true) {
+      const int32_t next = *reinterpret_cast<volatile int32_t*>(m + r);
+      if (next >= r) break;
+      r = next;
+    }
+    if (r < mu) {
+      atomicMin(m + u, r);
+      any = true;
+      mu = r;
+    }
+    for (int64_t p = a; p < b; ++p) {
+      if (__ldg(dist + p) <= eps) {
+        const int32_t w = __ldg(indices + p);
+        if (*reinterpret_cast<volatile int32_t*>(m + w) > mu) {
+          const int32_t old = atomicMin(m + w, mu);
+          any |= old > mu;
+        }
       }
     }
+    if (*reinterpret_cast<volatile int32_t*>(m + u) >= mu) break;
   }
   if (any) *changed = 1;
 }
@@ -348,7 +353,8 @@ int flc_dbscan(const float* dist, const int32_t* indices, const int64_t* indptr,
   int sweeps = 0;
   while (changed) {
     FLC_CUDA(cudaMemsetAsync(L.changed, 0, sizeof(int32_t), stream));
-    for (int rep = 0; rep < 2; ++rep) {
+    // two sweeps before the first look at the flag (the second usually only confirms), one afterwards
+    for (int rep = 0; rep < (sweeps == 0 ? 2 : 1); ++rep) {
       timed("dbscan_propagate", stream, [&] { dbscan_propagate_kernel<<<wblocks, 256, 0, stream>>>(dist, indices, indptr, n, eps, L.core, L.m,
                                                            L.changed); });
       FLC_LAUNCH_CHECK();

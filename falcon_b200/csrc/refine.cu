@@ -25,6 +25,9 @@ namespace flc {
 
 constexpr int kRefineWarps = 8;
 constexpr uint64_t kKeyMax = ~uint64_t(0);
+constexpr int kBlockQueries = 32;   // refine_block_kernel: queries per step of a CTA
+constexpr int kBlockThreads = 384;  // four threads per candidate pair in the scoring phase
+constexpr int kBlockPairs = 1024;   // candidate pairs of one query block it keeps in shared memory
 
 __global__ void pair_hist_kernel(const uint64_t* __restrict__ pairs, const uint64_t* __restrict__ pair_count,
                                  uint64_t capacity, int64_t n, uint32_t* __restrict__ cnt) {
@@ -161,7 +164,7 @@ __device__ __forceinline__ float exact_ip(const RefineParams& P, const float* xq
 // scattered in from its sparse copy and scattered back out to zero afterwards.
 __global__ void __launch_bounds__(kRefineWarps * 32)
 refine_kernel(RefineParams P, const int64_t* __restrict__ off, uint64_t* __restrict__ grouped,
-              int32_t* __restrict__ row_count) {
+              int32_t* __restrict__ row_count, const int32_t* __restrict__ deferred) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -171,12 +174,15 @@ refine_kernel(RefineParams P, const int64_t* __restrict__ off, uint64_t* __restr
   uint64_t* buf = reinterpret_cast<uint64_t*>(smem_raw + warp * per_warp);
   float* xq = reinterpret_cast<float*>(buf + 2 * P.ka_pow2);
   const bool sparse = P.ell_idx != nullptr;
+  // With `deferred` this kernel only finishes the query blocks refine_block_kernel passed on.
+  if (deferred != nullptr && deferred[0] == 0) return;
   if (sparse) {
     for (uint32_t i = lane; i < P.low_dim; i += 32) xq[i] = 0.f;
     __syncwarp();
   }
   const int64_t warps_total = static_cast<int64_t>(gridDim.x) * kRefineWarps;
   for (int64_t q = static_cast<int64_t>(blockIdx.x) * kRefineWarps + warp; q < P.n; q += warps_total) {
+    if (deferred != nullptr && deferred[1 + q / kBlockQueries] == 0) continue;
     const int64_t base = off[q];
     const int64_t m = off[q + 1] - base;
     if (m == 0) {
@@ -302,6 +308,166 @@ refine_kernel(RefineParams P, const int64_t* __restrict__ off, uint64_t* __restr
   }
 }
 
+// Fast path for sparse rows: a CTA takes 32 consecutive queries, holds their rows
+// densely in shared memory and gives every candidate pair four threads -- the
+// sparse candidate row streams through registers (independent 16-byte loads),
+// products accumulate in float64, two shuffles join the quad.  Ranks come from counting smaller keys among
+// the query's pairs (shared memory), then the same top-k_ann / tolerance / first-k
+// selection as refine_kernel.  Query blocks with more than kBlockPairs pairs are
+// flagged in `deferred` (deferred[0] = any) and left to refine_kernel.
+__global__ void __launch_bounds__(kBlockThreads)
+refine_block_kernel(RefineParams P, const int64_t* __restrict__ off, uint64_t* __restrict__ grouped,
+                    int32_t* __restrict__ row_count, int32_t* __restrict__ deferred) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float* xq = reinterpret_cast<float*>(smem_raw);                                   // [32][low_dim]
+  uint64_t* keys = reinterpret_cast<uint64_t*>(xq + kBlockQueries * P.low_dim);      // [kBlockPairs]
+  uint8_t* flags = reinterpret_cast<uint8_t*>(keys + kBlockPairs);                  // bit 0: passes tolerance, bit 1: and within k_ann
+  __shared__ int32_t qoff[kBlockQueries + 1];
+  const int tid = threadIdx.x;
+  const int W = P.ell_width;
+  const int cpr = W >> 3;  // 8-slot chunks per row
+  const int64_t n_blocks = (P.n + kBlockQueries - 1) / kBlockQueries;
+  for (uint32_t i = tid; i < kBlockQueries * P.low_dim; i += kBlockThreads) xq[i] = 0.f;
+
+  for (int64_t blk = blockIdx.x; blk < n_blocks; blk += gridDim.x) {
+    const int64_t q0 = blk * kBlockQueries;
+    const int nq = static_cast<int>(min(static_cast<int64_t>(kBlockQueries), P.n - q0));
+    const int64_t base = off[q0];
+    const int64_t pb64 = off[q0 + nq] - base;
+    if (pb64 > kBlockPairs) {  // uniform
+      if (tid == 0) { deferred[1 + blk] = 1; deferred[0] = 1; }
+      continue;
+    }
+    const int pb = static_cast<int>(pb64);
+    __syncthreads();  // previous block's shared memory is free
+    if (tid <= nq) qoff[tid] = static_cast<int32_t>(off[q0 + tid] - base);
+    // ---- query rows -> dense
+    for (int it = tid; it < nq * cpr; it += kBlockThreads) {
+      const int r = it / cpr, j0 = (it - r * cpr) << 3;
+      const int64_t g = (q0 + r) * W + j0;
+      const float4 v0 = __ldg(reinterpret_cast<const float4*>(P.ell_val + g));
+      if (v0.x == 0.f) continue;  // packed rows: nothing further
+      const float4 v1 = __ldg(reinterpret_cast<const float4*>(P.ell_val + g + 4));
+      const uint4 ki = __ldg(reinterpret_cast<const uint4*>(P.ell_idx + g));
+      float* xr = xq + r * P.low_dim;
+      const float vv[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+      const uint32_t kk[4] = {ki.x, ki.y, ki.z, ki.w};
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        if (vv[u] != 0.f) xr[(kk[u >> 1] >> ((u & 1) * 16)) & 0xffffu] = vv[u];
+    }
+    __syncthreads();
+    // ---- four threads per candidate pair: membership, exact score, tolerance.  The
+    // quad splits the candidate's 8-slot chunks (all loads independent, zero padding
+    // multiplies to an exact zero) and adds its partial sums with two shuffles.
+    {
+      const int lane = tid & 31, sub = tid & 3;
+      for (int p0 = (tid >> 5) * 8; p0 < pb; p0 += kBlockThreads / 4) {
+        const int p = p0 + (lane >> 2);
+        const bool have = p < pb;
+        int lo = 0;
+        uint32_t c = 0;
+        double acc = 0.0;
+        if (have) {
+          int hi = nq;  // query of pair p: last r with qoff[r] <= p
+          while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (qoff[mid] <= p) lo = mid; else hi = mid;
+          }
+          c = static_cast<uint32_t>(grouped[base + p]);
+          const float* xr = xq + lo * P.low_dim;
+          const int64_t rb = static_cast<int64_t>(c) * W;
+#pragma unroll 2
+          for (int j0 = 8 * sub; j0 < W; j0 += 32) {
+            const float4 v0 = __ldg(reinterpret_cast<const float4*>(P.ell_val + rb + j0));
+            const float4 v1 = __ldg(reinterpret_cast<const float4*>(P.ell_val + rb + j0 + 4));
+            const uint4 ki = __ldg(reinterpret_cast<const uint4*>(P.ell_idx + rb + j0));
+            acc = fma(static_cast<double>(v0.x), static_cast<double>(xr[ki.x & 0xffffu]), acc);
+            acc = fma(static_cast<double>(v0.y), static_cast<double>(xr[ki.x >> 16]), acc);
+            acc = fma(static_cast<double>(v0.z), static_cast<double>(xr[ki.y & 0xffffu]), acc);
+            acc = fma(static_cast<double>(v0.w), static_cast<double>(xr[ki.y >> 16]), acc);
+            acc = fma(static_cast<double>(v1.x), static_cast<double>(xr[ki.z & 0xffffu]), acc);
+            acc = fma(static_cast<double>(v1.y), static_cast<double>(xr[ki.z >> 16]), acc);
+            acc = fma(static_cast<double>(v1.z), static_cast<double>(xr[ki.w & 0xffffu]), acc);
+            acc = fma(static_cast<double>(v1.w), static_cast<double>(xr[ki.w >> 16]), acc);
+          }
+        }
+        acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+        if (have && sub == 0) {
+          const int64_t q = q0 + lo;
+          bool member = true;
+          if (P.list_id != nullptr) {
+            const int32_t lc = __ldg(P.list_id + c);
+            bool hit = false;
+            for (int32_t t = 0; t < P.max_nprobe; ++t) hit |= (__ldg(P.probes + q * P.max_nprobe + t) == lc);
+            member = hit;
+          }
+          uint64_t key = kKeyMax;
+          uint8_t flag = 0;
+          const float ip = static_cast<float>(acc);
+          const float dist = fmaxf(1.0f - ip, 0.0f);
+          if (member && (!P.use_eps || dist <= P.eps)) {
+            key = (static_cast<uint64_t>(ip_key_desc(ip)) << 32) | c;
+            flag = tolerance_ok(P, P.mz[q], P.rt ? P.rt[q] : 0.f, P.mz[c], P.rt ? P.rt[c] : 0.f) ? 1 : 0;
+          }
+          keys[p] = key;
+          flags[p] = flag;
+        }
+      }
+    }
+    __syncthreads();
+    // ---- rank among the query's pairs; only the k_ann best are eligible
+    for (int p = tid; p < pb; p += kBlockThreads) {
+      const uint64_t key = keys[p];
+      if (key == kKeyMax || !(flags[p] & 1)) continue;
+      int lo = 0, hi = nq;
+      while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (qoff[mid] <= p) lo = mid; else hi = mid;
+      }
+      int rank = 0;
+      for (int j = qoff[lo]; j < qoff[lo + 1]; ++j) rank += keys[j] < key ? 1 : 0;
+      if (rank < P.k_ann) flags[p] |= 2;
+    }
+    __syncthreads();
+    // ---- position among the eligible ones that pass the tolerance: first k are kept
+    for (int p = tid; p < pb; p += kBlockThreads) {
+      if (!(flags[p] & 2)) continue;
+      const uint64_t key = keys[p];
+      int lo = 0, hi = nq;
+      while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (qoff[mid] <= p) lo = mid; else hi = mid;
+      }
+      int prank = 0;
+      for (int j = qoff[lo]; j < qoff[lo + 1]; ++j) prank += ((flags[j] & 2) && keys[j] < key) ? 1 : 0;
+      if (prank < P.k) {
+        const float ip = ip_from_key(static_cast<uint32_t>(key >> 32));
+        const float dist = fmaxf(1.0f - ip, 0.0f);
+        grouped[base + qoff[lo] + prank] = (static_cast<uint64_t>(__float_as_uint(dist)) << 32) | (key & 0xffffffffull);
+      }
+    }
+    if (tid < nq) {
+      int kept = 0;
+      for (int j = qoff[tid]; j < qoff[tid + 1]; ++j) kept += (flags[j] & 2) ? 1 : 0;
+      row_count[q0 + tid] = min(kept, P.k);
+    }
+    // ---- query rows back to zero
+    for (int it = tid; it < nq * cpr; it += kBlockThreads) {
+      const int r = it / cpr, j0 = (it - r * cpr) << 3;
+      const int64_t g = (q0 + r) * W + j0;
+      const float4 v0 = __ldg(reinterpret_cast<const float4*>(P.ell_val + g));
+      if (v0.x == 0.f) continue;
+      const uint4 ki = __ldg(reinterpret_cast<const uint4*>(P.ell_idx + g));
+      float* xr = xq + r * P.low_dim;
+      const uint32_t kk[4] = {ki.x, ki.y, ki.z, ki.w};
+#pragma unroll
+      for (int u = 0; u < 8; ++u) xr[(kk[u >> 1] >> ((u & 1) * 16)) & 0xffffu] = 0.f;
+    }
+  }
+}
+
 __global__ void csr_compact_kernel(const uint64_t* __restrict__ grouped, const int64_t* __restrict__ off,
                                    const int64_t* __restrict__ indptr, int64_t n, uint64_t nnz_capacity,
                                    float* __restrict__ dist, int32_t* __restrict__ indices) {
@@ -325,6 +491,7 @@ struct KnnLayout {
   int64_t* off;      // [n + 1]
   int32_t* row_count;  // [n + 1]
   uint64_t* grouped;   // [n_pairs]
+  int32_t* deferred;   // [1 + query blocks]
   void* cub_tmp;
   size_t cub_bytes;
 };
@@ -335,6 +502,7 @@ static void knn_layout(Workspace& ws, int64_t n, uint64_t n_pairs, KnnLayout& L)
   L.off = ws.take<int64_t>(n + 1);
   L.row_count = ws.take<int32_t>(n + 1);
   L.grouped = ws.take<uint64_t>(n_pairs ? n_pairs : 1);
+  L.deferred = ws.take<int32_t>(2 + static_cast<size_t>((n + kBlockQueries - 1) / kBlockQueries));
   size_t b1 = 0, b2 = 0;
   cub::DeviceScan::ExclusiveSum(nullptr, b1, (uint32_t*)nullptr, (int64_t*)nullptr, static_cast<int>(n + 1));
   cub::DeviceScan::ExclusiveSum(nullptr, b2, (int32_t*)nullptr, (int64_t*)nullptr, static_cast<int>(n + 1));
@@ -430,7 +598,24 @@ int flc_knn_csr(const uint64_t* pairs, const uint64_t* pair_count, uint64_t pair
               "ELL arrays must be even-width and 4/8-byte aligned");
   const unsigned rblocks = static_cast<unsigned>(
       std::min<int64_t>((n + kRefineWarps - 1) / kRefineWarps, static_cast<int64_t>(kNumSMs) * 16));
-  timed("refine", stream, [&] { refine_kernel<<<rblocks, kRefineWarps * 32, smem, stream>>>(P, L.off, L.grouped, L.row_count); });
+  const int32_t* deferred = nullptr;
+  const size_t bsmem = static_cast<size_t>(kBlockQueries) * low_dim * sizeof(float) + kBlockPairs * 9;
+  const bool block_path = ell_idx != nullptr && (ell_width % 8) == 0 && bsmem <= 100 * 1024 &&
+                          (reinterpret_cast<uintptr_t>(ell_idx) % 16) == 0 && (reinterpret_cast<uintptr_t>(ell_val) % 16) == 0;
+  if (block_path) {
+    const int64_t n_qblocks = (n + kBlockQueries - 1) / kBlockQueries;
+    FLC_CUDA(cudaMemsetAsync(L.deferred, 0, sizeof(int32_t) * (1 + n_qblocks), stream));
+    FLC_CUDA(cudaFuncSetAttribute(refine_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  static_cast<int>(bsmem)));
+    const int64_t per_sm = std::max<int64_t>(1, (227 * 1024) / static_cast<int64_t>(bsmem + 1024));
+    const unsigned bblocks = static_cast<unsigned>(std::min<int64_t>(n_qblocks, static_cast<int64_t>(kNumSMs) * per_sm));
+    timed("refine_block", stream, [&] { refine_block_kernel<<<bblocks, kBlockThreads, bsmem, stream>>>(
+        P, L.off, L.grouped, L.row_count, L.deferred); });
+    FLC_LAUNCH_CHECK();
+    deferred = L.deferred;
+  }
+  timed("refine", stream, [&] { refine_kernel<<<rblocks, kRefineWarps * 32, smem, stream>>>(
+      P, L.off, L.grouped, L.row_count, deferred); });
   FLC_LAUNCH_CHECK();
   tmp = L.cub_bytes;
   FLC_CUDA(cub::DeviceScan::ExclusiveSum(L.cub_tmp, tmp, L.row_count, indptr, static_cast<int>(n + 1), stream));
