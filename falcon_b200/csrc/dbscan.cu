@@ -179,6 +179,32 @@ __global__ void split_group_kernel(const int64_t* __restrict__ gstart, const int
   const int32_t m = static_cast<int32_t>(e - s);
   if (m < 2) return;
   const double* v = vs + s;
+  if (m <= 32) {
+    // Whole group in one warp: lane j holds element j, the run starts are a bit mask.
+    // Boundary j separates the run ending at j - 1 from the run starting at j; its
+    // merge distance is the span of both runs.  d of the neighbouring boundaries is
+    // what the lanes at the previous / next run start computed.
+    const double val = lane < m ? v[lane] : 0.0;
+    uint32_t heads = m == 32 ? 0xffffffffu : ((1u << m) - 1u);
+    while (true) {
+      const bool is_b = lane >= 1 && lane < m && ((heads >> lane) & 1u);
+      const uint32_t lower = heads & ((1u << lane) - 1u);
+      const int ps = lower ? 31 - __clz(lower) : 0;                       // start of the run before the boundary
+      const uint32_t above = lane < 31 ? (heads >> (lane + 1)) : 0u;
+      const int ne = above ? min(lane + __ffs(above), m) : m;             // end of the run after the boundary
+      const double d = split_distance(__shfl_sync(0xffffffffu, val, ps), __shfl_sync(0xffffffffu, val, ne - 1), tol_mode);
+      const double dl = __shfl_sync(0xffffffffu, d, ps);
+      const double dr = __shfl_sync(0xffffffffu, d, ne < m ? ne : 0);
+      bool merge = is_b && d <= tol;
+      if (merge && ps >= 1 && !(d < dl)) merge = false;
+      if (merge && ne < m && !(d <= dr)) merge = false;
+      const uint32_t mb = __ballot_sync(0xffffffffu, merge);
+      if (mb == 0u) break;
+      heads &= ~mb;
+    }
+    if (lane < m && ((heads >> lane) & 1u)) runhead[s + lane] = 1;
+    return;
+  }
   int32_t* cur = list_a + s;
   int32_t* nxt = list_b + s;
   for (int32_t j = lane; j < m; j += 32) cur[j] = j;

@@ -25,9 +25,9 @@ namespace flc {
 
 constexpr int kRefineWarps = 8;
 constexpr uint64_t kKeyMax = ~uint64_t(0);
-constexpr int kBlockQueries = 32;   // refine_block_kernel: queries per step of a CTA
-constexpr int kBlockThreads = 384;  // four threads per candidate pair in the scoring phase
-constexpr int kBlockPairs = 1024;   // candidate pairs of one query block it keeps in shared memory
+constexpr int kBlockQueries = 16;   // refine_block_kernel: queries per step of a CTA
+constexpr int kBlockThreads = 192;  // four threads per candidate pair in the scoring phase
+constexpr int kBlockPairs = 512;    // candidate pairs of one query block it keeps in shared memory
 
 __global__ void pair_hist_kernel(const uint64_t* __restrict__ pairs, const uint64_t* __restrict__ pair_count,
                                  uint64_t capacity, int64_t n, uint32_t* __restrict__ cnt) {
@@ -308,7 +308,7 @@ refine_kernel(RefineParams P, const int64_t* __restrict__ off, uint64_t* __restr
   }
 }
 
-// Fast path for sparse rows: a CTA takes 32 consecutive queries, holds their rows
+// Fast path for sparse rows: a CTA takes 16 consecutive queries, holds their rows
 // densely in shared memory and gives every candidate pair four threads -- the
 // sparse candidate row streams through registers (independent 16-byte loads),
 // products accumulate in float64, two shuffles join the quad.  Ranks come from counting smaller keys among
@@ -323,6 +323,7 @@ refine_block_kernel(RefineParams P, const int64_t* __restrict__ off, uint64_t* _
   uint64_t* keys = reinterpret_cast<uint64_t*>(xq + kBlockQueries * P.low_dim);      // [kBlockPairs]
   uint8_t* flags = reinterpret_cast<uint8_t*>(keys + kBlockPairs);                  // bit 0: passes tolerance, bit 1: and within k_ann
   __shared__ int32_t qoff[kBlockQueries + 1];
+  static_assert(kBlockThreads > kBlockQueries, "one thread per query offset");
   const int tid = threadIdx.x;
   const int W = P.ell_width;
   const int cpr = W >> 3;  // 8-slot chunks per row
@@ -346,7 +347,6 @@ refine_block_kernel(RefineParams P, const int64_t* __restrict__ off, uint64_t* _
       const int r = it / cpr, j0 = (it - r * cpr) << 3;
       const int64_t g = (q0 + r) * W + j0;
       const float4 v0 = __ldg(reinterpret_cast<const float4*>(P.ell_val + g));
-      if (v0.x == 0.f) continue;  // packed rows: nothing further
       const float4 v1 = __ldg(reinterpret_cast<const float4*>(P.ell_val + g + 4));
       const uint4 ki = __ldg(reinterpret_cast<const uint4*>(P.ell_idx + g));
       float* xr = xq + r * P.low_dim;
@@ -458,12 +458,14 @@ refine_block_kernel(RefineParams P, const int64_t* __restrict__ off, uint64_t* _
       const int r = it / cpr, j0 = (it - r * cpr) << 3;
       const int64_t g = (q0 + r) * W + j0;
       const float4 v0 = __ldg(reinterpret_cast<const float4*>(P.ell_val + g));
-      if (v0.x == 0.f) continue;
+      const float4 v1 = __ldg(reinterpret_cast<const float4*>(P.ell_val + g + 4));
       const uint4 ki = __ldg(reinterpret_cast<const uint4*>(P.ell_idx + g));
       float* xr = xq + r * P.low_dim;
+      const float vv[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
       const uint32_t kk[4] = {ki.x, ki.y, ki.z, ki.w};
 #pragma unroll
-      for (int u = 0; u < 8; ++u) xr[(kk[u >> 1] >> ((u & 1) * 16)) & 0xffffu] = 0.f;
+      for (int u = 0; u < 8; ++u)  // padding slots carry column 0: only real entries are cleared
+        if (vv[u] != 0.f) xr[(kk[u >> 1] >> ((u & 1) * 16)) & 0xffffu] = 0.f;
     }
   }
 }
