@@ -25,9 +25,17 @@ namespace flc {
 
 constexpr int kRefineWarps = 8;
 constexpr uint64_t kKeyMax = ~uint64_t(0);
-constexpr int kBlockQueries = 16;   // refine_block_kernel: queries per step of a CTA
-constexpr int kBlockThreads = 192;  // four threads per candidate pair in the scoring phase
-constexpr int kBlockPairs = 512;    // candidate pairs of one query block it keeps in shared memory
+constexpr int kWarpQueries = 4;   // refine_block_kernel: queries a warp handles at a time
+constexpr int kWarpPairs = 64;    // candidate pairs of one query group it keeps in shared memory
+constexpr int kBlockWarps = 8;
+
+// qo[r] with a run-time r out of a register array (unrolled select)
+__device__ __forceinline__ int qo_at(const int (&qo)[kWarpQueries + 1], int r) {
+  int v = qo[0];
+#pragma unroll
+  for (int t = 1; t <= kWarpQueries; ++t) v = (r == t) ? qo[t] : v;
+  return v;
+}
 
 __global__ void pair_hist_kernel(const uint64_t* __restrict__ pairs, const uint64_t* __restrict__ pair_count,
                                  uint64_t capacity, int64_t n, uint32_t* __restrict__ cnt) {
@@ -182,7 +190,7 @@ refine_kernel(RefineParams P, const int64_t* __restrict__ off, uint64_t* __restr
   }
   const int64_t warps_total = static_cast<int64_t>(gridDim.x) * kRefineWarps;
   for (int64_t q = static_cast<int64_t>(blockIdx.x) * kRefineWarps + warp; q < P.n; q += warps_total) {
-    if (deferred != nullptr && deferred[1 + q / kBlockQueries] == 0) continue;
+    if (deferred != nullptr && deferred[1 + q / kWarpQueries] == 0) continue;
     const int64_t base = off[q];
     const int64_t m = off[q + 1] - base;
     if (m == 0) {
@@ -308,42 +316,59 @@ refine_kernel(RefineParams P, const int64_t* __restrict__ off, uint64_t* __restr
   }
 }
 
-// Fast path for sparse rows: a CTA takes 16 consecutive queries, holds their rows
-// densely in shared memory and gives every candidate pair four threads -- the
-// sparse candidate row streams through registers (independent 16-byte loads),
-// products accumulate in float64, two shuffles join the quad.  Ranks come from counting smaller keys among
-// the query's pairs (shared memory), then the same top-k_ann / tolerance / first-k
-// selection as refine_kernel.  Query blocks with more than kBlockPairs pairs are
-// flagged in `deferred` (deferred[0] = any) and left to refine_kernel.
-__global__ void __launch_bounds__(kBlockThreads)
+// Fast path for sparse rows: every WARP takes four consecutive queries at a time (no
+// block-wide barriers), holds their rows densely in its slice of shared memory
+// and gives every candidate pair four lanes -- the sparse candidate row streams
+// through registers (independent 16-byte loads, zero padding multiplies to an exact
+// zero), products accumulate in float64, two shuffles join the quad.  Ranks come
+// from counting smaller keys among the query's pairs, then the same top-k_ann /
+// tolerance / first-k selection as refine_kernel.  Query groups with more than
+// kWarpPairs pairs are flagged in `deferred` (deferred[0] = any) and left to
+// refine_kernel.
+__global__ void __launch_bounds__(kBlockWarps * 32)
 refine_block_kernel(RefineParams P, const int64_t* __restrict__ off, uint64_t* __restrict__ grouped,
                     int32_t* __restrict__ row_count, int32_t* __restrict__ deferred) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  float* xq = reinterpret_cast<float*>(smem_raw);                                   // [32][low_dim]
-  uint64_t* keys = reinterpret_cast<uint64_t*>(xq + kBlockQueries * P.low_dim);      // [kBlockPairs]
-  uint8_t* flags = reinterpret_cast<uint8_t*>(keys + kBlockPairs);                  // bit 0: passes tolerance, bit 1: and within k_ann
-  __shared__ int32_t qoff[kBlockQueries + 1];
-  static_assert(kBlockThreads > kBlockQueries, "one thread per query offset");
-  const int tid = threadIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, sub = lane & 3;
+  const size_t per_warp = static_cast<size_t>(kWarpQueries) * P.low_dim * sizeof(float) + kWarpPairs * 9 + 16;
+  float* xq = reinterpret_cast<float*>(smem_raw + warp * ((per_warp + 15) & ~size_t(15)));  // [4][low_dim]
+  uint64_t* keys = reinterpret_cast<uint64_t*>(xq + kWarpQueries * P.low_dim);           // [kWarpPairs]
+  uint8_t* flags = reinterpret_cast<uint8_t*>(keys + kWarpPairs);  // bit 0: passes tolerance, bit 1: and within k_ann
   const int W = P.ell_width;
   const int cpr = W >> 3;  // 8-slot chunks per row
-  const int64_t n_blocks = (P.n + kBlockQueries - 1) / kBlockQueries;
-  for (uint32_t i = tid; i < kBlockQueries * P.low_dim; i += kBlockThreads) xq[i] = 0.f;
+  const int64_t n_groups = (P.n + kWarpQueries - 1) / kWarpQueries;
+  const int64_t warps_total = static_cast<int64_t>(gridDim.x) * kBlockWarps;
+  for (uint32_t i = lane; i < kWarpQueries * P.low_dim; i += 32) xq[i] = 0.f;
+  __syncwarp();
 
-  for (int64_t blk = blockIdx.x; blk < n_blocks; blk += gridDim.x) {
-    const int64_t q0 = blk * kBlockQueries;
-    const int nq = static_cast<int>(min(static_cast<int64_t>(kBlockQueries), P.n - q0));
-    const int64_t base = off[q0];
-    const int64_t pb64 = off[q0 + nq] - base;
-    if (pb64 > kBlockPairs) {  // uniform
-      if (tid == 0) { deferred[1 + blk] = 1; deferred[0] = 1; }
+  for (int64_t grp = static_cast<int64_t>(blockIdx.x) * kBlockWarps + warp; grp < n_groups; grp += warps_total) {
+    const int64_t q0 = grp * kWarpQueries;
+    const int nq = static_cast<int>(min(static_cast<int64_t>(kWarpQueries), P.n - q0));
+    // offsets of the group's queries: lane r holds off[q0 + r] - off[q0]
+    const int64_t my_off = off[q0 + min(lane, nq)];
+    const int64_t base = __shfl_sync(0xffffffffu, my_off, 0);
+    const int64_t pb64 = __shfl_sync(0xffffffffu, my_off, nq) - base;
+    if (pb64 > kWarpPairs) {  // uniform
+      if (lane == 0) { deferred[1 + grp] = 1; deferred[0] = 1; }
       continue;
     }
     const int pb = static_cast<int>(pb64);
-    __syncthreads();  // previous block's shared memory is free
-    if (tid <= nq) qoff[tid] = static_cast<int32_t>(off[q0 + tid] - base);
+    const int rel = static_cast<int>(my_off - base);
+    int qo[kWarpQueries + 1];
+#pragma unroll
+    for (int r = 0; r <= kWarpQueries; ++r) qo[r] = __shfl_sync(0xffffffffu, rel, min(r, nq));
+    if (pb == 0) {
+      if (lane < nq) row_count[q0 + lane] = 0;
+      continue;
+    }
+    auto query_of = [&](int p) {  // last r with qo[r] <= p
+      int r = 0;
+#pragma unroll
+      for (int t = 1; t < kWarpQueries; ++t) r += (t < nq && qo[t] <= p) ? 1 : 0;
+      return r;
+    };
     // ---- query rows -> dense
-    for (int it = tid; it < nq * cpr; it += kBlockThreads) {
+    for (int it = lane; it < nq * cpr; it += 32) {
       const int r = it / cpr, j0 = (it - r * cpr) << 3;
       const int64_t g = (q0 + r) * W + j0;
       const float4 v0 = __ldg(reinterpret_cast<const float4*>(P.ell_val + g));
@@ -356,105 +381,89 @@ refine_block_kernel(RefineParams P, const int64_t* __restrict__ off, uint64_t* _
       for (int u = 0; u < 8; ++u)
         if (vv[u] != 0.f) xr[(kk[u >> 1] >> ((u & 1) * 16)) & 0xffffu] = vv[u];
     }
-    __syncthreads();
-    // ---- four threads per candidate pair: membership, exact score, tolerance.  The
-    // quad splits the candidate's 8-slot chunks (all loads independent, zero padding
-    // multiplies to an exact zero) and adds its partial sums with two shuffles.
-    {
-      const int lane = tid & 31, sub = tid & 3;
-      for (int p0 = (tid >> 5) * 8; p0 < pb; p0 += kBlockThreads / 4) {
-        const int p = p0 + (lane >> 2);
-        const bool have = p < pb;
-        int lo = 0;
-        uint32_t c = 0;
-        double acc = 0.0;
-        if (have) {
-          int hi = nq;  // query of pair p: last r with qoff[r] <= p
-          while (hi - lo > 1) {
-            const int mid = (lo + hi) >> 1;
-            if (qoff[mid] <= p) lo = mid; else hi = mid;
-          }
-          c = static_cast<uint32_t>(grouped[base + p]);
-          const float* xr = xq + lo * P.low_dim;
-          const int64_t rb = static_cast<int64_t>(c) * W;
+    __syncwarp();
+    // ---- four lanes per candidate pair: membership, exact score, tolerance
+    for (int p0 = 0; p0 < pb; p0 += 8) {
+      const int p = p0 + (lane >> 2);
+      const bool have = p < pb;
+      int lo = 0;
+      uint32_t c = 0;
+      double acc = 0.0;
+      if (have) {
+        lo = query_of(p);
+        c = static_cast<uint32_t>(grouped[base + p]);
+        const float* xr = xq + lo * P.low_dim;
+        const int64_t rb = static_cast<int64_t>(c) * W;
 #pragma unroll 2
-          for (int j0 = 8 * sub; j0 < W; j0 += 32) {
-            const float4 v0 = __ldg(reinterpret_cast<const float4*>(P.ell_val + rb + j0));
-            const float4 v1 = __ldg(reinterpret_cast<const float4*>(P.ell_val + rb + j0 + 4));
-            const uint4 ki = __ldg(reinterpret_cast<const uint4*>(P.ell_idx + rb + j0));
-            acc = fma(static_cast<double>(v0.x), static_cast<double>(xr[ki.x & 0xffffu]), acc);
-            acc = fma(static_cast<double>(v0.y), static_cast<double>(xr[ki.x >> 16]), acc);
-            acc = fma(static_cast<double>(v0.z), static_cast<double>(xr[ki.y & 0xffffu]), acc);
-            acc = fma(static_cast<double>(v0.w), static_cast<double>(xr[ki.y >> 16]), acc);
-            acc = fma(static_cast<double>(v1.x), static_cast<double>(xr[ki.z & 0xffffu]), acc);
-            acc = fma(static_cast<double>(v1.y), static_cast<double>(xr[ki.z >> 16]), acc);
-            acc = fma(static_cast<double>(v1.z), static_cast<double>(xr[ki.w & 0xffffu]), acc);
-            acc = fma(static_cast<double>(v1.w), static_cast<double>(xr[ki.w >> 16]), acc);
-          }
-        }
-        acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-        acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-        if (have && sub == 0) {
-          const int64_t q = q0 + lo;
-          bool member = true;
-          if (P.list_id != nullptr) {
-            const int32_t lc = __ldg(P.list_id + c);
-            bool hit = false;
-            for (int32_t t = 0; t < P.max_nprobe; ++t) hit |= (__ldg(P.probes + q * P.max_nprobe + t) == lc);
-            member = hit;
-          }
-          uint64_t key = kKeyMax;
-          uint8_t flag = 0;
-          const float ip = static_cast<float>(acc);
-          const float dist = fmaxf(1.0f - ip, 0.0f);
-          if (member && (!P.use_eps || dist <= P.eps)) {
-            key = (static_cast<uint64_t>(ip_key_desc(ip)) << 32) | c;
-            flag = tolerance_ok(P, P.mz[q], P.rt ? P.rt[q] : 0.f, P.mz[c], P.rt ? P.rt[c] : 0.f) ? 1 : 0;
-          }
-          keys[p] = key;
-          flags[p] = flag;
+        for (int j0 = 8 * sub; j0 < W; j0 += 32) {
+          const float4 v0 = __ldg(reinterpret_cast<const float4*>(P.ell_val + rb + j0));
+          const float4 v1 = __ldg(reinterpret_cast<const float4*>(P.ell_val + rb + j0 + 4));
+          const uint4 ki = __ldg(reinterpret_cast<const uint4*>(P.ell_idx + rb + j0));
+          acc = fma(static_cast<double>(v0.x), static_cast<double>(xr[ki.x & 0xffffu]), acc);
+          acc = fma(static_cast<double>(v0.y), static_cast<double>(xr[ki.x >> 16]), acc);
+          acc = fma(static_cast<double>(v0.z), static_cast<double>(xr[ki.y & 0xffffu]), acc);
+          acc = fma(static_cast<double>(v0.w), static_cast<double>(xr[ki.y >> 16]), acc);
+          acc = fma(static_cast<double>(v1.x), static_cast<double>(xr[ki.z & 0xffffu]), acc);
+          acc = fma(static_cast<double>(v1.y), static_cast<double>(xr[ki.z >> 16]), acc);
+          acc = fma(static_cast<double>(v1.z), static_cast<double>(xr[ki.w & 0xffffu]), acc);
+          acc = fma(static_cast<double>(v1.w), static_cast<double>(xr[ki.w >> 16]), acc);
         }
       }
+      acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+      if (have && sub == 0) {
+        const int64_t q = q0 + lo;
+        bool member = true;
+        if (P.list_id != nullptr) {
+          const int32_t lc = __ldg(P.list_id + c);
+          bool hit = false;
+          for (int32_t t = 0; t < P.max_nprobe; ++t) hit |= (__ldg(P.probes + q * P.max_nprobe + t) == lc);
+          member = hit;
+        }
+        uint64_t key = kKeyMax;
+        uint8_t flag = 0;
+        const float ip = static_cast<float>(acc);
+        const float dist = fmaxf(1.0f - ip, 0.0f);
+        if (member && (!P.use_eps || dist <= P.eps)) {
+          key = (static_cast<uint64_t>(ip_key_desc(ip)) << 32) | c;
+          flag = tolerance_ok(P, P.mz[q], P.rt ? P.rt[q] : 0.f, P.mz[c], P.rt ? P.rt[c] : 0.f) ? 1 : 0;
+        }
+        keys[p] = key;
+        flags[p] = flag;
+      }
     }
-    __syncthreads();
+    __syncwarp();
     // ---- rank among the query's pairs; only the k_ann best are eligible
-    for (int p = tid; p < pb; p += kBlockThreads) {
+    for (int p = lane; p < pb; p += 32) {
       const uint64_t key = keys[p];
       if (key == kKeyMax || !(flags[p] & 1)) continue;
-      int lo = 0, hi = nq;
-      while (hi - lo > 1) {
-        const int mid = (lo + hi) >> 1;
-        if (qoff[mid] <= p) lo = mid; else hi = mid;
-      }
+      const int lo = query_of(p);
       int rank = 0;
-      for (int j = qoff[lo]; j < qoff[lo + 1]; ++j) rank += keys[j] < key ? 1 : 0;
+      for (int j = qo_at(qo, lo); j < qo_at(qo, lo + 1); ++j) rank += keys[j] < key ? 1 : 0;
       if (rank < P.k_ann) flags[p] |= 2;
     }
-    __syncthreads();
-    // ---- position among the eligible ones that pass the tolerance: first k are kept
-    for (int p = tid; p < pb; p += kBlockThreads) {
+    __syncwarp();
+    // ---- position among the eligible ones that pass the tolerance: the first k are kept
+    for (int p = lane; p < pb; p += 32) {
       if (!(flags[p] & 2)) continue;
       const uint64_t key = keys[p];
-      int lo = 0, hi = nq;
-      while (hi - lo > 1) {
-        const int mid = (lo + hi) >> 1;
-        if (qoff[mid] <= p) lo = mid; else hi = mid;
-      }
+      const int lo = query_of(p);
+      const int j0 = qo_at(qo, lo), j1 = qo_at(qo, lo + 1);
       int prank = 0;
-      for (int j = qoff[lo]; j < qoff[lo + 1]; ++j) prank += ((flags[j] & 2) && keys[j] < key) ? 1 : 0;
+      for (int j = j0; j < j1; ++j) prank += ((flags[j] & 2) && keys[j] < key) ? 1 : 0;
       if (prank < P.k) {
         const float ip = ip_from_key(static_cast<uint32_t>(key >> 32));
         const float dist = fmaxf(1.0f - ip, 0.0f);
-        grouped[base + qoff[lo] + prank] = (static_cast<uint64_t>(__float_as_uint(dist)) << 32) | (key & 0xffffffffull);
+        grouped[base + j0 + prank] = (static_cast<uint64_t>(__float_as_uint(dist)) << 32) | (key & 0xffffffffull);
       }
     }
-    if (tid < nq) {
+    if (lane < nq) {
       int kept = 0;
-      for (int j = qoff[tid]; j < qoff[tid + 1]; ++j) kept += (flags[j] & 2) ? 1 : 0;
-      row_count[q0 + tid] = min(kept, P.k);
+      for (int j = qo_at(qo, lane); j < qo_at(qo, lane + 1); ++j) kept += (flags[j] & 2) ? 1 : 0;
+      row_count[q0 + lane] = min(kept, P.k);
     }
     // ---- query rows back to zero
-    for (int it = tid; it < nq * cpr; it += kBlockThreads) {
+    for (int it = lane; it < nq * cpr; it += 32) {
       const int r = it / cpr, j0 = (it - r * cpr) << 3;
       const int64_t g = (q0 + r) * W + j0;
       const float4 v0 = __ldg(reinterpret_cast<const float4*>(P.ell_val + g));
@@ -467,6 +476,7 @@ refine_block_kernel(RefineParams P, const int64_t* __restrict__ off, uint64_t* _
       for (int u = 0; u < 8; ++u)  // padding slots carry column 0: only real entries are cleared
         if (vv[u] != 0.f) xr[(kk[u >> 1] >> ((u & 1) * 16)) & 0xffffu] = 0.f;
     }
+    __syncwarp();
   }
 }
 
@@ -504,7 +514,7 @@ static void knn_layout(Workspace& ws, int64_t n, uint64_t n_pairs, KnnLayout& L)
   L.off = ws.take<int64_t>(n + 1);
   L.row_count = ws.take<int32_t>(n + 1);
   L.grouped = ws.take<uint64_t>(n_pairs ? n_pairs : 1);
-  L.deferred = ws.take<int32_t>(2 + static_cast<size_t>((n + kBlockQueries - 1) / kBlockQueries));
+  L.deferred = ws.take<int32_t>(2 + static_cast<size_t>((n + kWarpQueries - 1) / kWarpQueries));
   size_t b1 = 0, b2 = 0;
   cub::DeviceScan::ExclusiveSum(nullptr, b1, (uint32_t*)nullptr, (int64_t*)nullptr, static_cast<int>(n + 1));
   cub::DeviceScan::ExclusiveSum(nullptr, b2, (int32_t*)nullptr, (int64_t*)nullptr, static_cast<int>(n + 1));
@@ -601,17 +611,19 @@ int flc_knn_csr(const uint64_t* pairs, const uint64_t* pair_count, uint64_t pair
   const unsigned rblocks = static_cast<unsigned>(
       std::min<int64_t>((n + kRefineWarps - 1) / kRefineWarps, static_cast<int64_t>(kNumSMs) * 16));
   const int32_t* deferred = nullptr;
-  const size_t bsmem = static_cast<size_t>(kBlockQueries) * low_dim * sizeof(float) + kBlockPairs * 9;
+  const size_t warp_bytes = ((static_cast<size_t>(kWarpQueries) * low_dim * sizeof(float) + kWarpPairs * 9 + 16) + 15) & ~size_t(15);
+  const size_t bsmem = warp_bytes * kBlockWarps;
   const bool block_path = ell_idx != nullptr && (ell_width % 8) == 0 && bsmem <= 100 * 1024 &&
                           (reinterpret_cast<uintptr_t>(ell_idx) % 16) == 0 && (reinterpret_cast<uintptr_t>(ell_val) % 16) == 0;
   if (block_path) {
-    const int64_t n_qblocks = (n + kBlockQueries - 1) / kBlockQueries;
-    FLC_CUDA(cudaMemsetAsync(L.deferred, 0, sizeof(int32_t) * (1 + n_qblocks), stream));
+    const int64_t n_groups = (n + kWarpQueries - 1) / kWarpQueries;
+    FLC_CUDA(cudaMemsetAsync(L.deferred, 0, sizeof(int32_t) * (1 + n_groups), stream));
     FLC_CUDA(cudaFuncSetAttribute(refine_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   static_cast<int>(bsmem)));
     const int64_t per_sm = std::max<int64_t>(1, (227 * 1024) / static_cast<int64_t>(bsmem + 1024));
-    const unsigned bblocks = static_cast<unsigned>(std::min<int64_t>(n_qblocks, static_cast<int64_t>(kNumSMs) * per_sm));
-    timed("refine_block", stream, [&] { refine_block_kernel<<<bblocks, kBlockThreads, bsmem, stream>>>(
+    const unsigned bblocks = static_cast<unsigned>(
+        std::min<int64_t>((n_groups + kBlockWarps - 1) / kBlockWarps, static_cast<int64_t>(kNumSMs) * per_sm));
+    timed("refine_block", stream, [&] { refine_block_kernel<<<bblocks, kBlockWarps * 32, bsmem, stream>>>(
         P, L.off, L.grouped, L.row_count, L.deferred); });
     FLC_LAUNCH_CHECK();
     deferred = L.deferred;

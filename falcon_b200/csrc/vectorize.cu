@@ -60,12 +60,11 @@ struct Peak {
   bool valid;
 };
 
-// Bin + hash of peak p (invalid beyond p1 or outside [0, vec_len)).
-__device__ __forceinline__ Peak load_peak(const VecParams& P, int64_t p, int64_t p1, double vec_len_d) {
-  Peak k{0u, 0.f, false};
-  if (p < p1) {
-    const float m = __ldg(P.mz + p);
-    k.x = __ldg(P.intensity + p);
+// Bin + hash of one peak (m/z, intensity) at peak position p; `have` = the lane holds a peak.
+__device__ __forceinline__ Peak make_peak(const VecParams& P, bool have, float m, float x, int64_t p,
+                                          double vec_len_d) {
+  Peak k{0u, x, false};
+  if (have) {
     // floor((m - min_mz) / bin_size) in float64.  The quotient is first taken as a
     // product with 1 / bin_size (relative error < 2^-51); only when that lands within
     // 1e-4 of an integer is the exact division needed to get the reference's floor.
@@ -84,6 +83,38 @@ __device__ __forceinline__ Peak load_peak(const VecParams& P, int64_t p, int64_t
     if (P.out_hash_idx) P.out_hash_idx[p] = k.valid ? static_cast<int32_t>(k.col) : -1;
   }
   return k;
+}
+
+__device__ __forceinline__ Peak load_peak(const VecParams& P, int64_t p, int64_t p1, double vec_len_d) {
+  const bool have = p < p1;
+  return make_peak(P, have, have ? __ldg(P.mz + p) : 0.f, have ? __ldg(P.intensity + p) : 0.f, p, vec_len_d);
+}
+
+// Software pipeline of the spectrum loop: where a spectrum's peaks are (two
+// iterations ahead) and its first 64 peaks (one iteration ahead) are already in
+// flight while the current spectrum is hashed.
+struct SpecMeta {
+  int64_t r, p0, p1;
+};
+struct SpecRaw {
+  float m0, x0, m1, x1;
+};
+__device__ __forceinline__ SpecMeta load_meta(const VecParams& P, int64_t rr) {
+  SpecMeta s{0, 0, 0};
+  if (rr < P.n) {
+    const int64_t src = P.order ? static_cast<int64_t>(__ldg(P.order + rr)) : rr;
+    s.r = P.dest ? static_cast<int64_t>(__ldg(P.dest + rr)) : rr;
+    s.p0 = __ldg(P.indptr + src);
+    s.p1 = __ldg(P.indptr + src + 1);
+  }
+  return s;
+}
+__device__ __forceinline__ SpecRaw load_raw(const VecParams& P, const SpecMeta& s, int lane) {
+  SpecRaw w{0.f, 0.f, 0.f, 0.f};
+  const int64_t pa = s.p0 + lane, pb = pa + 32;
+  if (pa < s.p1) { w.m0 = __ldg(P.mz + pa); w.x0 = __ldg(P.intensity + pa); }
+  if (pb < s.p1) { w.m1 = __ldg(P.mz + pb); w.x1 = __ldg(P.intensity + pb); }
+  return w;
 }
 
 // row[col] += x for the 32 peaks of one pass, colliding lanes in peak order.
@@ -110,7 +141,7 @@ __device__ __forceinline__ bool accumulate_pass(float* row, const Peak& k, int l
 // One warp per spectrum.  Per-warp shared memory: the float32 accumulation row,
 // a bfloat16 staging row (both all-zero between spectra) and a stamp row that
 // tells which columns an earlier pass of the same spectrum already owns.
-__global__ void __launch_bounds__(kVecWarps * 32)
+__global__ void __launch_bounds__(kVecWarps * 32, 4)
 vectorize_kernel(const VecParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31;
@@ -132,11 +163,17 @@ vectorize_kernel(const VecParams P) {
   __syncwarp();
   uint32_t serial = 0;
 
-  for (int64_t rr = static_cast<int64_t>(blockIdx.x) * kVecWarps + warp; rr < P.n; rr += warps_total) {
-    const int64_t src = P.order ? static_cast<int64_t>(__ldg(P.order + rr)) : rr;
-    const int64_t r = P.dest ? static_cast<int64_t>(__ldg(P.dest + rr)) : rr;
-    const int64_t p0 = __ldg(P.indptr + src);
-    const int64_t p1 = __ldg(P.indptr + src + 1);
+  const int64_t rr0 = static_cast<int64_t>(blockIdx.x) * kVecWarps + warp;
+  SpecMeta cur = load_meta(P, rr0), nxt = load_meta(P, rr0 + warps_total);
+  SpecRaw raw = load_raw(P, cur, lane);
+  for (int64_t rr = rr0; rr < P.n; rr += warps_total) {
+    const SpecMeta nn = load_meta(P, rr + 2 * warps_total);
+    const SpecRaw raw_nxt = load_raw(P, nxt, lane);
+    const int64_t r = cur.r, p0 = cur.p0, p1 = cur.p1;
+    const SpecRaw w = raw;
+    cur = nxt;
+    nxt = nn;
+    raw = raw_nxt;
     float* dst_f = P.out_f32 ? P.out_f32 + r * P.ld_f32 : nullptr;
     uint16_t* dst_b = P.out_bf16 ? P.out_bf16 + r * P.ld_bf16 : nullptr;
     uint16_t* di = P.ell_idx ? P.ell_idx + r * P.ell_width : nullptr;
@@ -151,8 +188,8 @@ vectorize_kernel(const VecParams P) {
         __syncwarp();
       }
       const uint16_t tag = static_cast<uint16_t>(serial);
-      const Peak a = load_peak(P, p0 + lane, p1, vec_len_d);
-      const Peak b = load_peak(P, p0 + 32 + lane, p1, vec_len_d);
+      const Peak a = make_peak(P, p0 + lane < p1, w.m0, w.x0, p0 + lane, vec_len_d);
+      const Peak b = make_peak(P, p0 + 32 + lane < p1, w.m1, w.x1, p0 + 32 + lane, vec_len_d);
       const bool own0 = accumulate_pass(row, a, lane, below);
       bool own1 = false;
       if (p1 - p0 > 32) {
