@@ -676,16 +676,24 @@ kmeans_tiled_init_kernel(TiledArgs A, int64_t total) {
   }
 }
 
-constexpr int kTiledRows = 256;  // rows (threads) per CTA
-constexpr int kTiledG = 32;      // lists staged per pass
+constexpr int kTiledThreads = 256;
+constexpr int kTiledRounds = 4;                              // rows per thread
+constexpr int kTiledRows = kTiledThreads * kTiledRounds;     // rows per CTA
+constexpr int kTiledG = 32;                                  // lists staged per pass
 
-__global__ void __launch_bounds__(kTiledRows)
+// Assignment + incremental accumulation.  A CTA owns 1024 consecutive rows; for
+// every tiled bucket segment inside them it stages the centroids 32 lists at a
+// time ([column][32]) and each thread scores its rows from 16-byte row chunks.
+// Rows whose list changed move their fixed-point values between the lists' global
+// int64 sums with atomics (integer: order free, exact).
+__global__ void __launch_bounds__(kTiledThreads)
 kmeans_tiled_assign_kernel(TiledArgs A) {
   extern __shared__ __align__(16) float Cs[];  // [d][kTiledG]
   const int tid = threadIdx.x;
   const int64_t i0 = static_cast<int64_t>(blockIdx.x) * kTiledRows;
   const int64_t i1 = min(i0 + kTiledRows, A.n);
   const int d = static_cast<int>(A.low_dim);
+  const int W = A.W;
   int64_t b = find_segment(A.bucket_ptr, A.n_buckets, i0);
   for (; b < A.n_buckets && A.bucket_ptr[b] < i1; ++b) {
     if (A.q.bclass[b] != kClsTiled || A.bstate[2 * b + 1] != 0) continue;  // uniform
@@ -693,59 +701,79 @@ kmeans_tiled_assign_kernel(TiledArgs A) {
     const int32_t L = A.nlist[b];
     const int64_t c0 = A.centroid_ptr[b];
     const float* ctb = A.ct + c0 * d;
-    const int64_t i = s + tid;
-    const bool active = i < e;
-    const int m = active ? min(static_cast<int>(A.ell_nnz[i]), A.W) : 0;
-    const uint16_t* ir = A.ell_idx + i * A.W;
-    const float* vr = A.ell_val + i * A.W;
-    float best = -INFINITY;
-    int best_c = 0;
+    float best[kTiledRounds];
+    int best_c[kTiledRounds];
+#pragma unroll
+    for (int t = 0; t < kTiledRounds; ++t) { best[t] = -INFINITY; best_c[t] = 0; }
     for (int g0 = 0; g0 < L; g0 += kTiledG) {
       const int G = min(kTiledG, L - g0);
       __syncthreads();
-      for (int t = tid; t < d * kTiledG; t += kTiledRows) {
+      for (int t = tid; t < d * kTiledG; t += kTiledThreads) {
         const int k = t / kTiledG, g = t - k * kTiledG;
         Cs[t] = g < G ? __ldg(ctb + static_cast<int64_t>(k) * L + g0 + g) : 0.f;
       }
       __syncthreads();
-      if (active) {
+#pragma unroll
+      for (int rnd = 0; rnd < kTiledRounds; ++rnd) {
+        const int64_t i = s + rnd * kTiledThreads + tid;
+        if (i >= e) continue;
+        const int m = min(static_cast<int>(A.ell_nnz[i]), W);
         float a[kTiledG];
 #pragma unroll
         for (int u = 0; u < kTiledG; ++u) a[u] = 0.f;
-        for (int j = 0; j < m; ++j) {
-          const float v = __ldg(vr + j);
-          const float* cr = Cs + static_cast<int>(__ldg(ir + j)) * kTiledG;
+        for (int j0 = 0; j0 < m; j0 += 8) {
+          const uint4 ki = __ldg(reinterpret_cast<const uint4*>(A.ell_idx + i * W + j0));
+          const float4 v0 = __ldg(reinterpret_cast<const float4*>(A.ell_val + i * W + j0));
+          const float4 v1 = __ldg(reinterpret_cast<const float4*>(A.ell_val + i * W + j0 + 4));
+          const float vv[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+          const uint32_t kk[4] = {ki.x, ki.y, ki.z, ki.w};
 #pragma unroll
-          for (int u = 0; u < kTiledG; u += 4) {
-            if (u < G) {  // uniform across the CTA
-              const float4 c4 = *reinterpret_cast<const float4*>(cr + u);
-              a[u] = fmaf(v, c4.x, a[u]);
-              a[u + 1] = fmaf(v, c4.y, a[u + 1]);
-              a[u + 2] = fmaf(v, c4.z, a[u + 2]);
-              a[u + 3] = fmaf(v, c4.w, a[u + 3]);
+          for (int t = 0; t < 8; ++t) {  // zero padding multiplies to zero
+            const float v = vv[t];
+            const float* cr = Cs + ((kk[t >> 1] >> ((t & 1) * 16)) & 0xffffu) * kTiledG;
+#pragma unroll
+            for (int u = 0; u < kTiledG; u += 4) {
+              if (u < G) {  // uniform across the CTA
+                const float4 c4 = *reinterpret_cast<const float4*>(cr + u);
+                a[u] = fmaf(v, c4.x, a[u]);
+                a[u + 1] = fmaf(v, c4.y, a[u + 1]);
+                a[u + 2] = fmaf(v, c4.z, a[u + 2]);
+                a[u + 3] = fmaf(v, c4.w, a[u + 3]);
+              }
             }
           }
         }
 #pragma unroll
         for (int u = 0; u < kTiledG; ++u)
-          if (u < G && a[u] > best) { best = a[u]; best_c = g0 + u; }
+          if (u < G && a[u] > best[rnd]) { best[rnd] = a[u]; best_c[rnd] = g0 + u; }
       }
     }
-    if (active) {
-      if (A.gassign[i] != best_c) {
-        A.gassign[i] = best_c;
-        A.bstate[2 * b] = 1;  // benign race: every writer stores 1
+#pragma unroll
+    for (int rnd = 0; rnd < kTiledRounds; ++rnd) {
+      const int64_t i = s + rnd * kTiledThreads + tid;
+      if (i >= e) continue;
+      const int old_c = A.gassign[i];
+      const int new_c = best_c[rnd];
+      if (old_c == new_c) continue;
+      A.gassign[i] = new_c;
+      A.bstate[2 * b] = 1;  // benign race: every writer stores 1
+      atomicAdd(A.gcnt + c0 + new_c, 1);
+      if (old_c >= 0) atomicSub(A.gcnt + c0 + old_c, 1);
+      unsigned long long* add = reinterpret_cast<unsigned long long*>(A.gsum + (c0 + new_c) * d);
+      unsigned long long* sub = reinterpret_cast<unsigned long long*>(A.gsum + (c0 + max(old_c, 0)) * d);
+      const int m = min(static_cast<int>(A.ell_nnz[i]), W);
+      for (int j = 0; j < m; ++j) {
+        const uint32_t k = __ldg(A.ell_idx + i * W + j);
+        const long long q = __float2ll_rn(__ldg(A.ell_val + i * W + j) * kFixScaleF);
+        atomicAdd(add + k, static_cast<unsigned long long>(q));
+        if (old_c >= 0) atomicAdd(sub + k, static_cast<unsigned long long>(-q));
       }
-      atomicAdd(A.gcnt + c0 + best_c, 1);
-      unsigned long long* dst = reinterpret_cast<unsigned long long*>(A.gsum + (c0 + best_c) * d);
-      for (int j = 0; j < m; ++j)
-        atomicAdd(dst + __ldg(ir + j), static_cast<unsigned long long>(__float2ll_rn(__ldg(vr + j) * kFixScaleF)));
     }
   }
 }
 
 // One CTA per tiled bucket: means, re-seeding of empty lists, normalisation; writes
-// both centroid layouts, clears the accumulators, records convergence.
+// both centroid layouts, records convergence.
 __global__ void __launch_bounds__(256)
 kmeans_tiled_update_kernel(TiledArgs A) {
   __shared__ int32_t cj_s;
@@ -770,7 +798,6 @@ kmeans_tiled_update_kernel(TiledArgs A) {
         for (int k = tid; k < d; k += 256) {
           cent[static_cast<int64_t>(c) * d + k] =
               static_cast<float>(__ll2double_rn(gs[static_cast<int64_t>(c) * d + k]) * scale);
-          gs[static_cast<int64_t>(c) * d + k] = 0;
         }
       } else {
         any_empty = true;
@@ -822,13 +849,65 @@ kmeans_tiled_update_kernel(TiledArgs A) {
         ctb[static_cast<int64_t>(k) * L + c] = v;
       }
     }
-    for (int32_t c = tid; c < L; c += 256) A.gcnt[c0 + c] = 0;
-    if (tid == 0) {
+    if (tid == 0) {  // sums and counts persist: the assign kernel maintains them incrementally
       if (A.bstate[2 * b] == 0 && !any_empty) A.bstate[2 * b + 1] = 1;
       A.bstate[2 * b] = 0;
     }
     __syncthreads();
   }
+}
+
+// Final assignment + probe list for the rows of tiled buckets: one warp per row,
+// one LANE per list (strips of 32 lists): the row's entries are broadcast with
+// shuffles, the transposed training copy of the centroids ([column][list]) makes
+// the gathers coalesced, and there is no reduction across lanes.  float64 inner
+// products, best-first insertion in list order (ties to the lower id) -- the
+// same results as ivf_assign_kernel.
+__global__ void __launch_bounds__(256)
+ivf_assign_tiled_kernel(TiledArgs A, const int32_t* __restrict__ nprobe, int32_t max_nprobe,
+                        int32_t* __restrict__ list_id, int32_t* __restrict__ probes) {
+  const int lane = threadIdx.x & 31;
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  if (i >= A.n) return;
+  const int64_t b = find_segment(A.bucket_ptr, A.n_buckets, i);
+  if (A.q.bclass[b] != kClsTiled) return;
+  const int32_t L = A.nlist[b];
+  const int32_t P = min(nprobe[b], L);
+  const int d = static_cast<int>(A.low_dim);
+  const float* ctb = A.ct + A.centroid_ptr[b] * d;
+  const int m = min(static_cast<int>(A.ell_nnz[i]), A.W);
+  double my_score = -INFINITY;  // lane j: j-th best so far
+  int32_t my_id = -1;
+  for (int32_t s0 = 0; s0 < L; s0 += 32) {
+    const int32_t c = s0 + lane;
+    double acc = 0.0;
+    for (int j0 = 0; j0 < m; j0 += 32) {
+      const int j = j0 + lane;
+      const uint32_t kj = j < m ? static_cast<uint32_t>(__ldg(A.ell_idx + i * A.W + j)) : 0u;
+      const float vj = j < m ? __ldg(A.ell_val + i * A.W + j) : 0.f;
+      const int cnt = min(32, m - j0);
+      for (int t = 0; t < cnt; ++t) {
+        const uint32_t k = __shfl_sync(0xffffffffu, kj, t);
+        const float v = __shfl_sync(0xffffffffu, vj, t);
+        if (c < L) acc = fma(static_cast<double>(v), static_cast<double>(__ldg(ctb + static_cast<int64_t>(k) * L + c)), acc);
+      }
+    }
+    const int n_here = min(32, L - s0);
+    for (int t = 0; t < n_here; ++t) {
+      const double sc = __shfl_sync(0xffffffffu, acc, t);
+      // entries ahead of the newcomer: strictly better, or equal (earlier id wins)
+      const uint32_t ahead = __ballot_sync(0xffffffffu, my_id >= 0 && my_score >= sc);
+      const int pos = __popc(ahead);
+      if (pos < P) {
+        const double up_s = __shfl_up_sync(0xffffffffu, my_score, 1);
+        const int32_t up_i = __shfl_up_sync(0xffffffffu, my_id, 1);
+        if (lane > pos) { my_score = up_s; my_id = up_i; }
+        if (lane == pos) { my_score = sc; my_id = s0 + t; }
+      }
+    }
+  }
+  if (lane < max_nprobe) probes[i * max_nprobe + lane] = lane < P ? my_id : -1;
+  if (lane == 0) list_id[i] = my_id;
 }
 
 struct KmeansLayout {
@@ -976,22 +1055,18 @@ int flc_kmeans_train(const uint16_t* ell_idx, const float* ell_val, const uint16
   FLC_CUDA(cudaFuncSetAttribute(kmeans_tiled_assign_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 static_cast<int>(smem)));
   const unsigned row_blocks = static_cast<unsigned>((n + kTiledRows - 1) / kTiledRows);
+  static_assert(kTiledThreads == 256, "launch configuration below assumes 256 threads");
   const unsigned upd_blocks = static_cast<unsigned>(std::min<int64_t>(n_buckets, 4 * kNumSMs));
   for (int it = 0; it < niter; ++it) {
     timed("kmeans_tiled_assign", stream, [&] {
-      kmeans_tiled_assign_kernel<<<row_blocks, kTiledRows, smem, stream>>>(T); });
+      kmeans_tiled_assign_kernel<<<row_blocks, kTiledThreads, smem, stream>>>(T); });
     FLC_LAUNCH_CHECK();
     timed("kmeans_tiled_update", stream, [&] { kmeans_tiled_update_kernel<<<upd_blocks, 256, 0, stream>>>(T); });
     FLC_LAUNCH_CHECK();
   }
   if (list_id != nullptr) {
-    const size_t smem_a = static_cast<size_t>(8) * low_dim * sizeof(float);
-    if (smem_a > 48 * 1024)
-      FLC_CUDA(cudaFuncSetAttribute(ivf_assign_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    static_cast<int>(smem_a)));
-    timed("ivf_assign", stream, [&] { ivf_assign_kernel<<<static_cast<unsigned>((n + 7) / 8), 256, smem_a, stream>>>(
-        nullptr, 0, n, low_dim, bucket_ptr, n_buckets, nlist, nprobe, centroid_ptr, centroids, max_nprobe, ell_idx,
-        ell_val, W, K.bclass, list_id, probes); });
+    timed("ivf_assign_tiled", stream, [&] { ivf_assign_tiled_kernel<<<static_cast<unsigned>((n + 7) / 8), 256, 0, stream>>>(
+        T, nprobe, max_nprobe, list_id, probes); });
     FLC_LAUNCH_CHECK();
   }
   return FLC_OK;
