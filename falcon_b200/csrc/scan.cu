@@ -9,8 +9,9 @@
 namespace flc {
 
 // ---------------------------------------------------------------- tile schedule
-// Bucket b with n_b rows owns ceil(n_b / kTileM) * ceil(n_b / kTileN) tiles
-// (query tile x candidate tile).  tile_off = exclusive scan over buckets.
+// Bucket b with n_b rows owns ceil(n_b / kTileM) query tiles ("units"); a unit is
+// scanned against the bucket's ceil(n_b / kTileN) candidate tiles.  tile_off =
+// exclusive scan of the unit counts over buckets.
 __global__ void tile_count_kernel(const int64_t* __restrict__ bucket_ptr, int64_t n_buckets,
                                   int64_t* __restrict__ tiles) {
   const int64_t b = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -20,9 +21,7 @@ __global__ void tile_count_kernel(const int64_t* __restrict__ bucket_ptr, int64_
     return;
   }
   const int64_t nb = bucket_ptr[b + 1] - bucket_ptr[b];
-  const int64_t tq = (nb + kTileM - 1) / kTileM;
-  const int64_t tc = (nb + kTileN - 1) / kTileN;
-  tiles[b] = tq * tc;
+  tiles[b] = (nb + kTileM - 1) / kTileM;
 }
 
 // ---------------------------------------------------------------- SIMT verification kernel
@@ -63,16 +62,31 @@ scan_simt_kernel(const uint16_t* __restrict__ x, int64_t ld, int64_t n, uint32_t
   }
 }
 
+// Unit descriptors (first query row, bucket start, bucket end, candidate tiles):
+// one warp per bucket writes those of the bucket's units.
+__global__ void unit_desc_kernel(const int64_t* __restrict__ bucket_ptr, const int64_t* __restrict__ tile_off,
+                                 int64_t n_buckets, int4* __restrict__ unit_desc) {
+  const int lane = threadIdx.x & 31;
+  const int64_t b = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  if (b >= n_buckets) return;
+  const int64_t s = bucket_ptr[b], e = bucket_ptr[b + 1], u0 = tile_off[b];
+  const int tiles_c = static_cast<int>((e - s + kTileN - 1) / kTileN);
+  for (int64_t u = u0 + lane; u < tile_off[b + 1]; u += 32)
+    unit_desc[u] = make_int4(static_cast<int>(s + (u - u0) * kTileM), static_cast<int>(s), static_cast<int>(e), tiles_c);
+}
+
 struct ScanLayout {
-  int64_t* tiles;     // [n_buckets + 1]
-  int64_t* tile_off;  // [n_buckets + 1]
+  int64_t* tiles;        // [n_buckets + 1]
+  int64_t* tile_off;     // [n_buckets + 1]
+  int4* unit_desc;       // [n / kTileM + n_buckets + 1]
   void* cub_tmp;
   size_t cub_bytes;
 };
 
-static void scan_layout(Workspace& ws, int64_t n_buckets, ScanLayout& L) {
+static void scan_layout(Workspace& ws, int64_t n, int64_t n_buckets, ScanLayout& L) {
   L.tiles = ws.take<int64_t>(n_buckets + 1);
   L.tile_off = ws.take<int64_t>(n_buckets + 1);
+  L.unit_desc = ws.take<int4>(static_cast<size_t>(n / kTileM + n_buckets + 1));
   size_t b = 0;
   cub::DeviceScan::ExclusiveSum(nullptr, b, (int64_t*)nullptr, (int64_t*)nullptr,
                                 static_cast<int>(n_buckets + 1));
@@ -85,11 +99,10 @@ static void scan_layout(Workspace& ws, int64_t n_buckets, ScanLayout& L) {
 extern "C" {
 
 size_t flc_scan_workspace_bytes(int64_t n, int64_t n_buckets) {
-  (void)n;
   if (n_buckets <= 0) return 256;
   flc::Workspace ws(nullptr, 0);
   flc::ScanLayout L;
-  flc::scan_layout(ws, n_buckets, L);
+  flc::scan_layout(ws, n > 0 ? n : 0, n_buckets, L);
   return ws.used + 256;
 }
 
@@ -120,7 +133,7 @@ int flc_scan_pairs(const uint16_t* x_bf16, int64_t ld_bf16, int64_t n, uint32_t 
   }
   Workspace ws(workspace, workspace_bytes);
   ScanLayout L;
-  scan_layout(ws, n_buckets, L);
+  scan_layout(ws, n, n_buckets, L);
   if (!ws.ok) return set_error(FLC_ERR_WORKSPACE, "scan workspace too small: need %zu", ws.used);
   timed("tile_count", stream, [&] { tile_count_kernel<<<static_cast<unsigned>((n_buckets + 1 + 255) / 256), 256, 0, stream>>>(
       bucket_ptr, n_buckets, L.tiles); });
@@ -129,7 +142,10 @@ int flc_scan_pairs(const uint16_t* x_bf16, int64_t ld_bf16, int64_t n, uint32_t 
   FLC_CUDA(cub::DeviceScan::ExclusiveSum(L.cub_tmp, tmp, L.tiles, L.tile_off,
                                          static_cast<int>(n_buckets + 1), stream));
   count_launch(2);
-  return launch_scan_tc(x_bf16, ld_bf16, n, low_dim, bucket_ptr, n_buckets, L.tile_off, threshold, pairs,
+  timed("unit_desc", stream, [&] { unit_desc_kernel<<<static_cast<unsigned>((n_buckets * 32 + 255) / 256), 256, 0, stream>>>(
+      bucket_ptr, L.tile_off, n_buckets, L.unit_desc); });
+  FLC_LAUNCH_CHECK();
+  return launch_scan_tc(x_bf16, ld_bf16, n, low_dim, bucket_ptr, n_buckets, L.tile_off, L.unit_desc, threshold, pairs,
                         pair_capacity, reinterpret_cast<unsigned long long*>(pair_count), stream);
 }
 

@@ -21,9 +21,9 @@
 //           compare into a per-row bit mask, warp prefix sum, ONE atomicAdd per
 //           warp and 32-column chunk that has survivors, coalesced pair stores.
 //
-// Persistent grid: one CTA per SM, each walking a contiguous range of the
-// bucket-major tile sequence (queries outer, candidates inner, so the A rows of
-// consecutive tiles hit L2).
+// Persistent grid: one CTA per SM.  Query tiles are dealt round-robin, so the CTAs
+// running together stream the candidate rows of the same bucket(s): HBM sees a
+// row once, L2 serves the re-reads.
 //
 // Roofline: tensor-core bound for buckets >~ 4k rows, 2 * low_dim * n_b^2 FLOP
 // per bucket; HBM/L2-latency bound for small buckets (n_b * low_dim * 2 bytes
@@ -141,45 +141,37 @@ struct Tile {
   int64_t end;  // end row of the bucket
 };
 
+// Walks the tiles of one CTA.  A unit = one query tile (128 rows) against all
+// candidate tiles of its bucket.  Units are dealt round-robin (unit u goes to CTA
+// u mod grid): the CTAs running at any moment then stream the candidate rows of
+// the same one or two buckets, so those rows are fetched from HBM once and served
+// from L2 to everybody else.
 struct TileWalker {
-  const int64_t* bucket_ptr;
-  const int64_t* tile_off;
-  int64_t n_buckets;
-  int64_t b, b_start, b_end, tiles_c, local, b_tiles;
+  const int4* unit_desc;
+  int64_t total, stride, u;
+  int4 cur, nxt;  // descriptor of unit u and (prefetched) of unit u + stride
+  int ct;
 
-  __device__ void load_bucket() {
-    b_start = bucket_ptr[b];
-    b_end = bucket_ptr[b + 1];
-    const int64_t nb = b_end - b_start;
-    tiles_c = (nb + kTileN - 1) / kTileN;
-    b_tiles = ((nb + kTileM - 1) / kTileM) * tiles_c;
+  __device__ void init(const int4* ud, int64_t n_units, int64_t first, int64_t step) {
+    unit_desc = ud; total = n_units; stride = step; u = first; ct = 0;
+    cur = nxt = make_int4(0, 0, 0, 0);
+    if (u < total) cur = __ldg(unit_desc + u);
+    if (u + stride < total) nxt = __ldg(unit_desc + u + stride);
   }
-  __device__ void init(const int64_t* bp, const int64_t* to, int64_t nbk, int64_t t) {
-    bucket_ptr = bp; tile_off = to; n_buckets = nbk;
-    int64_t lo = 0, hi = nbk;  // last b with tile_off[b] <= t
-    while (hi - lo > 1) {
-      const int64_t mid = (lo + hi) >> 1;
-      if (tile_off[mid] <= t) lo = mid; else hi = mid;
-    }
-    b = lo;
-    local = t - tile_off[b];
-    load_bucket();
-  }
+  __device__ bool valid() const { return u < total; }
   __device__ Tile get() const {
     Tile t;
-    t.q0 = b_start + (local / tiles_c) * kTileM;
-    t.c0 = b_start + (local % tiles_c) * kTileN;
-    t.end = b_end;
+    t.q0 = cur.x;
+    t.c0 = static_cast<int64_t>(cur.y) + static_cast<int64_t>(ct) * kTileN;
+    t.end = cur.z;
     return t;
   }
   __device__ void next() {
-    if (++local >= b_tiles) {
-      local = 0;
-      do {
-        ++b;
-        if (b >= n_buckets) return;
-        load_bucket();
-      } while (b_tiles == 0);
+    if (++ct >= cur.w) {
+      ct = 0;
+      u += stride;
+      cur = nxt;
+      if (u + stride < total) nxt = __ldg(unit_desc + u + stride);
     }
   }
 };
@@ -188,7 +180,7 @@ struct TileWalker {
 __global__ void __launch_bounds__(kScanThreads, 1)
 scan_tc_kernel(const __grid_constant__ CUtensorMap tmap, uint32_t low_dim,
                const int64_t* __restrict__ bucket_ptr, int64_t n_buckets,
-               const int64_t* __restrict__ tile_off, float threshold,
+               const int64_t* __restrict__ tile_off, const int4* __restrict__ unit_desc, float threshold,
                uint64_t* __restrict__ pairs, uint64_t capacity, unsigned long long* __restrict__ pair_count) {
   extern __shared__ unsigned char smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -228,22 +220,18 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap, uint32_t low_dim,
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
-  // Contiguous range of tiles for this CTA.
-  const int64_t total = tile_off[n_buckets];
-  const int64_t per = (total + gridDim.x - 1) / gridDim.x;
-  const int64_t t_begin = min(total, per * static_cast<int64_t>(blockIdx.x));
-  const int64_t t_end = min(total, t_begin + per);
   const int num_kb = static_cast<int>((low_dim + kBoxK - 1) / kBoxK);
+  const int64_t n_units = tile_off[n_buckets];
+  (void)bucket_ptr;
 
-  if (t_begin < t_end) {
+  {
     if (warp == 0) {
       // ===================== TMA producer =====================
       if (lane == 0) {
         TileWalker w;
-        w.init(bucket_ptr, tile_off, n_buckets, t_begin);
         int stage = 0;
         uint32_t phase = 0;
-        for (int64_t t = t_begin; t < t_end; ++t, w.next()) {
+        for (w.init(unit_desc, n_units, blockIdx.x, gridDim.x); w.valid(); w.next()) {
           const Tile tile = w.get();
           const bool two = (tile.end - tile.c0) > kBoxRows;
           const uint32_t bytes = kABytes + (two ? 2 : 1) * kBoxBytes;
@@ -264,12 +252,11 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap, uint32_t low_dim,
     } else if (warp == 1) {
       // ===================== MMA issuer =====================
       TileWalker w;
-      w.init(bucket_ptr, tile_off, n_buckets, t_begin);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int64_t t = t_begin; t < t_end; ++t, w.next()) {
+      for (w.init(unit_desc, n_units, blockIdx.x, gridDim.x); w.valid(); w.next()) {
         const Tile tile = w.get();
         const int64_t nc = min(static_cast<int64_t>(kTileN), tile.end - tile.c0);
         const uint32_t n_mma = static_cast<uint32_t>(max(static_cast<int64_t>(16), (nc + 15) & ~int64_t(15)));
@@ -303,10 +290,9 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap, uint32_t low_dim,
       // ===================== epilogue (warps 2..5) =====================
       const int quarter = warp & 3;  // TMEM lanes [32 * quarter, 32 * quarter + 32)
       TileWalker w;
-      w.init(bucket_ptr, tile_off, n_buckets, t_begin);
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int64_t t = t_begin; t < t_end; ++t, w.next()) {
+      for (w.init(unit_desc, n_units, blockIdx.x, gridDim.x); w.valid(); w.next()) {
         const Tile tile = w.get();
         const int64_t nc = min(static_cast<int64_t>(kTileN), tile.end - tile.c0);
         const int64_t q = tile.q0 + quarter * 32 + lane;
@@ -385,9 +371,9 @@ static EncodeTiledFn get_encode_fn() {
 }
 
 int launch_scan_tc(const uint16_t* x_bf16, int64_t ld_bf16, int64_t n, uint32_t low_dim,
-                   const int64_t* bucket_ptr, int64_t n_buckets, const int64_t* tile_off, float threshold,
-                   uint64_t* pairs, uint64_t pair_capacity, unsigned long long* pair_count,
-                   cudaStream_t stream) {
+                   const int64_t* bucket_ptr, int64_t n_buckets, const int64_t* tile_off,
+                   const int4* unit_desc, float threshold, uint64_t* pairs, uint64_t pair_capacity,
+                   unsigned long long* pair_count, cudaStream_t stream) {
   EncodeTiledFn encode = get_encode_fn();
   if (!encode) return set_error(FLC_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
   FLC_REQUIRE((reinterpret_cast<uintptr_t>(x_bf16) & 15) == 0, "x_bf16 must be 16-byte aligned");
@@ -407,7 +393,7 @@ int launch_scan_tc(const uint16_t* x_bf16, int64_t ld_bf16, int64_t n, uint32_t 
     attr_set = true;
   }
   timed("scan_tc", stream, [&] { scan_tc_kernel<<<kNumSMs, kScanThreads, kSmemBytes, stream>>>(tmap, low_dim, bucket_ptr, n_buckets, tile_off,
-                                                               threshold, pairs, pair_capacity, pair_count); });
+                                                               unit_desc, threshold, pairs, pair_capacity, pair_count); });
   FLC_LAUNCH_CHECK();
   return FLC_OK;
 }
