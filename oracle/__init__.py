@@ -24,5 +24,7 @@ buckets / IVF / filter SURVEY.md Appendix A.2 (published falcon 0.1.x +      **p
 DBSCAN                 sklearn/cluster/_dbscan_inner.pyx:11-41               sklearn ``dbscan_inner`` itself
 precursor split        /root/reference/falcon/cluster/cluster.py:334-509     reference functions executed ->
                                                                              tests/golden/postprocess.npz
+representatives        SURVEY.md Appendix A.5 (published falcon 0.1.x; the   **parity unpinned** (hand-worked example
+                       snapshot keeps a dense descendant, cluster.py:512-553)  in tests/test_oracle_pipeline.py)
 =====================  ====================================================  =====================================
 """
