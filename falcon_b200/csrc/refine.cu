@@ -559,20 +559,15 @@ int flc_knn_csr(const uint64_t* pairs, const uint64_t* pair_count, uint64_t pair
     FLC_CUDA(cudaStreamSynchronize(stream));
     return FLC_OK;
   }
-  // The pair count decides the layout: read it (this op returns nnz anyway).
-  uint64_t total = 0;
-  FLC_CUDA(cudaMemcpyAsync(&total, pair_count, sizeof(total), cudaMemcpyDeviceToHost, stream));
-  FLC_CUDA(cudaStreamSynchronize(stream));
-  if (total > pair_capacity)
-    return set_error(FLC_ERR_CAPACITY, "scan produced %llu candidate pairs, capacity %llu",
-                     static_cast<unsigned long long>(total),
-                     static_cast<unsigned long long>(pair_capacity));
+  // The workspace is laid out for pair_capacity pairs; whether the scan overflowed it is
+  // checked with the one synchronisation at the end (this op returns nnz anyway).
   Workspace ws(workspace, workspace_bytes);
   KnnLayout L;
-  knn_layout(ws, n, total, L);
+  knn_layout(ws, n, pair_capacity, L);
   if (!ws.ok)
     return set_error(FLC_ERR_WORKSPACE, "knn_csr workspace too small: need %zu bytes for %llu pairs",
-                     ws.used, static_cast<unsigned long long>(total));
+                     ws.used, static_cast<unsigned long long>(pair_capacity));
+  const uint64_t total = pair_capacity;  // upper bound for grid sizing; kernels read *pair_count
   FLC_CUDA(cudaMemsetAsync(L.cnt, 0, sizeof(uint32_t) * (n + 1), stream));
   FLC_CUDA(cudaMemsetAsync(L.cursor, 0, sizeof(uint32_t) * (n + 1), stream));
   FLC_CUDA(cudaMemsetAsync(L.row_count, 0, sizeof(int32_t) * (n + 1), stream));
@@ -635,8 +630,13 @@ int flc_knn_csr(const uint64_t* pairs, const uint64_t* pair_count, uint64_t pair
   FLC_CUDA(cub::DeviceScan::ExclusiveSum(L.cub_tmp, tmp, L.row_count, indptr, static_cast<int>(n + 1), stream));
   count_launch(2);
   int64_t total_nnz = 0;
+  uint64_t n_pairs = 0;
   FLC_CUDA(cudaMemcpyAsync(&total_nnz, indptr + n, sizeof(int64_t), cudaMemcpyDeviceToHost, stream));
+  FLC_CUDA(cudaMemcpyAsync(&n_pairs, pair_count, sizeof(n_pairs), cudaMemcpyDeviceToHost, stream));
   FLC_CUDA(cudaStreamSynchronize(stream));
+  if (n_pairs > pair_capacity)
+    return set_error(FLC_ERR_CAPACITY, "scan produced %llu candidate pairs, capacity %llu",
+                     static_cast<unsigned long long>(n_pairs), static_cast<unsigned long long>(pair_capacity));
   *nnz = total_nnz;
   if (static_cast<uint64_t>(total_nnz) > nnz_capacity)
     return set_error(FLC_ERR_CAPACITY, "CSR needs %lld entries, capacity %llu",

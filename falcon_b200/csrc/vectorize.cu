@@ -205,7 +205,7 @@ vectorize_kernel(const VecParams P) {
         double ss = static_cast<double>(v0) * static_cast<double>(v0);
         ss = fma(static_cast<double>(v1), static_cast<double>(v1), ss);
         ss = warp_sum_f64(ss);
-        scale = ss > 0.0 ? 1.0 / sqrt(ss) : 1.0;
+        scale = ss > 0.0 ? rsqrt(ss) : 1.0;
       }
       const float s0 = static_cast<float>(static_cast<double>(v0) * scale);
       const float s1 = static_cast<float>(static_cast<double>(v1) * scale);
@@ -251,7 +251,7 @@ vectorize_kernel(const VecParams P) {
         double ss = 0.0;
         for (uint32_t i = lane; i < P.low_dim; i += 32) ss = fma(static_cast<double>(row[i]), static_cast<double>(row[i]), ss);
         ss = warp_sum_f64(ss);
-        scale = ss > 0.0 ? 1.0 / sqrt(ss) : 1.0;
+        scale = ss > 0.0 ? rsqrt(ss) : 1.0;
       }
       for (uint32_t base = 0; base < P.row_len; base += 32) {
         const uint32_t i = base + lane;

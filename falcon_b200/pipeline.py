@@ -137,7 +137,13 @@ class KnnGraph:
     indices: torch.Tensor  # int32 [nnz]
     indptr: torch.Tensor  # int64 [n + 1]
     nnz: int
-    n_pairs: int
+    pair_count: object = 0  # candidate pairs the scan produced (int, or the device-side counter)
+
+    @property
+    def n_pairs(self) -> int:
+        if isinstance(self.pair_count, torch.Tensor):
+            self.pair_count = int(self.pair_count.item())
+        return int(self.pair_count)
 
 
 @dataclasses.dataclass
@@ -178,8 +184,18 @@ class HotPath:
     def _empty(self, n, dtype):
         return torch.empty(int(n), dtype=dtype, device=self.device)
 
-    def _ws(self, nbytes: int) -> torch.Tensor:
-        return torch.empty(int(nbytes) + 256, dtype=torch.uint8, device=self.device)
+    def _ws(self, nbytes: int, name: Optional[str] = None) -> torch.Tensor:
+        """Workspace of at least ``nbytes``.  Named workspaces are pure scratch of one
+        stage call: they are kept and reused by later calls (grown when needed), so a
+        steady-state step does not go through the allocator for them."""
+        nbytes = int(nbytes) + 256
+        if name is None:
+            return torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        cache = self.__dict__.setdefault("_scratch", {})
+        buf = cache.get(name)
+        if buf is None or buf.numel() < nbytes:
+            buf = cache[name] = torch.empty(nbytes + nbytes // 8, dtype=torch.uint8, device=self.device)
+        return buf
 
     # ------------------------------------------------------------------ a5
     def bucket_sort(self, precursor_mz: torch.Tensor, charge: torch.Tensor,
@@ -191,7 +207,7 @@ class HotPath:
         bucket_ptr = self._empty(n + 1, torch.int64)
         nb = C.c_int64(0)
         with self.timer("bucket_sort"):
-            ws = self._ws(lib.flc_bucket_sort_workspace_bytes(n))
+            ws = self._ws(lib.flc_bucket_sort_workspace_bytes(n), "bucket_sort")
             check(lib.flc_bucket_sort(ptr(precursor_mz), ptr(charge), n, self.s.mz_interval,
                                       ptr(order), ptr(key), ptr(mz_sorted), ptr(bucket_ptr),
                                       C.byref(nb), ptr(ws), ws.numel(), _stream()))
@@ -276,7 +292,7 @@ class HotPath:
                 if v.ell_idx is None:
                     raise ValueError("k-means trains on the sparse rows: vectorize(..., want_ell=True)")
                 centroids = torch.empty((max(total, 1), d), dtype=torch.float32, device=self.device)
-                ws = self._ws(lib.flc_kmeans_workspace_bytes(n, buckets.n_buckets, total, maxb, v.ell_width, d))
+                ws = self._ws(lib.flc_kmeans_workspace_bytes(n, buckets.n_buckets, total, maxb, v.ell_width, d), "kmeans")
                 check(lib.flc_kmeans_train(ptr(v.ell_idx), ptr(v.ell_val), ptr(v.ell_nnz), v.ell_width, n, d,
                                            ptr(buckets.bucket_ptr), buckets.n_buckets, ptr(nlist), ptr(cptr),
                                            total, maxb, self.s.kmeans_iters, ptr(centroids), ptr(nprobe), maxp,
@@ -309,9 +325,9 @@ class HotPath:
             sizes = (buckets.bucket_ptr[1:] - buckets.bucket_ptr[:-1])
             pair_capacity = int((sizes * sizes).sum().item()) + 1024
         pair_count = torch.zeros(1, dtype=torch.int64, device=self.device)
-        ws = self._ws(lib.flc_scan_workspace_bytes(n, buckets.n_buckets))
+        ws = self._ws(lib.flc_scan_workspace_bytes(n, buckets.n_buckets), "scan")
         while True:
-            pairs = self._empty(pair_capacity, torch.int64)
+            pairs = self._ws(8 * pair_capacity, "pairs")
             with self.timer("scan"):
                 check(lib.flc_scan_pairs(ptr(xb), xb.stride(0), n, d, ptr(buckets.bucket_ptr),
                                          buckets.n_buckets,
@@ -319,37 +335,42 @@ class HotPath:
                                          ivf.max_nprobe if ivf else 0, ptr(ivf.nlist) if ivf else None,
                                          thr, s.scan_impl, ptr(pairs), pair_capacity, ptr(pair_count),
                                          ptr(ws), ws.numel(), _stream()))
-            n_pairs = int(pair_count.item())
-            if n_pairs <= pair_capacity:
+            # no host round trip here: flc_knn_csr works off the device-side count and reports an
+            # overflow of the candidate buffer together with nnz (one synchronisation)
+            nnz_cap = max(1, min(pair_capacity, n * s.n_neighbors))
+            dist = self._empty(nnz_cap, torch.float32)
+            indices = self._empty(nnz_cap, torch.int32)
+            indptr = self._empty(n + 1, torch.int64)
+            nnz = C.c_int64(0)
+            try:
+                with self.timer("knn_csr"):
+                    ws2 = self._ws(lib.flc_knn_csr_workspace_bytes(n, pair_capacity), "knn_csr")
+                    check(lib.flc_knn_csr(ptr(pairs), ptr(pair_count), pair_capacity,
+                                          ptr(x), x.stride(0) if x is not None else d,
+                                          ptr(v.ell_idx), ptr(v.ell_val), v.ell_width, n, d,
+                                          ptr(buckets.mz), ptr(buckets.rt) if s.rt_tol is not None else None,
+                                          ptr(ivf.list_id) if ivf else None, ptr(ivf.probes) if ivf else None,
+                                          ivf.max_nprobe if ivf else 0,
+                                          s.precursor_tol_mass, _lib.TOL_MODES[s.precursor_tol_mode],
+                                          -1.0 if s.rt_tol is None else float(s.rt_tol),
+                                          s.n_neighbors, s.n_neighbors_ann,
+                                          float(np.float32(s.eps)) if s.eps_cut else float("nan"),
+                                          ptr(dist), ptr(indices), nnz_cap, ptr(indptr), C.byref(nnz),
+                                          ptr(ws2), ws2.numel(), _stream()))
                 break
-            pair_capacity = n_pairs + 1024  # candidate buffer was too small: rescan
-        nnz_cap = max(1, min(n_pairs, n * s.n_neighbors))
-        dist = self._empty(nnz_cap, torch.float32)
-        indices = self._empty(nnz_cap, torch.int32)
-        indptr = self._empty(n + 1, torch.int64)
-        nnz = C.c_int64(0)
-        with self.timer("knn_csr"):
-            ws2 = self._ws(lib.flc_knn_csr_workspace_bytes(n, n_pairs))
-            check(lib.flc_knn_csr(ptr(pairs), ptr(pair_count), pair_capacity,
-                                  ptr(x), x.stride(0) if x is not None else d,
-                                  ptr(v.ell_idx), ptr(v.ell_val), v.ell_width, n, d,
-                                  ptr(buckets.mz), ptr(buckets.rt) if s.rt_tol is not None else None,
-                                  ptr(ivf.list_id) if ivf else None, ptr(ivf.probes) if ivf else None,
-                                  ivf.max_nprobe if ivf else 0,
-                                  s.precursor_tol_mass, _lib.TOL_MODES[s.precursor_tol_mode],
-                                  -1.0 if s.rt_tol is None else float(s.rt_tol),
-                                  s.n_neighbors, s.n_neighbors_ann,
-                                  float(np.float32(s.eps)) if s.eps_cut else float("nan"),
-                                  ptr(dist), ptr(indices), nnz_cap, ptr(indptr), C.byref(nnz),
-                                  ptr(ws2), ws2.numel(), _stream()))
-        return KnnGraph(dist[: nnz.value], indices[: nnz.value], indptr, int(nnz.value), n_pairs)
+            except _lib.CapacityError:
+                n_pairs = int(pair_count.item())
+                if n_pairs <= pair_capacity:
+                    raise
+                pair_capacity = n_pairs + 1024  # candidate buffer was too small: rescan
+        return KnnGraph(dist[: nnz.value], indices[: nnz.value], indptr, int(nnz.value), pair_count)
 
     # ------------------------------------------------------------------ a10
     def dbscan(self, g: KnnGraph, n: int):
         labels = self._empty(n, torch.int32)
         nc = C.c_int64(0)
         with self.timer("dbscan"):
-            ws = self._ws(lib.flc_dbscan_workspace_bytes(n))
+            ws = self._ws(lib.flc_dbscan_workspace_bytes(n), "dbscan")
             check(lib.flc_dbscan(ptr(g.dist), ptr(g.indices), ptr(g.indptr), n,
                                  float(np.float32(self.s.eps)), self.s.min_samples, ptr(labels),
                                  C.byref(nc), ptr(ws), ws.numel(), _stream()))
@@ -361,7 +382,7 @@ class HotPath:
         out = self._empty(n, torch.int32)
         nc = C.c_int64(0)
         with self.timer("split"):
-            ws = self._ws(lib.flc_split_workspace_bytes(n))
+            ws = self._ws(lib.flc_split_workspace_bytes(n), "split")
             check(lib.flc_split_clusters(ptr(labels), ptr(mz), n, self.s.precursor_tol_mass,
                                          _lib.TOL_MODES[self.s.precursor_tol_mode],
                                          -1.0 if self.s.rt_tol is None else float(self.s.rt_tol),
@@ -374,7 +395,7 @@ class HotPath:
         """Row index (in the matrix' row order) of the representative of every cluster."""
         out = self._empty(n_clusters, torch.int32)
         with self.timer("medoids"):
-            ws = self._ws(lib.flc_medoids_workspace_bytes(n_clusters))
+            ws = self._ws(lib.flc_medoids_workspace_bytes(n_clusters), "medoids")
             check(lib.flc_medoids(ptr(g.dist), ptr(g.indices), ptr(g.indptr), labels.shape[0], ptr(labels),
                                   n_clusters, ptr(out), ptr(ws), ws.numel(), _stream()))
         return out
@@ -383,11 +404,11 @@ class HotPath:
     def _cluster_vectors(self, v: Vectors, buckets: Buckets, n: int, keep: bool):
         ivf = None if self.s.exhaustive else self.build_ivf(v, buckets)
         graph = self.knn_graph(v, buckets, ivf)
+        db_labels, _ = self.dbscan(graph, n)
+        sorted_labels, n_clusters = self.split(db_labels, buckets.mz, values_sorted=True)
         if v.overflow is not None and int(v.overflow.item()) > 0:  # the stream was just synchronised
             raise RuntimeError(f"a spectrum hashed to {int(v.overflow.item())} distinct columns but the sparse rows "
                                f"hold {v.ell_width}: pass the true max_peaks")
-        db_labels, _ = self.dbscan(graph, n)
-        sorted_labels, n_clusters = self.split(db_labels, buckets.mz, values_sorted=True)
         labels = self._empty(n, torch.int32)
         with self.timer("scatter"):
             check(lib.flc_scatter32(ptr(sorted_labels), ptr(buckets.order), n, ptr(labels), _stream()))

@@ -25,7 +25,14 @@ dev = hp.device
 d = {k: torch.from_numpy(v).to(dev) for k, v in dict(
     mz=sp.mz, intensity=sp.intensity, indptr=sp.indptr, precursor_mz=sp.precursor_mz,
     charge=sp.precursor_charge).items()}
+import time  # noqa: E402
+
 for i in range(args.steps):
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    a.record()
     labels, nc = hp.run(d["mz"], d["intensity"], d["indptr"], d["precursor_mz"], d["charge"])
+    b.record()
     torch.cuda.synchronize()
-    print(f"step {i}: {nc} clusters", flush=True)
+    print(f"step {i}: {nc} clusters, {a.elapsed_time(b):.3f} ms on the stream, {(time.perf_counter() - t0) * 1e3:.3f} ms wall, "
+          f"reserved {torch.cuda.memory_reserved() >> 20} MiB", flush=True)
