@@ -21,6 +21,9 @@ FLC_ERR_UNSUPPORTED = -5
 TOL_MODES = {"Da": 0, "ppm": 1}
 
 
+SCALING = {None: 0, "root": 1, "log": 2, "rank": 3}  # flc_preprocess scaling codes
+
+
 class CapacityError(RuntimeError):
     """A caller-provided device buffer was too small (FLC_ERR_CAPACITY)."""
 
@@ -66,6 +69,9 @@ SIGNATURES = {
                                    _p, _p, _i32, _p, _p, _p, _sz, _p]),
     "flc_ivf_assign": (C.c_int, [_p, _i64, _i64, _u32, _p, _i64, _p, _p, _p, _p, _i32,
                                  _p, _p, _i32, _p, _p, _p]),
+    "flc_preprocess_workspace_bytes": (_sz, [_i64, _i64]),
+    "flc_preprocess": (C.c_int, [_p, _p, _p, _i64, _i64, _p, _p, _i32, _f32, _f32, _f32, _f32, _f32, _i32, C.c_int,
+                                 _p, _p, _p, _p, C.POINTER(_i64), _p, _sz, _p]),
     "flc_medoids_workspace_bytes": (_sz, [_i64]),
     "flc_medoids": (C.c_int, [_p, _p, _p, _i64, _p, _i64, _p, _p, _sz, _p]),
     "flc_scan_workspace_bytes": (_sz, [_i64, _i64]),

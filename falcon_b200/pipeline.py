@@ -217,6 +217,40 @@ class HotPath:
                 check(lib.flc_gather(ptr(rt), ptr(order), n, 4, ptr(rt_sorted), _stream()))
         return Buckets(order, key, mz_sorted, rt_sorted, bucket_ptr[: nb.value + 1], int(nb.value))
 
+    # ------------------------------------------------------------------ 8f-1: preprocessing
+    def preprocess(self, mz: torch.Tensor, intensity: torch.Tensor, indptr: torch.Tensor,
+                   precursor_mz: torch.Tensor, charge: Optional[torch.Tensor], min_peaks: int = 5,
+                   min_mz_range: float = 250.0, mz_min: Optional[float] = 101.0, mz_max: Optional[float] = 1500.0,
+                   remove_precursor_tolerance: Optional[float] = 1.5, min_intensity: Optional[float] = 0.01,
+                   max_peaks_used: Optional[int] = 50, scaling: Optional[str] = "off"):
+        """``process_spectrum`` (/root/reference/falcon/cluster/spectrum.py:73-169) for all spectra
+        at once; defaults are falcon's (/root/reference/falcon/config.py:127-183).  Returns
+        (out_mz, out_intensity, out_indptr, valid): compact CSR peaks (rejected spectra keep none)
+        and the uint8 validity mask."""
+        if scaling == "off":
+            scaling = None
+        if scaling not in _lib.SCALING:
+            raise ValueError("Unknown intensity scaling")
+        n = indptr.shape[0] - 1
+        n_peaks = int(mz.shape[0])
+        out_mz = self._empty(max(n_peaks, 1), torch.float32)
+        out_int = self._empty(max(n_peaks, 1), torch.float32)
+        out_indptr = self._empty(n + 1, torch.int64)
+        valid = self._empty(max(n, 1), torch.uint8)
+        total = C.c_int64(0)
+        nan = float("nan")
+        with self.timer("preprocess"):
+            ws = self._ws(lib.flc_preprocess_workspace_bytes(n, n_peaks), "preprocess")
+            check(lib.flc_preprocess(ptr(mz), ptr(intensity), ptr(indptr), n, n_peaks, ptr(precursor_mz), ptr(charge),
+                                     int(min_peaks), float(min_mz_range), nan if mz_min is None else float(mz_min),
+                                     nan if mz_max is None else float(mz_max),
+                                     -1.0 if remove_precursor_tolerance is None else float(remove_precursor_tolerance),
+                                     -1.0 if min_intensity is None else float(min_intensity),
+                                     0 if max_peaks_used is None else int(max_peaks_used), _lib.SCALING[scaling],
+                                     ptr(out_mz), ptr(out_int), ptr(out_indptr), ptr(valid), C.byref(total),
+                                     ptr(ws), ws.numel(), _stream()))
+        return out_mz[: total.value], out_int[: total.value], out_indptr, valid[:n]
+
     # ------------------------------------------------------------------ a2-a4
     def _ell_width(self, indptr: torch.Tensor, max_peaks: Optional[int]) -> int:
         if max_peaks is None:  # a row has at most as many non-zeros as the spectrum has peaks

@@ -235,6 +235,26 @@ FLC_API int flc_medoids(const float* dist, const int32_t* indices, const int64_t
                 const int32_t* labels, int64_t n_clusters, int32_t* medoids,
                 void* workspace, size_t workspace_bytes, flc_stream_t stream);
 
+/* ------------------------------------------------------------------ preprocessing
+ * falcon/cluster/spectrum.py:73-169 (process_spectrum on spectrum_utils 0.3.5): m/z
+ * window [mz_min, mz_max] (NaN = open), removal of the precursor peak of every charge
+ * state within remove_precursor_tol Da (< 0 = keep), base-peak intensity threshold
+ * (min_intensity < 0 = none) and top max_peaks_used cut (0 = none), intensity scaling
+ * (0 none, 1 root, 2 log2(1 + x), 3 rank) and L2 normalisation; a spectrum must keep
+ * >= min_peaks peaks spanning >= min_mz_range after every step (spectrum.py:27-52).
+ * Input peaks ascending in m/z per spectrum.  Outputs: compact CSR of the survivors
+ * (out_mz / out_intensity need room for n_peaks, out_indptr [n + 1]; a rejected
+ * spectrum keeps zero peaks) and valid[n].  Synchronises; returns the number of
+ * surviving peaks on the host. */
+FLC_API size_t flc_preprocess_workspace_bytes(int64_t n, int64_t n_peaks);
+FLC_API int flc_preprocess(const float* mz, const float* intensity, const int64_t* indptr, int64_t n,
+                   int64_t n_peaks, const double* precursor_mz, const int32_t* charge /*nullable: 1*/,
+                   int32_t min_peaks, float min_mz_range, float mz_min, float mz_max,
+                   float remove_precursor_tol, float min_intensity, int32_t max_peaks_used, int scaling,
+                   float* out_mz, float* out_intensity, int64_t* out_indptr, uint8_t* valid,
+                   int64_t* n_out_peaks /*host*/, void* workspace, size_t workspace_bytes,
+                   flc_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,81 @@
+"""Host-side pieces of the CLI drop-in: MGF IO and the settings parser."""
+import io
+
+import numpy as np
+import pytest
+
+from falcon_b200 import config as fconfig
+from falcon_b200 import synth
+from falcon_b200.ms_io import mgf_io
+
+
+def test_mgf_round_trip(tmp_path):
+    sp = synth.generate(300, 3)
+    dicts = sp.as_dicts()
+    dicts[5]["precursor_charge"] = None  # absent charge is allowed (mgf_io.py:55-58)
+    path = str(tmp_path / "s.mgf")
+    mgf_io.write_spectra(path, dicts)
+    back = list(mgf_io.get_spectra(path))
+    assert len(back) == 300
+    for a, b in zip(dicts, back):
+        assert b["identifier"] == a["identifier"] and b["filename"] == path
+        assert b["precursor_charge"] == a["precursor_charge"]
+        assert b["precursor_mz"] == pytest.approx(a["precursor_mz"], abs=0) and b["retention_time"] == a["retention_time"]
+        assert np.array_equal(b["mz"], a["mz"]) and np.array_equal(b["intensity"], a["intensity"])
+    ss, ids, files = mgf_io.read_mgf(path)
+    assert len(ss) == 300 and ids[7] == "synth:7" and ss.precursor_charge[5] == 0
+    assert np.array_equal(ss.mz, sp.mz)
+
+
+def test_mgf_parser_tolerates_real_world_files():
+    text = """# comment
+BEGIN IONS
+TITLE=spec one
+PEPMASS=500.25 12345.6
+CHARGE=2+
+RTINSECONDS=12.5
+SCANS=17
+300.5 10
+100.25 5.5
+200.0\t7
+END IONS
+
+BEGIN IONS
+TITLE=broken
+PEPMASS=abc
+100 1
+END IONS
+BEGIN IONS
+TITLE=no charge
+PEPMASS=400.0
+END IONS
+"""
+    spectra = list(mgf_io.get_spectra(io.StringIO(text)))
+    assert [s["identifier"] for s in spectra] == ["spec one", "no charge"]  # the unparsable one is skipped
+    s = spectra[0]
+    assert s["precursor_mz"] == 500.25 and s["precursor_charge"] == 2 and s["retention_time"] == 12.5
+    assert s["mz"].tolist() == [100.25, 200.0, 300.5] and s["intensity"].tolist() == [5.5, 7.0, 10.0]  # sorted by m/z
+    assert spectra[1]["precursor_charge"] is None and spectra[1]["retention_time"] == -1 and len(spectra[1]["mz"]) == 0
+
+
+def test_config_defaults_ini_and_command_line(tmp_path):
+    cfg = fconfig.Config()
+    with pytest.raises(RuntimeError):
+        cfg.eps
+    cfg.parse(["in.mgf", "out"])
+    # falcon's defaults (/root/reference/falcon/config.py:77-183)
+    assert (cfg.eps, cfg.low_dim, cfg.n_neighbors, cfg.n_neighbors_ann, cfg.n_probe) == (0.1, 400, 64, 128, 32)
+    assert cfg.precursor_tol == [20.0, "ppm"] and cfg.fragment_tol == 0.05 and cfg.rt_tol is None
+    assert (cfg.min_peaks, cfg.min_mz_range, cfg.min_mz, cfg.max_mz) == (5, 250.0, 101.0, 1500.0)
+    assert (cfg.remove_precursor_tol, cfg.min_intensity, cfg.max_peaks_used, cfg.scaling) == (1.5, 0.01, 50, "off")
+    ini = tmp_path / "my.ini"
+    ini.write_text("# settings\neps = 0.25\nprecursor_tol = 0.5 Da\nexport_representatives = true\nscaling = rank\n")
+    cfg.parse(["-c", str(ini), "a.mgf", "b.mgf", "out", "--eps", "0.3"])
+    assert cfg.eps == 0.3 and cfg.precursor_tol == [0.5, "Da"] and cfg.export_representatives and cfg.scaling == "rank"
+    assert cfg.input_filenames == ["a.mgf", "b.mgf"] and cfg["output_filename"] == "out"
+    with pytest.raises(ValueError):
+        cfg.parse(["in.mgf", "out", "--precursor_tol", "20", "Th"])
+    with pytest.raises(ValueError):
+        cfg.parse(["in.mgf", "out", "--n_neighbors", "64", "--n_neighbors_ann", "32"])
+    cfg.parse(["in.mgf", "out", "--distance_threshold", "0.15"])
+    assert cfg.eps == 0.15

@@ -136,3 +136,49 @@ def test_full_size_properties_1m():
     # exhaustive mode finds a superset of the default-n_probe neighbours: never fewer clustered spectra
     labels_ex, _, _ = pipeline.cluster_host(sp, pipeline.Settings(exhaustive=True))
     assert (labels_ex >= 0).sum() >= m.sum()
+
+
+@pytest.mark.gpu
+def test_cli_mgf_to_csv_matches_oracle(tmp_path):
+    """BASELINE configs[0] in miniature, through the `falcon` command: MGF in -> preprocessing ->
+    per-charge clustering -> CSV (+ representatives MGF).  The partition must equal the oracle's
+    (oracle preprocessing + oracle pipeline, exhaustive mode) on the same file."""
+    import pandas as pd
+
+    from falcon_b200 import falcon as fmain
+    from falcon_b200.ms_io import mgf_io
+    from oracle import preprocess as opre
+
+    sp = synth.generate(4000, 17, mass_range=(1000.0, 1015.0))
+    dicts = sp.as_dicts()
+    path, out = str(tmp_path / "in.mgf"), str(tmp_path / "res")
+    mgf_io.write_spectra(path, dicts)
+    assert fmain.main([path, out, "--exhaustive", "--export_representatives"]) == 0
+    with open(out + ".csv") as fh:
+        header = [l for l in fh if l.startswith("#")]
+    assert header[0].startswith("# falcon version") and any(l.startswith("# eps = 0.100") for l in header)
+    df = pd.read_csv(out + ".csv", comment="#")
+    assert list(df.columns) == ["filename", "spectrum_id", "precursor_charge", "precursor_mz", "retention_time", "cluster"]
+    # oracle: same preprocessing, same path
+    raw, ids, _ = mgf_io.read_mgf(path)
+    valid, mz, it, indptr = opre.process_spectra(raw, min_peaks=5, min_mz_range=250.0, mz_min=101.0, mz_max=1500.0,
+                                                 remove_precursor_tolerance=1.5, min_intensity=0.01, max_peaks_used=50,
+                                                 scaling=None)
+    keep = np.flatnonzero(valid)
+    assert sorted(df["spectrum_id"]) == sorted(ids[i] for i in keep)
+    proc = synth.SpectrumSet(mz, it, indptr, raw.precursor_mz, raw.precursor_charge, raw.retention_time).take(keep)
+    o = helpers.oracle_pipeline(proc, exhaustive=True)
+    ref = np.empty(len(proc), np.int64)
+    ref[o["order"]] = o["labels"]
+    by_id = dict(zip(df["spectrum_id"], df["cluster"]))
+    got = np.array([by_id[ids[i]] for i in keep])
+    assert odb.same_partition(got, ref)
+    # labels of the two charges are disjoint and consecutive
+    lab = df[df["cluster"] >= 0]
+    assert lab.groupby("cluster")["precursor_charge"].nunique().max() == 1
+    assert sorted(lab["cluster"].unique()) == list(range(lab["cluster"].nunique()))
+    # one representative per cluster, each a member of its cluster
+    reps = list(mgf_io.get_spectra(out + ".mgf"))
+    assert len(reps) == lab["cluster"].nunique()
+    # second run without --overwrite leaves the result alone
+    assert fmain.main([path, out, "--exhaustive"]) == 0

@@ -441,3 +441,67 @@ def test_rt_tolerance_split_is_reported_unsupported(hp):
     z = torch.zeros(4, dtype=torch.int32, device=h.device)
     with pytest.raises(NotImplementedError, match="rt_tol"):
         h.split(z, torch.ones(4, dtype=torch.float64, device=h.device), False)
+
+
+# ------------------------------------------------------------------ preprocessing
+def _raw_spectra(n, seed):
+    """Unprocessed-looking spectra: 0-400 peaks over 50-2000 m/z (ascending), intensities with
+    exact ties and zeros, a peak planted on the precursor m/z of every charge state."""
+    rng = np.random.default_rng(seed)
+    counts = rng.integers(0, 400, n)
+    counts[rng.random(n) < 0.05] = rng.integers(0, 8, int((rng.random(n) < 0.05).sum()) or 1)[0]
+    pmz = rng.uniform(300.0, 1200.0, n)
+    z = rng.integers(0, 5, n).astype(np.int32)
+    mzs, ints, indptr = [], [], [0]
+    for i in range(n):
+        m = rng.uniform(50.0, 2000.0, counts[i])
+        zz = max(int(z[i]), 1)
+        neutral = (pmz[i] - 1.0072766) * zz
+        planted = [neutral / c + 1.0072766 + rng.uniform(-2.0, 2.0) for c in range(1, zz + 1)]
+        m = np.sort(np.r_[m, planted]).astype(np.float32)
+        it = np.round(rng.lognormal(3.0, 1.5, m.shape[0]), 0 if i % 3 == 0 else 3).astype(np.float32)
+        it[rng.random(m.shape[0]) < 0.02] = 0.0
+        mzs.append(m)
+        ints.append(it)
+        indptr.append(indptr[-1] + m.shape[0])
+    return synth.SpectrumSet(np.concatenate(mzs), np.concatenate(ints), np.asarray(indptr, np.int64), pmz, z,
+                             np.zeros(n, np.float32))
+
+
+@pytest.mark.parametrize("kw", [
+    dict(min_peaks=5, min_mz_range=250.0, mz_min=101.0, mz_max=1500.0, remove_precursor_tolerance=1.5,
+         min_intensity=0.01, max_peaks_used=50, scaling=None),  # falcon's defaults (config.py:127-183)
+    dict(min_peaks=5, min_mz_range=250.0, mz_min=101.0, mz_max=1500.0, remove_precursor_tolerance=1.5,
+         min_intensity=0.01, max_peaks_used=50, scaling="rank"),
+    dict(min_peaks=3, min_mz_range=100.0, mz_min=None, mz_max=None, remove_precursor_tolerance=None,
+         min_intensity=None, max_peaks_used=None, scaling="root"),
+    dict(min_peaks=12, min_mz_range=0.0, mz_min=200.0, mz_max=None, remove_precursor_tolerance=0.5,
+         min_intensity=0.2, max_peaks_used=None, scaling="log"),
+    dict(min_peaks=5, min_mz_range=600.0, mz_min=None, mz_max=900.0, remove_precursor_tolerance=None,
+         min_intensity=None, max_peaks_used=7, scaling=None),
+])
+def test_preprocess_matches_oracle(hp, kw):
+    from oracle import preprocess as opre
+
+    sp = _raw_spectra(1500, 11)
+    dev = hp.device
+    t = lambda a: torch.from_numpy(a).to(dev)  # noqa: E731
+    mz, it, indptr, valid = hp.preprocess(t(sp.mz), t(sp.intensity), t(sp.indptr), t(sp.precursor_mz),
+                                          t(sp.precursor_charge), **{**kw, "scaling": kw["scaling"] or "off"})
+    v_ref, mz_ref, it_ref, ip_ref = opre.process_spectra(sp, **kw)
+    assert 0 < v_ref.sum() < len(sp)  # both outcomes occur
+    assert np.array_equal(_cpu(valid).astype(bool), v_ref)
+    assert np.array_equal(_cpu(indptr), ip_ref)
+    assert np.array_equal(_cpu(mz), mz_ref)
+    np.testing.assert_allclose(_cpu(it), it_ref, rtol=0, atol=1e-6)
+
+
+def test_preprocess_edge_cases(hp):
+    dev = hp.device
+    e = torch.empty(0, device=dev)
+    mz, it, indptr, valid = hp.preprocess(e.float(), e.float(), torch.zeros(1, dtype=torch.int64, device=dev),
+                                          e.double(), e.int())
+    assert mz.shape == (0,) and valid.shape == (0,) and _cpu(indptr).tolist() == [0]
+    with pytest.raises(ValueError):
+        hp.preprocess(e.float(), e.float(), torch.zeros(1, dtype=torch.int64, device=dev), e.double(), e.int(),
+                      scaling="cube")

@@ -119,3 +119,20 @@ def test_medoid_oracle_hand_example():
     assert got.tolist() == [1, 5]
     assert omed.cluster_medoids(np.zeros(0, np.float32), np.zeros(0, np.int32), np.zeros(1, np.int64),
                                 np.zeros(0, np.int32)).shape == (0,)
+
+
+def test_preprocess_oracle_hand_example():
+    """process_spectrum on a worked example: window, precursor peaks of charge 2 and 1,
+    1 % base-peak threshold, top 4, rank scaling, unit norm."""
+    from oracle import preprocess as opre
+
+    mz = np.float32([100, 150, 200.5, 300, 400, 500, 600, 700])
+    it = np.float32([1, 5, 2, 9, 9, 0.05, 3, 4])
+    kw = dict(min_peaks=3, min_mz_range=100.0, mz_min=101, mz_max=1500, remove_precursor_tolerance=1.5,
+              min_intensity=0.01, max_peaks_used=4)
+    m, i = opre.process_spectrum(mz, it, 300.0, 2, scaling="rank", **kw)
+    assert m.tolist() == [150.0, 200.5, 400.0, 700.0]
+    np.testing.assert_allclose(i, np.float32([3, 1, 4, 2]) / np.sqrt(np.float32(30)), atol=1e-7)
+    assert opre.process_spectrum(mz, it, 300.0, 2, scaling=None, **{**kw, "min_peaks": 5}) is None
+    m, i = opre.process_spectrum(mz, it, 300.0, 2, scaling="root", **{**kw, "max_peaks_used": None})
+    assert m.tolist() == [150.0, 200.5, 400.0, 700.0] and abs(float((i.astype(np.float64) ** 2).sum()) - 1) < 1e-6
