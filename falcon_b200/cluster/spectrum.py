@@ -94,3 +94,59 @@ def df_row_to_spec(row) -> MsmsSpectrumNb:
     """spectrum.py:299-322."""
     return MsmsSpectrumNb(row["filename"], row["identifier"], row["precursor_mz"], row["precursor_charge"],
                           row["retention_time"], row["mz"], row["intensity"])
+
+
+def process_spectra(
+    spectra: Union[Sequence, synth.SpectrumSet],
+    min_peaks: int,
+    min_mz_range: float,
+    mz_min: Optional[float] = None,
+    mz_max: Optional[float] = None,
+    remove_precursor_tolerance: Optional[float] = None,
+    min_intensity: Optional[float] = None,
+    max_peaks_used: Optional[int] = None,
+    scaling: Optional[str] = None,
+):
+    """``process_spectrum`` (spectrum.py:73-169) for a whole batch on the GPU (``flc_preprocess``).
+
+    Returns ``(processed, valid)``: a ``SpectrumSet`` holding only the spectra that pass the
+    quality checks (processed peaks, metadata carried over) and the boolean mask over the input."""
+    ss = _as_spectrum_set(spectra)
+    hp = pipeline.HotPath(pipeline.Settings())
+    dev = hp.device
+    up = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a, dtype=dt)).to(dev)  # noqa: E731
+    mz, inten, indptr, valid = hp.preprocess(
+        up(ss.mz, np.float32), up(ss.intensity, np.float32), up(ss.indptr, np.int64),
+        up(ss.precursor_mz, np.float64), up(ss.precursor_charge, np.int32), min_peaks, min_mz_range, mz_min, mz_max,
+        remove_precursor_tolerance, min_intensity, max_peaks_used, "off" if scaling is None else scaling)
+    valid_h = valid.cpu().numpy().astype(bool)
+    full = synth.SpectrumSet(mz.cpu().numpy(), inten.cpu().numpy(), indptr.cpu().numpy(), ss.precursor_mz,
+                             ss.precursor_charge, ss.retention_time, ss.template)
+    return full.take(np.flatnonzero(valid_h)), valid_h
+
+
+def process_spectrum(
+    spectrum,
+    min_peaks: int,
+    min_mz_range: float,
+    mz_min: Optional[float] = None,
+    mz_max: Optional[float] = None,
+    remove_precursor_tolerance: Optional[float] = None,
+    min_intensity: Optional[float] = None,
+    max_peaks_used: Optional[int] = None,
+    scaling: Optional[str] = None,
+) -> Optional[Dict]:
+    """Process one spectrum -- same signature and result as the reference (spectrum.py:73-169):
+    a spectrum dict (or an object with the ``MsmsSpectrum`` attributes) in, the processed spectrum
+    dict or ``None`` out.  Prefer ``process_spectra`` for more than a handful of spectra."""
+    get = (lambda k, d=None: spectrum.get(k, d)) if isinstance(spectrum, dict) else \
+        (lambda k, d=None: getattr(spectrum, k, d))
+    one = {"mz": get("mz"), "intensity": get("intensity"), "precursor_mz": get("precursor_mz"),
+           "precursor_charge": get("precursor_charge"), "retention_time": get("retention_time")}
+    out, valid = process_spectra([one], min_peaks, min_mz_range, mz_min, mz_max, remove_precursor_tolerance,
+                                 min_intensity, max_peaks_used, scaling)
+    if not valid[0]:
+        return None
+    return {"identifier": get("identifier"), "precursor_mz": get("precursor_mz"),
+            "precursor_charge": get("precursor_charge"), "mz": out.mz, "intensity": out.intensity,
+            "retention_time": get("retention_time"), "filename": get("filename")}

@@ -182,3 +182,22 @@ def test_cli_mgf_to_csv_matches_oracle(tmp_path):
     assert len(reps) == lab["cluster"].nunique()
     # second run without --overwrite leaves the result alone
     assert fmain.main([path, out, "--exhaustive"]) == 0
+
+
+@pytest.mark.gpu
+def test_facade_process_spectrum():
+    from oracle import preprocess as opre
+
+    mz = np.float32([100, 150, 200.5, 300, 400, 500, 600, 700])
+    it = np.float32([1, 5, 2, 9, 9, 0.05, 3, 4])
+    raw = {"identifier": "x", "precursor_mz": 300.0, "precursor_charge": 2, "mz": mz, "intensity": it,
+           "retention_time": 1.0, "filename": "f.mgf"}
+    kw = dict(min_peaks=3, min_mz_range=100.0, mz_min=101, mz_max=1500, remove_precursor_tolerance=1.5,
+              min_intensity=0.01, max_peaks_used=4, scaling="rank")
+    got = spectrum.process_spectrum(raw, **kw)
+    ref_mz, ref_it = opre.process_spectrum(mz, it, 300.0, 2, **kw)
+    assert got["identifier"] == "x" and got["filename"] == "f.mgf" and got["precursor_charge"] == 2
+    assert np.array_equal(got["mz"], ref_mz) and np.allclose(got["intensity"], ref_it, atol=1e-7)
+    assert spectrum.process_spectrum(raw, **{**kw, "min_peaks": 5}) is None
+    with pytest.raises(ValueError):
+        spectrum.process_spectrum(raw, **{**kw, "scaling": "cube"})
