@@ -138,6 +138,28 @@ def test_full_size_properties_1m():
     assert (labels_ex >= 0).sum() >= m.sum()
 
 
+def test_full_size_exhaustive_parity_1m():
+    """BASELINE config 2 (1M spectra, n_probe = nlist): neighbour lists, distances and the
+    partition against the oracle at full size (the oracle spreads its buckets over the host cores)."""
+    import os
+
+    from oracle import pipeline as opipe
+
+    n = 1_000_000
+    sp = helpers.dataset(n, 42)
+    h = pipeline.HotPath(pipeline.Settings(exhaustive=True))
+    d = helpers.to_device(sp, h.device)
+    labels, nc, keep = h.run(d["mz"], d["intensity"], d["indptr"], d["precursor_mz"], d["charge"], keep=True)
+    ref_labels, _, ref = opipe.run(sp, exhaustive=True, n_jobs=len(os.sched_getaffinity(0)), f32_gemm=False)
+    g = keep["graph"]
+    cut = oivf.eps_cut(ref, 0.1)
+    assert np.array_equal(_cpu(g.indptr), cut.indptr)
+    assert np.array_equal(_cpu(g.indices), cut.indices)  # same neighbours in the same order
+    np.testing.assert_allclose(_cpu(g.dist), cut.data, rtol=0, atol=1e-5)
+    assert odb.same_partition(_cpu(labels), ref_labels)
+    assert nc == int(ref_labels.max()) + 1
+
+
 @pytest.mark.gpu
 def test_cli_mgf_to_csv_matches_oracle(tmp_path):
     """BASELINE configs[0] in miniature, through the `falcon` command: MGF in -> preprocessing ->
