@@ -69,6 +69,7 @@ SIGNATURES = {
                                    _p, _p, _i32, _p, _p, _p, _sz, _p]),
     "flc_ivf_assign": (C.c_int, [_p, _i64, _i64, _u32, _p, _i64, _p, _p, _p, _p, _i32,
                                  _p, _p, _i32, _p, _p, _p]),
+    "flc_debug_kmeans_timing": (C.c_int, [_p]),
     "flc_preprocess_workspace_bytes": (_sz, [_i64, _i64]),
     "flc_preprocess": (C.c_int, [_p, _p, _p, _i64, _i64, _p, _p, _i32, _f32, _f32, _f32, _f32, _f32, _i32, C.c_int,
                                  _p, _p, _p, _p, C.POINTER(_i64), _p, _sz, _p]),

@@ -55,18 +55,19 @@ __host__ __device__ constexpr int fused_threads(int cls) { return cls == 0 ? 256
 // (nb, L) comes first, so it can be placed before the row pitch is known.
 struct FusedPlan {
   uint32_t rnnz, dlist, assign, C, acc, val, idx, total;
-  int lp;
+  int lp, copies;
 };
-__host__ __device__ inline FusedPlan fused_plan(int nb, int pitch, int L, int d) {
+__host__ __device__ inline FusedPlan fused_plan(int nb, int pitch, int L, int d, int warps) {
   FusedPlan p;
   p.lp = L <= 4 ? 4 : 8;  // centroid row length in shared memory
+  p.copies = max(1, warps / (L <= 2 ? 2 : (L <= 4 ? 4 : 8)));  // warps (and accumulator copies) per list
   uint32_t o = 0;
   p.dlist = o;  o += 4u * nb * L;  // per list: rows that entered / left it this iteration
   p.rnnz = o;   o += 2u * nb;
   p.assign = o; o += nb;
   o = (o + 15u) & ~15u;
   p.C = o;      o += 4u * d * p.lp;
-  p.acc = o;    o += 8u * d * L;
+  p.acc = o;    o += 8u * d * L * p.copies;
   p.val = o;    o += 4u * nb * pitch;
   p.idx = o;    o += 2u * nb * pitch;
   p.total = (o + 15u) & ~15u;
@@ -232,7 +233,7 @@ kmeans_classify_kernel(const uint16_t* __restrict__ ell_nnz, uint32_t low_dim,
   int cls = kClsTiled;
   if (L <= kFusedMaxL && nb <= 32767 && !force_tiled) {
     for (int c = 1; c >= 0; --c)
-      if (fused_plan(static_cast<int>(nb), wb | 1, L, static_cast<int>(low_dim)).total <= fused_smem_limit(c)) cls = c;
+      if (fused_plan(static_cast<int>(nb), wb | 1, L, static_cast<int>(low_dim), fused_threads(c) / 32).total <= fused_smem_limit(c)) cls = c;
   }
   if (lane == 0) {
     q.bclass[b] = static_cast<uint8_t>(cls);
@@ -279,6 +280,30 @@ struct FusedArgs {
   int32_t max_nprobe;
   int32_t* list_id;
   int32_t* probes;
+  unsigned long long* timing;  // nullable: per-phase cycle counters (FLC_KMEANS_TIMING=1)
+};
+
+// Per-phase cycle counters of the fused trainer (debug aid, thread 0 of every CTA):
+// 0 queue + row populations, 1 row load, 2 init, 3 assign, 4 update, 5 means, 6 normalise,
+// 7 final assignment + write-out, 8 iterations run, 9 buckets.
+__device__ unsigned long long g_kmeans_timing[16];
+
+struct PhaseClock {
+  unsigned long long* out;
+  long long t;
+  __device__ PhaseClock(unsigned long long* o) : out(threadIdx.x == 0 ? o : nullptr), t(0) {
+    if (out) t = clock64();
+  }
+  __device__ void mark(int phase) {
+    if (out) {
+      const long long now = clock64();
+      atomicAdd(out + phase, static_cast<unsigned long long>(now - t));
+      t = now;
+    }
+  }
+  __device__ void count(int slot, unsigned long long v) {
+    if (out) atomicAdd(out + slot, v);
+  }
 };
 
 struct FusedStatic {  // static shared memory of the fused kernel
@@ -296,7 +321,7 @@ struct FusedStatic {  // static shared memory of the fused kernel
 // row length in shared memory (4 or 8 lists), NT = threads of the CTA.
 template <int LP, int NT>
 __device__ void fused_train_bucket(const FusedArgs& A, const FusedPlan& pl, unsigned char* smem, FusedStatic& S,
-                                   int nb, int L, int pitch, int64_t s, int64_t c0, int P) {
+                                   int nb, int L, int pitch, int64_t s, int64_t c0, int P, PhaseClock& clk) {
   constexpr int kWarps = NT / 32;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int d = static_cast<int>(A.low_dim);
@@ -358,55 +383,68 @@ __device__ void fused_train_bucket(const FusedArgs& A, const FusedPlan& pl, unsi
       }
     }
     changed = __syncthreads_or(changed);
+    clk.mark(3);
     bool any_empty = false;
 #pragma unroll
     for (int u = 0; u < LP; ++u) any_empty |= (u < L && S.cnt[u] == 0);
     if (it > 0 && !changed && !any_empty) break;  // fixed point
     if (tid < L) S.scale[tid] = S.cnt[tid] > 0 ? kFixInv / static_cast<double>(S.cnt[tid]) : 0.0;
-    // ---- update: warp c walks list c's delta list; lanes take the row's columns
-    // (distinct within a row, so no conflicts inside a step).
-    if (warp < L) {
-      long long* acc_c = acc + warp * d;
-      const uint32_t* dl = dlist + warp * nb;
-      const int n_c = S.dn[warp];
-      uint32_t e_next = n_c > 1 ? dl[1] : 0u;
-      uint32_t e = n_c > 0 ? dl[0] : 0u;
-      int k = 0;
-      float v = 0.f;
-      if (n_c > 0 && lane < static_cast<int>(e >> 16)) {
-        const int o = static_cast<int>(e & 0x7fffu) * pitch + lane;
-        k = idx[o];
-        v = val[o];
-      }
-      for (int i = 0; i < n_c; ++i) {
-        const uint32_t ce = e;
-        const int ck = k;
-        const float cv = v;
-        // operands of the next two rows are in flight during this row's read-modify-write
-        e = e_next;
-        e_next = i + 2 < n_c ? dl[i + 2] : 0u;
-        if (i + 1 < n_c && lane < static_cast<int>(e >> 16)) {
-          const int o = static_cast<int>(e & 0x7fffu) * pitch + lane;
-          k = idx[o];
-          v = val[o];
-        }
-        const int m = static_cast<int>(ce >> 16);
-        const bool neg = (ce & 0x8000u) != 0u;
-        if (lane < m) {
-          const long long q = __float2ll_rn(cv * kFixScaleF);
-          acc_c[ck] += neg ? -q : q;
-        }
-        if (m > 32) {  // uniform
-          const int o = static_cast<int>(ce & 0x7fffu) * pitch;
-          for (int j = 32 + lane; j < m; j += 32) {
-            const long long q = __float2ll_rn(val[o + j] * kFixScaleF);
-            acc_c[idx[o + j]] += neg ? -q : q;
+    // ---- update: the warps split every list's delta list (`copies` warps per list, each
+    // with its own accumulator copy, added up in the means phase).  Lanes take the row's
+    // columns (distinct within a row, so no conflicts inside a step): slots lane and lane + 32
+    // in one step; the operands -- already converted to fixed point -- of the next row are in
+    // flight during this row's read-modify-write.
+    {
+      const int copies = pl.copies;
+      const int c = warp / copies, part = warp - c * copies;
+      if (c < L) {
+        long long* acc_c = acc + (part * L + c) * d;
+        const uint32_t* dl = dlist + c * nb;
+        const int n_c = S.dn[c];
+        int k0 = 0, k1 = 0;
+        long long q0 = 0, q1 = 0;
+        uint32_t e = 0;
+        auto fetch = [&](int i) {
+          e = dl[i];
+          const int m = static_cast<int>(e >> 16);
+          const int o = static_cast<int>(e & 0x7fffu) * pitch;
+          const bool neg = (e & 0x8000u) != 0u;
+          q0 = 0; q1 = 0;
+          if (lane < m) {
+            k0 = idx[o + lane];
+            const long long q = __float2ll_rn(val[o + lane] * kFixScaleF);
+            q0 = neg ? -q : q;
           }
+          if (lane + 32 < m) {
+            k1 = idx[o + lane + 32];
+            const long long q = __float2ll_rn(val[o + lane + 32] * kFixScaleF);
+            q1 = neg ? -q : q;
+          }
+        };
+        if (part < n_c) fetch(part);
+        for (int i = part; i < n_c; i += copies) {
+          const uint32_t ce = e;
+          const int ck0 = k0, ck1 = k1;
+          const long long cq0 = q0, cq1 = q1;
+          if (i + copies < n_c) fetch(i + copies);
+          const int m = static_cast<int>(ce >> 16);
+          if (lane < m) acc_c[ck0] += cq0;
+          if (lane + 32 < m) acc_c[ck1] += cq1;
+          if (m > 64) {  // uniform; rows wider than two slots per lane (rare)
+            const int o = static_cast<int>(ce & 0x7fffu) * pitch;
+            const bool neg = (ce & 0x8000u) != 0u;
+            for (int j = 64 + lane; j < m; j += 32) {
+              const long long q = __float2ll_rn(val[o + j] * kFixScaleF);
+              acc_c[idx[o + j]] += neg ? -q : q;
+            }
+          }
+          __syncwarp();  // two rows may share a column: keep their read-modify-writes apart
         }
-        __syncwarp();  // two rows may share a column: keep their read-modify-writes apart
       }
     }
     __syncthreads();
+    clk.mark(4);
+    clk.count(8, 1);
     // ---- means (one thread per column), partial square norms
     {
       double ssq[LP];
@@ -422,7 +460,8 @@ __device__ void fused_train_bucket(const FusedArgs& A, const FusedPlan& pl, unsi
 #pragma unroll
         for (int u = 0; u < LP; ++u) {
           if (u < L) {
-            const long long sum = acc[u * d + k];
+            long long sum = 0;
+            for (int cp = 0; cp < pl.copies; ++cp) sum += acc[(cp * L + u) * d + k];
             if (S.cnt[u] > 0) m[u] = static_cast<float>(__ll2double_rn(sum) * S.scale[u]);
             ssq[u] = fma(static_cast<double>(m[u]), static_cast<double>(m[u]), ssq[u]);
           }
@@ -438,6 +477,7 @@ __device__ void fused_train_bucket(const FusedArgs& A, const FusedPlan& pl, unsi
       }
     }
     __syncthreads();
+    clk.mark(5);
     if (any_empty) {
       // ---- slow path: re-seed every empty list from the (currently) largest one
       if (tid < L) S.cntd[tid] = static_cast<double>(S.cnt[tid]);
@@ -505,6 +545,7 @@ __device__ void fused_train_bucket(const FusedArgs& A, const FusedPlan& pl, unsi
       }
     }
     __syncthreads();
+    clk.mark(6);
   }
   // ---- centroids out: [list][column]
   for (int t = tid; t < L * d; t += NT) {
@@ -551,13 +592,14 @@ kmeans_fused_kernel(FusedArgs A, int cls) {
     __syncthreads();
     const int qi = S.qi;
     if (qi >= n_queued) break;
+    PhaseClock clk(A.timing);
     const int64_t b = queue[qi];
     const int L = A.nlist[b];
     const int64_t s = A.bucket_ptr[b];
     const int nb = static_cast<int>(A.bucket_ptr[b + 1] - s);
     const int64_t c0 = A.centroid_ptr[b];
     // ---- row populations, widest row -> pitch
-    FusedPlan pl = fused_plan(nb, 1, L, d);
+    FusedPlan pl = fused_plan(nb, 1, L, d, kWarps);
     uint16_t* rnnz = reinterpret_cast<uint16_t*>(smem + pl.rnnz);
     int wb = 1;
     for (int t = tid; t < nb; t += NT) {
@@ -572,42 +614,63 @@ kmeans_fused_kernel(FusedArgs A, int cls) {
     __syncthreads();
 #pragma unroll
     for (int w = 0; w < kWarps; ++w) wb = max(wb, S.wmax[w]);
+    clk.mark(0);
     const int pitch = wb | 1;  // odd: one thread per row reads without bank conflicts
-    pl = fused_plan(nb, pitch, L, d);
+    pl = fused_plan(nb, pitch, L, d, kWarps);
     float* val = reinterpret_cast<float*>(smem + pl.val);
     uint16_t* idx = reinterpret_cast<uint16_t*>(smem + pl.idx);
     float* C = reinterpret_cast<float*>(smem + pl.C);
     long long* acc = reinterpret_cast<long long*>(smem + pl.acc);
     uint8_t* assign = smem + pl.assign;
-    // ---- rows: coalesced 16-byte loads of 8 slots, scattered into the odd-pitch layout
+    // ---- rows: coalesced 16-byte loads of 8 slots (four chunks per thread in flight before
+    // the first store), scattered into the odd-pitch layout
     {
       const int cpr = W >> 3;
       const int items = nb * cpr;
-#pragma unroll 2
-      for (int i = tid; i < items; i += NT) {
-        const int r = i / cpr, j0 = (i - r * cpr) << 3;
-        const int m = rnnz[r];
-        if (j0 < m) {
-          const int64_t g = (s + r) * W + j0;
-          const uint4 ki = __ldg(reinterpret_cast<const uint4*>(A.ell_idx + g));
-          const float4 v0 = __ldg(reinterpret_cast<const float4*>(A.ell_val + g));
-          const float4 v1 = __ldg(reinterpret_cast<const float4*>(A.ell_val + g + 4));
-          const float vv[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
-          const uint32_t kk[4] = {ki.x, ki.y, ki.z, ki.w};
+      constexpr int kBatch = 4;
+      for (int i0 = tid; i0 < items; i0 += NT * kBatch) {
+        uint4 ki[kBatch];
+        float4 v0[kBatch], v1[kBatch];
+        int rr[kBatch], jj[kBatch], mm[kBatch];
 #pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            if (j0 + u < m) {
-              val[r * pitch + j0 + u] = vv[u];
-              idx[r * pitch + j0 + u] = static_cast<uint16_t>((kk[u >> 1] >> ((u & 1) * 16)) & 0xffffu);
+        for (int t = 0; t < kBatch; ++t) {
+          const int i = i0 + t * NT;
+          mm[t] = 0;
+          if (i < items) {
+            rr[t] = i / cpr;
+            jj[t] = (i - rr[t] * cpr) << 3;
+            mm[t] = rnnz[rr[t]];
+            if (jj[t] < mm[t]) {
+              const int64_t g = (s + rr[t]) * W + jj[t];
+              ki[t] = __ldg(reinterpret_cast<const uint4*>(A.ell_idx + g));
+              v0[t] = __ldg(reinterpret_cast<const float4*>(A.ell_val + g));
+              v1[t] = __ldg(reinterpret_cast<const float4*>(A.ell_val + g + 4));
+            } else {
+              mm[t] = 0;
+            }
+          }
+        }
+#pragma unroll
+        for (int t = 0; t < kBatch; ++t) {
+          if (mm[t] > 0) {
+            const float vv[8] = {v0[t].x, v0[t].y, v0[t].z, v0[t].w, v1[t].x, v1[t].y, v1[t].z, v1[t].w};
+            const uint32_t kk[4] = {ki[t].x, ki[t].y, ki[t].z, ki[t].w};
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              if (jj[t] + u < mm[t]) {
+                val[rr[t] * pitch + jj[t] + u] = vv[u];
+                idx[rr[t] * pitch + jj[t] + u] = static_cast<uint16_t>((kk[u >> 1] >> ((u & 1) * 16)) & 0xffffu);
+              }
             }
           }
         }
       }
     }
     for (int t = tid; t < d * pl.lp; t += NT) C[t] = 0.f;
-    for (int t = tid; t < d * L; t += NT) acc[t] = 0;
+    for (int t = tid; t < d * L * pl.copies; t += NT) acc[t] = 0;
     for (int t = tid; t < nb; t += NT) assign[t] = 0xff;
     __syncthreads();
+    clk.mark(1);
     // ---- initial centroids: evenly strided rows
     for (int t = tid; t < L * wb; t += NT) {
       const int c = t / wb, j = t - c * wb;
@@ -616,10 +679,14 @@ kmeans_fused_kernel(FusedArgs A, int cls) {
     }
     __syncthreads();
     const int P = A.list_id != nullptr ? min(A.nprobe[b], L) : 0;
+    clk.mark(2);
     if (pl.lp == 4)
-      fused_train_bucket<4, NT>(A, pl, smem, S, nb, L, pitch, s, c0, P);
+      fused_train_bucket<4, NT>(A, pl, smem, S, nb, L, pitch, s, c0, P, clk);
     else
-      fused_train_bucket<8, NT>(A, pl, smem, S, nb, L, pitch, s, c0, P);
+      fused_train_bucket<8, NT>(A, pl, smem, S, nb, L, pitch, s, c0, P, clk);
+    __syncthreads();
+    clk.mark(7);
+    clk.count(9, 1);
   }
 }
 
@@ -948,7 +1015,7 @@ static bool kmeans_needs_tiled(int64_t n, int64_t max_ivf_bucket, int32_t W, uin
   if (nb > 32767) return true;
   const int32_t L = nlist_rule(nb);
   if (L > kFusedMaxL) return true;
-  return fused_plan(static_cast<int>(nb), W | 1, L, static_cast<int>(low_dim)).total > fused_smem_limit(1);
+  return fused_plan(static_cast<int>(nb), W | 1, L, static_cast<int>(low_dim), fused_threads(1) / 32).total > fused_smem_limit(1);
 }
 
 }  // namespace flc
@@ -1023,8 +1090,12 @@ int flc_kmeans_train(const uint16_t* ell_idx, const float* ell_val, const uint16
   FLC_LAUNCH_CHECK();
   if (total_centroids == 0) return FLC_OK;
   // ---- fused classes
+  unsigned long long* timing = nullptr;
+  const char* timing_env = getenv("FLC_KMEANS_TIMING");
+  if (timing_env != nullptr && timing_env[0] == '1')
+    FLC_CUDA(cudaGetSymbolAddress(reinterpret_cast<void**>(&timing), g_kmeans_timing));
   FusedArgs A{ell_idx, ell_val, ell_nnz, W, low_dim, bucket_ptr, n_buckets, nlist, centroid_ptr, niter, q,
-              centroids, nprobe, max_nprobe, list_id, probes};
+              centroids, nprobe, max_nprobe, list_id, probes, timing};
   {
     FLC_CUDA(cudaFuncSetAttribute(kmeans_fused_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   static_cast<int>(fused_smem_limit(0))));
@@ -1069,6 +1140,18 @@ int flc_kmeans_train(const uint16_t* ell_idx, const float* ell_val, const uint16
         T, nprobe, max_nprobe, list_id, probes); });
     FLC_LAUNCH_CHECK();
   }
+  return FLC_OK;
+}
+
+/* Debug aid: copies out and clears the 16 per-phase cycle counters of the fused trainer
+ * (filled when FLC_KMEANS_TIMING=1; see g_kmeans_timing). */
+int flc_debug_kmeans_timing(unsigned long long* out16) {
+  using namespace flc;
+  FLC_REQUIRE(out16 != nullptr, "null output");
+  FLC_CUDA(cudaDeviceSynchronize());
+  FLC_CUDA(cudaMemcpyFromSymbol(out16, g_kmeans_timing, 16 * sizeof(unsigned long long)));
+  const unsigned long long zero[16] = {0};
+  FLC_CUDA(cudaMemcpyToSymbol(g_kmeans_timing, zero, sizeof(zero)));
   return FLC_OK;
 }
 

@@ -146,6 +146,8 @@ FLC_API int flc_kmeans_train(const uint16_t* ell_idx, const float* ell_val, cons
                      /* optional final assignment (same outputs as flc_ivf_assign; both or neither): */
                      const int32_t* nprobe, int32_t max_nprobe, int32_t* list_id, int32_t* probes,
                      void* workspace, size_t workspace_bytes, flc_stream_t stream);
+/* Debug aid: per-phase cycle counters of the fused trainer (FLC_KMEANS_TIMING=1). */
+FLC_API int flc_debug_kmeans_timing(unsigned long long* out16);
 /*  list_id[i] (int32, bucket-local list of row i, 0 for flat buckets) and
  *  probes[i * max_nprobe + j] (int32 list ids best first, -1 padded), both from
  *  float64 inner products with ties to the lower id. */
