@@ -65,7 +65,7 @@ SIGNATURES = {
     "flc_ivf_plan": (C.c_int, [_p, _i64, _i32, C.c_int, _p, _p, _p, C.POINTER(_i64), C.POINTER(_i32),
                                C.POINTER(_i64), _p]),
     "flc_kmeans_workspace_bytes": (_sz, [_i64, _i64, _i64, _i64, _i32, _u32]),
-    "flc_kmeans_train": (C.c_int, [_p, _p, _p, _i32, _i64, _u32, _p, _i64, _p, _p, _i64, _i64, C.c_int,
+    "flc_kmeans_train": (C.c_int, [_p, _p, _p, _i32, _p, _i64, _i64, _u32, _p, _i64, _p, _p, _i64, _i64, C.c_int,
                                    _p, _p, _i32, _p, _p, _p, _sz, _p]),
     "flc_ivf_assign": (C.c_int, [_p, _i64, _i64, _u32, _p, _i64, _p, _p, _p, _p, _i32,
                                  _p, _p, _i32, _p, _p, _p]),

@@ -27,6 +27,7 @@
 #include <cstdlib>
 
 #include "common.cuh"
+#include "kmeans_tc.cuh"
 
 namespace flc {
 
@@ -713,6 +714,11 @@ struct TiledArgs {
   double* gcntd;     // [total] (re-seeding of empty lists)
   int32_t* gassign;  // [n] previous assignment
   int32_t* bstate;   // [n_buckets][2]: changed flag, converged flag
+  // tensor-core assignment (kmeans_tc.cu); cb == nullptr: SIMT assignment
+  uint16_t* cb;      // [total][ld_c] bf16 copy of the centroids (TMA operand)
+  int64_t ld_c;
+  int32_t* tc_best;  // [n] arg-max list by bf16 scores (exact after the fix kernel)
+  uint8_t* tc_unsure;  // [n] 1: the two best bf16 scores are within the margin
 };
 
 __global__ void __launch_bounds__(128)
@@ -729,10 +735,13 @@ kmeans_tiled_init_kernel(TiledArgs A, int64_t total) {
   const uint32_t d = A.low_dim;
   float* cr = A.centroids + gc * d;
   float* ctb = A.ct + c0 * d;
+  uint16_t* cbr = A.cb ? A.cb + gc * A.ld_c : nullptr;
   for (uint32_t k = threadIdx.x; k < d; k += blockDim.x) {
     cr[k] = 0.f;
     ctb[static_cast<int64_t>(k) * L + c] = 0.f;
   }
+  if (cbr)
+    for (int64_t k = threadIdx.x; k < A.ld_c; k += blockDim.x) cbr[k] = 0;
   __syncthreads();
   const int m = min(static_cast<int>(A.ell_nnz[row]), A.W);
   for (int j = threadIdx.x; j < m; j += blockDim.x) {
@@ -740,6 +749,94 @@ kmeans_tiled_init_kernel(TiledArgs A, int64_t total) {
     const float v = A.ell_val[row * A.W + j];
     cr[k] = v;
     ctb[static_cast<int64_t>(k) * L + c] = v;
+    if (cbr) cbr[k] = f32_to_bf16_rne(v);
+  }
+}
+
+// Unit descriptors of the tensor-core assignment: every tiled bucket contributes
+// ceil(rows / 128) query tiles (first row, bucket end, first / end centroid row).
+__global__ void kmeans_tc_units_kernel(TiledArgs A, int4* __restrict__ units, int32_t* __restrict__ n_units) {
+  const int32_t qi = blockIdx.x * blockDim.x + threadIdx.x;
+  if (qi >= A.q.cnt[kClsTiled]) return;
+  const int64_t b = A.q.queue[static_cast<int64_t>(kClsTiled) * A.n_buckets + qi];
+  const int64_t s = A.bucket_ptr[b], e = A.bucket_ptr[b + 1];
+  const int64_t c0 = A.centroid_ptr[b];
+  const int32_t tq = static_cast<int32_t>((e - s + 127) / 128);
+  const int32_t base = atomicAdd(n_units, tq);
+  for (int32_t t = 0; t < tq; ++t)
+    units[base + t] = make_int4(static_cast<int>(s + 128 * t), static_cast<int>(e), static_cast<int>(c0),
+                                static_cast<int>(c0 + A.nlist[b]));
+}
+
+// Exact float32 arg-max (the fused trainer's arithmetic: products added in slot order
+// with fmaf, ties to the lower list) for the rows the tensor-core pass could not decide.
+// One warp per row, one lane per list.
+__global__ void __launch_bounds__(256)
+kmeans_tiled_fix_kernel(TiledArgs A) {
+  const int lane = threadIdx.x & 31;
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  if (i >= A.n || !A.tc_unsure[i]) return;
+  const int64_t b = find_segment(A.bucket_ptr, A.n_buckets, i);
+  if (A.q.bclass[b] != kClsTiled || A.bstate[2 * b + 1] != 0) return;
+  const int32_t L = A.nlist[b];
+  const float* ctb = A.ct + A.centroid_ptr[b] * A.low_dim;
+  const int m = min(static_cast<int>(A.ell_nnz[i]), A.W);
+  float best = -INFINITY;
+  int best_c = 0x7fffffff;
+  for (int32_t s0 = 0; s0 < L; s0 += 32) {
+    const int32_t c = s0 + lane;
+    float acc = 0.f;
+    for (int j0 = 0; j0 < m; j0 += 32) {
+      const int j = j0 + lane;
+      const uint32_t kj = j < m ? static_cast<uint32_t>(__ldg(A.ell_idx + i * A.W + j)) : 0u;
+      const float vj = j < m ? __ldg(A.ell_val + i * A.W + j) : 0.f;
+      const int cnt = min(32, m - j0);
+      for (int t = 0; t < cnt; ++t) {
+        const uint32_t k = __shfl_sync(0xffffffffu, kj, t);
+        const float v = __shfl_sync(0xffffffffu, vj, t);
+        if (c < L) acc = fmaf(v, __ldg(ctb + static_cast<int64_t>(k) * L + c), acc);
+      }
+    }
+    if (c < L && acc > best) { best = acc; best_c = c; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oc = __shfl_xor_sync(0xffffffffu, best_c, o);
+    if (ov > best || (ov == best && oc < best_c)) { best = ov; best_c = oc; }
+  }
+  if (lane == 0) A.tc_best[i] = best_c;
+}
+
+// Rows whose list changed move their fixed-point values between the lists' sums.
+__global__ void __launch_bounds__(256)
+kmeans_tiled_apply_kernel(TiledArgs A) {
+  __shared__ int64_t b0_s;
+  const int64_t i0 = static_cast<int64_t>(blockIdx.x) * 256;
+  if (threadIdx.x == 0) b0_s = find_segment(A.bucket_ptr, A.n_buckets, i0);
+  __syncthreads();
+  const int64_t i = i0 + threadIdx.x;
+  if (i >= A.n) return;
+  int64_t b = b0_s;
+  while (A.bucket_ptr[b + 1] <= i) ++b;
+  if (A.q.bclass[b] != kClsTiled || A.bstate[2 * b + 1] != 0) return;
+  const int old_c = A.gassign[i];
+  const int new_c = A.tc_best[i];
+  if (old_c == new_c) return;
+  const int d = static_cast<int>(A.low_dim);
+  const int64_t c0 = A.centroid_ptr[b];
+  A.gassign[i] = new_c;
+  A.bstate[2 * b] = 1;  // benign race: every writer stores 1
+  atomicAdd(A.gcnt + c0 + new_c, 1);
+  if (old_c >= 0) atomicSub(A.gcnt + c0 + old_c, 1);
+  unsigned long long* add = reinterpret_cast<unsigned long long*>(A.gsum + (c0 + new_c) * d);
+  unsigned long long* sub = reinterpret_cast<unsigned long long*>(A.gsum + (c0 + max(old_c, 0)) * d);
+  const int m = min(static_cast<int>(A.ell_nnz[i]), A.W);
+  for (int j = 0; j < m; ++j) {
+    const uint32_t k = __ldg(A.ell_idx + i * A.W + j);
+    const long long q = __float2ll_rn(__ldg(A.ell_val + i * A.W + j) * kFixScaleF);
+    atomicAdd(add + k, static_cast<unsigned long long>(q));
+    if (old_c >= 0) atomicAdd(sub + k, static_cast<unsigned long long>(-q));
   }
 }
 
@@ -910,10 +1007,12 @@ kmeans_tiled_update_kernel(TiledArgs A) {
       }
       ss = warp_sum_f64(ss);
       const double inv = ss > 0.0 ? 1.0 / sqrt(ss) : 1.0;
+      uint16_t* cbr = A.cb ? A.cb + (c0 + c) * A.ld_c : nullptr;
       for (int k = lane; k < d; k += 32) {
         const float v = static_cast<float>(static_cast<double>(cr[k]) * inv);
         cr[k] = v;
         ctb[static_cast<int64_t>(k) * L + c] = v;
+        if (cbr) cbr[k] = f32_to_bf16_rne(v);
       }
     }
     if (tid == 0) {  // sums and counts persist: the assign kernel maintains them incrementally
@@ -988,15 +1087,21 @@ struct KmeansLayout {
   double* gcntd;
   int32_t* gassign;
   int32_t* bstate;
+  // tensor-core assignment
+  uint16_t* cb;
+  int32_t* tc_best;
+  uint8_t* tc_unsure;
+  int4* units;
 };
 
 static void kmeans_layout(Workspace& ws, int64_t n, int64_t n_buckets, int64_t total, uint32_t low_dim,
                           bool tiled, KmeansLayout& L) {
   const size_t nbk = static_cast<size_t>(n_buckets > 0 ? n_buckets : 1);
-  L.qctr = ws.take<int32_t>(8);
+  L.qctr = ws.take<int32_t>(16);  // [0,4) pull counters, [4,8) queue lengths, [8] tensor-core units
   L.queue = ws.take<int32_t>(3 * nbk);
   L.bclass = ws.take<uint8_t>(nbk);
   L.ct = nullptr; L.gsum = nullptr; L.gcnt = nullptr; L.gcntd = nullptr; L.gassign = nullptr; L.bstate = nullptr;
+  L.cb = nullptr; L.tc_best = nullptr; L.tc_unsure = nullptr; L.units = nullptr;
   if (tiled) {
     const size_t t = static_cast<size_t>(total > 0 ? total : 1);
     L.ct = ws.take<float>(t * low_dim);
@@ -1005,6 +1110,11 @@ static void kmeans_layout(Workspace& ws, int64_t n, int64_t n_buckets, int64_t t
     L.gcntd = ws.take<double>(t);
     L.gassign = ws.take<int32_t>(static_cast<size_t>(n > 0 ? n : 1));
     L.bstate = ws.take<int32_t>(2 * nbk);
+    const size_t nn = static_cast<size_t>(n > 0 ? n : 1);
+    L.cb = ws.take<uint16_t>(t * ((low_dim + 7u) & ~7u));
+    L.tc_best = ws.take<int32_t>(nn);
+    L.tc_unsure = ws.take<uint8_t>(nn);
+    L.units = ws.take<int4>(nn / 128 + nbk + 1);
   }
 }
 
@@ -1054,6 +1164,7 @@ size_t flc_kmeans_workspace_bytes(int64_t n, int64_t n_buckets, int64_t total_ce
 }
 
 int flc_kmeans_train(const uint16_t* ell_idx, const float* ell_val, const uint16_t* ell_nnz, int32_t ell_width,
+                     const uint16_t* x_bf16, int64_t ld_bf16,
                      int64_t n, uint32_t low_dim, const int64_t* bucket_ptr, int64_t n_buckets,
                      const int32_t* nlist, const int64_t* centroid_ptr, int64_t total_centroids,
                      int64_t max_ivf_bucket, int niter, float* centroids, const int32_t* nprobe,
@@ -1083,7 +1194,7 @@ int flc_kmeans_train(const uint16_t* ell_idx, const float* ell_val, const uint16
   kmeans_layout(ws, n, n_buckets, total_centroids, low_dim, tiled, K);
   if (!ws.ok) return set_error(FLC_ERR_WORKSPACE, "kmeans workspace too small: need %zu", ws.used);
   TrainQueues q{K.qctr, K.qctr + 4, K.queue, K.bclass};
-  FLC_CUDA(cudaMemsetAsync(K.qctr, 0, 8 * sizeof(int32_t), stream));
+  FLC_CUDA(cudaMemsetAsync(K.qctr, 0, 16 * sizeof(int32_t), stream));
   timed("kmeans_classify", stream, [&] {
     kmeans_classify_kernel<<<static_cast<unsigned>((n_buckets + 7) / 8), 256, 0, stream>>>(
         ell_nnz, low_dim, bucket_ptr, n_buckets, nlist, q, force_tiled, max_nprobe, list_id, probes); });
@@ -1112,8 +1223,16 @@ int flc_kmeans_train(const uint16_t* ell_idx, const float* ell_val, const uint16
   }
   if (!tiled) return FLC_OK;
   // ---- tiled trainer for what is left
+  // Tensor-core assignment needs the bf16 rows of unit-norm vectors (what flc_vectorize emits with norm = 1);
+  // FLC_KMEANS_NO_TC=1 keeps the SIMT assignment (tests compare the two).
+  const char* no_tc_env = getenv("FLC_KMEANS_NO_TC");
+  const bool use_tc = x_bf16 != nullptr && !(no_tc_env != nullptr && no_tc_env[0] == '1') &&
+                      (ld_bf16 % 8) == 0 && (reinterpret_cast<uintptr_t>(x_bf16) & 15) == 0;
+  const int64_t ld_c = (static_cast<int64_t>(low_dim) + 7) & ~int64_t(7);
   TiledArgs T{ell_idx, ell_val, ell_nnz, W, low_dim, n, bucket_ptr, n_buckets, nlist, centroid_ptr, q,
-              centroids, K.ct, K.gsum, K.gcnt, K.gcntd, K.gassign, K.bstate};
+              centroids, K.ct, K.gsum, K.gcnt, K.gcntd, K.gassign, K.bstate,
+              use_tc ? K.cb : nullptr, ld_c, K.tc_best, K.tc_unsure};
+  int32_t* n_units = K.qctr + 8;
   FLC_CUDA(cudaMemsetAsync(K.gsum, 0, static_cast<size_t>(total_centroids) * low_dim * sizeof(long long), stream));
   FLC_CUDA(cudaMemsetAsync(K.gcnt, 0, static_cast<size_t>(total_centroids) * sizeof(int32_t), stream));
   FLC_CUDA(cudaMemsetAsync(K.gassign, 0xff, static_cast<size_t>(n) * sizeof(int32_t), stream));
@@ -1128,10 +1247,28 @@ int flc_kmeans_train(const uint16_t* ell_idx, const float* ell_val, const uint16
   const unsigned row_blocks = static_cast<unsigned>((n + kTiledRows - 1) / kTiledRows);
   static_assert(kTiledThreads == 256, "launch configuration below assumes 256 threads");
   const unsigned upd_blocks = static_cast<unsigned>(std::min<int64_t>(n_buckets, 4 * kNumSMs));
-  for (int it = 0; it < niter; ++it) {
-    timed("kmeans_tiled_assign", stream, [&] {
-      kmeans_tiled_assign_kernel<<<row_blocks, kTiledThreads, smem, stream>>>(T); });
+  if (use_tc) {
+    timed("kmeans_tc_units", stream, [&] {
+      kmeans_tc_units_kernel<<<static_cast<unsigned>((n_buckets + 255) / 256), 256, 0, stream>>>(T, K.units, n_units); });
     FLC_LAUNCH_CHECK();
+  }
+  for (int it = 0; it < niter; ++it) {
+    if (use_tc) {
+      // bf16 scores on the tensor cores decide every row whose two best lists are further apart than
+      // twice the rounding error (2^-7 for unit vectors, plus slack); the rest is re-scored exactly
+      FLC_TRY(launch_kmeans_tc(x_bf16, ld_bf16, n, K.cb, ld_c, total_centroids, low_dim, K.units, n_units,
+                               0.008f, K.tc_best, K.tc_unsure, stream));
+      timed("kmeans_tiled_fix", stream, [&] {
+        kmeans_tiled_fix_kernel<<<static_cast<unsigned>((n + 7) / 8), 256, 0, stream>>>(T); });
+      FLC_LAUNCH_CHECK();
+      timed("kmeans_tiled_apply", stream, [&] {
+        kmeans_tiled_apply_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(T); });
+      FLC_LAUNCH_CHECK();
+    } else {
+      timed("kmeans_tiled_assign", stream, [&] {
+        kmeans_tiled_assign_kernel<<<row_blocks, kTiledThreads, smem, stream>>>(T); });
+      FLC_LAUNCH_CHECK();
+    }
     timed("kmeans_tiled_update", stream, [&] { kmeans_tiled_update_kernel<<<upd_blocks, 256, 0, stream>>>(T); });
     FLC_LAUNCH_CHECK();
   }

@@ -28,111 +28,9 @@
 // Roofline: tensor-core bound for buckets >~ 4k rows, 2 * low_dim * n_b^2 FLOP
 // per bucket; HBM/L2-latency bound for small buckets (n_b * low_dim * 2 bytes
 // read once).
-#include <cuda.h>
-
-#include "scan.cuh"
+#include "tc_common.cuh"
 
 namespace flc {
-
-constexpr int kStages = 4;
-constexpr int kBoxRows = 128;
-constexpr int kBoxBytes = kBoxRows * kBoxK * 2;           // 16 KiB
-constexpr int kABytes = kBoxBytes;                        // 128 x 64 bf16
-constexpr int kBBytes = 2 * kBoxBytes;                    // 256 x 64 bf16
-constexpr int kStageBytes = kABytes + kBBytes;            // 48 KiB
-constexpr int kScanThreads = 192;                         // 6 warps
-constexpr int kTmemCols = 512;                            // 2 accumulators x 256 columns
-constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
-constexpr long long kWatchdogCycles = 4000000000ll;       // ~2 s: trap instead of hanging
-
-// ---------------------------------------------------------------- PTX wrappers
-__device__ __forceinline__ uint32_t smem_u32(const void* p) {
-  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
-}
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-      "selp.u32 %0, 1, 0, p;\n"
-      "}\n"
-      : "=r"(ok)
-      : "r"(bar), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > kWatchdogCycles) __trap();
-  }
-}
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int32_t c0, int32_t c1,
-                                            uint32_t bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(bar)
-      : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                            uint32_t accumulate) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
-      "}\n" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void tc_ld_32x32(uint32_t taddr, uint32_t (&v)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
-        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
-        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-      : "r"(taddr)
-      : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
-// Shared-memory matrix descriptor: K-major operand, SWIZZLE_128B, rows of 128
-// bytes, 8-row groups 1024 bytes apart (cute::UMMA::SmemDescriptor bit layout:
-// start >> 4 [0,14), LBO >> 4 [16,30), SBO >> 4 [32,46), version = 1 [46,48),
-// layout type SWIZZLE_128B = 2 [61,64)).
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
-  uint64_t d = 0;
-  d |= static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4);
-  d |= static_cast<uint64_t>(1) << 16;
-  d |= static_cast<uint64_t>(1024 >> 4) << 32;
-  d |= static_cast<uint64_t>(1) << 46;
-  d |= static_cast<uint64_t>(2) << 61;
-  return d;
-}
-// Instruction descriptor, kind::f16: D = f32, A = B = bf16, both K-major
-// (cute::UMMA::InstrDescriptor: c_format [4,6), a_format [7,10), b_format
-// [10,13), n >> 3 [17,23), m >> 4 [24,29)).
-__device__ __forceinline__ uint32_t make_idesc(uint32_t m, uint32_t n) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((n >> 3) << 17) | ((m >> 4) << 24);
-}
 
 // ---------------------------------------------------------------- tile walker
 struct Tile {
@@ -352,41 +250,13 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap, uint32_t low_dim,
   }
 }
 
-// ---------------------------------------------------------------- host
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
-                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
-                                  CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn get_encode_fn() {
-  static EncodeTiledFn fn = nullptr;
-  if (fn) return fn;
-  void* p = nullptr;
-  cudaDriverEntryPointQueryResult qres;
-  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
-      qres != cudaDriverEntryPointSuccess)
-    return nullptr;
-  fn = reinterpret_cast<EncodeTiledFn>(p);
-  return fn;
-}
-
 int launch_scan_tc(const uint16_t* x_bf16, int64_t ld_bf16, int64_t n, uint32_t low_dim,
                    const int64_t* bucket_ptr, int64_t n_buckets, const int64_t* tile_off,
                    const int4* unit_desc, float threshold, uint64_t* pairs, uint64_t pair_capacity,
                    unsigned long long* pair_count, cudaStream_t stream) {
-  EncodeTiledFn encode = get_encode_fn();
-  if (!encode) return set_error(FLC_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
   FLC_REQUIRE((reinterpret_cast<uintptr_t>(x_bf16) & 15) == 0, "x_bf16 must be 16-byte aligned");
   CUtensorMap tmap;
-  const cuuint64_t gdim[2] = {static_cast<cuuint64_t>(low_dim), static_cast<cuuint64_t>(n)};
-  const cuuint64_t gstride[1] = {static_cast<cuuint64_t>(ld_bf16) * 2};
-  const cuuint32_t box[2] = {kBoxK, kBoxRows};
-  const cuuint32_t estr[2] = {1, 1};
-  const CUresult rc = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
-                             const_cast<uint16_t*>(x_bf16), gdim, gstride, box, estr,
-                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (rc != CUDA_SUCCESS) return set_error(FLC_ERR_CUDA, "cuTensorMapEncodeTiled failed with %d", (int)rc);
+  FLC_TRY(make_bf16_tmap(&tmap, x_bf16, static_cast<uint64_t>(n), low_dim, ld_bf16));
   static bool attr_set = false;
   if (!attr_set) {
     FLC_CUDA(cudaFuncSetAttribute(scan_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));

@@ -327,7 +327,8 @@ class HotPath:
                     raise ValueError("k-means trains on the sparse rows: vectorize(..., want_ell=True)")
                 centroids = torch.empty((max(total, 1), d), dtype=torch.float32, device=self.device)
                 ws = self._ws(lib.flc_kmeans_workspace_bytes(n, buckets.n_buckets, total, maxb, v.ell_width, d), "kmeans")
-                check(lib.flc_kmeans_train(ptr(v.ell_idx), ptr(v.ell_val), ptr(v.ell_nnz), v.ell_width, n, d,
+                check(lib.flc_kmeans_train(ptr(v.ell_idx), ptr(v.ell_val), ptr(v.ell_nnz), v.ell_width,
+                                           ptr(v.xb), v.xb.stride(0) if v.xb is not None else 0, n, d,
                                            ptr(buckets.bucket_ptr), buckets.n_buckets, ptr(nlist), ptr(cptr),
                                            total, maxb, self.s.kmeans_iters, ptr(centroids), ptr(nprobe), maxp,
                                            ptr(list_id), ptr(probes), ptr(ws), ws.numel(), _stream()))

@@ -137,7 +137,11 @@ FLC_API int flc_ivf_plan(const int64_t* bucket_ptr, int64_t n_buckets, int32_t n
 FLC_API size_t flc_kmeans_workspace_bytes(int64_t n, int64_t n_buckets, int64_t total_centroids,
                                   int64_t max_ivf_bucket, int32_t ell_width, uint32_t low_dim);
 FLC_API int flc_kmeans_train(const uint16_t* ell_idx, const float* ell_val, const uint16_t* ell_nnz,
-                     int32_t ell_width, int64_t n, uint32_t low_dim,
+                     int32_t ell_width,
+                     const uint16_t* x_bf16, int64_t ld_bf16 /*nullable: bf16 copy of the (unit-norm) rows; lets
+                       large buckets take their assignment from tcgen05 tensor cores (exact: close calls are
+                       re-scored in float32)*/,
+                     int64_t n, uint32_t low_dim,
                      const int64_t* bucket_ptr, int64_t n_buckets,
                      const int32_t* nlist, const int64_t* centroid_ptr,
                      int64_t total_centroids, int64_t max_ivf_bucket /*from flc_ivf_plan, 0 = unknown*/,

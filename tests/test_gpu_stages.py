@@ -259,7 +259,7 @@ def test_ivf_shared_centroids_exact_and_recall(sparse):
     assert np.array_equal(gp, ref.indptr) and np.array_equal(gi, ref.indices)
 
 
-def _train(n, seed, lo, hi, force_tiled=False, monkeypatch=None):
+def _train(n, seed, lo, hi, force_tiled=False, monkeypatch=None, want_bf16=False):
     if monkeypatch is not None:
         if force_tiled:
             monkeypatch.setenv("FLC_KMEANS_FORCE_TILED", "1")
@@ -269,17 +269,19 @@ def _train(n, seed, lo, hi, force_tiled=False, monkeypatch=None):
     sp = helpers.dataset(n, seed, lo, hi)
     d = helpers.to_device(sp, h.device)
     b = h.bucket_sort(d["precursor_mz"], d["charge"])
-    v = h.vectorize(d["mz"], d["intensity"], d["indptr"], b.order, want_bf16=False)
+    v = h.vectorize(d["mz"], d["intensity"], d["indptr"], b.order, want_bf16=want_bf16)
     return h, b, v, h.build_ivf(v, b)
 
 
-@pytest.mark.parametrize("n,hi", [(6000, 1003.0), (30000, 1002.0), (12000, 1012.0)])
-def test_kmeans_quality_close_to_oracle(n, hi):
+@pytest.mark.parametrize("n,hi,bf16", [(6000, 1003.0, False), (30000, 1002.0, False), (30000, 1002.0, True),
+                                        (12000, 1012.0, False)])
+def test_kmeans_quality_close_to_oracle(n, hi, bf16):
     """n = 30000 over 2 Da makes buckets of ~7500 rows: too large for the fused
     trainer, so that run exercises the tiled trainer; the other two are fused
-    (two size classes).  Same arithmetic conventions as the oracle, so the
+    (two size classes).  With the bf16 rows the tiled trainer takes its assignment
+    from the tensor cores.  Same arithmetic conventions as the oracle, so the
     objective is the same up to float32 arg-max near-ties."""
-    h, b, v, ivf = _train(n, 29, 1000.0, hi)
+    h, b, v, ivf = _train(n, 29, 1000.0, hi, want_bf16=bf16)
     xs, bptr, nlist, cptr = _cpu(v.x), _cpu(b.bucket_ptr), _cpu(ivf.nlist), _cpu(ivf.centroid_ptr)
     cents = _cpu(ivf.centroids)
     lid = _cpu(ivf.list_id)
@@ -301,13 +303,15 @@ def test_kmeans_quality_close_to_oracle(n, hi):
 
 def test_kmeans_fused_and_tiled_give_the_same_bits(monkeypatch):
     """List sums are fixed point, so the schedule (fused shared-memory trainer vs
-    tiled multi-launch trainer with atomics) cannot change a single bit, and
-    neither can a re-run."""
+    tiled multi-launch trainer with atomics, SIMT or tensor-core assignment) cannot
+    change a single bit, and neither can a re-run."""
     _, b, _, fused = _train(9000, 31, 1000.0, 1010.0, False, monkeypatch)
     _, _, _, tiled = _train(9000, 31, 1000.0, 1010.0, True, monkeypatch)
     _, _, _, again = _train(9000, 31, 1000.0, 1010.0, True, monkeypatch)
+    # with the bf16 rows the tiled trainer assigns on the tensor cores (close calls re-scored exactly)
+    _, _, _, tensor = _train(9000, 31, 1000.0, 1010.0, True, monkeypatch, want_bf16=True)
     assert fused.total_centroids > 0
-    for other in (tiled, again):
+    for other in (tiled, again, tensor):
         assert torch.equal(fused.centroids, other.centroids)
         assert torch.equal(fused.list_id, other.list_id)
         assert torch.equal(fused.probes, other.probes)
