@@ -343,7 +343,9 @@ def run_ours(args):
     total = args.n * world
 
     # one instrumented pass for the roofline statistics (outside the timed regions)
-    hp2 = pipeline.HotPath(settings, dev, profile=True)
+    hp2 = pipeline.HotPath(settings, dev, profile=False)
+    hp2.run(d["mz"], d["intensity"], d["indptr"], d["precursor_mz"], d["charge"], max_peaks=max_peaks)  # warm scratch
+    hp2.timer = pipeline._Timer(True)
     _, _, keep = hp2.run(d["mz"], d["intensity"], d["indptr"], d["precursor_mz"], d["charge"], keep=True)
     stage_ms = hp2.timer.result()
     sizes = (keep["buckets"].bucket_ptr[1:] - keep["buckets"].bucket_ptr[:-1]).double()

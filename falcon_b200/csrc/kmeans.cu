@@ -718,7 +718,10 @@ struct TiledArgs {
   uint16_t* cb;      // [total][ld_c] bf16 copy of the centroids (TMA operand)
   int64_t ld_c;
   int32_t* tc_best;  // [n] arg-max list by bf16 scores (exact after the fix kernel)
-  uint8_t* tc_unsure;  // [n] 1: the two best bf16 scores are within the margin
+  int32_t* tc_unsure;  // [n] rows whose two best bf16 scores are within the margin (first *tc_counts[1])
+  int4* units;       // query tiles of the tiled buckets still training
+  int32_t* unit_bucket;
+  int32_t* tc_counts;  // [0] units, [1] unsure rows
 };
 
 __global__ void __launch_bounds__(128)
@@ -755,17 +758,20 @@ kmeans_tiled_init_kernel(TiledArgs A, int64_t total) {
 
 // Unit descriptors of the tensor-core assignment: every tiled bucket contributes
 // ceil(rows / 128) query tiles (first row, bucket end, first / end centroid row).
-__global__ void kmeans_tc_units_kernel(TiledArgs A, int4* __restrict__ units, int32_t* __restrict__ n_units) {
+__global__ void kmeans_tc_units_kernel(TiledArgs A) {
   const int32_t qi = blockIdx.x * blockDim.x + threadIdx.x;
   if (qi >= A.q.cnt[kClsTiled]) return;
   const int64_t b = A.q.queue[static_cast<int64_t>(kClsTiled) * A.n_buckets + qi];
+  if (A.bstate[2 * b + 1] != 0) return;  // converged: nothing left to do
   const int64_t s = A.bucket_ptr[b], e = A.bucket_ptr[b + 1];
   const int64_t c0 = A.centroid_ptr[b];
   const int32_t tq = static_cast<int32_t>((e - s + 127) / 128);
-  const int32_t base = atomicAdd(n_units, tq);
-  for (int32_t t = 0; t < tq; ++t)
-    units[base + t] = make_int4(static_cast<int>(s + 128 * t), static_cast<int>(e), static_cast<int>(c0),
-                                static_cast<int>(c0 + A.nlist[b]));
+  const int32_t base = atomicAdd(A.tc_counts, tq);
+  for (int32_t t = 0; t < tq; ++t) {
+    A.units[base + t] = make_int4(static_cast<int>(s + 128 * t), static_cast<int>(e), static_cast<int>(c0),
+                                  static_cast<int>(c0 + A.nlist[b]));
+    A.unit_bucket[base + t] = static_cast<int32_t>(b);
+  }
 }
 
 // Exact float32 arg-max (the fused trainer's arithmetic: products added in slot order
@@ -774,10 +780,11 @@ __global__ void kmeans_tc_units_kernel(TiledArgs A, int4* __restrict__ units, in
 __global__ void __launch_bounds__(256)
 kmeans_tiled_fix_kernel(TiledArgs A) {
   const int lane = threadIdx.x & 31;
-  const int64_t i = static_cast<int64_t>(blockIdx.x) * 8 + (threadIdx.x >> 5);
-  if (i >= A.n || !A.tc_unsure[i]) return;
+  const int64_t warps_total = static_cast<int64_t>(gridDim.x) * 8;
+  const int32_t n_fix = A.tc_counts[1];
+  for (int64_t w = static_cast<int64_t>(blockIdx.x) * 8 + (threadIdx.x >> 5); w < n_fix; w += warps_total) {
+  const int64_t i = A.tc_unsure[w];
   const int64_t b = find_segment(A.bucket_ptr, A.n_buckets, i);
-  if (A.q.bclass[b] != kClsTiled || A.bstate[2 * b + 1] != 0) return;
   const int32_t L = A.nlist[b];
   const float* ctb = A.ct + A.centroid_ptr[b] * A.low_dim;
   const int m = min(static_cast<int>(A.ell_nnz[i]), A.W);
@@ -806,25 +813,23 @@ kmeans_tiled_fix_kernel(TiledArgs A) {
     if (ov > best || (ov == best && oc < best_c)) { best = ov; best_c = oc; }
   }
   if (lane == 0) A.tc_best[i] = best_c;
+  }
 }
 
-// Rows whose list changed move their fixed-point values between the lists' sums.
-__global__ void __launch_bounds__(256)
+// Rows whose list changed move their fixed-point values between the lists' sums.  One CTA
+// of 128 threads per query tile of the buckets still training.
+__global__ void __launch_bounds__(128)
 kmeans_tiled_apply_kernel(TiledArgs A) {
-  __shared__ int64_t b0_s;
-  const int64_t i0 = static_cast<int64_t>(blockIdx.x) * 256;
-  if (threadIdx.x == 0) b0_s = find_segment(A.bucket_ptr, A.n_buckets, i0);
-  __syncthreads();
-  const int64_t i = i0 + threadIdx.x;
-  if (i >= A.n) return;
-  int64_t b = b0_s;
-  while (A.bucket_ptr[b + 1] <= i) ++b;
-  if (A.q.bclass[b] != kClsTiled || A.bstate[2 * b + 1] != 0) return;
+  for (int64_t u = blockIdx.x; u < A.tc_counts[0]; u += gridDim.x) {
+  const int4 ud = A.units[u];
+  const int64_t i = static_cast<int64_t>(ud.x) + threadIdx.x;
+  if (i >= ud.y) continue;
+  const int64_t b = A.unit_bucket[u];
   const int old_c = A.gassign[i];
   const int new_c = A.tc_best[i];
-  if (old_c == new_c) return;
+  if (old_c == new_c) continue;
   const int d = static_cast<int>(A.low_dim);
-  const int64_t c0 = A.centroid_ptr[b];
+  const int64_t c0 = ud.z;
   A.gassign[i] = new_c;
   A.bstate[2 * b] = 1;  // benign race: every writer stores 1
   atomicAdd(A.gcnt + c0 + new_c, 1);
@@ -837,6 +842,7 @@ kmeans_tiled_apply_kernel(TiledArgs A) {
     const long long q = __float2ll_rn(__ldg(A.ell_val + i * A.W + j) * kFixScaleF);
     atomicAdd(add + k, static_cast<unsigned long long>(q));
     if (old_c >= 0) atomicAdd(sub + k, static_cast<unsigned long long>(-q));
+  }
   }
 }
 
@@ -1090,8 +1096,9 @@ struct KmeansLayout {
   // tensor-core assignment
   uint16_t* cb;
   int32_t* tc_best;
-  uint8_t* tc_unsure;
+  int32_t* tc_unsure;
   int4* units;
+  int32_t* unit_bucket;
 };
 
 static void kmeans_layout(Workspace& ws, int64_t n, int64_t n_buckets, int64_t total, uint32_t low_dim,
@@ -1101,7 +1108,7 @@ static void kmeans_layout(Workspace& ws, int64_t n, int64_t n_buckets, int64_t t
   L.queue = ws.take<int32_t>(3 * nbk);
   L.bclass = ws.take<uint8_t>(nbk);
   L.ct = nullptr; L.gsum = nullptr; L.gcnt = nullptr; L.gcntd = nullptr; L.gassign = nullptr; L.bstate = nullptr;
-  L.cb = nullptr; L.tc_best = nullptr; L.tc_unsure = nullptr; L.units = nullptr;
+  L.cb = nullptr; L.tc_best = nullptr; L.tc_unsure = nullptr; L.units = nullptr; L.unit_bucket = nullptr;
   if (tiled) {
     const size_t t = static_cast<size_t>(total > 0 ? total : 1);
     L.ct = ws.take<float>(t * low_dim);
@@ -1113,8 +1120,9 @@ static void kmeans_layout(Workspace& ws, int64_t n, int64_t n_buckets, int64_t t
     const size_t nn = static_cast<size_t>(n > 0 ? n : 1);
     L.cb = ws.take<uint16_t>(t * ((low_dim + 7u) & ~7u));
     L.tc_best = ws.take<int32_t>(nn);
-    L.tc_unsure = ws.take<uint8_t>(nn);
+    L.tc_unsure = ws.take<int32_t>(nn);
     L.units = ws.take<int4>(nn / 128 + nbk + 1);
+    L.unit_bucket = ws.take<int32_t>(nn / 128 + nbk + 1);
   }
 }
 
@@ -1231,8 +1239,7 @@ int flc_kmeans_train(const uint16_t* ell_idx, const float* ell_val, const uint16
   const int64_t ld_c = (static_cast<int64_t>(low_dim) + 7) & ~int64_t(7);
   TiledArgs T{ell_idx, ell_val, ell_nnz, W, low_dim, n, bucket_ptr, n_buckets, nlist, centroid_ptr, q,
               centroids, K.ct, K.gsum, K.gcnt, K.gcntd, K.gassign, K.bstate,
-              use_tc ? K.cb : nullptr, ld_c, K.tc_best, K.tc_unsure};
-  int32_t* n_units = K.qctr + 8;
+              use_tc ? K.cb : nullptr, ld_c, K.tc_best, K.tc_unsure, K.units, K.unit_bucket, K.qctr + 8};
   FLC_CUDA(cudaMemsetAsync(K.gsum, 0, static_cast<size_t>(total_centroids) * low_dim * sizeof(long long), stream));
   FLC_CUDA(cudaMemsetAsync(K.gcnt, 0, static_cast<size_t>(total_centroids) * sizeof(int32_t), stream));
   FLC_CUDA(cudaMemsetAsync(K.gassign, 0xff, static_cast<size_t>(n) * sizeof(int32_t), stream));
@@ -1247,22 +1254,21 @@ int flc_kmeans_train(const uint16_t* ell_idx, const float* ell_val, const uint16
   const unsigned row_blocks = static_cast<unsigned>((n + kTiledRows - 1) / kTiledRows);
   static_assert(kTiledThreads == 256, "launch configuration below assumes 256 threads");
   const unsigned upd_blocks = static_cast<unsigned>(std::min<int64_t>(n_buckets, 4 * kNumSMs));
-  if (use_tc) {
-    timed("kmeans_tc_units", stream, [&] {
-      kmeans_tc_units_kernel<<<static_cast<unsigned>((n_buckets + 255) / 256), 256, 0, stream>>>(T, K.units, n_units); });
-    FLC_LAUNCH_CHECK();
-  }
+  const unsigned unit_blocks = static_cast<unsigned>(std::min<int64_t>(n / 128 + n_buckets + 1, 1 << 20));
   for (int it = 0; it < niter; ++it) {
     if (use_tc) {
+      // query tiles of the buckets that have not converged yet
+      FLC_CUDA(cudaMemsetAsync(T.tc_counts, 0, 2 * sizeof(int32_t), stream));
+      timed("kmeans_tc_units", stream, [&] {
+        kmeans_tc_units_kernel<<<static_cast<unsigned>((n_buckets + 255) / 256), 256, 0, stream>>>(T); });
+      FLC_LAUNCH_CHECK();
       // bf16 scores on the tensor cores decide every row whose two best lists are further apart than
       // twice the rounding error (2^-7 for unit vectors, plus slack); the rest is re-scored exactly
-      FLC_TRY(launch_kmeans_tc(x_bf16, ld_bf16, n, K.cb, ld_c, total_centroids, low_dim, K.units, n_units,
-                               0.008f, K.tc_best, K.tc_unsure, stream));
-      timed("kmeans_tiled_fix", stream, [&] {
-        kmeans_tiled_fix_kernel<<<static_cast<unsigned>((n + 7) / 8), 256, 0, stream>>>(T); });
+      FLC_TRY(launch_kmeans_tc(x_bf16, ld_bf16, n, K.cb, ld_c, total_centroids, low_dim, K.units, T.tc_counts,
+                               0.008f, K.tc_best, K.tc_unsure, T.tc_counts + 1, stream));
+      timed("kmeans_tiled_fix", stream, [&] { kmeans_tiled_fix_kernel<<<kNumSMs * 8, 256, 0, stream>>>(T); });
       FLC_LAUNCH_CHECK();
-      timed("kmeans_tiled_apply", stream, [&] {
-        kmeans_tiled_apply_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(T); });
+      timed("kmeans_tiled_apply", stream, [&] { kmeans_tiled_apply_kernel<<<unit_blocks, 128, 0, stream>>>(T); });
       FLC_LAUNCH_CHECK();
     } else {
       timed("kmeans_tiled_assign", stream, [&] {

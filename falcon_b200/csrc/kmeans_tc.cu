@@ -58,7 +58,8 @@ struct UnitWalker {
 __global__ void __launch_bounds__(kScanThreads, 1)
 kmeans_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_c,
                  uint32_t low_dim, const int4* __restrict__ units, const int32_t* __restrict__ n_units_ptr,
-                 float margin, int32_t* __restrict__ best_out, uint8_t* __restrict__ unsure_out) {
+                 float margin, int32_t* __restrict__ best_out, int32_t* __restrict__ unsure_list,
+                 int32_t* __restrict__ n_unsure) {
   extern __shared__ unsigned char smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t tiles_base = (raw + 1023u) & ~1023u;
@@ -190,9 +191,19 @@ kmeans_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
       if (lane == 0) mbar_arrive(tempty_bar(acc));
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1u;
-      if (t.last && q < t.q_end) {
-        best_out[q] = best_id;
-        unsure_out[q] = (best - second > margin) ? 0 : 1;  // a single list: second = -inf, sure
+      if (t.last) {
+        const bool have = q < t.q_end;
+        if (have) best_out[q] = best_id;
+        // rows the bf16 scores cannot decide (a single list: second = -inf, decided) go on the
+        // re-score list: one atomic per warp
+        const bool unsure = have && !(best - second > margin);
+        const uint32_t ub = __ballot_sync(0xffffffffu, unsure);
+        if (ub != 0u) {
+          int base = 0;
+          if (lane == 0) base = atomicAdd(n_unsure, __popc(ub));
+          base = __shfl_sync(0xffffffffu, base, 0);
+          if (unsure) unsure_list[base + __popc(ub & ((1u << lane) - 1u))] = q;
+        }
       }
     }
   }
@@ -208,7 +219,7 @@ kmeans_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
 
 int launch_kmeans_tc(const uint16_t* x_bf16, int64_t ld_bf16, int64_t n, const uint16_t* c_bf16, int64_t ld_c,
                      int64_t total_centroids, uint32_t low_dim, const int4* units, const int32_t* n_units,
-                     float margin, int32_t* best, uint8_t* unsure, cudaStream_t stream) {
+                     float margin, int32_t* best, int32_t* unsure_list, int32_t* n_unsure, cudaStream_t stream) {
   FLC_REQUIRE((reinterpret_cast<uintptr_t>(x_bf16) & 15) == 0 && (reinterpret_cast<uintptr_t>(c_bf16) & 15) == 0,
               "bf16 matrices must be 16-byte aligned");
   FLC_REQUIRE((ld_bf16 % 8) == 0 && (ld_c % 8) == 0, "bf16 row pitches must be multiples of 8");
@@ -221,7 +232,7 @@ int launch_kmeans_tc(const uint16_t* x_bf16, int64_t ld_bf16, int64_t n, const u
     attr_set = true;
   }
   timed("kmeans_tc", stream, [&] { kmeans_tc_kernel<<<kNumSMs, kScanThreads, kSmemBytes, stream>>>(
-      tmap_x, tmap_c, low_dim, units, n_units, margin, best, unsure); });
+      tmap_x, tmap_c, low_dim, units, n_units, margin, best, unsure_list, n_unsure); });
   FLC_LAUNCH_CHECK();
   return FLC_OK;
 }
