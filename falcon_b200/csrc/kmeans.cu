@@ -947,6 +947,7 @@ kmeans_tiled_assign_kernel(TiledArgs A) {
 __global__ void __launch_bounds__(256)
 kmeans_tiled_update_kernel(TiledArgs A) {
   __shared__ int32_t cj_s;
+  __shared__ float tile[32][33];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int d = static_cast<int>(A.low_dim);
   const float eps = 1.0f / 1024.0f;
@@ -1003,7 +1004,7 @@ kmeans_tiled_update_kernel(TiledArgs A) {
         __syncthreads();
       }
     }
-    // normalise: one warp per list
+    // normalise: one warp per list (row-major float32 + bf16 copies, coalesced)
     for (int32_t c = warp; c < L; c += 8) {
       float* cr = cent + static_cast<int64_t>(c) * d;
       double ss = 0.0;
@@ -1017,8 +1018,26 @@ kmeans_tiled_update_kernel(TiledArgs A) {
       for (int k = lane; k < d; k += 32) {
         const float v = static_cast<float>(static_cast<double>(cr[k]) * inv);
         cr[k] = v;
-        ctb[static_cast<int64_t>(k) * L + c] = v;
         if (cbr) cbr[k] = f32_to_bf16_rne(v);
+      }
+    }
+    __syncthreads();
+    // transposed training copy ct[column][list] through 32 x 32 shared-memory tiles, so that
+    // both the reads (rows of `cent`) and the writes (rows of `ct`) are coalesced
+    for (int32_t ci = 0; ci < L; ci += 32) {
+      for (int ki = 0; ki < d; ki += 32) {
+        for (int r = warp; r < 32; r += 8) {
+          const int32_t c = ci + r;
+          const int k = ki + lane;
+          tile[r][lane] = (c < L && k < d) ? cent[static_cast<int64_t>(c) * d + k] : 0.f;
+        }
+        __syncthreads();
+        for (int r = warp; r < 32; r += 8) {
+          const int k = ki + r;
+          const int32_t c = ci + lane;
+          if (k < d && c < L) ctb[static_cast<int64_t>(k) * L + c] = tile[lane][r];
+        }
+        __syncthreads();
       }
     }
     if (tid == 0) {  // sums and counts persist: the assign kernel maintains them incrementally
@@ -1065,6 +1084,24 @@ ivf_assign_tiled_kernel(TiledArgs A, const int32_t* __restrict__ nprobe, int32_t
       }
     }
     const int n_here = min(32, L - s0);
+    if (L <= 32 && P <= 8) {
+      // one strip, few probes: P rounds of warp arg-max (ties to the lower id) beat 32 insertions
+      double mine = c < L ? acc : -INFINITY;
+      bool taken = c >= L;
+      for (int t = 0; t < P; ++t) {
+        double bv = taken ? -INFINITY : mine;
+        int bc = taken ? 0x7fffffff : static_cast<int>(c);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+          const int oc = __shfl_xor_sync(0xffffffffu, bc, o);
+          if (oc != 0x7fffffff && (bc == 0x7fffffff || ov > bv || (ov == bv && oc < bc))) { bv = ov; bc = oc; }
+        }
+        if (lane == t) { my_score = bv; my_id = bc; }
+        if (static_cast<int>(c) == bc) taken = true;
+      }
+      break;
+    }
     for (int t = 0; t < n_here; ++t) {
       const double sc = __shfl_sync(0xffffffffu, acc, t);
       // entries ahead of the newcomer: strictly better, or equal (earlier id wins)
@@ -1253,7 +1290,7 @@ int flc_kmeans_train(const uint16_t* ell_idx, const float* ell_val, const uint16
                                 static_cast<int>(smem)));
   const unsigned row_blocks = static_cast<unsigned>((n + kTiledRows - 1) / kTiledRows);
   static_assert(kTiledThreads == 256, "launch configuration below assumes 256 threads");
-  const unsigned upd_blocks = static_cast<unsigned>(std::min<int64_t>(n_buckets, 4 * kNumSMs));
+  const unsigned upd_blocks = static_cast<unsigned>(std::min<int64_t>(n_buckets, 1 << 20));  // latency-bound: one CTA per bucket
   const unsigned unit_blocks = static_cast<unsigned>(std::min<int64_t>(n / 128 + n_buckets + 1, 1 << 20));
   for (int it = 0; it < niter; ++it) {
     if (use_tc) {

@@ -274,10 +274,11 @@ def _train(n, seed, lo, hi, force_tiled=False, monkeypatch=None, want_bf16=False
 
 
 @pytest.mark.parametrize("n,hi,bf16", [(6000, 1003.0, False), (30000, 1002.0, False), (30000, 1002.0, True),
-                                        (12000, 1012.0, False)])
+                                        (12000, 1012.0, False), (24000, 1010.0, True)])
 def test_kmeans_quality_close_to_oracle(n, hi, bf16):
-    """n = 30000 over 2 Da makes buckets of ~7500 rows: too large for the fused
-    trainer, so that run exercises the tiled trainer; the other two are fused
+    """n = 30000 over 2 Da makes buckets of ~7500 rows (128 lists), n = 24000 over 10 Da buckets
+    of ~1200 rows (16 lists, 2 probes): too large for the fused trainer, so those runs
+    exercise the tiled trainer; the other two are fused
     (two size classes).  With the bf16 rows the tiled trainer takes its assignment
     from the tensor cores.  Same arithmetic conventions as the oracle, so the
     objective is the same up to float32 arg-max near-ties."""
@@ -295,8 +296,10 @@ def test_kmeans_quality_close_to_oracle(n, hi, bf16):
             obj_gpu = (xb_ @ c_gpu.T).max(axis=1).sum()
             obj_cpu = (xb_ @ c_cpu.T).max(axis=1).sum()
             assert obj_gpu >= 0.98 * obj_cpu
-            # the final assignment belongs to the trained centroids
+            # the final assignment and the probe lists belong to the trained centroids
             assert np.array_equal(lid[bptr[i]: bptr[i + 1]], oivf.assign_lists(xb_, c_gpu))
+            p = oivf.n_probe_rule(int(nlist[i]), 32)
+            assert np.array_equal(_cpu(ivf.probes)[bptr[i]: bptr[i + 1], :p], oivf.probe_lists(xb_, c_gpu, p))
             checked += 1
     assert checked > 0
 
