@@ -165,7 +165,9 @@ def run_reference_arm(args):
 
 def workload_config(args):
     return {
-        "workload": f"{args.n} synthetic spectra per GPU (seed 42+rank, charge 2/3, 101-1500 m/z, <=50 peaks), "
+        "workload": (f"{args.total} synthetic spectra in total, precursor-mass range split across the GPUs, "
+                     if args.total else "") +
+                    f"{args.n} synthetic spectra per GPU (seed 42+rank, charge 2/3, 101-1500 m/z, <=50 peaks), "
                     "falcon defaults low_dim=400 eps=0.10 n_probe=32 n_neighbors=64/128 precursor_tol=20ppm"
                     + (" exhaustive (n_probe=nlist)" if args.exhaustive else "")
                     + (f" neutral mass {args.mass_range[0]:g}-{args.mass_range[1]:g} Da" if args.mass_range else ""),
@@ -250,6 +252,12 @@ def run_ours(args):
 
     t0 = time.perf_counter()
     kw = {"mass_range": tuple(args.mass_range)} if args.mass_range else {}
+    if args.total:
+        # strong scaling (BASELINE configs[3]): args.total spectra over the whole precursor-mass range; rank r
+        # owns the r-th slice of the range, i.e. whole precursor buckets, with the full data set's bucket sizes
+        lo, hi = args.mass_range if args.mass_range else (700.0, 3500.0)
+        args.n = args.total // world
+        kw = {"mass_range": (lo + (hi - lo) * rank / world, lo + (hi - lo) * (rank + 1) / world)}
     sp = synth.generate(args.n, 42 + rank, **kw)
     log(f"[rank {rank}] generated {len(sp)} spectra / {sp.n_peaks} peaks in {time.perf_counter() - t0:.1f}s")
     host = {k: torch.from_numpy(np.ascontiguousarray(v)).pin_memory() for k, v in dict(
@@ -417,7 +425,8 @@ def run_ours(args):
         bsz = sizes.cpu().numpy()
         out = {
             "metric": METRIC, "value": total / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "strong" if args.total else "weak",
             "vs_baseline": None, "dtype": "bf16 scan / f32 vectors / f64 re-score", "data": "synthetic",
             "config": workload_config(args),
             "e2e": {"value": total / (ms_pipe * 1e-3), "unit": UNIT, "ms_per_step": ms_pipe,
@@ -451,6 +460,9 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=1_000_000,
                     help="spectra in the CPU-baseline sample (whole buckets; ~10 s of CPU work at 1M)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--total", type=int, default=0,
+                    help="strong scaling: this many spectra in total, the precursor-mass range (whole buckets) "
+                         "split across the ranks -- BASELINE configs[3] is --total 10000000")
     ap.add_argument("--mass-range", type=float, nargs=2, default=None, metavar=("LO", "HI"),
                     help="neutral mass range of the synthetic peptides (default 700-3500 Da); a narrow range "
                          "makes large precursor buckets (tensor-core regime of the scan)")
