@@ -32,6 +32,24 @@ def test_end_to_end_exhaustive_partition_identical(n, lo, hi):
     assert odb.same_partition(labels, ref)
 
 
+@pytest.mark.parametrize("low_dim,eps,tol,mode,mz_interval", [
+    (200, 0.05, 20.0, "ppm", 1), (800, 0.30, 20.0, "ppm", 1), (400, 0.20, 0.02, "Da", 2), (100, 0.10, 50.0, "ppm", 1)])
+def test_end_to_end_settings_sweep(low_dim, eps, tol, mode, mz_interval):
+    """BASELINE config 4's axes (low_dim 200 / 400 / 800, eps 0.05 - 0.30) plus the Da tolerance and a
+    coarser bucket interval, at a size the oracle checks exhaustively: identical partitions."""
+    n = 12000
+    sp = helpers.dataset(n, 44, 1000.0, 1012.0)
+    s = pipeline.Settings(exhaustive=True, low_dim=low_dim, eps=eps, precursor_tol_mass=tol, precursor_tol_mode=mode,
+                          mz_interval=mz_interval)
+    labels, nc, _ = pipeline.cluster_host(sp, s)
+    o = helpers.oracle_pipeline(sp, exhaustive=True, low_dim=low_dim, eps=eps, tol=tol, mode=mode,
+                                mz_interval=mz_interval)
+    ref = np.empty(n, np.int64)
+    ref[o["order"]] = o["labels"]
+    assert nc == ref.max() + 1 and nc > 100
+    assert odb.same_partition(labels, ref)
+
+
 def test_end_to_end_default_nprobe_shared_centroids():
     sp = helpers.dataset(20000, 43, 1000.0, 1020.0)
     h = pipeline.HotPath(pipeline.Settings(exhaustive=False))
