@@ -8,8 +8,9 @@
 // Peaks that collide on a hashed column are added in peak order
 // (__match_any_sync gives every lane its rank among same-column lanes) so the
 // float32 sum is bit-identical to the sequential reference loop (A.1).  The
-// squared norm is reduced in float64 with warp shuffles.  Spectra of up to 64
-// peaks (falcon keeps at most 50) never sweep the dense row: the first lane of
+// squared norm is reduced in float64 with shuffles.  Spectra of up to 64 peaks
+// (falcon keeps at most 50) take HALF a warp each -- two spectra per warp share the
+// bookkeeping instructions -- and never sweep the dense row: the first lane of
 // every distinct column owns it and emits its value to the float32 row
 // (optional), the bfloat16 row (tcgen05 scan operand, staged in shared memory
 // and copied out 16 bytes per lane) and the sparse ELL copy that k-means and
@@ -138,24 +139,92 @@ __device__ __forceinline__ bool accumulate_pass(float* row, const Peak& k, int l
   return k.valid && rank == 0;
 }
 
-// One warp per spectrum.  Per-warp shared memory: the float32 accumulation row,
-// a bfloat16 staging row (both all-zero between spectra) and a stamp row that
-// tells which columns an earlier pass of the same spectrum already owns.
-__global__ void __launch_bounds__(kVecWarps * 32, 4)
+// ---------------------------------------------------------------- wide spectra (> 64 peaks)
+// Full warp on one spectrum: accumulate pass by pass, then sweep the dense row for the
+// norm and every output.  `row` must be all zero on entry and is all zero on exit.
+__device__ void vectorize_wide(const VecParams& P, float* row, int64_t r, int64_t p0, int64_t p1, int lane,
+                               double vec_len_d) {
+  const uint32_t below = (1u << lane) - 1u;
+  float* dst_f = P.out_f32 ? P.out_f32 + r * P.ld_f32 : nullptr;
+  uint16_t* dst_b = P.out_bf16 ? P.out_bf16 + r * P.ld_bf16 : nullptr;
+  uint16_t* di = P.ell_idx ? P.ell_idx + r * P.ell_width : nullptr;
+  float* dv = P.ell_idx ? P.ell_val + r * P.ell_width : nullptr;
+  for (int64_t base = p0; base < p1; base += 32)
+    accumulate_pass(row, load_peak(P, base + lane, p1, vec_len_d), lane, below);
+  double scale = 1.0;
+  if (P.norm) {
+    double ss = 0.0;
+    for (uint32_t i = lane; i < P.low_dim; i += 32) ss = fma(static_cast<double>(row[i]), static_cast<double>(row[i]), ss);
+    ss = warp_sum_f64(ss);
+    scale = ss > 0.0 ? rsqrt(ss) : 1.0;
+  }
+  int count = 0;
+  for (uint32_t base = 0; base < P.row_len; base += 32) {
+    const uint32_t i = base + lane;
+    const float sv = static_cast<float>(static_cast<double>(row[i]) * scale);
+    row[i] = 0.f;
+    if (dst_f && i < P.low_dim) dst_f[i] = sv;
+    if (dst_b && static_cast<int64_t>(i) < P.ld_bf16) dst_b[i] = __bfloat16_as_ushort(__float2bfloat16_rn(sv));
+    if (di) {
+      const bool nz = sv != 0.f;
+      const uint32_t bal = __ballot_sync(0xffffffffu, nz);
+      const int pos = count + __popc(bal & below);
+      if (nz && pos < P.ell_width) { di[pos] = static_cast<uint16_t>(i); dv[pos] = sv; }
+      count += __popc(bal);
+    }
+  }
+  if (di) {
+    for (int pos = count + lane; pos < P.ell_width; pos += 32) {  // zero padding
+      di[pos] = 0;
+      dv[pos] = 0.f;
+    }
+    if (lane == 0) {
+      if (P.ell_nnz) P.ell_nnz[r] = static_cast<uint16_t>(min(count, P.ell_width));
+      if (count > P.ell_width) atomicMax(P.ell_overflow, count);
+    }
+  }
+  __syncwarp();
+}
+
+// ---------------------------------------------------------------- main kernel
+// HALF a warp per spectrum (falcon keeps at most 50 peaks: four passes of 16 lanes), two
+// spectra per warp side by side, so the per-spectrum bookkeeping instructions are shared.
+// Per half-warp shared memory: the float32 accumulation row, a bfloat16 staging row (both
+// all-zero between spectra) and a stamp row that tells which columns an earlier pass of the
+// same spectrum already owns.  Spectra with more than 64 peaks are handed to the full warp.
+constexpr int kPasses = 4;
+struct HalfRaw {
+  float m[kPasses], x[kPasses];
+};
+__device__ __forceinline__ HalfRaw load_half_raw(const VecParams& P, const SpecMeta& s, int hl) {
+  HalfRaw w;
+#pragma unroll
+  for (int t = 0; t < kPasses; ++t) {
+    const int64_t p = s.p0 + 16 * t + hl;
+    const bool have = p < s.p1 && s.p1 - s.p0 <= 16 * kPasses;
+    w.m[t] = have ? __ldg(P.mz + p) : 0.f;
+    w.x[t] = have ? __ldg(P.intensity + p) : 0.f;
+  }
+  return w;
+}
+
+__global__ void __launch_bounds__(kVecWarps * 32, 3)
 vectorize_kernel(const VecParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
-  const size_t per_warp = static_cast<size_t>(P.row_len) * 8;
-  float* row = reinterpret_cast<float*>(smem_raw + warp * per_warp);
+  const int h = lane >> 4, hl = lane & 15;
+  const size_t per_half = static_cast<size_t>(P.row_len) * 8;
+  float* row = reinterpret_cast<float*>(smem_raw + (warp * 2 + h) * per_half);
   uint16_t* brow = reinterpret_cast<uint16_t*>(row + P.row_len);
   uint16_t* stamp = brow + P.row_len;
-  const int64_t warps_total = static_cast<int64_t>(gridDim.x) * kVecWarps;
+  const int64_t halves_total = static_cast<int64_t>(gridDim.x) * kVecWarps * 2;
   const uint32_t below = (1u << lane) - 1u;
+  const uint32_t below_h = (1u << hl) - 1u;
   const double vec_len_d = static_cast<double>(P.vec_len);
   const bool bf16_vec = P.out_bf16 != nullptr && (P.ld_bf16 & 7) == 0 && (reinterpret_cast<uintptr_t>(P.out_bf16) & 15) == 0;
 
-  for (uint32_t i = lane; i < P.row_len; i += 32) {
+  for (uint32_t i = hl; i < P.row_len; i += 16) {
     row[i] = 0.f;
     brow[i] = 0;
     stamp[i] = 0;
@@ -163,119 +232,151 @@ vectorize_kernel(const VecParams P) {
   __syncwarp();
   uint32_t serial = 0;
 
-  const int64_t rr0 = static_cast<int64_t>(blockIdx.x) * kVecWarps + warp;
-  SpecMeta cur = load_meta(P, rr0), nxt = load_meta(P, rr0 + warps_total);
-  SpecRaw raw = load_raw(P, cur, lane);
-  for (int64_t rr = rr0; rr < P.n; rr += warps_total) {
-    const SpecMeta nn = load_meta(P, rr + 2 * warps_total);
-    const SpecRaw raw_nxt = load_raw(P, nxt, lane);
-    const int64_t r = cur.r, p0 = cur.p0, p1 = cur.p1;
-    const SpecRaw w = raw;
+  // software pipeline: offsets two spectra ahead, raw peaks one spectrum ahead
+  const int64_t rr0 = (static_cast<int64_t>(blockIdx.x) * kVecWarps + warp) * 2 + h;
+  SpecMeta cur = load_meta(P, rr0), nxt = load_meta(P, rr0 + halves_total);
+  HalfRaw raw = load_half_raw(P, cur, hl);
+  for (int64_t rr = rr0; __any_sync(0xffffffffu, rr < P.n); rr += halves_total) {
+    const SpecMeta nn = load_meta(P, rr + 2 * halves_total);
+    const HalfRaw raw_nxt = load_half_raw(P, nxt, hl);
+    const bool active = rr < P.n;
+    const int64_t r = cur.r, p0 = cur.p0, p1 = active ? cur.p1 : cur.p0;
+    const HalfRaw w = raw;
     cur = nxt;
     nxt = nn;
     raw = raw_nxt;
-    float* dst_f = P.out_f32 ? P.out_f32 + r * P.ld_f32 : nullptr;
-    uint16_t* dst_b = P.out_bf16 ? P.out_bf16 + r * P.ld_bf16 : nullptr;
-    uint16_t* di = P.ell_idx ? P.ell_idx + r * P.ell_width : nullptr;
-    float* dv = P.ell_idx ? P.ell_val + r * P.ell_width : nullptr;
-    int count = 0;
+    const int np = static_cast<int>(min(p1 - p0, static_cast<int64_t>(1 << 20)));
 
-    if (p1 - p0 <= 64) {
-      // ---- fast path: both passes stay in registers; no sweep over the dense row
-      if (++serial == 0x10000u) {  // stamps are 16 bit: start over before a tag could repeat
-        for (uint32_t i = lane; i < P.row_len; i += 32) stamp[i] = 0;
-        serial = 1;
+    if (__any_sync(0xffffffffu, np > 16 * kPasses)) {
+      // a wide spectrum in this pair: the full warp takes both spectra one after the other
+      for (int hh = 0; hh < 2; ++hh) {
+        const int src_lane = hh * 16;
+        const int64_t wr = __shfl_sync(0xffffffffu, r, src_lane);
+        const int64_t wp0 = __shfl_sync(0xffffffffu, p0, src_lane);
+        const int64_t wp1 = __shfl_sync(0xffffffffu, p1, src_lane);
+        const int wact = __shfl_sync(0xffffffffu, active ? 1 : 0, src_lane);
+        float* wrow = reinterpret_cast<float*>(smem_raw + (warp * 2 + hh) * per_half);
+        if (wact) vectorize_wide(P, wrow, wr, wp0, wp1, lane, vec_len_d);
+      }
+      continue;
+    }
+    if (++serial == 0x10000u) {  // stamps are 16 bit: start over before a tag could repeat
+      for (uint32_t i = hl; i < P.row_len; i += 16) stamp[i] = 0;
+      serial = 1;
+      __syncwarp();
+    }
+    const uint16_t tag = static_cast<uint16_t>(serial);
+    int np_max = max(__shfl_sync(0xffffffffu, np, 0), __shfl_sync(0xffffffffu, np, 16));
+
+    uint32_t col[kPasses];
+    float val[kPasses];
+    bool own[kPasses];
+#pragma unroll
+    for (int t = 0; t < kPasses; ++t) {
+      own[t] = false;
+      col[t] = 0;
+      val[t] = 0.f;
+      if (16 * t < np_max) {  // uniform
+        const int64_t p = p0 + 16 * t + hl;
+        const Peak k = make_peak(P, p < p1, w.m[t], w.x[t], p, vec_len_d);
+        col[t] = k.col;
+        // rank among the lanes of this half that hit the same column (peak order)
+        const uint32_t key = k.valid ? (k.col | (static_cast<uint32_t>(h) << 20)) : (0x80000000u | lane);
+        const uint32_t same = __match_any_sync(0xffffffffu, key);
+        const int rank = __popc(same & below);
+        if (__all_sync(0xffffffffu, (same & (same - 1u)) == 0u)) {
+          if (k.valid) row[k.col] += k.x;  // no two lanes share a column
+        } else {
+          int rounds = __popc(same);
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) rounds = max(rounds, __shfl_xor_sync(0xffffffffu, rounds, o));
+          for (int q = 0; q < rounds; ++q) {
+            if (k.valid && rank == q) row[k.col] += k.x;
+            __syncwarp();
+          }
+        }
+        // the first lane of a column owns it unless an earlier pass already does
+        if (k.valid && rank == 0 && stamp[k.col] != tag) {
+          own[t] = true;
+          stamp[k.col] = tag;
+        }
         __syncwarp();
       }
-      const uint16_t tag = static_cast<uint16_t>(serial);
-      const Peak a = make_peak(P, p0 + lane < p1, w.m0, w.x0, p0 + lane, vec_len_d);
-      const Peak b = make_peak(P, p0 + 32 + lane < p1, w.m1, w.x1, p0 + 32 + lane, vec_len_d);
-      const bool own0 = accumulate_pass(row, a, lane, below);
-      bool own1 = false;
-      if (p1 - p0 > 32) {
-        if (own0) stamp[a.col] = tag;
-        __syncwarp();
-        own1 = accumulate_pass(row, b, lane, below);
-        own1 = own1 && stamp[b.col] != tag;
+    }
+    // ---- norm over the owned columns (float64, within the half)
+    double scale = 1.0;
+    {
+      double ss = 0.0;
+#pragma unroll
+      for (int t = 0; t < kPasses; ++t) {
+        if (own[t]) {
+          val[t] = row[col[t]];
+          row[col[t]] = 0.f;  // leave the row zeroed
+          ss = fma(static_cast<double>(val[t]), static_cast<double>(val[t]), ss);
+        }
       }
-      const float v0 = own0 ? row[a.col] : 0.f;
-      const float v1 = own1 ? row[b.col] : 0.f;
-      double scale = 1.0;
       if (P.norm) {
-        double ss = static_cast<double>(v0) * static_cast<double>(v0);
-        ss = fma(static_cast<double>(v1), static_cast<double>(v1), ss);
-        ss = warp_sum_f64(ss);
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
         scale = ss > 0.0 ? rsqrt(ss) : 1.0;
       }
-      const float s0 = static_cast<float>(static_cast<double>(v0) * scale);
-      const float s1 = static_cast<float>(static_cast<double>(v1) * scale);
-      if (own0) row[a.col] = 0.f;
-      if (own1) row[b.col] = 0.f;
-      if (dst_f) {  // dense float32 row: zero fill, then the owners scatter
-        for (uint32_t i = lane; i < P.low_dim; i += 32) dst_f[i] = 0.f;
-        __syncwarp();
-        if (own0) dst_f[a.col] = s0;
-        if (own1) dst_f[b.col] = s1;
-      }
-      if (dst_b) {
-        if (own0) brow[a.col] = __bfloat16_as_ushort(__float2bfloat16_rn(s0));
-        if (own1) brow[b.col] = __bfloat16_as_ushort(__float2bfloat16_rn(s1));
-        __syncwarp();
+    }
+#pragma unroll
+    for (int t = 0; t < kPasses; ++t) val[t] = static_cast<float>(static_cast<double>(val[t]) * scale);
+
+    // ---- outputs
+    if (P.out_f32) {  // dense float32 row: zero fill, then the owners scatter
+      float* dst_f = P.out_f32 + r * P.ld_f32;
+      if (active)
+        for (uint32_t i = hl; i < P.low_dim; i += 16) dst_f[i] = 0.f;
+      __syncwarp();
+#pragma unroll
+      for (int t = 0; t < kPasses; ++t)
+        if (own[t]) dst_f[col[t]] = val[t];
+    }
+    if (P.out_bf16) {
+      uint16_t* dst_b = P.out_bf16 + r * P.ld_bf16;
+#pragma unroll
+      for (int t = 0; t < kPasses; ++t)
+        if (own[t]) brow[col[t]] = __bfloat16_as_ushort(__float2bfloat16_rn(val[t]));
+      __syncwarp();
+      if (active) {
         if (bf16_vec) {
-          for (int64_t i = 8 * lane; i < P.ld_bf16; i += 256) {
+          for (int64_t i = 8 * hl; i < P.ld_bf16; i += 128) {
             *reinterpret_cast<uint4*>(dst_b + i) = *reinterpret_cast<const uint4*>(brow + i);
             *reinterpret_cast<uint4*>(brow + i) = make_uint4(0u, 0u, 0u, 0u);
           }
         } else {
-          for (int64_t i = lane; i < P.ld_bf16; i += 32) {
+          for (int64_t i = hl; i < P.ld_bf16; i += 16) {
             dst_b[i] = brow[i];
             brow[i] = 0;
           }
         }
       }
-      if (di) {  // sparse copy: the owners' non-zero values, in peak order
-        const bool nz0 = own0 && s0 != 0.f, nz1 = own1 && s1 != 0.f;
-        const uint32_t b0 = __ballot_sync(0xffffffffu, nz0);
-        const uint32_t b1 = __ballot_sync(0xffffffffu, nz1);
-        const int pos0 = __popc(b0 & below), pos1 = __popc(b0) + __popc(b1 & below);
-        if (nz0 && pos0 < P.ell_width) { di[pos0] = static_cast<uint16_t>(a.col); dv[pos0] = s0; }
-        if (nz1 && pos1 < P.ell_width) { di[pos1] = static_cast<uint16_t>(b.col); dv[pos1] = s1; }
-        count = __popc(b0) + __popc(b1);
-      }
-    } else {
-      // ---- general path (more than 64 peaks): accumulate pass by pass, then sweep the dense row
-      for (int64_t base = p0; base < p1; base += 32)
-        accumulate_pass(row, load_peak(P, base + lane, p1, vec_len_d), lane, below);
-      double scale = 1.0;
-      if (P.norm) {
-        double ss = 0.0;
-        for (uint32_t i = lane; i < P.low_dim; i += 32) ss = fma(static_cast<double>(row[i]), static_cast<double>(row[i]), ss);
-        ss = warp_sum_f64(ss);
-        scale = ss > 0.0 ? rsqrt(ss) : 1.0;
-      }
-      for (uint32_t base = 0; base < P.row_len; base += 32) {
-        const uint32_t i = base + lane;
-        const float sv = static_cast<float>(static_cast<double>(row[i]) * scale);
-        row[i] = 0.f;
-        if (dst_f && i < P.low_dim) dst_f[i] = sv;
-        if (dst_b && static_cast<int64_t>(i) < P.ld_bf16) dst_b[i] = __bfloat16_as_ushort(__float2bfloat16_rn(sv));
-        if (di) {
-          const bool nz = sv != 0.f;
-          const uint32_t bal = __ballot_sync(0xffffffffu, nz);
-          const int pos = count + __popc(bal & below);
-          if (nz && pos < P.ell_width) { di[pos] = static_cast<uint16_t>(i); dv[pos] = sv; }
+    }
+    if (P.ell_idx) {  // sparse copy: the owners' non-zero values, in peak order
+      uint16_t* di = P.ell_idx + r * P.ell_width;
+      float* dv = P.ell_val + r * P.ell_width;
+      int count = 0;
+#pragma unroll
+      for (int t = 0; t < kPasses; ++t) {
+        if (16 * t < np_max) {  // uniform
+          const bool nz = own[t] && val[t] != 0.f;
+          const uint32_t bal = (__ballot_sync(0xffffffffu, nz) >> (16 * h)) & 0xffffu;
+          const int pos = count + __popc(bal & below_h);
+          if (nz && pos < P.ell_width) { di[pos] = static_cast<uint16_t>(col[t]); dv[pos] = val[t]; }
           count += __popc(bal);
         }
       }
-    }
-    if (di) {
-      for (int pos = count + lane; pos < P.ell_width; pos += 32) {  // zero padding
-        di[pos] = 0;
-        dv[pos] = 0.f;
-      }
-      if (lane == 0) {
-        if (P.ell_nnz) P.ell_nnz[r] = static_cast<uint16_t>(min(count, P.ell_width));
-        if (count > P.ell_width) atomicMax(P.ell_overflow, count);
+      if (active) {
+        for (int pos = count + hl; pos < P.ell_width; pos += 16) {  // zero padding
+          di[pos] = 0;
+          dv[pos] = 0.f;
+        }
+        if (hl == 0) {
+          if (P.ell_nnz) P.ell_nnz[r] = static_cast<uint16_t>(min(count, P.ell_width));
+          if (count > P.ell_width) atomicMax(P.ell_overflow, count);
+        }
       }
     }
     __syncwarp();
@@ -327,13 +428,13 @@ int flc_vectorize(const float* mz, const float* intensity, const int64_t* indptr
   P.ell_idx = ell_idx; P.ell_val = ell_val; P.ell_nnz = ell_nnz; P.ell_width = ell_width;
   P.ell_overflow = ell_overflow;
   FLC_REQUIRE(!out_bf16 || ld_bf16 <= static_cast<int64_t>(P.row_len), "ld_bf16 exceeds low_dim rounded up to 64");
-  const size_t smem = static_cast<size_t>(flc::kVecWarps) * P.row_len * 8;  // f32 row + bf16 row + stamps
+  const size_t smem = static_cast<size_t>(flc::kVecWarps) * 2 * P.row_len * 8;  // per half-warp: f32 row + bf16 row + stamps
   FLC_REQUIRE(smem <= 200 * 1024, "low_dim too large");
   if (smem > 48 * 1024)
     FLC_CUDA(cudaFuncSetAttribute(flc::vectorize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   static_cast<int>(smem)));
-  int64_t blocks = (n + flc::kVecWarps - 1) / flc::kVecWarps;
-  const int64_t max_blocks = static_cast<int64_t>(flc::kNumSMs) * 8;
+  int64_t blocks = (n + 2 * flc::kVecWarps - 1) / (2 * flc::kVecWarps);
+  const int64_t max_blocks = static_cast<int64_t>(flc::kNumSMs) * 3;  // what fits an SM at once (shared memory, registers)
   if (blocks > max_blocks) blocks = max_blocks;
   flc::timed("vectorize", stream, [&] {
     flc::vectorize_kernel<<<static_cast<unsigned>(blocks), flc::kVecWarps * 32, smem, flc::as_stream(stream)>>>(P); });
