@@ -208,16 +208,16 @@ __device__ __forceinline__ HalfRaw load_half_raw(const VecParams& P, const SpecM
   return w;
 }
 
-__global__ void __launch_bounds__(kVecWarps * 32, 3)
+__global__ void __launch_bounds__(kVecWarps * 32, 4)
 vectorize_kernel(const VecParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int h = lane >> 4, hl = lane & 15;
-  const size_t per_half = static_cast<size_t>(P.row_len) * 8;
+  const size_t per_half = static_cast<size_t>(P.row_len) * 7;  // f32 row + bf16 row + 8-bit stamps
   float* row = reinterpret_cast<float*>(smem_raw + (warp * 2 + h) * per_half);
   uint16_t* brow = reinterpret_cast<uint16_t*>(row + P.row_len);
-  uint16_t* stamp = brow + P.row_len;
+  uint8_t* stamp = reinterpret_cast<uint8_t*>(brow + P.row_len);
   const int64_t halves_total = static_cast<int64_t>(gridDim.x) * kVecWarps * 2;
   const uint32_t below = (1u << lane) - 1u;
   const uint32_t below_h = (1u << hl) - 1u;
@@ -260,12 +260,12 @@ vectorize_kernel(const VecParams P) {
       }
       continue;
     }
-    if (++serial == 0x10000u) {  // stamps are 16 bit: start over before a tag could repeat
+    if (++serial == 0x100u) {  // stamps are 8 bit: start over before a tag could repeat
       for (uint32_t i = hl; i < P.row_len; i += 16) stamp[i] = 0;
       serial = 1;
       __syncwarp();
     }
-    const uint16_t tag = static_cast<uint16_t>(serial);
+    const uint8_t tag = static_cast<uint8_t>(serial);
     int np_max = max(__shfl_sync(0xffffffffu, np, 0), __shfl_sync(0xffffffffu, np, 16));
 
     uint32_t col[kPasses];
@@ -428,13 +428,13 @@ int flc_vectorize(const float* mz, const float* intensity, const int64_t* indptr
   P.ell_idx = ell_idx; P.ell_val = ell_val; P.ell_nnz = ell_nnz; P.ell_width = ell_width;
   P.ell_overflow = ell_overflow;
   FLC_REQUIRE(!out_bf16 || ld_bf16 <= static_cast<int64_t>(P.row_len), "ld_bf16 exceeds low_dim rounded up to 64");
-  const size_t smem = static_cast<size_t>(flc::kVecWarps) * 2 * P.row_len * 8;  // per half-warp: f32 row + bf16 row + stamps
+  const size_t smem = static_cast<size_t>(flc::kVecWarps) * 2 * P.row_len * 7;  // per half-warp: f32 row + bf16 row + stamps
   FLC_REQUIRE(smem <= 200 * 1024, "low_dim too large");
   if (smem > 48 * 1024)
     FLC_CUDA(cudaFuncSetAttribute(flc::vectorize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   static_cast<int>(smem)));
   int64_t blocks = (n + 2 * flc::kVecWarps - 1) / (2 * flc::kVecWarps);
-  const int64_t max_blocks = static_cast<int64_t>(flc::kNumSMs) * 3;  // what fits an SM at once (shared memory, registers)
+  const int64_t max_blocks = static_cast<int64_t>(flc::kNumSMs) * 4;  // what fits an SM at once (shared memory, registers)
   if (blocks > max_blocks) blocks = max_blocks;
   flc::timed("vectorize", stream, [&] {
     flc::vectorize_kernel<<<static_cast<unsigned>(blocks), flc::kVecWarps * 32, smem, flc::as_stream(stream)>>>(P); });
