@@ -190,7 +190,8 @@ def kernel_rooflines(stats: dict, peaks: dict) -> dict:
         # HBM floor of the scan: every bf16 row read once, pairs written once
         "scan_tc": ("hbm", n * ldb * 2 + pairs * 8),
         # pairs in/out + exact re-score rows (L2-resident in practice) + m/z + row counts
-        "refine": ("hbm", pairs * 16 + pairs * stats.get("ell_width", 0) * 6
+        # re-score + selection (refine_block and, for the query groups it defers, refine: one logical launch)
+        "refine_block": ("hbm", pairs * 16 + pairs * stats.get("ell_width", 0) * 6
                    + n * (stats.get("ell_width", 0) * 6 + 8 + 8 + 4)),
         "pair_hist": ("hbm", pairs * 8 + pairs * 4),
         "pair_scatter": ("hbm", pairs * 16 + pairs * 12),
@@ -344,6 +345,9 @@ def run_ours(args):
         big = kernels.pop("kmeans_fused_large")
         small = kernels.get("kmeans_fused", (0.0, big[1]))
         kernels["kmeans_fused"] = (small[0] + big[0], small[1])
+    if "refine_block" in kernels and "refine" in kernels:  # fast path + the query groups it defers
+        rest = kernels.pop("refine")
+        kernels["refine_block"] = (kernels["refine_block"][0] + rest[0], kernels["refine_block"][1])
     ms_e2e, _, _, _ = timed(step_e2e, args.steps, max(1, args.warmup - 1))
     # the same K batches, software-pipelined two deep (one call = K steps)
     ms_pipe, _, _, _ = timed(lambda: run_e2e_pipelined(args.steps), 1, 1)

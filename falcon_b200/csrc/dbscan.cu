@@ -378,9 +378,10 @@ int flc_dbscan(const float* dist, const int32_t* indices, const int64_t* indptr,
   int32_t changed = 1;
   int sweeps = 0;
   while (changed) {
-    FLC_CUDA(cudaMemsetAsync(L.changed, 0, sizeof(int32_t), stream));
-    // two sweeps before the first look at the flag (the second usually only confirms), one afterwards
+    // two sweeps before the first look at the flag (only the second one's changes count: the first
+    // always changes something), one sweep per look afterwards
     for (int rep = 0; rep < (sweeps == 0 ? 2 : 1); ++rep) {
+      FLC_CUDA(cudaMemsetAsync(L.changed, 0, sizeof(int32_t), stream));
       timed("dbscan_propagate", stream, [&] { dbscan_propagate_kernel<<<wblocks, 256, 0, stream>>>(dist, indices, indptr, n, eps, L.core, L.m,
                                                            L.changed); });
       FLC_LAUNCH_CHECK();
