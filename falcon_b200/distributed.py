@@ -45,10 +45,11 @@ def gather_labels(labels: torch.Tensor, n_clusters: int, group=None):
     rank = dist.get_rank(group)
     dev = labels.device
     meta = torch.tensor([labels.shape[0], n_clusters], dtype=torch.int64, device=dev)
-    metas = [torch.empty_like(meta) for _ in range(world)]
-    dist.all_gather(metas, meta, group=group)
-    lens = [int(m[0]) for m in metas]
-    ncl = [int(m[1]) for m in metas]
+    metas = torch.empty(world * 2, dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(metas, meta, group=group)
+    metas_h = metas.view(world, 2).cpu().tolist()  # one synchronisation for all ranks' counts
+    lens = [int(m[0]) for m in metas_h]
+    ncl = [int(m[1]) for m in metas_h]
     offset = sum(ncl[:rank])
     shifted = torch.where(labels >= 0, labels + offset, labels)
     max_len = max(lens) if lens else 0
@@ -68,10 +69,11 @@ def gather_representatives(representatives: torch.Tensor, n_spectra: int, group=
     rank = dist.get_rank(group)
     dev = representatives.device
     meta = torch.tensor([representatives.shape[0], n_spectra], dtype=torch.int64, device=dev)
-    metas = [torch.empty_like(meta) for _ in range(world)]
-    dist.all_gather(metas, meta, group=group)
-    lens = [int(m[0]) for m in metas]
-    offset = sum(int(m[1]) for m in metas[:rank])
+    metas = torch.empty(world * 2, dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(metas, meta, group=group)
+    metas_h = metas.view(world, 2).cpu().tolist()
+    lens = [int(m[0]) for m in metas_h]
+    offset = sum(int(m[1]) for m in metas_h[:rank])
     max_len = max(lens) if lens else 0
     padded = torch.full((max_len,), -1, dtype=torch.int64, device=dev)
     padded[: representatives.shape[0]] = representatives.to(torch.int64) + offset
