@@ -166,15 +166,13 @@ __device__ __forceinline__ double split_distance(double lo, double hi, int tol_m
 
 // One warp per DBSCAN cluster.  list_a / list_b: per-element scratch holding
 // the current run starts (offsets inside the group), ping-pong.
-__global__ void split_group_kernel(const int64_t* __restrict__ gstart, const int64_t* __restrict__ n_groups_ptr,
-                                   const uint32_t* __restrict__ key_sorted, const double* __restrict__ vs,
-                                   int64_t n, double tol, int tol_mode, int32_t* list_a, int32_t* list_b,
-                                   uint8_t* __restrict__ runhead) {
+__device__ void split_group_one(int64_t g, int64_t n_groups, const int64_t* __restrict__ gstart,
+                                const uint32_t* __restrict__ key_sorted, const double* __restrict__ vs,
+                                int64_t n, double tol, int tol_mode, int32_t* list_a, int32_t* list_b,
+                                uint8_t* __restrict__ runhead) {
   const int lane = threadIdx.x & 31;
-  const int64_t g = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
-  if (g >= *n_groups_ptr) return;
   const int64_t s = gstart[g];
-  const int64_t e = (g + 1 < *n_groups_ptr) ? gstart[g + 1] : n;
+  const int64_t e = (g + 1 < n_groups) ? gstart[g + 1] : n;
   if (key_sorted[s] == kNoiseKey) return;
   const int32_t m = static_cast<int32_t>(e - s);
   if (m < 2) return;
@@ -246,6 +244,19 @@ __global__ void split_group_kernel(const int64_t* __restrict__ gstart, const int
     r = r_new;
   }
   for (int32_t j = lane; j < r; j += 32) runhead[s + __ldcg(cur + j)] = 1;
+}
+
+// Warps stride over the groups (their number is only known on the device).
+__global__ void __launch_bounds__(256)
+split_group_kernel(const int64_t* __restrict__ gstart, const int64_t* __restrict__ n_groups_ptr,
+                   const uint32_t* __restrict__ key_sorted, const double* __restrict__ vs, int64_t n, double tol,
+                   int tol_mode, int32_t* list_a, int32_t* list_b, uint8_t* __restrict__ runhead) {
+  const int64_t n_groups = *n_groups_ptr;
+  const int64_t warps_total = static_cast<int64_t>(gridDim.x) * (blockDim.x >> 5);
+  for (int64_t g = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5; g < n_groups; g += warps_total) {
+    split_group_one(g, n_groups, gstart, key_sorted, vs, n, tol, tol_mode, list_a, list_b, runhead);
+    __syncwarp();
+  }
 }
 
 // run id of every element = inclusive scan of runhead - 1; run start positions
@@ -467,8 +478,8 @@ int flc_split_clusters(const int32_t* labels_in, const double* precursor_mz, int
   FLC_CUDA(cub::DeviceSelect::Flagged(L.cub_tmp, tmp, cub::CountingInputIterator<int64_t>(0), L.ghead,
                                       L.gstart, L.n_groups, num, stream));
   count_launch(2);
-  // Upper bound on the number of groups is n: launch one warp per possible group.
-  const unsigned gblocks = static_cast<unsigned>((n * 32 + 255) / 256);
+  // The number of groups is only known on the device: a resident grid of warps strides over them.
+  const unsigned gblocks = static_cast<unsigned>(std::min<int64_t>((n * 32 + 255) / 256, static_cast<int64_t>(kNumSMs) * 8));
   timed("split_group", stream, [&] { split_group_kernel<<<gblocks, 256, 0, stream>>>(L.gstart, L.n_groups, key_sorted, L.vs, n, tol, tol_mode,
                                                   L.list_a, L.list_b, L.runhead); });
   FLC_LAUNCH_CHECK();
