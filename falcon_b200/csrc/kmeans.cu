@@ -335,6 +335,7 @@ __device__ void fused_train_bucket(const FusedArgs& A, const FusedPlan& pl, unsi
   const uint16_t* idx = reinterpret_cast<const uint16_t*>(smem + pl.idx);
   const float eps = 1.0f / 1024.0f;
 
+  bool converged = false;
   for (int it = 0; it < A.niter; ++it) {
     // ---- assign: one thread per row.  A row that moves from list a to list b is
     // queued as "+row" on b's delta list and "-row" on a's: the sums are integers,
@@ -347,16 +348,24 @@ __device__ void fused_train_bucket(const FusedArgs& A, const FusedPlan& pl, unsi
         float a[LP];
         m = rnnz[r];
         row_scores<LP, float>(val + r * pitch, idx + r * pitch, m, C, a);
-        float best = -INFINITY;
+        float best = -INFINITY, second = -INFINITY;
         int best_c = 0;
 #pragma unroll
-        for (int u = 0; u < LP; ++u)
-          if (u < L && a[u] > best) { best = a[u]; best_c = u; }
+        for (int u = 0; u < LP; ++u) {
+          if (u < L) {
+            if (a[u] > best) { second = best; best = a[u]; best_c = u; }
+            else if (a[u] > second) { second = a[u]; }
+          }
+        }
+        // bit 7: the runner-up is far enough behind (>> float32 rounding) that the float64 final
+        // assignment cannot pick another list
+        const int clear = (best - second > 1e-4f) ? 0x80 : 0;
         const int prev = assign[r];
-        if (prev != best_c) {
-          old_c = prev == 0xff ? -1 : prev;
+        const int prev_c = prev == 0xff ? -1 : (prev & 0x7f);
+        assign[r] = static_cast<uint8_t>(best_c | clear);
+        if (prev_c != best_c) {
+          old_c = prev_c;
           new_c = best_c;
-          assign[r] = static_cast<uint8_t>(best_c);
           changed = 1;
         }
       }
@@ -388,7 +397,10 @@ __device__ void fused_train_bucket(const FusedArgs& A, const FusedPlan& pl, unsi
     bool any_empty = false;
 #pragma unroll
     for (int u = 0; u < LP; ++u) any_empty |= (u < L && S.cnt[u] == 0);
-    if (it > 0 && !changed && !any_empty) break;  // fixed point
+    if (it > 0 && !changed && !any_empty) {  // fixed point
+      converged = true;
+      break;
+    }
     if (tid < L) S.scale[tid] = S.cnt[tid] > 0 ? kFixInv / static_cast<double>(S.cnt[tid]) : 0.0;
     // ---- update: the warps split every list's delta list (`copies` warps per list, each
     // with its own accumulator copy, added up in the means phase).  Lanes take the row's
@@ -555,7 +567,17 @@ __device__ void fused_train_bucket(const FusedArgs& A, const FusedPlan& pl, unsi
   }
   // ---- final assignment + probe list (one thread per row, float64, ties to the lower id)
   if (A.list_id != nullptr) {
+    // At a fixed point the last training assignment was made against these very centroids: rows
+    // whose float32 runner-up was clearly behind keep that list without the float64 pass.
+    const bool shortcut = converged && P == 1;
     for (int r = tid; r < nb; r += NT) {
+      if (shortcut && (assign[r] & 0x80)) {
+        int32_t* pr = A.probes + (s + r) * A.max_nprobe;
+        pr[0] = assign[r] & 0x7f;
+        for (int t = 1; t < A.max_nprobe; ++t) pr[t] = -1;
+        A.list_id[s + r] = assign[r] & 0x7f;
+        continue;
+      }
       double a[LP];
       row_scores<LP, double>(val + r * pitch, idx + r * pitch, rnnz[r], C, a);
       uint32_t used = 0;
