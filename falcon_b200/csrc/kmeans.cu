@@ -291,9 +291,17 @@ __device__ unsigned long long g_kmeans_timing[16];
 
 struct PhaseClock {
   unsigned long long* out;
-  long long t;
-  __device__ PhaseClock(unsigned long long* o) : out(threadIdx.x == 0 ? o : nullptr), t(0) {
-    if (out) t = clock64();
+  long long t, t0;
+  __device__ PhaseClock(unsigned long long* o) : out(threadIdx.x == 0 ? o : nullptr), t(0), t0(0) {
+    if (out) t = t0 = clock64();
+  }
+  // slowest bucket so far: [10] cycles, [11] rows << 32 | lists << 8 (best effort, racy)
+  __device__ void finish(int nb, int L) {
+    if (out) {
+      const unsigned long long total = static_cast<unsigned long long>(clock64() - t0);
+      if (atomicMax(out + 10, total) < total)
+        out[11] = (static_cast<unsigned long long>(nb) << 32) | (static_cast<unsigned long long>(L) << 8);
+    }
   }
   __device__ void mark(int phase) {
     if (out) {
@@ -598,7 +606,7 @@ __device__ void fused_train_bucket(const FusedArgs& A, const FusedPlan& pl, unsi
 }
 
 template <int NT>
-__global__ void __launch_bounds__(NT)
+__global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1)  // class 0 must keep two CTAs per SM: <= 128 registers
 kmeans_fused_kernel(FusedArgs A, int cls) {
   extern __shared__ __align__(16) unsigned char smem[];
   __shared__ FusedStatic S;
@@ -710,6 +718,7 @@ kmeans_fused_kernel(FusedArgs A, int cls) {
     __syncthreads();
     clk.mark(7);
     clk.count(9, 1);
+    clk.finish(nb, L);
   }
 }
 

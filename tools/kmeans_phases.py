@@ -23,5 +23,6 @@ for i in range(3):
 names = ["queue+nnz", "row load", "init", "assign", "update", "means", "normalise", "final+out"]
 tot = sum(buf[i] for i in range(8))
 print(f"buckets {buf[9]}, iterations/bucket {buf[8] / max(buf[9], 1):.2f}, cycles/bucket {tot / max(buf[9], 1):.0f}")
+print(f"slowest bucket: {buf[10]} cycles, rows {buf[11] >> 32}, lists {(buf[11] >> 8) & 0xffffff}")
 for i, nm in enumerate(names):
     print(f"  {nm:10s} {buf[i] / max(buf[9], 1):9.0f} cycles/bucket {100 * buf[i] / max(tot, 1):5.1f}%")
