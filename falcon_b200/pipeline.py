@@ -540,22 +540,26 @@ class HotPath:
             return self._empty(0, torch.int32), 0
         n = st["n"]
         compute = torch.cuda.current_stream()
-        compute.wait_event(st["ev_meta"])
-        buckets = self.bucket_sort(st["pmz"], st["z"], st["rt"])
-        rank = self._empty(n, torch.int32)  # input position -> bucket-order row
-        check(lib.flc_scatter32(None, ptr(buckets.order), n, ptr(rank), _stream()))
-        v = self.alloc_vectors(n, st["width"], want_f32=self.s.dense_f32)
-        overflow = torch.zeros(1, dtype=torch.int32, device=self.device)
-        bounds = st["bounds"]
-        for c, ev in enumerate(st["events"]):
-            compute.wait_event(ev)
-            i0, i1 = bounds[c], bounds[c + 1]
-            self.vectorize_into(v, st["mz"], st["intensity"], st["indptr"][i0:], i1 - i0, dest=rank[i0:],
-                                overflow=overflow)
-        v.overflow = overflow
-        st["slot"]["free"] = torch.cuda.Event()  # the staged inputs are not read past this point
-        st["slot"]["free"].record(compute)
-        st["slot"]["pending"] = False
+        try:
+            compute.wait_event(st["ev_meta"])
+            buckets = self.bucket_sort(st["pmz"], st["z"], st["rt"])
+            rank = self._empty(n, torch.int32)  # input position -> bucket-order row
+            check(lib.flc_scatter32(None, ptr(buckets.order), n, ptr(rank), _stream()))
+            v = self.alloc_vectors(n, st["width"], want_f32=self.s.dense_f32)
+            overflow = torch.zeros(1, dtype=torch.int32, device=self.device)
+            bounds = st["bounds"]
+            for c, ev in enumerate(st["events"]):
+                compute.wait_event(ev)
+                i0, i1 = bounds[c], bounds[c + 1]
+                self.vectorize_into(v, st["mz"], st["intensity"], st["indptr"][i0:], i1 - i0, dest=rank[i0:],
+                                    overflow=overflow)
+            v.overflow = overflow
+        finally:
+            # the staged inputs are not read past this point (also when a stage raised: the slot
+            # must not stay blocked)
+            st["slot"]["free"] = torch.cuda.Event()
+            st["slot"]["free"].record(compute)
+            st["slot"]["pending"] = False
         labels, n_clusters = self._cluster_vectors(v, buckets, n, False)
         if labels_out is not None:
             labels_out.copy_(labels, non_blocking=True)
