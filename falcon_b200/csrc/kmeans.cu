@@ -975,12 +975,21 @@ kmeans_tiled_assign_kernel(TiledArgs A) {
 
 // One CTA per tiled bucket: means, re-seeding of empty lists, normalisation; writes
 // both centroid layouts, records convergence.
+// Common case (no empty list): one WARP per list, eight lists in flight.  The mean goes to a
+// [32 lists][d + 1] shared-memory tile while its sum of squares is accumulated, the second pass
+// scales the tile in place and writes the row-major float32 and bf16 copies, and the transposed
+// training copy ct[column][list] is then written straight from the tile (row stride d + 1 is odd:
+// the column reads are conflict free, the global writes are coalesced).  Same arithmetic, in the
+// same order, as the general path below, which stays for buckets with an empty list.
 __global__ void __launch_bounds__(256)
 kmeans_tiled_update_kernel(TiledArgs A) {
+  extern __shared__ float mean_tile[];  // [32][d + 1]
   __shared__ int32_t cj_s;
+  __shared__ int32_t empty_s;
   __shared__ float tile[32][33];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int d = static_cast<int>(A.low_dim);
+  const int ldt = d + 1;
   const float eps = 1.0f / 1024.0f;
   const int32_t n_queued = A.q.cnt[kClsTiled];
   const int32_t* queue = A.q.queue + static_cast<int64_t>(kClsTiled) * A.n_buckets;
@@ -992,6 +1001,51 @@ kmeans_tiled_update_kernel(TiledArgs A) {
     float* cent = A.centroids + c0 * d;
     float* ctb = A.ct + c0 * d;
     long long* gs = A.gsum + c0 * d;
+    if (tid == 0) empty_s = 0;
+    __syncthreads();
+    for (int32_t c = tid; c < L; c += 256)
+      if (A.gcnt[c0 + c] <= 0) empty_s = 1;  // benign race: every writer stores 1
+    __syncthreads();
+    if (empty_s == 0) {
+      for (int32_t ci = 0; ci < L; ci += 32) {
+        const int32_t c_end = min(L, ci + 32);
+        for (int32_t c = ci + warp; c < c_end; c += 8) {
+          const double scale = kFixInv / static_cast<double>(A.gcnt[c0 + c]);
+          const long long* gr = gs + static_cast<int64_t>(c) * d;
+          float* tr = mean_tile + (c - ci) * ldt;
+          double ss = 0.0;
+#pragma unroll 4
+          for (int k = lane; k < d; k += 32) {
+            const float v = static_cast<float>(__ll2double_rn(gr[k]) * scale);
+            tr[k] = v;
+            const double vd = static_cast<double>(v);
+            ss = fma(vd, vd, ss);
+          }
+          ss = warp_sum_f64(ss);
+          const double inv = ss > 0.0 ? 1.0 / sqrt(ss) : 1.0;
+          float* cr = cent + static_cast<int64_t>(c) * d;
+          uint16_t* cbr = A.cb ? A.cb + (c0 + c) * A.ld_c : nullptr;
+#pragma unroll 4
+          for (int k = lane; k < d; k += 32) {
+            const float v = static_cast<float>(static_cast<double>(tr[k]) * inv);
+            tr[k] = v;
+            cr[k] = v;
+            if (cbr) cbr[k] = f32_to_bf16_rne(v);
+          }
+        }
+        __syncthreads();
+        const int32_t c = ci + lane;
+        if (c < L)
+          for (int k = warp; k < d; k += 8) ctb[static_cast<int64_t>(k) * L + c] = mean_tile[lane * ldt + k];
+        __syncthreads();
+      }
+      if (tid == 0) {
+        if (A.bstate[2 * b] == 0) A.bstate[2 * b + 1] = 1;
+        A.bstate[2 * b] = 0;
+      }
+      __syncthreads();
+      continue;
+    }
     bool any_empty = false;
     for (int32_t c = 0; c < L; ++c) {
       const int32_t n_c = A.gcnt[c0 + c];
@@ -1079,7 +1133,136 @@ kmeans_tiled_update_kernel(TiledArgs A) {
   }
 }
 
-// Final assignment + probe list for the rows of tiled buckets: one warp per row,
+// Final assignment + probe list for the rows of tiled buckets, first pass: one THREAD per row,
+// float32 scores against all (<= 32) lists of the bucket at once.  A block covers 256 consecutive
+// rows; for every tiled bucket it touches it stages the transposed training copy of the centroids
+// ([column][32 lists], zero padded) in shared memory, and each thread walks its sparse row once,
+// reading the 32 scores' operands as eight float4.  Thread t reads them in the rotated order
+// (r + t) mod 8, so the eight threads of a quarter warp always hit eight different bank groups
+// whatever their columns are; the accumulators stay in that rotated order (static register
+// indices) and are un-rotated only when the best lists are named.
+// The float32 order is final only where it is provably the float64 order: every gap between
+// consecutive scores of the P + 1 best exceeds `gap` * sum|row values| (above twice the float32
+// rounding bound of the sequential fmaf inner product with a unit-norm centroid).  All other rows, and the rows of buckets with more than 32 lists or
+// more than 8 probes, are appended to `slow_rows` for the float64 kernel below.
+constexpr int kAssignRows = 256;
+
+__global__ void __launch_bounds__(kAssignRows, 3)
+ivf_assign_tiled_f32_kernel(TiledArgs A, const int32_t* __restrict__ nprobe, int32_t max_nprobe, float gap,
+                            int32_t* __restrict__ list_id, int32_t* __restrict__ probes,
+                            int32_t* __restrict__ slow_rows, int32_t* __restrict__ slow_count) {
+  extern __shared__ float4 cs4[];  // [d][8] float4 = [column][32 lists]
+  const int tid = threadIdx.x;
+  const int lane = tid & 31;
+  const int d = static_cast<int>(A.low_dim);
+  const int64_t row0 = static_cast<int64_t>(blockIdx.x) * kAssignRows;
+  const int64_t row1 = min(A.n, row0 + kAssignRows);
+  if (row0 >= row1) return;
+  int64_t b = find_segment(A.bucket_ptr, A.n_buckets, row0);
+  for (int64_t seg = row0; seg < row1; ++b) {
+    const int64_t seg_end = min(row1, A.bucket_ptr[b + 1]);
+    const int64_t i = seg + tid;
+    const bool active = i < seg_end;
+    seg = seg_end;
+    if (A.q.bclass[b] != kClsTiled) continue;
+    const int32_t L = A.nlist[b];
+    const int32_t P = min(nprobe[b], L);
+    bool slow = active;
+    if (L <= 32 && P <= 8) {
+      __syncthreads();  // the previous bucket's centroids are no longer read
+      const float* ctb = A.ct + A.centroid_ptr[b] * d;
+      if (L == 32) {
+        const float4* src = reinterpret_cast<const float4*>(ctb);  // centroid_ptr * d * 4 bytes: 16-byte aligned when d % 4 == 0
+        if ((reinterpret_cast<uintptr_t>(ctb) & 15) == 0) {
+          for (int e = tid; e < d * 8; e += kAssignRows) cs4[e] = __ldg(src + e);
+        } else {
+          float* cs = reinterpret_cast<float*>(cs4);
+          for (int e = tid; e < d * 32; e += kAssignRows) cs[e] = __ldg(ctb + e);
+        }
+      } else {
+        float* cs = reinterpret_cast<float*>(cs4);
+        for (int e = tid; e < d * 32; e += kAssignRows) {
+          const int k = e >> 5, c = e & 31;
+          cs[e] = c < L ? __ldg(ctb + static_cast<int64_t>(k) * L + c) : 0.f;
+        }
+      }
+      __syncthreads();
+      if (active) {
+        float acc[8][4];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) acc[r][0] = acc[r][1] = acc[r][2] = acc[r][3] = 0.f;
+        const int rot = tid & 7;
+        float sabs = 0.f;  // sum |value|: scales the rounding bound (centroid entries are <= 1 in magnitude)
+        const int m = min(static_cast<int>(A.ell_nnz[i]), A.W);
+        const uint4* ip = reinterpret_cast<const uint4*>(A.ell_idx + i * A.W);   // W % 8 == 0: 16-byte aligned rows
+        const float4* vp = reinterpret_cast<const float4*>(A.ell_val + i * A.W);
+        for (int j0 = 0; j0 < m; j0 += 8) {
+          const uint4 iw = __ldg(ip + (j0 >> 3));
+          const float4 va = __ldg(vp + (j0 >> 2)), vb = __ldg(vp + (j0 >> 2) + 1);
+          const uint32_t ks[8] = {iw.x & 0xffffu, iw.x >> 16, iw.y & 0xffffu, iw.y >> 16,
+                                  iw.z & 0xffffu, iw.z >> 16, iw.w & 0xffffu, iw.w >> 16};
+          const float vs[8] = {va.x, va.y, va.z, va.w, vb.x, vb.y, vb.z, vb.w};
+#pragma unroll
+          for (int t = 0; t < 8; ++t) {
+            // slots past the row's population are zero padded (column 0, value 0): they add nothing
+            const float4* rowp = cs4 + ks[t] * 8u;
+            const float v = vs[t];
+            sabs += fabsf(v);
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+              const float4 c = rowp[(r + rot) & 7];
+              acc[r][0] = fmaf(v, c.x, acc[r][0]);
+              acc[r][1] = fmaf(v, c.y, acc[r][1]);
+              acc[r][2] = fmaf(v, c.z, acc[r][2]);
+              acc[r][3] = fmaf(v, c.w, acc[r][3]);
+            }
+          }
+        }
+        // register slot r*4+e holds list 4*((r + rot) & 7) + e; lists past L do not exist
+#pragma unroll
+        for (int r = 0; r < 8; ++r)
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            if (4 * ((r + rot) & 7) + e >= L) acc[r][e] = -INFINITY;
+        const int T = min(P + 1, L);  // the runner-up after the last probe decides whether the cut is safe
+        const float need = gap * sabs;
+        float prev = 0.f;
+        slow = false;
+        for (int t = 0; t < T; ++t) {
+          float bv = -INFINITY;
+          int bs = 0;
+#pragma unroll
+          for (int r = 0; r < 8; ++r)
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              if (acc[r][e] > bv) { bv = acc[r][e]; bs = r * 4 + e; }
+#pragma unroll
+          for (int r = 0; r < 8; ++r)
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              if (bs == r * 4 + e) acc[r][e] = -INFINITY;
+          if (t > 0 && !(prev - bv > need)) slow = true;
+          prev = bv;
+          if (t < P) {
+            const int32_t id = 4 * (((bs >> 2) + rot) & 7) + (bs & 3);
+            if (t < max_nprobe) probes[i * max_nprobe + t] = id;
+            if (t == 0) list_id[i] = id;
+          }
+        }
+        for (int t = P; t < max_nprobe; ++t) probes[i * max_nprobe + t] = -1;
+      }
+    }
+    const uint32_t vote = __ballot_sync(0xffffffffu, slow);
+    if (vote != 0u) {
+      int32_t base = 0;
+      if (lane == 0) base = atomicAdd(slow_count, __popc(vote));
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (slow) slow_rows[base + __popc(vote & ((1u << lane) - 1u))] = static_cast<int32_t>(i);
+    }
+  }
+}
+
+// Second pass, for the rows the first pass could not decide: one warp per row,
 // one LANE per list (strips of 32 lists): the row's entries are broadcast with
 // shuffles, the transposed training copy of the centroids ([column][list]) makes
 // the gathers coalesced, and there is no reduction across lanes.  float64 inner
@@ -1087,12 +1270,13 @@ kmeans_tiled_update_kernel(TiledArgs A) {
 // same results as ivf_assign_kernel.
 __global__ void __launch_bounds__(256)
 ivf_assign_tiled_kernel(TiledArgs A, const int32_t* __restrict__ nprobe, int32_t max_nprobe,
+                        const int32_t* __restrict__ rows, const int32_t* __restrict__ n_rows,
                         int32_t* __restrict__ list_id, int32_t* __restrict__ probes) {
   const int lane = threadIdx.x & 31;
-  const int64_t i = static_cast<int64_t>(blockIdx.x) * 8 + (threadIdx.x >> 5);
-  if (i >= A.n) return;
+  const int32_t total_rows = *n_rows;
+  for (int32_t w = blockIdx.x * 8 + (threadIdx.x >> 5); w < total_rows; w += gridDim.x * 8) {
+  const int64_t i = rows[w];
   const int64_t b = find_segment(A.bucket_ptr, A.n_buckets, i);
-  if (A.q.bclass[b] != kClsTiled) return;
   const int32_t L = A.nlist[b];
   const int32_t P = min(nprobe[b], L);
   const int d = static_cast<int>(A.low_dim);
@@ -1148,6 +1332,7 @@ ivf_assign_tiled_kernel(TiledArgs A, const int32_t* __restrict__ nprobe, int32_t
   }
   if (lane < max_nprobe) probes[i * max_nprobe + lane] = lane < P ? my_id : -1;
   if (lane == 0) list_id[i] = my_id;
+  }
 }
 
 struct KmeansLayout {
@@ -1323,6 +1508,10 @@ int flc_kmeans_train(const uint16_t* ell_idx, const float* ell_val, const uint16
   static_assert(kTiledThreads == 256, "launch configuration below assumes 256 threads");
   const unsigned upd_blocks = static_cast<unsigned>(std::min<int64_t>(n_buckets, 1 << 20));  // latency-bound: one CTA per bucket
   const unsigned unit_blocks = static_cast<unsigned>(std::min<int64_t>(n / 128 + n_buckets + 1, 1 << 20));
+  const size_t upd_smem = 32 * (static_cast<size_t>(low_dim) + 1) * sizeof(float);
+  FLC_REQUIRE(upd_smem <= 200 * 1024, "low_dim too large for the tiled trainer");
+  FLC_CUDA(cudaFuncSetAttribute(kmeans_tiled_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                static_cast<int>(upd_smem)));
   for (int it = 0; it < niter; ++it) {
     if (use_tc) {
       // query tiles of the buckets that have not converged yet
@@ -1343,12 +1532,25 @@ int flc_kmeans_train(const uint16_t* ell_idx, const float* ell_val, const uint16
         kmeans_tiled_assign_kernel<<<row_blocks, kTiledThreads, smem, stream>>>(T); });
       FLC_LAUNCH_CHECK();
     }
-    timed("kmeans_tiled_update", stream, [&] { kmeans_tiled_update_kernel<<<upd_blocks, 256, 0, stream>>>(T); });
+    timed("kmeans_tiled_update", stream, [&] { kmeans_tiled_update_kernel<<<upd_blocks, 256, upd_smem, stream>>>(T); });
     FLC_LAUNCH_CHECK();
   }
   if (list_id != nullptr) {
-    timed("ivf_assign_tiled", stream, [&] { ivf_assign_tiled_kernel<<<static_cast<unsigned>((n + 7) / 8), 256, 0, stream>>>(
-        T, nprobe, max_nprobe, list_id, probes); });
+    // float32 pass for every row; what it cannot decide goes through the float64 kernel
+    const size_t asmem = static_cast<size_t>(low_dim) * 32 * sizeof(float);
+    FLC_REQUIRE(asmem <= 200 * 1024, "low_dim too large for the tiled assignment");
+    FLC_CUDA(cudaFuncSetAttribute(ivf_assign_tiled_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  static_cast<int>(asmem)));
+    FLC_CUDA(cudaMemsetAsync(T.tc_counts + 1, 0, sizeof(int32_t), stream));
+    // |float32 - float64| of W sequential fmaf <= W * 2^-24 * sum|v_j c_j| <= W * 2^-24 * sum|v_j|; the order of
+    // two scores is safe when they differ by more than twice that.  2x slack on top: (W + 8) * 2^-22 * sum|v_j|
+    const float gap = static_cast<float>(W + 8) * 2.384185791015625e-7f;
+    timed("ivf_assign_tiled_f32", stream, [&] {
+      ivf_assign_tiled_f32_kernel<<<static_cast<unsigned>((n + kAssignRows - 1) / kAssignRows), kAssignRows, asmem, stream>>>(
+          T, nprobe, max_nprobe, gap, list_id, probes, K.tc_unsure, T.tc_counts + 1); });
+    FLC_LAUNCH_CHECK();
+    timed("ivf_assign_tiled", stream, [&] { ivf_assign_tiled_kernel<<<kNumSMs * 8, 256, 0, stream>>>(
+        T, nprobe, max_nprobe, K.tc_unsure, T.tc_counts + 1, list_id, probes); });
     FLC_LAUNCH_CHECK();
   }
   return FLC_OK;

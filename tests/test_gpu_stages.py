@@ -274,11 +274,12 @@ def _train(n, seed, lo, hi, force_tiled=False, monkeypatch=None, want_bf16=False
 
 
 @pytest.mark.parametrize("n,hi,bf16", [(6000, 1003.0, False), (30000, 1002.0, False), (30000, 1002.0, True),
-                                        (12000, 1012.0, False), (24000, 1010.0, True)])
+                                        (12000, 1012.0, False), (24000, 1010.0, True), (36000, 1010.0, True)])
 def test_kmeans_quality_close_to_oracle(n, hi, bf16):
     """n = 30000 over 2 Da makes buckets of ~7500 rows (128 lists), n = 24000 over 10 Da buckets
-    of ~1200 rows (16 lists, 2 probes): too large for the fused trainer, so those runs
-    exercise the tiled trainer; the other two are fused
+    of ~1200 rows (16 lists, 2 probes), n = 36000 over 10 Da buckets of ~1800 rows (32 lists, 4 probes):
+    too large for the fused trainer, so those runs exercise the tiled trainer and its two-pass final
+    assignment (float32 thread-per-row pass, float64 pass for the close calls and for > 32 lists); the other two are fused
     (two size classes).  With the bf16 rows the tiled trainer takes its assignment
     from the tensor cores.  Same arithmetic conventions as the oracle, so the
     objective is the same up to float32 arg-max near-ties."""
