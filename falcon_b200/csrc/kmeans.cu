@@ -726,6 +726,16 @@ kmeans_fused_kernel(FusedArgs A, int cls) {
 // Rows stream from global memory once per iteration; the bucket's centroids are
 // staged in shared memory 32 lists at a time ([column][32], from the transposed
 // training copy `ct`); sums go to global int64 accumulators with atomics.
+// 16-byte shared-memory load by 32-bit shared address.  Used for the [column][32 lists] centroid
+// tiles of the thread-per-row kernels: thread t reads the eight 16-byte chunks of a 128-byte row
+// in the order chunk ^ (t & 7), so the eight threads of a quarter warp hit eight different bank
+// groups whatever their columns are (a plain chunk order would be an eight-way conflict).
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+
 struct TiledArgs {
   const uint16_t* ell_idx;
   const float* ell_val;
@@ -752,7 +762,9 @@ struct TiledArgs {
   int32_t* tc_unsure;  // [n] rows whose two best bf16 scores are within the margin (first *tc_counts[1])
   int4* units;       // query tiles of the tiled buckets still training
   int32_t* unit_bucket;
-  int32_t* tc_counts;  // [0] units, [1] unsure rows
+  int32_t* tc_counts;  // [0] units, [1] unsure rows, [2] units of the sparse-row kernel, [3] of the dense-row kernel
+  int4* units_sp;    // the same tiles, split by which tensor-core kernel scores them
+  int4* units_dn;
 };
 
 __global__ void __launch_bounds__(128)
@@ -789,19 +801,25 @@ kmeans_tiled_init_kernel(TiledArgs A, int64_t total) {
 
 // Unit descriptors of the tensor-core assignment: every tiled bucket contributes
 // ceil(rows / 128) query tiles (first row, bucket end, first / end centroid row).
-__global__ void kmeans_tc_units_kernel(TiledArgs A) {
+__global__ void kmeans_tc_units_kernel(TiledArgs A, int32_t min_lists, int32_t sparse_max_lists) {
   const int32_t qi = blockIdx.x * blockDim.x + threadIdx.x;
   if (qi >= A.q.cnt[kClsTiled]) return;
   const int64_t b = A.q.queue[static_cast<int64_t>(kClsTiled) * A.n_buckets + qi];
   if (A.bstate[2 * b + 1] != 0) return;  // converged: nothing left to do
+  if (A.nlist[b] < min_lists) return;     // the thread-per-row kernel owns the buckets with few lists
   const int64_t s = A.bucket_ptr[b], e = A.bucket_ptr[b + 1];
   const int64_t c0 = A.centroid_ptr[b];
   const int32_t tq = static_cast<int32_t>((e - s + 127) / 128);
   const int32_t base = atomicAdd(A.tc_counts, tq);
+  const bool sparse = A.nlist[b] <= sparse_max_lists;
+  int4* mine = sparse ? A.units_sp : A.units_dn;
+  const int32_t mbase = atomicAdd(A.tc_counts + (sparse ? 2 : 3), tq);
   for (int32_t t = 0; t < tq; ++t) {
-    A.units[base + t] = make_int4(static_cast<int>(s + 128 * t), static_cast<int>(e), static_cast<int>(c0),
-                                  static_cast<int>(c0 + A.nlist[b]));
+    const int4 ud = make_int4(static_cast<int>(s + 128 * t), static_cast<int>(e), static_cast<int>(c0),
+                              static_cast<int>(c0 + A.nlist[b]));
+    A.units[base + t] = ud;
     A.unit_bucket[base + t] = static_cast<int32_t>(b);
+    mine[mbase + t] = ud;  // consecutive tiles of a bucket stay consecutive: the sparse kernel keeps the centroids resident
   }
 }
 
@@ -884,34 +902,46 @@ constexpr int kTiledG = 32;                                  // lists staged per
 
 // Assignment + incremental accumulation.  A CTA owns 1024 consecutive rows; for
 // every tiled bucket segment inside them it stages the centroids 32 lists at a
-// time ([column][32]) and each thread scores its rows from 16-byte row chunks.
+// time ([column][32], chunk-swizzled reads: see lds128) and each thread scores its
+// rows from 16-byte row chunks: float32, products added in slot order with fmaf, ties
+// to the lower list -- the fused trainer's arithmetic.
 // Rows whose list changed move their fixed-point values between the lists' global
-// int64 sums with atomics (integer: order free, exact).
-__global__ void __launch_bounds__(kTiledThreads)
-kmeans_tiled_assign_kernel(TiledArgs A) {
-  extern __shared__ __align__(16) float Cs[];  // [d][kTiledG]
+// int64 sums with atomics (integer: order free, exact).  Buckets with more than
+// `max_lists` lists are left to the tensor-core assignment.
+__global__ void __launch_bounds__(kTiledThreads, 2)
+kmeans_tiled_assign_kernel(TiledArgs A, int32_t max_lists) {
+  extern __shared__ __align__(128) float Cs[];  // [d][kTiledG]
   const int tid = threadIdx.x;
   const int64_t i0 = static_cast<int64_t>(blockIdx.x) * kTiledRows;
   const int64_t i1 = min(i0 + kTiledRows, A.n);
   const int d = static_cast<int>(A.low_dim);
   const int W = A.W;
+  const uint32_t cs_addr = static_cast<uint32_t>(__cvta_generic_to_shared(Cs));  // 128-byte aligned
+  const uint32_t rot = static_cast<uint32_t>(tid & 7);
   int64_t b = find_segment(A.bucket_ptr, A.n_buckets, i0);
   for (; b < A.n_buckets && A.bucket_ptr[b] < i1; ++b) {
     if (A.q.bclass[b] != kClsTiled || A.bstate[2 * b + 1] != 0) continue;  // uniform
-    const int64_t s = max(A.bucket_ptr[b], i0), e = min(A.bucket_ptr[b + 1], i1);
     const int32_t L = A.nlist[b];
+    if (L > max_lists) continue;
+    const int64_t s = max(A.bucket_ptr[b], i0), e = min(A.bucket_ptr[b + 1], i1);
     const int64_t c0 = A.centroid_ptr[b];
     const float* ctb = A.ct + c0 * d;
     float best[kTiledRounds];
     int best_c[kTiledRounds];
 #pragma unroll
-    for (int t = 0; t < kTiledRounds; ++t) { best[t] = -INFINITY; best_c[t] = 0; }
+    for (int t = 0; t < kTiledRounds; ++t) { best[t] = -INFINITY; best_c[t] = 0x7fffffff; }
     for (int g0 = 0; g0 < L; g0 += kTiledG) {
       const int G = min(kTiledG, L - g0);
       __syncthreads();
-      for (int t = tid; t < d * kTiledG; t += kTiledThreads) {
-        const int k = t / kTiledG, g = t - k * kTiledG;
-        Cs[t] = g < G ? __ldg(ctb + static_cast<int64_t>(k) * L + g0 + g) : 0.f;
+      if (L == kTiledG && (reinterpret_cast<uintptr_t>(ctb) & 15) == 0) {
+        const float4* src = reinterpret_cast<const float4*>(ctb);
+        float4* dst = reinterpret_cast<float4*>(Cs);
+        for (int t = tid; t < d * (kTiledG / 4); t += kTiledThreads) dst[t] = __ldg(src + t);
+      } else {
+        for (int t = tid; t < d * kTiledG; t += kTiledThreads) {
+          const int k = t / kTiledG, g = t - k * kTiledG;
+          Cs[t] = g < G ? __ldg(ctb + static_cast<int64_t>(k) * L + g0 + g) : 0.f;
+        }
       }
       __syncthreads();
 #pragma unroll
@@ -931,22 +961,30 @@ kmeans_tiled_assign_kernel(TiledArgs A) {
 #pragma unroll
           for (int t = 0; t < 8; ++t) {  // zero padding multiplies to zero
             const float v = vv[t];
-            const float* cr = Cs + ((kk[t >> 1] >> ((t & 1) * 16)) & 0xffffu) * kTiledG;
+            const uint32_t row = cs_addr + (((kk[t >> 1] >> ((t & 1) * 16)) & 0xffffu) * (kTiledG * 4u)) + rot * 16u;
 #pragma unroll
             for (int u = 0; u < kTiledG; u += 4) {
-              if (u < G) {  // uniform across the CTA
-                const float4 c4 = *reinterpret_cast<const float4*>(cr + u);
-                a[u] = fmaf(v, c4.x, a[u]);
-                a[u + 1] = fmaf(v, c4.y, a[u + 1]);
-                a[u + 2] = fmaf(v, c4.z, a[u + 2]);
-                a[u + 3] = fmaf(v, c4.w, a[u + 3]);
-              }
+              const float4 c4 = lds128(row ^ (u * 4u));  // chunk (u / 4) ^ rot of the row
+              a[u] = fmaf(v, c4.x, a[u]);
+              a[u + 1] = fmaf(v, c4.y, a[u + 1]);
+              a[u + 2] = fmaf(v, c4.z, a[u + 2]);
+              a[u + 3] = fmaf(v, c4.w, a[u + 3]);
             }
           }
         }
+        // a[u + e] holds list g0 + (u ^ 4 rot) + e
 #pragma unroll
-        for (int u = 0; u < kTiledG; ++u)
-          if (u < G && a[u] > best[rnd]) { best[rnd] = a[u]; best_c[rnd] = g0 + u; }
+        for (int u = 0; u < kTiledG; u += 4) {
+          const int g = u ^ static_cast<int>(rot * 4u);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int c = g0 + g + q;
+            if (g + q < G && (a[u + q] > best[rnd] || (a[u + q] == best[rnd] && c < best_c[rnd]))) {
+              best[rnd] = a[u + q];
+              best_c[rnd] = c;
+            }
+          }
+        }
       }
     }
 #pragma unroll
@@ -954,7 +992,7 @@ kmeans_tiled_assign_kernel(TiledArgs A) {
       const int64_t i = s + rnd * kTiledThreads + tid;
       if (i >= e) continue;
       const int old_c = A.gassign[i];
-      const int new_c = best_c[rnd];
+      const int new_c = best_c[rnd] == 0x7fffffff ? 0 : best_c[rnd];
       if (old_c == new_c) continue;
       A.gassign[i] = new_c;
       A.bstate[2 * b] = 1;  // benign race: every writer stores 1
@@ -1137,10 +1175,10 @@ kmeans_tiled_update_kernel(TiledArgs A) {
 // float32 scores against all (<= 32) lists of the bucket at once.  A block covers 256 consecutive
 // rows; for every tiled bucket it touches it stages the transposed training copy of the centroids
 // ([column][32 lists], zero padded) in shared memory, and each thread walks its sparse row once,
-// reading the 32 scores' operands as eight float4.  Thread t reads them in the rotated order
-// (r + t) mod 8, so the eight threads of a quarter warp always hit eight different bank groups
-// whatever their columns are; the accumulators stay in that rotated order (static register
-// indices) and are un-rotated only when the best lists are named.
+// reading the 32 scores' operands as eight float4.  Thread t reads them in the swizzled order
+// r ^ (t & 7) (see lds128), so the eight threads of a quarter warp always hit eight different bank
+// groups whatever their columns are; the accumulators stay in that order (static register
+// indices) and are mapped back only when the best lists are named.
 // The float32 order is final only where it is provably the float64 order: every gap between
 // consecutive scores of the P + 1 best exceeds `gap` * sum|row values| (above twice the float32
 // rounding bound of the sequential fmaf inner product with a unit-norm centroid).  All other rows, and the rows of buckets with more than 32 lists or
@@ -1151,10 +1189,11 @@ __global__ void __launch_bounds__(kAssignRows, 3)
 ivf_assign_tiled_f32_kernel(TiledArgs A, const int32_t* __restrict__ nprobe, int32_t max_nprobe, float gap,
                             int32_t* __restrict__ list_id, int32_t* __restrict__ probes,
                             int32_t* __restrict__ slow_rows, int32_t* __restrict__ slow_count) {
-  extern __shared__ float4 cs4[];  // [d][8] float4 = [column][32 lists]
+  extern __shared__ __align__(128) float4 cs4[];  // [d][8] float4 = [column][32 lists]
   const int tid = threadIdx.x;
   const int lane = tid & 31;
   const int d = static_cast<int>(A.low_dim);
+  const uint32_t cs_addr = static_cast<uint32_t>(__cvta_generic_to_shared(cs4));  // 128-byte aligned
   const int64_t row0 = static_cast<int64_t>(blockIdx.x) * kAssignRows;
   const int64_t row1 = min(A.n, row0 + kAssignRows);
   if (row0 >= row1) return;
@@ -1205,12 +1244,12 @@ ivf_assign_tiled_f32_kernel(TiledArgs A, const int32_t* __restrict__ nprobe, int
 #pragma unroll
           for (int t = 0; t < 8; ++t) {
             // slots past the row's population are zero padded (column 0, value 0): they add nothing
-            const float4* rowp = cs4 + ks[t] * 8u;
+            const uint32_t rowa = cs_addr + ks[t] * 128u + static_cast<uint32_t>(rot) * 16u;
             const float v = vs[t];
             sabs += fabsf(v);
 #pragma unroll
             for (int r = 0; r < 8; ++r) {
-              const float4 c = rowp[(r + rot) & 7];
+              const float4 c = lds128(rowa ^ (r * 16u));  // chunk r ^ rot
               acc[r][0] = fmaf(v, c.x, acc[r][0]);
               acc[r][1] = fmaf(v, c.y, acc[r][1]);
               acc[r][2] = fmaf(v, c.z, acc[r][2]);
@@ -1218,12 +1257,12 @@ ivf_assign_tiled_f32_kernel(TiledArgs A, const int32_t* __restrict__ nprobe, int
             }
           }
         }
-        // register slot r*4+e holds list 4*((r + rot) & 7) + e; lists past L do not exist
+        // register slot r*4+e holds list 4*(r ^ rot) + e; lists past L do not exist
 #pragma unroll
         for (int r = 0; r < 8; ++r)
 #pragma unroll
           for (int e = 0; e < 4; ++e)
-            if (4 * ((r + rot) & 7) + e >= L) acc[r][e] = -INFINITY;
+            if (4 * (r ^ rot) + e >= L) acc[r][e] = -INFINITY;
         const int T = min(P + 1, L);  // the runner-up after the last probe decides whether the cut is safe
         const float need = gap * sabs;
         float prev = 0.f;
@@ -1244,7 +1283,7 @@ ivf_assign_tiled_f32_kernel(TiledArgs A, const int32_t* __restrict__ nprobe, int
           if (t > 0 && !(prev - bv > need)) slow = true;
           prev = bv;
           if (t < P) {
-            const int32_t id = 4 * (((bs >> 2) + rot) & 7) + (bs & 3);
+            const int32_t id = 4 * ((bs >> 2) ^ rot) + (bs & 3);
             if (t < max_nprobe) probes[i * max_nprobe + t] = id;
             if (t == 0) list_id[i] = id;
           }
@@ -1352,6 +1391,8 @@ struct KmeansLayout {
   int32_t* tc_unsure;
   int4* units;
   int32_t* unit_bucket;
+  int4* units_sp;
+  int4* units_dn;
 };
 
 static void kmeans_layout(Workspace& ws, int64_t n, int64_t n_buckets, int64_t total, uint32_t low_dim,
@@ -1362,6 +1403,7 @@ static void kmeans_layout(Workspace& ws, int64_t n, int64_t n_buckets, int64_t t
   L.bclass = ws.take<uint8_t>(nbk);
   L.ct = nullptr; L.gsum = nullptr; L.gcnt = nullptr; L.gcntd = nullptr; L.gassign = nullptr; L.bstate = nullptr;
   L.cb = nullptr; L.tc_best = nullptr; L.tc_unsure = nullptr; L.units = nullptr; L.unit_bucket = nullptr;
+  L.units_sp = nullptr; L.units_dn = nullptr;
   if (tiled) {
     const size_t t = static_cast<size_t>(total > 0 ? total : 1);
     L.ct = ws.take<float>(t * low_dim);
@@ -1376,6 +1418,8 @@ static void kmeans_layout(Workspace& ws, int64_t n, int64_t n_buckets, int64_t t
     L.tc_unsure = ws.take<int32_t>(nn);
     L.units = ws.take<int4>(nn / 128 + nbk + 1);
     L.unit_bucket = ws.take<int32_t>(nn / 128 + nbk + 1);
+    L.units_sp = ws.take<int4>(nn / 128 + nbk + 1);
+    L.units_dn = ws.take<int4>(nn / 128 + nbk + 1);
   }
 }
 
@@ -1492,7 +1536,8 @@ int flc_kmeans_train(const uint16_t* ell_idx, const float* ell_val, const uint16
   const int64_t ld_c = (static_cast<int64_t>(low_dim) + 7) & ~int64_t(7);
   TiledArgs T{ell_idx, ell_val, ell_nnz, W, low_dim, n, bucket_ptr, n_buckets, nlist, centroid_ptr, q,
               centroids, K.ct, K.gsum, K.gcnt, K.gcntd, K.gassign, K.bstate,
-              use_tc ? K.cb : nullptr, ld_c, K.tc_best, K.tc_unsure, K.units, K.unit_bucket, K.qctr + 8};
+              use_tc ? K.cb : nullptr, ld_c, K.tc_best, K.tc_unsure, K.units, K.unit_bucket, K.qctr + 8,
+              K.units_sp, K.units_dn};
   FLC_CUDA(cudaMemsetAsync(K.gsum, 0, static_cast<size_t>(total_centroids) * low_dim * sizeof(long long), stream));
   FLC_CUDA(cudaMemsetAsync(K.gcnt, 0, static_cast<size_t>(total_centroids) * sizeof(int32_t), stream));
   FLC_CUDA(cudaMemsetAsync(K.gassign, 0xff, static_cast<size_t>(n) * sizeof(int32_t), stream));
@@ -1512,24 +1557,43 @@ int flc_kmeans_train(const uint16_t* ell_idx, const float* ell_val, const uint16
   FLC_REQUIRE(upd_smem <= 200 * 1024, "low_dim too large for the tiled trainer");
   FLC_CUDA(cudaFuncSetAttribute(kmeans_tiled_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 static_cast<int>(upd_smem)));
+  // Who assigns: with the bf16 rows, every tiled bucket goes through the tensor cores (832 bytes a row, HBM
+  // bound: ~0.17 ms per million rows and iteration on B200, plus the exact re-score of the close calls).  The
+  // thread-per-row kernel reads the sparse rows (~200 bytes) but is bound by the shared-memory gathers at
+  // ~0.30 ms, so it is the fallback when there are no bf16 rows.  FLC_KMEANS_SIMT_SMALL=1 gives it the buckets
+  // of up to 32 lists (tests compare the schedules).
+  const char* simt_env = getenv("FLC_KMEANS_SIMT_SMALL");
+  const bool tc_all = use_tc && !(simt_env != nullptr && simt_env[0] == '1');
+  const bool tc_some = use_tc;
+  // FLC_KMEANS_TC_DENSE=1: every tensor-core tile reads the dense bf16 rows (tests compare the two kernels)
+  const char* dense_env = getenv("FLC_KMEANS_TC_DENSE");
+  const bool sparse_tc = use_tc && kmeans_tc_sparse_ok(low_dim, W) && !(dense_env != nullptr && dense_env[0] == '1');
+  const int32_t simt_max_lists = tc_all ? 0 : (tc_some ? kTiledG : 0x7fffffff);
   for (int it = 0; it < niter; ++it) {
-    if (use_tc) {
+    if (simt_max_lists > 0) {
+      timed("kmeans_tiled_assign", stream, [&] {
+        kmeans_tiled_assign_kernel<<<row_blocks, kTiledThreads, smem, stream>>>(T, simt_max_lists); });
+      FLC_LAUNCH_CHECK();
+    }
+    if (tc_some) {
       // query tiles of the buckets that have not converged yet
-      FLC_CUDA(cudaMemsetAsync(T.tc_counts, 0, 2 * sizeof(int32_t), stream));
+      FLC_CUDA(cudaMemsetAsync(T.tc_counts, 0, 4 * sizeof(int32_t), stream));
       timed("kmeans_tc_units", stream, [&] {
-        kmeans_tc_units_kernel<<<static_cast<unsigned>((n_buckets + 255) / 256), 256, 0, stream>>>(T); });
+        kmeans_tc_units_kernel<<<static_cast<unsigned>((n_buckets + 255) / 256), 256, 0, stream>>>(
+            T, tc_all ? 0 : kTiledG + 1, sparse_tc ? kSparseMaxLists : 0); });
       FLC_LAUNCH_CHECK();
       // bf16 scores on the tensor cores decide every row whose two best lists are further apart than
-      // twice the rounding error (2^-7 for unit vectors, plus slack); the rest is re-scored exactly
-      FLC_TRY(launch_kmeans_tc(x_bf16, ld_bf16, n, K.cb, ld_c, total_centroids, low_dim, K.units, T.tc_counts,
+      // twice the rounding error (2^-7 for unit vectors, plus slack); the rest is re-scored exactly.
+      // Buckets of up to 64 lists are scored from the sparse rows (expanded in shared memory), the others
+      // from the dense bf16 rows.
+      if (sparse_tc)
+        FLC_TRY(launch_kmeans_tc_sparse(ell_idx, ell_val, ell_nnz, W, K.cb, ld_c, total_centroids, low_dim, K.units_sp,
+                                        T.tc_counts + 2, 0.008f, K.tc_best, K.tc_unsure, T.tc_counts + 1, stream));
+      FLC_TRY(launch_kmeans_tc(x_bf16, ld_bf16, n, K.cb, ld_c, total_centroids, low_dim, K.units_dn, T.tc_counts + 3,
                                0.008f, K.tc_best, K.tc_unsure, T.tc_counts + 1, stream));
       timed("kmeans_tiled_fix", stream, [&] { kmeans_tiled_fix_kernel<<<kNumSMs * 8, 256, 0, stream>>>(T); });
       FLC_LAUNCH_CHECK();
       timed("kmeans_tiled_apply", stream, [&] { kmeans_tiled_apply_kernel<<<unit_blocks, 128, 0, stream>>>(T); });
-      FLC_LAUNCH_CHECK();
-    } else {
-      timed("kmeans_tiled_assign", stream, [&] {
-        kmeans_tiled_assign_kernel<<<row_blocks, kTiledThreads, smem, stream>>>(T); });
       FLC_LAUNCH_CHECK();
     }
     timed("kmeans_tiled_update", stream, [&] { kmeans_tiled_update_kernel<<<upd_blocks, 256, upd_smem, stream>>>(T); });

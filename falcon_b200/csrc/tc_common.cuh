@@ -125,13 +125,14 @@ inline EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-// 2-D bf16 tensor map over a row-major [rows, cols] matrix with a box of kBoxRows x kBoxK, SWIZZLE_128B.
-inline int make_bf16_tmap(CUtensorMap* tmap, const uint16_t* base, uint64_t rows, uint64_t cols, int64_t ld) {
+// 2-D bf16 tensor map over a row-major [rows, cols] matrix with a box of box_rows x kBoxK, SWIZZLE_128B.
+inline int make_bf16_tmap(CUtensorMap* tmap, const uint16_t* base, uint64_t rows, uint64_t cols, int64_t ld,
+                          uint32_t box_rows = kBoxRows) {
   EncodeTiledFn encode = get_encode_fn();
   if (!encode) return set_error(FLC_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
   const cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
   const cuuint64_t gstride[1] = {static_cast<cuuint64_t>(ld) * 2};
-  const cuuint32_t box[2] = {kBoxK, kBoxRows};
+  const cuuint32_t box[2] = {kBoxK, box_rows};
   const cuuint32_t estr[2] = {1, 1};
   const CUresult rc = encode(tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<uint16_t*>(base), gdim, gstride,
                              box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,

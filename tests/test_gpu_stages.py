@@ -259,12 +259,20 @@ def test_ivf_shared_centroids_exact_and_recall(sparse):
     assert np.array_equal(gp, ref.indptr) and np.array_equal(gi, ref.indices)
 
 
-def _train(n, seed, lo, hi, force_tiled=False, monkeypatch=None, want_bf16=False):
+def _train(n, seed, lo, hi, force_tiled=False, monkeypatch=None, want_bf16=False, tc_all=False, tc_dense=False):
     if monkeypatch is not None:
         if force_tiled:
             monkeypatch.setenv("FLC_KMEANS_FORCE_TILED", "1")
         else:
             monkeypatch.delenv("FLC_KMEANS_FORCE_TILED", raising=False)
+        if tc_all:
+            monkeypatch.delenv("FLC_KMEANS_SIMT_SMALL", raising=False)
+        else:
+            monkeypatch.setenv("FLC_KMEANS_SIMT_SMALL", "1")
+        if tc_dense:
+            monkeypatch.setenv("FLC_KMEANS_TC_DENSE", "1")
+        else:
+            monkeypatch.delenv("FLC_KMEANS_TC_DENSE", raising=False)
     h = pipeline.HotPath(pipeline.Settings(exhaustive=False))
     sp = helpers.dataset(n, seed, lo, hi)
     d = helpers.to_device(sp, h.device)
@@ -307,15 +315,19 @@ def test_kmeans_quality_close_to_oracle(n, hi, bf16):
 
 def test_kmeans_fused_and_tiled_give_the_same_bits(monkeypatch):
     """List sums are fixed point, so the schedule (fused shared-memory trainer vs
-    tiled multi-launch trainer with atomics, SIMT or tensor-core assignment) cannot
-    change a single bit, and neither can a re-run."""
+    tiled multi-launch trainer with atomics, thread-per-row or tensor-core assignment)
+    cannot change a single bit, and neither can a re-run."""
     _, b, _, fused = _train(9000, 31, 1000.0, 1010.0, False, monkeypatch)
     _, _, _, tiled = _train(9000, 31, 1000.0, 1010.0, True, monkeypatch)
     _, _, _, again = _train(9000, 31, 1000.0, 1010.0, True, monkeypatch)
-    # with the bf16 rows the tiled trainer assigns on the tensor cores (close calls re-scored exactly)
-    _, _, _, tensor = _train(9000, 31, 1000.0, 1010.0, True, monkeypatch, want_bf16=True)
+    # with the bf16 rows the tiled trainer assigns on the tensor cores (close calls re-scored exactly);
+    # "mixed" leaves the buckets of up to 32 lists (here: all) to the thread-per-row kernel
+    # (sparse rows expanded in shared memory; "dense": the bf16 rows through TMA)
+    _, _, _, tensor = _train(9000, 31, 1000.0, 1010.0, True, monkeypatch, want_bf16=True, tc_all=True)
+    _, _, _, dense = _train(9000, 31, 1000.0, 1010.0, True, monkeypatch, want_bf16=True, tc_all=True, tc_dense=True)
+    _, _, _, mixed = _train(9000, 31, 1000.0, 1010.0, True, monkeypatch, want_bf16=True)
     assert fused.total_centroids > 0
-    for other in (tiled, again, tensor):
+    for other in (tiled, again, tensor, dense, mixed):
         assert torch.equal(fused.centroids, other.centroids)
         assert torch.equal(fused.list_id, other.list_id)
         assert torch.equal(fused.probes, other.probes)
