@@ -758,11 +758,11 @@ struct TiledArgs {
   // tensor-core assignment (kmeans_tc.cu); cb == nullptr: SIMT assignment
   uint16_t* cb;      // [total][ld_c] bf16 copy of the centroids (TMA operand)
   int64_t ld_c;
-  int32_t* tc_best;  // [n] arg-max list by bf16 scores (exact after the fix kernel)
-  int32_t* tc_unsure;  // [n] rows whose two best bf16 scores are within the margin (first *tc_counts[1])
+  int32_t* tc_best;  // [n] arg-max list by bf16 scores; top bit: too close to call, re-scored by the apply kernel
+  int32_t* tc_unsure;  // [n] rows the float32 pass of the final assignment could not decide (first *tc_counts[1])
   int4* units;       // query tiles of the tiled buckets still training
   int32_t* unit_bucket;
-  int32_t* tc_counts;  // [0] units, [1] unsure rows, [2] units of the sparse-row kernel, [3] of the dense-row kernel
+  int32_t* tc_counts;  // [0] units, [1] rows of the float64 final pass, [2] units of the sparse-row kernel, [3] of the dense-row kernel
   int4* units_sp;    // the same tiles, split by which tensor-core kernel scores them
   int4* units_dn;
 };
@@ -823,75 +823,84 @@ __global__ void kmeans_tc_units_kernel(TiledArgs A, int32_t min_lists, int32_t s
   }
 }
 
-// Exact float32 arg-max (the fused trainer's arithmetic: products added in slot order
-// with fmaf, ties to the lower list) for the rows the tensor-core pass could not decide.
-// One warp per row, one lane per list.
-__global__ void __launch_bounds__(256)
-kmeans_tiled_fix_kernel(TiledArgs A) {
-  const int lane = threadIdx.x & 31;
-  const int64_t warps_total = static_cast<int64_t>(gridDim.x) * 8;
-  const int32_t n_fix = A.tc_counts[1];
-  for (int64_t w = static_cast<int64_t>(blockIdx.x) * 8 + (threadIdx.x >> 5); w < n_fix; w += warps_total) {
-  const int64_t i = A.tc_unsure[w];
-  const int64_t b = find_segment(A.bucket_ptr, A.n_buckets, i);
-  const int32_t L = A.nlist[b];
-  const float* ctb = A.ct + A.centroid_ptr[b] * A.low_dim;
-  const int m = min(static_cast<int>(A.ell_nnz[i]), A.W);
-  float best = -INFINITY;
-  int best_c = 0x7fffffff;
-  for (int32_t s0 = 0; s0 < L; s0 += 32) {
-    const int32_t c = s0 + lane;
-    float acc = 0.f;
-    for (int j0 = 0; j0 < m; j0 += 32) {
-      const int j = j0 + lane;
-      const uint32_t kj = j < m ? static_cast<uint32_t>(__ldg(A.ell_idx + i * A.W + j)) : 0u;
-      const float vj = j < m ? __ldg(A.ell_val + i * A.W + j) : 0.f;
-      const int cnt = min(32, m - j0);
-      for (int t = 0; t < cnt; ++t) {
-        const uint32_t k = __shfl_sync(0xffffffffu, kj, t);
-        const float v = __shfl_sync(0xffffffffu, vj, t);
-        if (c < L) acc = fmaf(v, __ldg(ctb + static_cast<int64_t>(k) * L + c), acc);
-      }
-    }
-    if (c < L && acc > best) { best = acc; best_c = c; }
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    const float ov = __shfl_xor_sync(0xffffffffu, best, o);
-    const int oc = __shfl_xor_sync(0xffffffffu, best_c, o);
-    if (ov > best || (ov == best && oc < best_c)) { best = ov; best_c = oc; }
-  }
-  if (lane == 0) A.tc_best[i] = best_c;
-  }
-}
-
-// Rows whose list changed move their fixed-point values between the lists' sums.  One CTA
-// of 128 threads per query tile of the buckets still training.
+// After the tensor-core pass: one CTA of 128 threads per query tile of the buckets still training.
+// (1) Rows the bf16 scores could not decide (top bit of tc_best set) get the exact float32 arg-max
+//     -- the fused trainer's arithmetic: products added in slot order with fmaf, ties to the lower
+//     list -- warp-cooperatively, one lane per list; the tile's descriptor names the bucket's
+//     centroids, so there is no search.
+// (2) Rows whose list changed move their fixed-point values between the lists' sums: the warp
+//     walks its changed rows and its lanes cover a row's slots (int64 global atomics).
 __global__ void __launch_bounds__(128)
 kmeans_tiled_apply_kernel(TiledArgs A) {
-  for (int64_t u = blockIdx.x; u < A.tc_counts[0]; u += gridDim.x) {
-  const int4 ud = A.units[u];
-  const int64_t i = static_cast<int64_t>(ud.x) + threadIdx.x;
-  if (i >= ud.y) continue;
-  const int64_t b = A.unit_bucket[u];
-  const int old_c = A.gassign[i];
-  const int new_c = A.tc_best[i];
-  if (old_c == new_c) continue;
+  const int lane = threadIdx.x & 31;
   const int d = static_cast<int>(A.low_dim);
-  const int64_t c0 = ud.z;
-  A.gassign[i] = new_c;
-  A.bstate[2 * b] = 1;  // benign race: every writer stores 1
-  atomicAdd(A.gcnt + c0 + new_c, 1);
-  if (old_c >= 0) atomicSub(A.gcnt + c0 + old_c, 1);
-  unsigned long long* add = reinterpret_cast<unsigned long long*>(A.gsum + (c0 + new_c) * d);
-  unsigned long long* sub = reinterpret_cast<unsigned long long*>(A.gsum + (c0 + max(old_c, 0)) * d);
-  const int m = min(static_cast<int>(A.ell_nnz[i]), A.W);
-  for (int j = 0; j < m; ++j) {
-    const uint32_t k = __ldg(A.ell_idx + i * A.W + j);
-    const long long q = __float2ll_rn(__ldg(A.ell_val + i * A.W + j) * kFixScaleF);
-    atomicAdd(add + k, static_cast<unsigned long long>(q));
-    if (old_c >= 0) atomicAdd(sub + k, static_cast<unsigned long long>(-q));
-  }
+  const int W = A.W;
+  for (int64_t u = blockIdx.x; u < A.tc_counts[0]; u += gridDim.x) {
+    const int4 ud = A.units[u];
+    const int64_t warp_row0 = static_cast<int64_t>(ud.x) + (threadIdx.x & ~31);
+    const int64_t i = warp_row0 + lane;
+    const bool have = i < ud.y;
+    const int64_t c0 = ud.z;
+    const int32_t L = ud.w - ud.z;
+    const float* ctb = A.ct + c0 * d;
+    int new_c = have ? A.tc_best[i] : 0;
+    uint32_t todo = __ballot_sync(0xffffffffu, have && new_c < 0);
+    while (todo != 0u) {
+      const int src = __ffs(todo) - 1;
+      todo &= todo - 1u;
+      const int64_t r = warp_row0 + src;
+      const int m = min(static_cast<int>(A.ell_nnz[r]), W);
+      float best = -INFINITY;
+      int best_c = 0x7fffffff;
+      for (int32_t s0 = 0; s0 < L; s0 += 32) {
+        const int32_t c = s0 + lane;
+        float acc = 0.f;
+        for (int j0 = 0; j0 < m; j0 += 32) {
+          const int j = j0 + lane;
+          const uint32_t kj = j < m ? static_cast<uint32_t>(__ldg(A.ell_idx + r * W + j)) : 0u;
+          const float vj = j < m ? __ldg(A.ell_val + r * W + j) : 0.f;
+          const int cnt = min(32, m - j0);
+          for (int t = 0; t < cnt; ++t) {
+            const uint32_t k = __shfl_sync(0xffffffffu, kj, t);
+            const float v = __shfl_sync(0xffffffffu, vj, t);
+            if (c < L) acc = fmaf(v, __ldg(ctb + static_cast<int64_t>(k) * L + c), acc);
+          }
+        }
+        if (c < L && acc > best) { best = acc; best_c = c; }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oc = __shfl_xor_sync(0xffffffffu, best_c, o);
+        if (ov > best || (ov == best && oc < best_c)) { best = ov; best_c = oc; }
+      }
+      if (lane == src) new_c = best_c;
+    }
+    const int old_c = have ? A.gassign[i] : 0;
+    const bool changed = have && old_c != new_c;
+    if (changed) {
+      A.gassign[i] = new_c;
+      atomicAdd(A.gcnt + c0 + new_c, 1);
+      if (old_c >= 0) atomicSub(A.gcnt + c0 + old_c, 1);
+    }
+    uint32_t moved = __ballot_sync(0xffffffffu, changed);
+    if (moved != 0u && lane == 0) A.bstate[2 * static_cast<int64_t>(A.unit_bucket[u])] = 1;  // benign race: every writer stores 1
+    while (moved != 0u) {
+      const int src = __ffs(moved) - 1;
+      moved &= moved - 1u;
+      const int nc = __shfl_sync(0xffffffffu, new_c, src);
+      const int oc = __shfl_sync(0xffffffffu, old_c, src);
+      const int64_t r = warp_row0 + src;
+      const int m = min(static_cast<int>(A.ell_nnz[r]), W);
+      unsigned long long* add = reinterpret_cast<unsigned long long*>(A.gsum + (c0 + nc) * d);
+      unsigned long long* sub = reinterpret_cast<unsigned long long*>(A.gsum + (c0 + max(oc, 0)) * d);
+      for (int j = lane; j < m; j += 32) {
+        const uint32_t k = __ldg(A.ell_idx + r * W + j);
+        const long long q = __float2ll_rn(__ldg(A.ell_val + r * W + j) * kFixScaleF);
+        atomicAdd(add + k, static_cast<unsigned long long>(q));
+        if (oc >= 0) atomicAdd(sub + k, static_cast<unsigned long long>(-q));
+      }
+    }
   }
 }
 
@@ -1583,16 +1592,15 @@ int flc_kmeans_train(const uint16_t* ell_idx, const float* ell_val, const uint16
             T, tc_all ? 0 : kTiledG + 1, sparse_tc ? kSparseMaxLists : 0); });
       FLC_LAUNCH_CHECK();
       // bf16 scores on the tensor cores decide every row whose two best lists are further apart than
-      // twice the rounding error (2^-7 for unit vectors, plus slack); the rest is re-scored exactly.
+      // twice the rounding error (2^-7 for unit vectors, plus slack); the rest is flagged and re-scored exactly
+      // by the apply kernel.
       // Buckets of up to 64 lists are scored from the sparse rows (expanded in shared memory), the others
       // from the dense bf16 rows.
       if (sparse_tc)
         FLC_TRY(launch_kmeans_tc_sparse(ell_idx, ell_val, ell_nnz, W, K.cb, ld_c, total_centroids, low_dim, K.units_sp,
-                                        T.tc_counts + 2, 0.008f, K.tc_best, K.tc_unsure, T.tc_counts + 1, stream));
+                                        T.tc_counts + 2, 0.008f, K.tc_best, stream));
       FLC_TRY(launch_kmeans_tc(x_bf16, ld_bf16, n, K.cb, ld_c, total_centroids, low_dim, K.units_dn, T.tc_counts + 3,
-                               0.008f, K.tc_best, K.tc_unsure, T.tc_counts + 1, stream));
-      timed("kmeans_tiled_fix", stream, [&] { kmeans_tiled_fix_kernel<<<kNumSMs * 8, 256, 0, stream>>>(T); });
-      FLC_LAUNCH_CHECK();
+                               0.008f, K.tc_best, stream));
       timed("kmeans_tiled_apply", stream, [&] { kmeans_tiled_apply_kernel<<<unit_blocks, 128, 0, stream>>>(T); });
       FLC_LAUNCH_CHECK();
     }

@@ -3,7 +3,7 @@
 // low_dim) from the bf16 rows the scan already uses and a bf16 copy of the bucket's
 // centroids.  The epilogue keeps the two best scores of every row; a row whose two
 // best lists are closer than the margin (2^-7 covers twice the bf16 rounding error of
-// unit vectors) is flagged and re-scored exactly by the caller, so the assignment is
+// unit vectors) is flagged (top bit of its entry) and re-scored exactly by the caller, so the assignment is
 // the float32 arg-max of the reference arithmetic -- the tensor cores only prove, for
 // most rows, which list that is.
 //
@@ -60,8 +60,7 @@ struct UnitWalker {
 __global__ void __launch_bounds__(kScanThreads, 1)
 kmeans_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_c,
                  uint32_t low_dim, const int4* __restrict__ units, const int32_t* __restrict__ n_units_ptr,
-                 float margin, int32_t* __restrict__ best_out, int32_t* __restrict__ unsure_list,
-                 int32_t* __restrict__ n_unsure) {
+                 float margin, int32_t* __restrict__ best_out) {
   extern __shared__ unsigned char smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t tiles_base = (raw + 1023u) & ~1023u;
@@ -194,18 +193,9 @@ kmeans_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1u;
       if (t.last) {
-        const bool have = q < t.q_end;
-        if (have) best_out[q] = best_id;
-        // rows the bf16 scores cannot decide (a single list: second = -inf, decided) go on the
-        // re-score list: one atomic per warp
-        const bool unsure = have && !(best - second > margin);
-        const uint32_t ub = __ballot_sync(0xffffffffu, unsure);
-        if (ub != 0u) {
-          int base = 0;
-          if (lane == 0) base = atomicAdd(n_unsure, __popc(ub));
-          base = __shfl_sync(0xffffffffu, base, 0);
-          if (unsure) unsure_list[base + __popc(ub & ((1u << lane) - 1u))] = q;
-        }
+        // rows the bf16 scores cannot decide (a single list: second = -inf, decided) are flagged for the
+        // exact re-score
+        if (q < t.q_end) best_out[q] = (best - second > margin) ? best_id : (best_id | kTcUnsure);
       }
     }
   }
@@ -221,7 +211,7 @@ kmeans_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
 
 int launch_kmeans_tc(const uint16_t* x_bf16, int64_t ld_bf16, int64_t n, const uint16_t* c_bf16, int64_t ld_c,
                      int64_t total_centroids, uint32_t low_dim, const int4* units, const int32_t* n_units,
-                     float margin, int32_t* best, int32_t* unsure_list, int32_t* n_unsure, cudaStream_t stream) {
+                     float margin, int32_t* best, cudaStream_t stream) {
   FLC_REQUIRE((reinterpret_cast<uintptr_t>(x_bf16) & 15) == 0 && (reinterpret_cast<uintptr_t>(c_bf16) & 15) == 0,
               "bf16 matrices must be 16-byte aligned");
   FLC_REQUIRE((ld_bf16 % 8) == 0 && (ld_c % 8) == 0, "bf16 row pitches must be multiples of 8");
@@ -234,7 +224,7 @@ int launch_kmeans_tc(const uint16_t* x_bf16, int64_t ld_bf16, int64_t n, const u
     attr_set = true;
   }
   timed("kmeans_tc", stream, [&] { kmeans_tc_kernel<<<kNumSMs, kScanThreads, kSmemBytes, stream>>>(
-      tmap_x, tmap_c, low_dim, units, n_units, margin, best, unsure_list, n_unsure); });
+      tmap_x, tmap_c, low_dim, units, n_units, margin, best); });
   FLC_LAUNCH_CHECK();
   return FLC_OK;
 }
@@ -261,8 +251,7 @@ __global__ void __launch_bounds__(kSpThreads, 1)
 kmeans_tc_sparse_kernel(const __grid_constant__ CUtensorMap tmap_c, const uint16_t* __restrict__ ell_idx,
                         const float* __restrict__ ell_val, const uint16_t* __restrict__ ell_nnz, int32_t W,
                         uint32_t low_dim, const int4* __restrict__ units, const int32_t* __restrict__ n_units_ptr,
-                        float margin, int32_t* __restrict__ best_out, int32_t* __restrict__ unsure_list,
-                        int32_t* __restrict__ n_unsure) {
+                        float margin, int32_t* __restrict__ best_out) {
   extern __shared__ unsigned char smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t a_base = (raw + 1023u) & ~1023u;
@@ -386,16 +375,7 @@ kmeans_tc_sparse_kernel(const __grid_constant__ CUtensorMap tmap_c, const uint16
       if (lane == 0) mbar_arrive(tempty_bar(acc));
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1u;
-      const bool have = q < d.y;
-      if (have) best_out[q] = best_id;
-      const bool unsure = have && !(best - second > margin);
-      const uint32_t ub = __ballot_sync(0xffffffffu, unsure);
-      if (ub != 0u) {
-        int base = 0;
-        if (lane == 0) base = atomicAdd(n_unsure, __popc(ub));
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (unsure) unsure_list[base + __popc(ub & ((1u << lane) - 1u))] = q;
-      }
+      if (q < d.y) best_out[q] = (best - second > margin) ? best_id : (best_id | kTcUnsure);
     }
   } else if (warp >= 6) {
     // ===================== builders: sparse rows -> swizzled bf16 tile =====================
@@ -496,7 +476,7 @@ kmeans_tc_sparse_kernel(const __grid_constant__ CUtensorMap tmap_c, const uint16
 int launch_kmeans_tc_sparse(const uint16_t* ell_idx, const float* ell_val, const uint16_t* ell_nnz, int32_t ell_width,
                             const uint16_t* c_bf16, int64_t ld_c, int64_t total_centroids, uint32_t low_dim,
                             const int4* units, const int32_t* n_units, float margin, int32_t* best,
-                            int32_t* unsure_list, int32_t* n_unsure, cudaStream_t stream) {
+                            cudaStream_t stream) {
   FLC_REQUIRE(kmeans_tc_sparse_ok(low_dim, ell_width), "shape not supported by the sparse tensor-core assignment");
   FLC_REQUIRE((reinterpret_cast<uintptr_t>(c_bf16) & 15) == 0 && (ld_c % 8) == 0, "bf16 centroids must be 16-byte aligned");
   FLC_REQUIRE((reinterpret_cast<uintptr_t>(ell_idx) & 15) == 0 && (reinterpret_cast<uintptr_t>(ell_val) & 15) == 0,
@@ -509,7 +489,7 @@ int launch_kmeans_tc_sparse(const uint16_t* ell_idx, const float* ell_val, const
     attr_set = true;
   }
   timed("kmeans_tc_sparse", stream, [&] { kmeans_tc_sparse_kernel<<<kNumSMs, kSpThreads, kSpSmemBytes, stream>>>(
-      tmap_c, ell_idx, ell_val, ell_nnz, ell_width, low_dim, units, n_units, margin, best, unsure_list, n_unsure); });
+      tmap_c, ell_idx, ell_val, ell_nnz, ell_width, low_dim, units, n_units, margin, best); });
   FLC_LAUNCH_CHECK();
   return FLC_OK;
 }

@@ -6,11 +6,12 @@ namespace flc {
 
 // units[u] = (first row, bucket end row, first centroid row, end centroid row) of one 128-row
 // query tile; *n_units on the device.  best[i] = arg-max list of row i by bf16 scores; rows
-// whose two best scores are closer than `margin` are appended to unsure_list (length
-// *n_unsure, on the device): the caller re-scores those exactly.
+// whose two best scores are closer than `margin` have the top bit of best[i] set
+// (kTcUnsure): the caller re-scores those exactly.
+constexpr int32_t kTcUnsure = static_cast<int32_t>(0x80000000u);
 int launch_kmeans_tc(const uint16_t* x_bf16, int64_t ld_bf16, int64_t n, const uint16_t* c_bf16, int64_t ld_c,
                      int64_t total_centroids, uint32_t low_dim, const int4* units, const int32_t* n_units,
-                     float margin, int32_t* best, int32_t* unsure_list, int32_t* n_unsure, cudaStream_t stream);
+                     float margin, int32_t* best, cudaStream_t stream);
 
 // The same assignment for buckets of up to kSparseMaxLists lists, from the SPARSE rows: builder
 // warps expand each 128-row tile into the swizzled bf16 operand layout in shared memory (zero fill +
@@ -27,6 +28,6 @@ inline bool kmeans_tc_sparse_ok(uint32_t low_dim, int32_t ell_width) {
 int launch_kmeans_tc_sparse(const uint16_t* ell_idx, const float* ell_val, const uint16_t* ell_nnz, int32_t ell_width,
                             const uint16_t* c_bf16, int64_t ld_c, int64_t total_centroids, uint32_t low_dim,
                             const int4* units, const int32_t* n_units, float margin, int32_t* best,
-                            int32_t* unsure_list, int32_t* n_unsure, cudaStream_t stream);
+                            cudaStream_t stream);
 
 }  // namespace flc
