@@ -802,7 +802,9 @@ kmeans_tiled_init_kernel(TiledArgs A, int64_t total) {
 // Unit descriptors of the tensor-core assignment: every tiled bucket contributes
 // ceil(rows / 128) query tiles (first row, bucket end, first / end centroid row).
 __global__ void kmeans_tc_units_kernel(TiledArgs A, int32_t min_lists, int32_t sparse_max_lists) {
-  const int32_t qi = blockIdx.x * blockDim.x + threadIdx.x;
+  // one warp per queued bucket: lane 0 reserves the ranges, the lanes write the descriptors
+  const int lane = threadIdx.x & 31;
+  const int32_t qi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (qi >= A.q.cnt[kClsTiled]) return;
   const int64_t b = A.q.queue[static_cast<int64_t>(kClsTiled) * A.n_buckets + qi];
   if (A.bstate[2 * b + 1] != 0) return;  // converged: nothing left to do
@@ -810,11 +812,16 @@ __global__ void kmeans_tc_units_kernel(TiledArgs A, int32_t min_lists, int32_t s
   const int64_t s = A.bucket_ptr[b], e = A.bucket_ptr[b + 1];
   const int64_t c0 = A.centroid_ptr[b];
   const int32_t tq = static_cast<int32_t>((e - s + 127) / 128);
-  const int32_t base = atomicAdd(A.tc_counts, tq);
   const bool sparse = A.nlist[b] <= sparse_max_lists;
   int4* mine = sparse ? A.units_sp : A.units_dn;
-  const int32_t mbase = atomicAdd(A.tc_counts + (sparse ? 2 : 3), tq);
-  for (int32_t t = 0; t < tq; ++t) {
+  int32_t base = 0, mbase = 0;
+  if (lane == 0) {
+    base = atomicAdd(A.tc_counts, tq);
+    mbase = atomicAdd(A.tc_counts + (sparse ? 2 : 3), tq);
+  }
+  base = __shfl_sync(0xffffffffu, base, 0);
+  mbase = __shfl_sync(0xffffffffu, mbase, 0);
+  for (int32_t t = lane; t < tq; t += 32) {
     const int4 ud = make_int4(static_cast<int>(s + 128 * t), static_cast<int>(e), static_cast<int>(c0),
                               static_cast<int>(c0 + A.nlist[b]));
     A.units[base + t] = ud;
@@ -860,10 +867,19 @@ kmeans_tiled_apply_kernel(TiledArgs A) {
           const uint32_t kj = j < m ? static_cast<uint32_t>(__ldg(A.ell_idx + r * W + j)) : 0u;
           const float vj = j < m ? __ldg(A.ell_val + r * W + j) : 0.f;
           const int cnt = min(32, m - j0);
-          for (int t = 0; t < cnt; ++t) {
-            const uint32_t k = __shfl_sync(0xffffffffu, kj, t);
-            const float v = __shfl_sync(0xffffffffu, vj, t);
-            if (c < L) acc = fmaf(v, __ldg(ctb + static_cast<int64_t>(k) * L + c), acc);
+          const int cl = min(c, L - 1);  // lanes past the last list read a valid address and are ignored below
+          for (int t0 = 0; t0 < cnt; t0 += 8) {
+            // eight independent gathers in flight, then the products in slot order
+            float cv[8], vv[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const uint32_t k = __shfl_sync(0xffffffffu, kj, (t0 + e) & 31);
+              vv[e] = __shfl_sync(0xffffffffu, vj, (t0 + e) & 31);
+              cv[e] = __ldg(ctb + static_cast<int64_t>(k) * L + cl);
+            }
+#pragma unroll
+            for (int e = 0; e < 8; ++e)
+              if (t0 + e < cnt) acc = fmaf(vv[e], cv[e], acc);
           }
         }
         if (c < L && acc > best) { best = acc; best_c = c; }
@@ -1588,7 +1604,7 @@ int flc_kmeans_train(const uint16_t* ell_idx, const float* ell_val, const uint16
       // query tiles of the buckets that have not converged yet
       FLC_CUDA(cudaMemsetAsync(T.tc_counts, 0, 4 * sizeof(int32_t), stream));
       timed("kmeans_tc_units", stream, [&] {
-        kmeans_tc_units_kernel<<<static_cast<unsigned>((n_buckets + 255) / 256), 256, 0, stream>>>(
+        kmeans_tc_units_kernel<<<static_cast<unsigned>((n_buckets + 7) / 8), 256, 0, stream>>>(
             T, tc_all ? 0 : kTiledG + 1, sparse_tc ? kSparseMaxLists : 0); });
       FLC_LAUNCH_CHECK();
       // bf16 scores on the tensor cores decide every row whose two best lists are further apart than
