@@ -207,8 +207,18 @@ def kernel_rooflines(stats: dict, peaks: dict) -> dict:
         # tiled trainer, per iteration: sparse rows + previous assignment in, 8-byte atomics out
         "kmeans_tiled_assign": ("hbm", stats.get("ivf_nnz", 0) * 6 + stats.get("ivf_rows", 0) * 10
                                 + stats.get("ivf_nnz", 0) * 8),
+        # tensor-core assignment from the sparse rows, per iteration: whole ELL rows (padding included: the
+        # kernel loads a tile's block contiguously) + populations in, one int32 per row out.  Credited with
+        # every IVF row, i.e. exact when all IVF buckets are tiled (the dense-bucket workloads)
+        "kmeans_tc_sparse": ("hbm", stats.get("ivf_rows", 0) * (stats.get("ell_width", 0) * 6 + 2 + 4)),
+        # float32 pass of the tiled final assignment: sparse rows in, list + probes out
+        "ivf_assign_tiled_f32": ("hbm", stats.get("ivf_nnz", 0) * 6 + stats.get("ivf_rows", 0) * 2
+                                 + stats.get("ivf_rows", 0) * 4 * (1 + stats.get("max_nprobe", 1))),
     }
     out = {}
+    if "kmeans_fused" in stats["kernels"]:  # some IVF buckets are not tiled: the tiled kernels' row counts are unknown
+        work.pop("kmeans_tc_sparse")
+        work.pop("ivf_assign_tiled_f32")
     for name, (bound, bytes_) in work.items():
         if name in stats["kernels"]:
             ms, launches = stats["kernels"][name]
@@ -217,6 +227,13 @@ def kernel_rooflines(stats: dict, peaks: dict) -> dict:
                 out[name] = {"bound": bound, "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm,
                              "ms_per_launch": ms / launches, "launches_per_step": launches / stats["steps"],
                              "algorithmic_bytes_per_launch": bytes_}
+    if "vectorize" in out:
+        # SURVEY 8(d)'s per-unit figure counts the dense float32 row the reference writes (N * d * 4); this kernel
+        # emits the sparse row instead, so `frac` above is over the bytes it really moves and this is the same time
+        # against the survey's formula: peaks + indptr + f32 row + bf16 row
+        b8d = p * 8 + (n + 1) * 8 + n * d * 4 + n * ldb * 2
+        a8d = b8d / (out["vectorize"]["ms_per_launch"] * 1e-3) / 1e9
+        out["vectorize"]["survey_8d"] = {"algorithmic_bytes_per_launch": b8d, "achieved": a8d, "frac": a8d / hbm}
     # tensor view of the scan: FLOPs the IVF semantics require
     if "scan_tc" in stats["kernels"]:
         ms, launches = stats["kernels"]["scan_tc"]
@@ -443,7 +460,10 @@ def run_ours(args):
             "stage_ms": stage_ms,
             "kernels_ms_per_step": {k: v[0] / args.steps for k, v in kernels.items()},
             "kernel_rooflines": {k: {"frac": v["frac"], "achieved": v["achieved"], "unit": v["unit"],
-                                     "ms_per_launch": v["ms_per_launch"]} for k, v in roof_all.items()},
+                                     "ms_per_launch": v["ms_per_launch"],
+                                     **({"survey_8d": v["survey_8d"]} if "survey_8d" in v else {}),
+                                     **({"tensor": v["tensor"]} if "tensor" in v else {})}
+                                 for k, v in roof_all.items()},
             "bucket_sizes": {"n_buckets": int(bsz.shape[0]), "mean": float(bsz.mean()), "p50": float(np.median(bsz)),
                              "p99": float(np.percentile(bsz, 99)), "max": float(bsz.max())},
             "n_pairs": keep["graph"].n_pairs, "nnz": keep["graph"].nnz,
