@@ -1423,7 +1423,7 @@ struct KmeansLayout {
 static void kmeans_layout(Workspace& ws, int64_t n, int64_t n_buckets, int64_t total, uint32_t low_dim,
                           bool tiled, KmeansLayout& L) {
   const size_t nbk = static_cast<size_t>(n_buckets > 0 ? n_buckets : 1);
-  L.qctr = ws.take<int32_t>(16);  // [0,4) pull counters, [4,8) queue lengths, [8] tensor-core units
+  L.qctr = ws.take<int32_t>(16);  // [0,4) pull counters, [4,8) queue lengths, [8,12) tensor-core counts, [12] negative value seen
   L.queue = ws.take<int32_t>(3 * nbk);
   L.bclass = ws.take<uint8_t>(nbk);
   L.ct = nullptr; L.gsum = nullptr; L.gcnt = nullptr; L.gcntd = nullptr; L.gassign = nullptr; L.bstate = nullptr;
@@ -1614,7 +1614,7 @@ int flc_kmeans_train(const uint16_t* ell_idx, const float* ell_val, const uint16
       // from the dense bf16 rows.
       if (sparse_tc)
         FLC_TRY(launch_kmeans_tc_sparse(ell_idx, ell_val, ell_nnz, W, K.cb, ld_c, total_centroids, low_dim, K.units_sp,
-                                        T.tc_counts + 2, 0.008f, K.tc_best, stream));
+                                        T.tc_counts + 2, 0.008f, K.qctr + 12, it > 0 ? 1 : 0, K.tc_best, stream));
       FLC_TRY(launch_kmeans_tc(x_bf16, ld_bf16, n, K.cb, ld_c, total_centroids, low_dim, K.units_dn, T.tc_counts + 3,
                                0.008f, K.tc_best, stream));
       timed("kmeans_tiled_apply", stream, [&] { kmeans_tiled_apply_kernel<<<unit_blocks, 128, 0, stream>>>(T); });

@@ -247,11 +247,16 @@ constexpr int kSpSmemBytes = kSpABytes + kSpBBytes + 1024 /*align*/ + 256 /*barr
 constexpr int kSpTmemCols = 128;                           // 2 accumulators x 64 columns
 constexpr int kSpChunks = kSparseMaxWidth / 8;
 
+// -0.0f also has the sign bit set but is not negative; an OR of bit patterns cannot tell, so any
+// set sign bit counts (conservative: the general margin is used).
+__device__ __forceinline__ bool vv_is_negative(uint32_t ored_bits) { return (ored_bits >> 31) != 0u; }
+
 __global__ void __launch_bounds__(kSpThreads, 1)
 kmeans_tc_sparse_kernel(const __grid_constant__ CUtensorMap tmap_c, const uint16_t* __restrict__ ell_idx,
                         const float* __restrict__ ell_val, const uint16_t* __restrict__ ell_nnz, int32_t W,
                         uint32_t low_dim, const int4* __restrict__ units, const int32_t* __restrict__ n_units_ptr,
-                        float margin, int32_t* __restrict__ best_out) {
+                        float margin, int32_t* __restrict__ neg_seen, int use_neg_seen,
+                        int32_t* __restrict__ best_out) {
   extern __shared__ unsigned char smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t a_base = (raw + 1023u) & ~1023u;
@@ -346,6 +351,8 @@ kmeans_tc_sparse_kernel(const __grid_constant__ CUtensorMap tmap_c, const uint16
     const int quarter = warp & 3;  // TMEM lanes [32 * quarter, 32 * quarter + 32)
     int acc = 0;
     uint32_t acc_phase = 0;
+    constexpr float kRelErr = 0.005f;
+    const bool tight = use_neg_seen != 0 && *neg_seen == 0;
     for (int64_t u = u0; u < u1; ++u) {
       const int4 d = __ldg(units + u);
       const int nc = min(kSparseMaxLists, d.w - d.z);
@@ -375,7 +382,13 @@ kmeans_tc_sparse_kernel(const __grid_constant__ CUtensorMap tmap_c, const uint16
       if (lane == 0) mbar_arrive(tempty_bar(acc));
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1u;
-      if (q < d.y) best_out[q] = (best - second > margin) ? best_id : (best_id | kTcUnsure);
+      // Non-negative operands (what spectra are): every product is >= 0, so a score's bf16 error is at most
+      // 2^-8 of the score itself (two roundings of 2^-9; plus the accumulator's own rounding), and the two
+      // best lists are in the right order once they differ by more than kRelErr * (best + second) -- a few
+      // times tighter than the general bound `margin`.  Whether any value was negative is known from the
+      // previous launch (neg_seen).
+      const float need = tight ? kRelErr * (best + second) + 1e-5f : margin;
+      if (q < d.y) best_out[q] = (best - second > need) ? best_id : (best_id | kTcUnsure);
     }
   } else if (warp >= 6) {
     // ===================== builders: sparse rows -> swizzled bf16 tile =====================
@@ -430,6 +443,7 @@ kmeans_tc_sparse_kernel(const __grid_constant__ CUtensorMap tmap_c, const uint16
     load_desc(u0);
     load_rows();
     load_desc(u0 + 1);
+    uint32_t sign_bits = 0u;  // OR of the scattered values' bit patterns: top bit = some value was negative
     for (int64_t u = u0; u < u1; ++u) {
       const uint32_t k = static_cast<uint32_t>(u - u0);
       if (k > 0) mbar_wait(a_empty, (k - 1u) & 1u);  // the MMAs of the previous tile have read A
@@ -452,6 +466,7 @@ kmeans_tc_sparse_kernel(const __grid_constant__ CUtensorMap tmap_c, const uint16
               // block of 64 columns, 16-byte chunk (swizzled with the row), element
               const uint32_t off = ((col >> 6) << 14) + ((((col >> 3) & 7u) << 4) ^ x7_i[i]) + ((col & 7u) << 1);
               *reinterpret_cast<__nv_bfloat16*>(row_ptr + off) = __float2bfloat16_rn(vv[t]);
+              sign_bits |= __float_as_uint(vv[t]);
             }
           }
         }
@@ -462,6 +477,7 @@ kmeans_tc_sparse_kernel(const __grid_constant__ CUtensorMap tmap_c, const uint16
       load_rows();         // tile u + 1: in flight during the MMAs and the next zero fill
       load_desc(u + 2);
     }
+    if (vv_is_negative(sign_bits)) *neg_seen = 1;  // benign race: every writer stores 1
   }
 
   tc_fence_before();
@@ -475,8 +491,8 @@ kmeans_tc_sparse_kernel(const __grid_constant__ CUtensorMap tmap_c, const uint16
 
 int launch_kmeans_tc_sparse(const uint16_t* ell_idx, const float* ell_val, const uint16_t* ell_nnz, int32_t ell_width,
                             const uint16_t* c_bf16, int64_t ld_c, int64_t total_centroids, uint32_t low_dim,
-                            const int4* units, const int32_t* n_units, float margin, int32_t* best,
-                            cudaStream_t stream) {
+                            const int4* units, const int32_t* n_units, float margin, int32_t* neg_seen,
+                            int use_neg_seen, int32_t* best, cudaStream_t stream) {
   FLC_REQUIRE(kmeans_tc_sparse_ok(low_dim, ell_width), "shape not supported by the sparse tensor-core assignment");
   FLC_REQUIRE((reinterpret_cast<uintptr_t>(c_bf16) & 15) == 0 && (ld_c % 8) == 0, "bf16 centroids must be 16-byte aligned");
   FLC_REQUIRE((reinterpret_cast<uintptr_t>(ell_idx) & 15) == 0 && (reinterpret_cast<uintptr_t>(ell_val) & 15) == 0,
@@ -489,7 +505,7 @@ int launch_kmeans_tc_sparse(const uint16_t* ell_idx, const float* ell_val, const
     attr_set = true;
   }
   timed("kmeans_tc_sparse", stream, [&] { kmeans_tc_sparse_kernel<<<kNumSMs, kSpThreads, kSpSmemBytes, stream>>>(
-      tmap_c, ell_idx, ell_val, ell_nnz, ell_width, low_dim, units, n_units, margin, best); });
+      tmap_c, ell_idx, ell_val, ell_nnz, ell_width, low_dim, units, n_units, margin, neg_seen, use_neg_seen, best); });
   FLC_LAUNCH_CHECK();
   return FLC_OK;
 }
