@@ -64,6 +64,7 @@ class ClockSampler:
         self.idx = device_index
         self.proc = None
         self.path = None
+        self.skip = 0
 
     def start(self):
         try:
@@ -74,6 +75,22 @@ class ClockSampler:
                  "-i", str(self.idx)], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
+
+    def wait_first_sample(self, timeout_s: float):
+        t0 = time.time()
+        while self.proc is not None and time.time() - t0 < timeout_s:
+            try:
+                if os.path.getsize(self.path) > 0:
+                    return
+            except OSError:
+                return
+            time.sleep(0.02)
+
+    def mark(self):
+        try:
+            self.skip = sum(1 for _ in open(self.path))
+        except OSError:
+            self.skip = 0
 
     def stop(self) -> dict:
         if self.proc is None:
@@ -86,9 +103,9 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for line in open(self.path):
+        for ln, line in enumerate(open(self.path)):
             f = [x.strip() for x in line.split(",")]
-            if len(f) < 9:
+            if len(f) < 9 or ln < self.skip:
                 continue
             try:
                 sm.append(float(f[1]))
@@ -327,12 +344,17 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     def timed(fn, steps, warmup, sample_clocks=False, profile=False):
+        # nvidia-smi takes ~0.1-0.5 s to initialise NVML (longer on a multi-GPU box) and holds driver locks while
+        # it does: start it BEFORE the warm-up, wait for its first sample, and only then run warm-up + timed steps,
+        # so that it samples during the timed region without its start-up landing inside it.  Rank 0 only.
+        sampler = ClockSampler(local) if (sample_clocks and rank == 0) else None
+        if sampler:
+            sampler.start()
+            sampler.wait_first_sample(5.0)
+            sampler.mark()  # samples before this point are idle clocks: not reported
         for _ in range(warmup):
             fn()
         barrier()
-        sampler = ClockSampler(local) if sample_clocks else None
-        if sampler:
-            sampler.start()
         if profile:
             _lib.profile_reset()
             _lib.profile_enable(True)
