@@ -21,6 +21,9 @@
 //           compare into a per-row bit mask, warp prefix sum, ONE atomicAdd per
 //           warp and 32-column chunk that has survivors, coalesced pair stores.
 //
+// S is symmetric: a query tile only meets the candidate tiles at or above its diagonal, and the
+// epilogue emits (q, c) and (c, q) for every hit with c > q -- about half the MMAs of a large bucket.
+//
 // Persistent grid: one CTA per SM.  Query tiles are dealt round-robin, so the CTAs
 // running together stream the candidate rows of the same bucket(s): HBM sees a
 // row once, L2 serves the re-reads.
@@ -209,7 +212,14 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap, uint32_t low_dim,
           const int64_t cols_left = nc - ch * 32;
           if (cols_left < 32) mask &= (1u << cols_left) - 1u;
           if (!q_valid) mask = 0;
-          const uint32_t cnt = __popc(mask);
+          // symmetry: only candidates at or above the diagonal count here (c >= q); every hit above it is
+          // emitted in both directions, the tile below the diagonal is never computed
+          const int64_t cbase_i = tile.c0 + ch * 32;
+          const int64_t below = q - cbase_i;  // columns j < below have c < q
+          if (below >= 32) mask = 0;
+          else if (below > 0) mask &= ~((1u << below) - 1u);
+          const uint32_t diag = (below >= 0 && below < 32) ? (mask & (1u << below)) : 0u;
+          const uint32_t cnt = 2u * __popc(mask) - (diag != 0u ? 1u : 0u);
           uint32_t incl = cnt;
 #pragma unroll
           for (int o = 1; o < 32; o <<= 1) {
@@ -222,13 +232,18 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap, uint32_t low_dim,
             if (lane == 31) base = atomicAdd(pair_count, static_cast<unsigned long long>(warp_total));
             base = __shfl_sync(0xffffffffu, base, 31);
             unsigned long long pos = base + incl - cnt;
-            const uint64_t qhi = static_cast<uint64_t>(q) << 32;
-            const uint64_t cbase = static_cast<uint64_t>(tile.c0 + ch * 32);
+            const uint64_t qq = static_cast<uint64_t>(q);
+            const uint64_t cbase = static_cast<uint64_t>(cbase_i);
             while (mask) {
               const int j = __ffs(mask) - 1;
               mask &= mask - 1;
-              if (pos < capacity) pairs[pos] = qhi | (cbase + j);
+              const uint64_t c = cbase + j;
+              if (pos < capacity) pairs[pos] = (qq << 32) | c;
               ++pos;
+              if (c != qq) {
+                if (pos < capacity) pairs[pos] = (c << 32) | qq;
+                ++pos;
+              }
             }
           }
         }

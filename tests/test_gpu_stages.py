@@ -259,7 +259,8 @@ def test_ivf_shared_centroids_exact_and_recall(sparse):
     assert np.array_equal(gp, ref.indptr) and np.array_equal(gi, ref.indices)
 
 
-def _train(n, seed, lo, hi, force_tiled=False, monkeypatch=None, want_bf16=False, tc_all=False, tc_dense=False):
+def _train(n, seed, lo, hi, force_tiled=False, monkeypatch=None, want_bf16=False, tc_all=False, tc_dense=False,
+           low_dim=400, negate=False):
     if monkeypatch is not None:
         if force_tiled:
             monkeypatch.setenv("FLC_KMEANS_FORCE_TILED", "1")
@@ -273,9 +274,12 @@ def _train(n, seed, lo, hi, force_tiled=False, monkeypatch=None, want_bf16=False
             monkeypatch.setenv("FLC_KMEANS_TC_DENSE", "1")
         else:
             monkeypatch.delenv("FLC_KMEANS_TC_DENSE", raising=False)
-    h = pipeline.HotPath(pipeline.Settings(exhaustive=False))
+    h = pipeline.HotPath(pipeline.Settings(exhaustive=False, low_dim=low_dim))
     sp = helpers.dataset(n, seed, lo, hi)
     d = helpers.to_device(sp, h.device)
+    if negate:  # every 7th peak negative: the operands of the assignment are no longer all >= 0
+        d["intensity"] = torch.where(torch.arange(d["intensity"].shape[0], device=h.device) % 7 == 0,
+                                     -d["intensity"], d["intensity"])
     b = h.bucket_sort(d["precursor_mz"], d["charge"])
     v = h.vectorize(d["mz"], d["intensity"], d["indptr"], b.order, want_bf16=want_bf16)
     return h, b, v, h.build_ivf(v, b)
@@ -331,6 +335,20 @@ def test_kmeans_fused_and_tiled_give_the_same_bits(monkeypatch):
         assert torch.equal(fused.centroids, other.centroids)
         assert torch.equal(fused.list_id, other.list_id)
         assert torch.equal(fused.probes, other.probes)
+
+
+@pytest.mark.parametrize("low_dim,negate", [(200, False), (800, False), (400, True)])
+def test_kmeans_tensor_core_schedules_other_shapes(monkeypatch, low_dim, negate):
+    """low_dim = 800 is past the sparse-row kernel's operand buffer (dense bf16 rows through TMA instead);
+    negative values switch the sparse-row kernel back to the general bf16 margin.  Same bits as the fused
+    trainer either way."""
+    kw = dict(low_dim=low_dim, negate=negate)
+    _, _, _, fused = _train(9000, 33, 1000.0, 1010.0, False, monkeypatch, **kw)
+    _, _, _, tensor = _train(9000, 33, 1000.0, 1010.0, True, monkeypatch, want_bf16=True, tc_all=True, **kw)
+    assert fused.total_centroids > 0
+    assert torch.equal(fused.centroids, tensor.centroids)
+    assert torch.equal(fused.list_id, tensor.list_id)
+    assert torch.equal(fused.probes, tensor.probes)
 
 
 # ------------------------------------------------------------------ DBSCAN + split
