@@ -405,13 +405,13 @@ def run_ours(args):
     _, _, keep = hp2.run(d["mz"], d["intensity"], d["indptr"], d["precursor_mz"], d["charge"], keep=True)
     stage_ms = hp2.timer.result()
     sizes = (keep["buckets"].bucket_ptr[1:] - keep["buckets"].bucket_ptr[:-1]).double()
-    # pairs the scan actually multiplies: query tile i (128 rows) of a bucket meets the candidate rows from the
-    # last multiple of 256 at or below its first row to the bucket's end (S = X X^T is symmetric: scan_tc.cu)
+    # pairs the scan actually multiplies: query tile i (128 rows) of a bucket meets the candidate rows from its
+    # own first row to the bucket's end (S = X X^T is symmetric: scan_tc.cu)
     nb_np = sizes.cpu().numpy()
     computed_pairs = 0.0
     for i in range(int(np.ceil(nb_np.max() / 128.0)) if nb_np.size else 0):
         rows_i = np.clip(nb_np - 128.0 * i, 0.0, 128.0)
-        computed_pairs += float((rows_i * np.maximum(nb_np - 256.0 * (i // 2), 0.0)).sum())
+        computed_pairs += float((rows_i * np.maximum(nb_np - 128.0 * i, 0.0)).sum())
     required_pairs = float((sizes * sizes).sum().item())
     ivf = keep["ivf"]
     stats_extra = {}

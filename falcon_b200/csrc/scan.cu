@@ -64,9 +64,10 @@ scan_simt_kernel(const uint16_t* __restrict__ x, int64_t ld, int64_t n, uint32_t
 
 // Unit descriptors (first query row, first candidate row, bucket end, candidate tiles): one warp per
 // bucket writes those of the bucket's units.  S = X X^T is symmetric, so a query tile is only scanned
-// against the candidate tiles that reach its diagonal or lie above it (the first one starts at the
-// last multiple of kTileN at or below the query tile's first row); the kernel emits both (q, c) and
-// (c, q) for every hit above the diagonal.  About half the tiles of a large bucket disappear.
+// against the candidate rows from its own first row on (candidate tiles start there: TMA boxes may
+// start at any row); the kernel emits both (q, c) and (c, q) for every hit above the diagonal.
+// About half the tiles of a large bucket disappear, and the second query tile of a small bucket
+// meets only the bucket's tail.
 __global__ void unit_desc_kernel(const int64_t* __restrict__ bucket_ptr, const int64_t* __restrict__ tile_off,
                                  int64_t n_buckets, int4* __restrict__ unit_desc) {
   const int lane = threadIdx.x & 31;
@@ -75,7 +76,7 @@ __global__ void unit_desc_kernel(const int64_t* __restrict__ bucket_ptr, const i
   const int64_t s = bucket_ptr[b], e = bucket_ptr[b + 1], u0 = tile_off[b];
   for (int64_t u = u0 + lane; u < tile_off[b + 1]; u += 32) {
     const int64_t q_rel = (u - u0) * kTileM;
-    const int64_t c_first = s + (q_rel / kTileN) * kTileN;
+    const int64_t c_first = s + q_rel;
     const int tiles_c = static_cast<int>((e - c_first + kTileN - 1) / kTileN);
     unit_desc[u] = make_int4(static_cast<int>(s + q_rel), static_cast<int>(c_first), static_cast<int>(e), tiles_c);
   }
