@@ -74,11 +74,17 @@ __global__ void unit_desc_kernel(const int64_t* __restrict__ bucket_ptr, const i
   const int64_t b = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   if (b >= n_buckets) return;
   const int64_t s = bucket_ptr[b], e = bucket_ptr[b + 1], u0 = tile_off[b];
-  for (int64_t u = u0 + lane; u < tile_off[b + 1]; u += 32) {
-    const int64_t q_rel = (u - u0) * kTileM;
+  // Position p of the bucket's descriptor list holds query tile p / 2 from the front (p even) or from the
+  // back (p odd): a query tile's cost falls linearly with its index (it only meets the candidate rows from
+  // its own first row on), so every consecutive PAIR of positions costs the same, and the kernel deals
+  // positions to CTAs in pairs.
+  const int64_t tiles_q = tile_off[b + 1] - u0;
+  for (int64_t p = lane; p < tiles_q; p += 32) {
+    const int64_t i = (p & 1) ? tiles_q - 1 - (p >> 1) : (p >> 1);
+    const int64_t q_rel = i * kTileM;
     const int64_t c_first = s + q_rel;
     const int tiles_c = static_cast<int>((e - c_first + kTileN - 1) / kTileN);
-    unit_desc[u] = make_int4(static_cast<int>(s + q_rel), static_cast<int>(c_first), static_cast<int>(e), tiles_c);
+    unit_desc[u0 + p] = make_int4(static_cast<int>(s + q_rel), static_cast<int>(c_first), static_cast<int>(e), tiles_c);
   }
 }
 

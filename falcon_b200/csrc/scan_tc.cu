@@ -42,24 +42,25 @@ struct Tile {
   int64_t end;  // end row of the bucket
 };
 
-// Walks the tiles of one CTA.  A unit = one query tile (128 rows) against all
-// candidate tiles of its bucket.  Units are dealt round-robin (unit u goes to CTA
-// u mod grid): the CTAs running at any moment then stream the candidate rows of
-// the same one or two buckets, so those rows are fetched from HBM once and served
-// from L2 to everybody else.
+// Walks the tiles of one CTA.  A unit = one query tile (128 rows) against the
+// candidate tiles of its bucket from its own first row on.  Units are dealt
+// round-robin in PAIRS of consecutive descriptor positions (pair p goes to CTA
+// p mod grid; unit_desc_kernel orders a bucket's units so that every pair costs
+// the same): the CTAs running at any moment stream the candidate rows of the same
+// one or two buckets, so those rows come from L2, and the CTAs finish together.
 struct TileWalker {
   const int4* unit_desc;
-  int64_t total, stride, u;
-  int4 cur, nxt;  // descriptor of unit u and (prefetched) of unit u + stride
-  int ct;
+  int64_t total, stride, u;  // u: even position of the current pair
+  int4 cur, nxt;  // descriptor of the current position and (prefetched) of the next one
+  int ct, half;
 
   __device__ void init(const int4* ud, int64_t n_units, int64_t first, int64_t step) {
-    unit_desc = ud; total = n_units; stride = step; u = first; ct = 0;
+    unit_desc = ud; total = n_units; stride = 2 * step; u = 2 * first; ct = 0; half = 0;
     cur = nxt = make_int4(0, 0, 0, 0);
     if (u < total) cur = __ldg(unit_desc + u);
-    if (u + stride < total) nxt = __ldg(unit_desc + u + stride);
+    if (u + 1 < total) nxt = __ldg(unit_desc + u + 1);
   }
-  __device__ bool valid() const { return u < total; }
+  __device__ bool valid() const { return u + half < total; }
   __device__ Tile get() const {
     Tile t;
     t.q0 = cur.x;
@@ -70,9 +71,10 @@ struct TileWalker {
   __device__ void next() {
     if (++ct >= cur.w) {
       ct = 0;
-      u += stride;
+      if (half == 0) { half = 1; } else { half = 0; u += stride; }
       cur = nxt;
-      if (u + stride < total) nxt = __ldg(unit_desc + u + stride);
+      const int64_t p = half == 0 ? u + 1 : u + stride;  // the position after the new current one
+      if (p < total) nxt = __ldg(unit_desc + p);
     }
   }
 };
