@@ -64,7 +64,10 @@ struct TileWalker {
   __device__ Tile get() const {
     Tile t;
     t.q0 = cur.x;
-    t.c0 = static_cast<int64_t>(cur.y) + static_cast<int64_t>(ct) * kTileN;
+    // candidate tiles from the bucket's end back to the query tile's own rows: the units of a bucket that
+    // run together then read the same tile at the same time (two interleaved families, by the parity of
+    // the query tile), so a row comes from HBM once or twice and from L2 for everybody else
+    t.c0 = static_cast<int64_t>(cur.y) + static_cast<int64_t>(cur.w - 1 - ct) * kTileN;
     t.end = cur.z;
     return t;
   }
