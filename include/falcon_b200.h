@@ -124,8 +124,13 @@ FLC_API int flc_scatter32(const void* in, const int32_t* order, int64_t n, void*
  * spherical k-means (niter iterations, stops early at a fixed point), assignment
  * = arg-max inner product.  Training reads the sparse (ELL) rows of flc_vectorize:
  * buckets whose rows fit in shared memory train in one fused kernel, larger ones
- * in a tiled multi-launch path; list sums are 2^-40 fixed point (int64), so both
- * give the same bits (csrc/kmeans.cu). */
+ * in a tiled multi-launch path whose assignment runs on tcgen05 tensor cores when
+ * x_bf16 (the unit-norm bf16 rows of flc_vectorize) is given -- from the sparse rows
+ * expanded in shared memory for buckets of up to 64 lists, from the bf16 rows
+ * otherwise -- with every close call re-scored exactly; list sums are 2^-40 fixed
+ * point (int64), so all schedules give the same bits (csrc/kmeans.cu, kmeans_tc.cu).
+ * Environment switches for A/B runs and tests: FLC_KMEANS_FORCE_TILED,
+ * FLC_KMEANS_NO_TC, FLC_KMEANS_TC_DENSE, FLC_KMEANS_SIMT_SMALL, FLC_KMEANS_TIMING. */
 /*  nlist[b], nprobe[b] (int32) and centroid_ptr[b] (int64 exclusive scan of nlist)
  *  for every bucket; exhaustive != 0 lifts the nprobe cap (nprobe = nlist).
  *  Synchronises the stream; returns the total number of centroids on the host. */
@@ -172,6 +177,9 @@ FLC_API int flc_ivf_assign(const float* x, int64_t ld, int64_t n, uint32_t low_d
  *   impl: 0 = tcgen05/TMA kernel, 1 = SIMT verification kernel (same bf16
  *         inputs, fp32 accumulation on CUDA cores; for bring-up and tests).
  *   list_id/probes NULL: exhaustive within the bucket.
+ * The product X X^T is symmetric: the tensor-core kernel only multiplies the
+ * tiles at or above the diagonal and appends both (q, c) and (c, q) for every
+ * hit with c > q.  Pairs arrive in no particular order.
  * *pair_count (device uint64) receives the number of pairs produced (may
  * exceed pair_capacity: then FLC_ERR_CAPACITY is reported by flc_knn_csr). */
 FLC_API size_t flc_scan_workspace_bytes(int64_t n, int64_t n_buckets);
