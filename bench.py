@@ -333,8 +333,9 @@ def run_ours(args):
     labels_host = torch.empty(len(sp), dtype=torch.int32).pin_memory()
 
     def gather(labels, n_clusters):
+        # every rank's batch has args.n spectra: one collective, label offsets computed on the device, no host sync
         if world > 1:
-            return fdist.gather_labels(labels, n_clusters)[0]
+            return fdist.gather_labels_padded(labels, n_clusters, max_len=args.n)[0]
         return labels
 
     max_peaks = int(np.diff(sp.indptr).max())  # falcon's max_peaks_used setting (known up front)

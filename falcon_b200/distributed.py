@@ -61,6 +61,34 @@ def gather_labels(labels: torch.Tensor, n_clusters: int, group=None):
     return torch.cat(parts) if parts else out, lens
 
 
+def gather_labels_padded(labels: torch.Tensor, n_clusters: int, max_len: int, group=None):
+    """``gather_labels`` in ONE collective and without a host synchronisation, for callers that know
+    an upper bound ``max_len`` of every rank's length (a fixed batch size): each rank sends
+    ``[len, n_clusters, labels..., padding]``; the running label offsets
+    (/root/reference/falcon/falcon.py:189-193) are computed on the device from the gathered headers.
+
+    Returns ``(padded, lens)``: ``padded[r, :lens[r]]`` are rank r's globally unique labels (-1 = noise
+    and beyond ``lens[r]``), ``lens`` an int64 device tensor."""
+    world = dist.get_world_size(group)
+    dev = labels.device
+    n = labels.shape[0]
+    if n > max_len:
+        raise ValueError(f"{n} labels exceed max_len = {max_len}")
+    buf = torch.empty(max_len + 2, dtype=torch.int32, device=dev)
+    buf[:2] = torch.tensor([n, n_clusters], dtype=torch.int32).to(dev, non_blocking=True)
+    buf[2: 2 + n] = labels
+    out = torch.empty(world * (max_len + 2), dtype=torch.int32, device=dev)
+    dist.all_gather_into_tensor(out, buf, group=group)
+    out = out.view(world, max_len + 2)
+    lens = out[:, 0].to(torch.int64)
+    ncl = out[:, 1].to(torch.int64)
+    offsets = (torch.cumsum(ncl, 0) - ncl).to(torch.int32)
+    lab = out[:, 2:]
+    valid = torch.arange(max_len, device=dev)[None, :] < lens[:, None]
+    padded = torch.where(valid & (lab >= 0), lab + offsets[:, None], torch.full_like(lab, -1))
+    return padded, lens
+
+
 def gather_representatives(representatives: torch.Tensor, n_spectra: int, group=None) -> torch.Tensor:
     """All ranks -> the representatives (medoid spectrum indices) of every cluster,
     in the global label order of ``gather_labels``: rank r's indices are offset by

@@ -24,7 +24,8 @@ def _worker(rank, world, port, q):
     out, lens = fd.gather_labels(labels, ncl)
     reps = [torch.tensor([0, 2], dtype=torch.int32), torch.tensor([1], dtype=torch.int32)][rank]
     rep_all = fd.gather_representatives(reps, labels.shape[0])
-    q.put((rank, out.tolist(), lens, rep_all.tolist()))
+    padded, plens = fd.gather_labels_padded(labels, ncl, max_len=6)
+    q.put((rank, out.tolist(), lens, rep_all.tolist(), padded.tolist(), plens.tolist()))
     dist.destroy_process_group()
 
 
@@ -39,8 +40,11 @@ def test_gather_labels_gloo_world2():
     for p in procs:
         p.join(60)
         assert p.exitcode == 0
-    for _, out, lens, reps in res:
+    for _, out, lens, reps, padded, plens in res:
         assert out == [0, -1, 1, 1, 0, -1, 2, 2] and lens == [5, 3]
+        # the single-collective variant: same labels, padded to max_len with -1
+        assert plens == [5, 3]
+        assert padded == [[0, -1, 1, 1, 0, -1], [-1, 2, 2, -1, -1, -1]]
         # cluster c's representative carries label c in the gathered labels
         assert reps == [0, 2, 6] and [out[i] for i in reps] == [0, 1, 2]
 
