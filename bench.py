@@ -332,11 +332,26 @@ def run_ours(args):
     d = {k: v.to(dev) for k, v in host.items()}
     labels_host = torch.empty(len(sp), dtype=torch.int32).pin_memory()
 
+    gather_stream = torch.cuda.Stream(device=dev) if world > 1 else None
+
     def gather(labels, n_clusters):
-        # every rank's batch has args.n spectra: one collective, label offsets computed on the device, no host sync
+        # Every rank's batch has args.n spectra: one collective, label offsets computed on the device, no host
+        # sync.  The collective runs on a side stream behind this batch's labels, so a rank that finishes its
+        # batch early starts the next one instead of idling in the all-gather until its peers arrive; the timed
+        # region ends only after every gather has completed (wait_gathers).
         if world > 1:
-            return fdist.gather_labels_padded(labels, n_clusters, max_len=args.n)[0]
+            done = torch.cuda.Event()
+            done.record()
+            with torch.cuda.stream(gather_stream):
+                gather_stream.wait_event(done)
+                out = fdist.gather_labels_padded(labels, n_clusters, max_len=args.n)[0]
+            labels.record_stream(gather_stream)
+            return out
         return labels
+
+    def wait_gathers():
+        if gather_stream is not None:
+            torch.cuda.current_stream().wait_stream(gather_stream)
 
     max_peaks = int(np.diff(sp.indptr).max())  # falcon's max_peaks_used setting (known up front)
 
@@ -394,6 +409,7 @@ def run_ours(args):
         a.record()
         for _ in range(steps):
             out = fn()
+        wait_gathers()
         b.record()
         torch.cuda.synchronize()
         launches = _lib.launch_count()
