@@ -25,7 +25,11 @@ def _worker(rank, world, port, q):
     reps = [torch.tensor([0, 2], dtype=torch.int32), torch.tensor([1], dtype=torch.int32)][rank]
     rep_all = fd.gather_representatives(reps, labels.shape[0])
     padded, plens = fd.gather_labels_padded(labels, ncl, max_len=6)
-    q.put((rank, out.tolist(), lens, rep_all.tolist(), padded.tolist(), plens.tolist()))
+    # a rank without spectra (an empty shard) still takes part
+    empty = labels if rank == 0 else labels[:0]
+    padded2, plens2 = fd.gather_labels_padded(empty, ncl if rank == 0 else 0, max_len=5)
+    q.put((rank, out.tolist(), lens, rep_all.tolist(), padded.tolist(), plens.tolist(), padded2.tolist(),
+           plens2.tolist()))
     dist.destroy_process_group()
 
 
@@ -40,7 +44,8 @@ def test_gather_labels_gloo_world2():
     for p in procs:
         p.join(60)
         assert p.exitcode == 0
-    for _, out, lens, reps, padded, plens in res:
+    for _, out, lens, reps, padded, plens, padded2, plens2 in res:
+        assert plens2 == [5, 0] and padded2 == [[0, -1, 1, 1, 0], [-1] * 5]
         assert out == [0, -1, 1, 1, 0, -1, 2, 2] and lens == [5, 3]
         # the single-collective variant: same labels, padded to max_len with -1
         assert plens == [5, 3]
