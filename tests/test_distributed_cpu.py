@@ -64,3 +64,33 @@ def test_shard_buckets_balances_cost():
         load = np.bincount(owner, weights=cost, minlength=world)
         assert load.max() / load.mean() < 1.05
     assert (fd.shard_buckets(sizes, 2, exhaustive=False) < 2).all()
+
+
+def test_sharded_clustering_equals_single_run():
+    """buckets are independent, so clustering each rank's buckets separately and merging
+    with the running label offset gives the single-run partition.  Oracle on the host, two and three
+    'ranks' by the production sharding rule."""
+    from oracle import dbscan as odb
+    from tests import helpers
+
+    sp = helpers.dataset(2500, 7, 1000.0, 1012.0)
+    whole = helpers.oracle_pipeline(sp, exhaustive=True)
+    order, bptr = whole["order"], whole["bucket_ptr"]
+    sizes = np.diff(bptr)
+    for world in (2, 3):
+        owner = fd.shard_buckets(sizes, world)
+        merged = np.full(len(sp), -1, np.int64)  # labels in the single run's bucket order
+        offset = 0
+        for r in range(world):
+            rows = np.concatenate([np.arange(bptr[b], bptr[b + 1]) for b in np.flatnonzero(owner == r)] or
+                                  [np.zeros(0, np.int64)]).astype(np.int64)
+            if rows.size == 0:
+                continue
+            part = helpers.oracle_pipeline(sp.take(order[rows]), exhaustive=True)
+            lab = np.asarray(part["labels"], np.int64)
+            # the shard is bucket-sorted again by the pipeline: undo its order
+            back = np.empty_like(lab)
+            back[part["order"]] = lab
+            merged[rows] = np.where(back >= 0, back + offset, -1)
+            offset += int(lab.max()) + 1 if lab.size and lab.max() >= 0 else 0
+        assert odb.same_partition(merged, np.asarray(whole["labels"], np.int64))
