@@ -84,8 +84,8 @@ SIGNATURES = {
                               C.POINTER(_i64), _p, _sz, _p]),
     "flc_dbscan_workspace_bytes": (_sz, [_i64]),
     "flc_dbscan": (C.c_int, [_p, _p, _p, _i64, _f32, _i32, _p, C.POINTER(_i64), _p, _sz, _p]),
-    "flc_split_workspace_bytes": (_sz, [_i64]),
-    "flc_split_clusters": (C.c_int, [_p, _p, _i64, _f64, C.c_int, _f64, _i32, C.c_int, _p,
+    "flc_split_workspace_bytes": (_sz, [_i64, C.c_int]),
+    "flc_split_clusters": (C.c_int, [_p, _p, _p, _i64, _f64, C.c_int, _f64, _i32, C.c_int, _p,
                                      C.POINTER(_i64), _p, _sz, _p]),
 }
 

@@ -148,13 +148,16 @@ def generate_clusters(
 
     ``min_samples = 2`` (/root/reference/falcon/cluster/cluster.py:66); clusters
     are then split so that no cluster exceeds the precursor tolerance
-    (cluster.py:334-509) and relabelled consecutively.
+    (cluster.py:334-509) -- nor, with ``rt_tol``, the retention-time tolerance
+    (cluster.py:418-429) -- and relabelled consecutively.
     """
     if precursor_tol_mode not in ("Da", "ppm"):
         raise ValueError("Unknown precursor tolerance mode")
     n = pairwise_dist_matrix.shape[0]
     if len(precursor_mzs) != n:
         raise ValueError("precursor_mzs does not match the distance matrix")
+    if rt_tol is not None and (rts is None or len(rts) != n):
+        raise ValueError("rt_tol is set but rts does not match the distance matrix")
     if n == 0:
         return np.zeros(0, np.int64)
     settings = pipeline.Settings(eps=float(eps), precursor_tol_mass=precursor_tol_mass,
@@ -165,7 +168,8 @@ def generate_clusters(
     g = pipeline.KnnGraph(up(pairwise_dist_matrix.data, np.float32), up(pairwise_dist_matrix.indices, np.int32),
                           up(pairwise_dist_matrix.indptr, np.int64), int(pairwise_dist_matrix.nnz), 0)
     labels, _ = hp.dbscan(g, n)
-    out, n_clusters = hp.split(labels, up(precursor_mzs, np.float64), values_sorted=False)
+    out, n_clusters = hp.split(labels, up(precursor_mzs, np.float64), values_sorted=False,
+                               rt=up(rts, np.float64) if rt_tol is not None else None)
     out = out.cpu().numpy().astype(np.int64)
     logger.info("%d spectra grouped in %d clusters, %d spectra remain as singletons",
                 int((out != -1).sum()), n_clusters, int((out == -1).sum()))

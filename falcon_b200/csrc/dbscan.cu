@@ -291,6 +291,179 @@ __global__ void u8_to_i32_kernel(const uint8_t* __restrict__ in, int64_t n, int3
   if (i < n) out[i] = in[i];
 }
 
+
+// ---------------------------------------------------------------- RT cut (cluster.py:418-429)
+// With rt_tol the reference cuts a second 1-D complete linkage (on retention time) and
+// combines the two flat assignments as np.unique(a_mz * 2 + a_rt * 3).  That map is not
+// injective, so the result depends on the ids scipy's fcluster hands out: a depth-first
+// walk of the dendrogram from the root (scipy/cluster/_hierarchy.pyx cluster_monocrit) --
+// left subtree, right subtree, then the children that are single observations, left before
+// right; a subtree at or below the cut gets one id when it is entered.  So the whole
+// dendrogram above the cut matters.  linkage_ids_one builds it with the same parallel
+// local-minimum rounds as the split (first without crossing the tolerance = the flat
+// clusters, then to the root) and turns the walk into range additions: merging nodes A
+// (left) and B (right) shifts the ids of A's flat clusters by off(A) and B's by off(B),
+//   A, B both single observations: 0, 1      A single only: |B|, 0
+//   B single only: 0, |A|                    neither: 0, |A|
+// (|X| = number of flat clusters in X); a flat cluster's id is the sum of the shifts on its
+// path to the root = prefix sum of a difference array over the flat clusters, which are
+// contiguous in sorted order.
+__device__ void linkage_ids_one(int64_t g, int64_t n_groups, const int64_t* __restrict__ gstart,
+                                const uint32_t* __restrict__ key_sorted, const double* __restrict__ vs,
+                                int64_t n, double tol, int tol_mode, int32_t* list_a, int32_t* list_b,
+                                int32_t* frank, int32_t* delta, int32_t* __restrict__ aid) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t lt = (1u << lane) - 1u;
+  const int64_t s = gstart[g];
+  const int64_t e = (g + 1 < n_groups) ? gstart[g + 1] : n;
+  if (key_sorted[s] == kNoiseKey) return;
+  const int32_t m = static_cast<int32_t>(e - s);
+  if (m < 2) {
+    if (lane == 0) aid[s] = 0;
+    return;
+  }
+  const double* v = vs + s;
+  int32_t* cur = list_a + s;
+  int32_t* nxt = list_b + s;
+  int32_t* fr = frank + s;
+  int32_t* dl_ = delta + s + g;  // r0 + 1 <= m + 1 entries per group
+  for (int32_t j = lane; j < m; j += 32) {
+    __stcg(cur + j, j);
+    __stcg(fr + j, 0);
+  }
+  __syncwarp();
+  int32_t r = m;
+  auto run_start = [&](int32_t j) -> int32_t { return __ldcg(cur + j); };
+  auto run_end = [&](int32_t j) -> int32_t { return j + 1 < r ? __ldcg(cur + j + 1) : m; };
+  int32_t r0 = -1;  // number of flat clusters once the tolerance-bounded rounds are over
+  while (r > 1) {
+    const bool bounded = r0 < 0;
+    int32_t r_new = 0;
+    bool merged_any = false;
+    for (int32_t base = 0; base < r; base += 32) {
+      const int32_t j = base + lane;
+      const bool valid = j < r;
+      bool merge = false;
+      if (valid && j >= 1) {
+        const int32_t sa = run_start(j - 1), sb = run_start(j), eb = run_end(j);
+        const double d = split_distance(v[sa], v[eb - 1], tol_mode);
+        if (!bounded || d <= tol) {
+          merge = true;
+          if (j >= 2) {
+            const double dl = split_distance(v[run_start(j - 2)], v[sb - 1], tol_mode);
+            if (!(d < dl)) merge = false;
+          }
+          if (merge && j + 1 < r) {
+            const double dr = split_distance(v[sb], v[run_end(j + 1) - 1], tol_mode);
+            if (!(d <= dr)) merge = false;
+          }
+        }
+        if (merge && !bounded) {
+          const int32_t fa = __ldcg(fr + sa), fb = __ldcg(fr + sb);
+          const int32_t fe = eb < m ? __ldcg(fr + eb) : r0;
+          const int32_t ca = fb - fa, cb = fe - fb;
+          const bool single_a = sb - sa == 1, single_b = eb - sb == 1;
+          const int32_t off_a = single_a ? (single_b ? 0 : cb) : 0;
+          const int32_t off_b = single_b ? (single_a ? 1 : ca) : (single_a ? 0 : ca);
+          if (off_a) {
+            atomicAdd(dl_ + fa, off_a);
+            atomicAdd(dl_ + fb, -off_a);
+          }
+          if (off_b) {
+            atomicAdd(dl_ + fb, off_b);
+            atomicAdd(dl_ + fe, -off_b);
+          }
+        }
+      }
+      const bool keep = valid && !merge;
+      const uint32_t ballot = __ballot_sync(0xffffffffu, keep);
+      if (keep) __stcg(nxt + r_new + __popc(ballot & lt), run_start(j));
+      r_new += __popc(ballot);
+      merged_any |= __any_sync(0xffffffffu, merge);
+    }
+    __syncwarp();
+    if (merged_any) {
+      int32_t* t = cur; cur = nxt; nxt = t;
+      r = r_new;
+    }
+    if (bounded && (!merged_any || r == 1)) {
+      // flat clusters fixed: rank of every element's flat cluster, cleared difference array
+      r0 = r;
+      for (int32_t j = lane; j < r; j += 32) __stcg(fr + __ldcg(cur + j), 1);
+      for (int32_t j = lane; j <= r; j += 32) __stcg(dl_ + j, 0);
+      __syncwarp();
+      int32_t carry = -1;
+      for (int32_t base = 0; base < m; base += 32) {
+        const int32_t j = base + lane;
+        const bool h = j < m && __ldcg(fr + j) != 0;
+        const uint32_t hb = __ballot_sync(0xffffffffu, h);
+        if (j < m) __stcg(fr + j, carry + __popc(hb & lt) + (h ? 1 : 0));
+        carry += __popc(hb);
+      }
+      __syncwarp();
+    }
+  }
+  // ids of the flat clusters = inclusive prefix sum of the difference array
+  int32_t carry = 0;
+  for (int32_t base = 0; base < r0; base += 32) {
+    const int32_t j = base + lane;
+    int32_t x = j < r0 ? __ldcg(dl_ + j) : 0;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int32_t y = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane >= o) x += y;
+    }
+    x += carry;
+    if (j < r0) __stcg(dl_ + j, x);
+    carry = __shfl_sync(0xffffffffu, x, 31);
+  }
+  __syncwarp();
+  for (int32_t j = lane; j < m; j += 32) aid[s + j] = __ldcg(dl_ + __ldcg(fr + j));
+}
+
+__global__ void __launch_bounds__(256)
+linkage_ids_kernel(const int64_t* __restrict__ gstart, const int64_t* __restrict__ n_groups_ptr,
+                   const uint32_t* __restrict__ key_sorted, const double* __restrict__ vs, int64_t n, double tol,
+                   int tol_mode, int32_t* list_a, int32_t* list_b, int32_t* frank, int32_t* delta,
+                   int32_t* __restrict__ aid) {
+  const int64_t n_groups = *n_groups_ptr;
+  const int64_t warps_total = static_cast<int64_t>(gridDim.x) * (blockDim.x >> 5);
+  for (int64_t g = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5; g < n_groups; g += warps_total) {
+    linkage_ids_one(g, n_groups, gstart, key_sorted, vs, n, tol, tol_mode, list_a, list_b, frank, delta, aid);
+    __syncwarp();
+  }
+}
+
+// Sorted position i of the RT order: combined key (label, a_mz * 2 + a_rt * 3).
+__global__ void split_combine_kernel(const uint32_t* __restrict__ key_sorted, const int32_t* __restrict__ perm,
+                                     const int32_t* __restrict__ a_mz /*by row*/, const int32_t* __restrict__ a_rt /*by position*/,
+                                     int64_t n, uint64_t* __restrict__ key64) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t k = key_sorted[i];
+  const uint64_t c = k == kNoiseKey ? 0ull
+                                     : static_cast<uint64_t>(static_cast<uint32_t>(a_mz[perm[i]])) * 2ull +
+                                           static_cast<uint64_t>(static_cast<uint32_t>(a_rt[i])) * 3ull;
+  key64[i] = (static_cast<uint64_t>(k) << 32) | c;
+}
+
+__global__ void scatter_by_perm_kernel(const int32_t* __restrict__ in, const int32_t* __restrict__ perm, int64_t n,
+                                       int32_t* __restrict__ out) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) out[perm[i]] = in[i];
+}
+
+// Runs of equal combined key are the final sub-clusters (noise rows: runs of their own).
+__global__ void split_runhead64_kernel(const uint64_t* __restrict__ key64_sorted, int64_t n,
+                                       uint8_t* __restrict__ runhead, uint32_t* __restrict__ key32) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint64_t k = key64_sorted[i];
+  const uint32_t label = static_cast<uint32_t>(k >> 32);
+  key32[i] = label;
+  runhead[i] = (i == 0 || k != key64_sorted[i - 1] || label == kNoiseKey) ? 1 : 0;
+}
+
 struct SplitLayout {
   uint32_t* key_a;
   uint32_t* key_b;
@@ -311,11 +484,15 @@ struct SplitLayout {
   int32_t* run_id;
   int32_t* kept;
   int32_t* new_id;
+  int32_t* frank;   // RT cut only
+  int32_t* delta;
+  int32_t* aid;
+  int32_t* a_mz;
   void* cub_tmp;
   size_t cub_bytes;
 };
 
-static void split_layout(Workspace& ws, int64_t n, SplitLayout& L) {
+static void split_layout(Workspace& ws, int64_t n, bool with_rt, SplitLayout& L) {
   L.key_a = ws.take<uint32_t>(n);
   L.key_b = ws.take<uint32_t>(n);
   L.idx_a = ws.take<int32_t>(n);
@@ -335,6 +512,13 @@ static void split_layout(Workspace& ws, int64_t n, SplitLayout& L) {
   L.run_id = ws.take<int32_t>(n);
   L.kept = ws.take<int32_t>(n + 1);
   L.new_id = ws.take<int32_t>(n + 1);
+  L.frank = L.delta = L.aid = L.a_mz = nullptr;
+  if (with_rt) {
+    L.frank = ws.take<int32_t>(n);
+    L.delta = ws.take<int32_t>(2 * n + 2);
+    L.aid = ws.take<int32_t>(n);
+    L.a_mz = ws.take<int32_t>(n);
+  }
   const int num = static_cast<int>(n);
   size_t b1 = 0, b2 = 0, b3 = 0, b4 = 0, b5 = 0;
   cub::DeviceRadixSort::SortPairs(nullptr, b1, (uint32_t*)nullptr, (uint32_t*)nullptr, (int32_t*)nullptr,
@@ -415,25 +599,26 @@ int flc_dbscan(const float* dist, const int32_t* indices, const int64_t* indptr,
   return FLC_OK;
 }
 
-size_t flc_split_workspace_bytes(int64_t n) {
+size_t flc_split_workspace_bytes(int64_t n, int with_rt) {
   if (n <= 0) return 256;
   flc::Workspace ws(nullptr, 0);
   flc::SplitLayout L;
-  flc::split_layout(ws, n, L);
+  flc::split_layout(ws, n, with_rt != 0, L);
   return ws.used + 256;
 }
 
-int flc_split_clusters(const int32_t* labels_in, const double* precursor_mz, int64_t n, double tol,
-                       int tol_mode, double rt_tol, int32_t min_samples, int values_sorted,
+int flc_split_clusters(const int32_t* labels_in, const double* precursor_mz, const double* rt, int64_t n,
+                       double tol, int tol_mode, double rt_tol, int32_t min_samples, int values_sorted,
                        int32_t* labels_out, int64_t* n_clusters, void* workspace, size_t workspace_bytes,
                        flc_stream_t stream_) {
   using namespace flc;
   FLC_REQUIRE(n >= 0 && n < (int64_t(1) << 31) - 1, "n out of range");
   FLC_REQUIRE(tol_mode == FLC_TOL_DA || tol_mode == FLC_TOL_PPM, "Unknown precursor tolerance mode");
   FLC_REQUIRE(n_clusters != nullptr, "null n_clusters");
-  if (rt_tol >= 0.0)
-    return set_error(FLC_ERR_UNSUPPORTED,
-                     "retention-time split (rt_tol) is not implemented on the device yet");
+  const bool with_rt = rt_tol >= 0.0;
+  FLC_REQUIRE(!with_rt || rt != nullptr, "rt_tol is set but no retention times were given");
+  // combined key = label << 32 | (a_mz * 2 + a_rt * 3), a_* < n
+  FLC_REQUIRE(!with_rt || n < (int64_t(1) << 29), "n out of range for the retention-time cut");
   cudaStream_t stream = as_stream(stream_);
   if (n == 0) {
     *n_clusters = 0;
@@ -441,48 +626,78 @@ int flc_split_clusters(const int32_t* labels_in, const double* precursor_mz, int
   }
   Workspace ws(workspace, workspace_bytes);
   SplitLayout L;
-  split_layout(ws, n, L);
+  split_layout(ws, n, with_rt, L);
   if (!ws.ok) return set_error(FLC_ERR_WORKSPACE, "split workspace too small: need %zu", ws.used);
   const int num = static_cast<int>(n);
   const unsigned tblocks = static_cast<unsigned>((n + 255) / 256);
   size_t tmp;
-  const int32_t* idx_in;
-  if (!values_sorted) {
-    // rows by precursor m/z first, then (stable) by label
-    timed("split_mzkey", stream, [&] { split_mzkey_kernel<<<tblocks, 256, 0, stream>>>(precursor_mz, n, L.mzkey_a, L.idx_a); });
+  // Rows grouped by label, ascending in `values` inside a group (stable sorts): L.key_b = sorted
+  // keys, *perm_out = sorted position -> row, L.vs = values, L.ghead / L.gstart / L.n_groups.
+  auto group_rows = [&](const double* values, bool sorted, const int32_t** perm_out) -> int {
+    const int32_t* idx_in;
+    if (!sorted) {
+      timed("split_mzkey", stream, [&] { split_mzkey_kernel<<<tblocks, 256, 0, stream>>>(values, n, L.mzkey_a, L.idx_a); });
+      FLC_LAUNCH_CHECK();
+      size_t t = L.cub_bytes;
+      FLC_CUDA(cub::DeviceRadixSort::SortPairs(L.cub_tmp, t, L.mzkey_a, L.mzkey_b, L.idx_a, L.idx_b, num, 0, 64,
+                                               stream));
+      count_launch(9);
+      // key of the value-sorted rows
+      timed("split_key", stream, [&] { split_key_kernel<<<tblocks, 256, 0, stream>>>(labels_in, n, L.key_b, L.idx_a); });
+      FLC_LAUNCH_CHECK();
+      FLC_TRY(flc_gather(L.key_b, L.idx_b, n, 4, L.key_a, stream_));
+      idx_in = L.idx_b;
+    } else {
+      timed("split_key", stream, [&] { split_key_kernel<<<tblocks, 256, 0, stream>>>(labels_in, n, L.key_a, L.idx_a); });
+      FLC_LAUNCH_CHECK();
+      idx_in = L.idx_a;
+    }
+    int32_t* perm = (idx_in == L.idx_a) ? L.idx_b : L.idx_a;
+    size_t t = L.cub_bytes;
+    FLC_CUDA(cub::DeviceRadixSort::SortPairs(L.cub_tmp, t, L.key_a, L.key_b, idx_in, perm, num, 0, 32, stream));
+    count_launch(5);
+    timed("split_prepare", stream, [&] { split_prepare_kernel<<<tblocks, 256, 0, stream>>>(L.key_b, perm, values, n, L.vs, L.ghead,
+                                                      L.runhead); });
     FLC_LAUNCH_CHECK();
-    tmp = L.cub_bytes;
-    FLC_CUDA(cub::DeviceRadixSort::SortPairs(L.cub_tmp, tmp, L.mzkey_a, L.mzkey_b, L.idx_a, L.idx_b, num, 0,
-                                             64, stream));
-    count_launch(9);
-    // key of the m/z-sorted rows
-    timed("split_key", stream, [&] { split_key_kernel<<<tblocks, 256, 0, stream>>>(labels_in, n, L.key_b, L.idx_a); });
-    FLC_LAUNCH_CHECK();
-    FLC_TRY(flc_gather(L.key_b, L.idx_b, n, 4, L.key_a, stream_));
-    idx_in = L.idx_b;
-  } else {
-    timed("split_key", stream, [&] { split_key_kernel<<<tblocks, 256, 0, stream>>>(labels_in, n, L.key_a, L.idx_a); });
-    FLC_LAUNCH_CHECK();
-    idx_in = L.idx_a;
-  }
-  // stable sort by label; perm -> L.idx_out
-  int32_t* perm = (idx_in == L.idx_a) ? L.idx_b : L.idx_a;
-  tmp = L.cub_bytes;
-  FLC_CUDA(cub::DeviceRadixSort::SortPairs(L.cub_tmp, tmp, L.key_a, L.key_b, idx_in, perm, num, 0, 32, stream));
-  count_launch(5);
+    t = L.cub_bytes;
+    FLC_CUDA(cub::DeviceSelect::Flagged(L.cub_tmp, t, cub::CountingInputIterator<int64_t>(0), L.ghead, L.gstart,
+                                        L.n_groups, num, stream));
+    count_launch(2);
+    *perm_out = perm;
+    return FLC_OK;
+  };
+  const int32_t* perm = nullptr;
+  FLC_TRY(group_rows(precursor_mz, values_sorted != 0, &perm));
   const uint32_t* key_sorted = L.key_b;
-  timed("split_prepare", stream, [&] { split_prepare_kernel<<<tblocks, 256, 0, stream>>>(key_sorted, perm, precursor_mz, n, L.vs, L.ghead,
-                                                    L.runhead); });
-  FLC_LAUNCH_CHECK();
-  tmp = L.cub_bytes;
-  FLC_CUDA(cub::DeviceSelect::Flagged(L.cub_tmp, tmp, cub::CountingInputIterator<int64_t>(0), L.ghead,
-                                      L.gstart, L.n_groups, num, stream));
-  count_launch(2);
   // The number of groups is only known on the device: a resident grid of warps strides over them.
   const unsigned gblocks = static_cast<unsigned>(std::min<int64_t>((n * 32 + 255) / 256, static_cast<int64_t>(kNumSMs) * 8));
-  timed("split_group", stream, [&] { split_group_kernel<<<gblocks, 256, 0, stream>>>(L.gstart, L.n_groups, key_sorted, L.vs, n, tol, tol_mode,
-                                                  L.list_a, L.list_b, L.runhead); });
-  FLC_LAUNCH_CHECK();
+  if (!with_rt) {
+    timed("split_group", stream, [&] { split_group_kernel<<<gblocks, 256, 0, stream>>>(L.gstart, L.n_groups, key_sorted, L.vs, n, tol, tol_mode,
+                                                    L.list_a, L.list_b, L.runhead); });
+    FLC_LAUNCH_CHECK();
+  } else {
+    // fcluster ids of the m/z cut (by row), then of the RT cut (by position in RT order),
+    // combined and sorted: equal (label, a_mz * 2 + a_rt * 3) = one sub-cluster
+    timed("linkage_ids", stream, [&] { linkage_ids_kernel<<<gblocks, 256, 0, stream>>>(L.gstart, L.n_groups, key_sorted, L.vs, n, tol, tol_mode,
+                                                    L.list_a, L.list_b, L.frank, L.delta, L.aid); });
+    FLC_LAUNCH_CHECK();
+    timed("split_scatter", stream, [&] { scatter_by_perm_kernel<<<tblocks, 256, 0, stream>>>(L.aid, perm, n, L.a_mz); });
+    FLC_LAUNCH_CHECK();
+    FLC_TRY(group_rows(rt, false, &perm));
+    timed("linkage_ids", stream, [&] { linkage_ids_kernel<<<gblocks, 256, 0, stream>>>(L.gstart, L.n_groups, key_sorted, L.vs, n, rt_tol, FLC_TOL_DA,
+                                                    L.list_a, L.list_b, L.frank, L.delta, L.aid); });
+    FLC_LAUNCH_CHECK();
+    timed("split_combine", stream, [&] { split_combine_kernel<<<tblocks, 256, 0, stream>>>(key_sorted, perm, L.a_mz, L.aid, n, L.mzkey_a); });
+    FLC_LAUNCH_CHECK();
+    int32_t* perm_f = (perm == L.idx_a) ? L.idx_b : L.idx_a;
+    tmp = L.cub_bytes;
+    FLC_CUDA(cub::DeviceRadixSort::SortPairs(L.cub_tmp, tmp, L.mzkey_a, L.mzkey_b, perm, perm_f, num, 0, 64, stream));
+    count_launch(9);
+    perm = perm_f;
+    timed("split_runhead", stream, [&] { split_runhead64_kernel<<<tblocks, 256, 0, stream>>>(L.mzkey_b, n, L.runhead, L.key_a); });
+    FLC_LAUNCH_CHECK();
+    key_sorted = L.key_a;
+  }
   tmp = L.cub_bytes;
   FLC_CUDA(cub::DeviceSelect::Flagged(L.cub_tmp, tmp, cub::CountingInputIterator<int64_t>(0), L.runhead,
                                       L.rstart, L.n_runs, num, stream));

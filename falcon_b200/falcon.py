@@ -94,7 +94,8 @@ def main(args: Optional[List[str]] = None) -> int:
     pmz_d, z_d = up(raw.precursor_mz, np.float64), up(raw.precursor_charge, np.int32)
     mz_d, in_d, indptr_d, valid = hp.preprocess(
         up(raw.mz, np.float32), up(raw.intensity, np.float32), up(raw.indptr, np.int64), pmz_d, z_d,
-        config.min_peaks, config.min_mz_range, config.min_mz, config.max_mz, config.remove_precursor_tol,
+        # the window get_dim adjusted to the bin grid, as falcon.py:120-133 passes it on
+        config.min_peaks, config.min_mz_range, hp.min_mz, hp.max_mz, config.remove_precursor_tol,
         config.min_intensity, config.max_peaks_used, config.scaling)
     valid_h = valid.cpu().numpy().astype(bool)
     has_charge = raw.precursor_charge != 0  # falcon clusters per charge; spectra without one are skipped

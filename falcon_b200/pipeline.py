@@ -353,6 +353,8 @@ class HotPath:
         n, d = v.n, v.low_dim
         x, xb = v.x, v.xb
         s = self.s
+        if s.rt_tol is not None and buckets.rt is None:
+            raise ValueError("rt_tol is set but no retention times were given")
         thr = self.scan_threshold()
         if pair_capacity is None:
             pair_capacity = 32 * n + (1 << 20) if s.eps_cut else None
@@ -412,13 +414,22 @@ class HotPath:
         return labels, int(nc.value)
 
     # ------------------------------------------------------------------ a11-a15
-    def split(self, labels: torch.Tensor, mz: torch.Tensor, values_sorted: bool):
+    def split(self, labels: torch.Tensor, mz: torch.Tensor, values_sorted: bool,
+              rt: Optional[torch.Tensor] = None):
+        """``_postprocess_cluster`` of every DBSCAN cluster (/root/reference/falcon/cluster/cluster.py:362-455);
+        with ``Settings.rt_tol`` also the retention-time cut (:418-429), which needs ``rt``."""
         n = labels.shape[0]
         out = self._empty(n, torch.int32)
         nc = C.c_int64(0)
+        with_rt = self.s.rt_tol is not None
+        if with_rt:
+            if rt is None:
+                raise ValueError("rt_tol is set but no retention times were given")
+            rt = rt.to(torch.float64)
         with self.timer("split"):
-            ws = self._ws(lib.flc_split_workspace_bytes(n), "split")
-            check(lib.flc_split_clusters(ptr(labels), ptr(mz), n, self.s.precursor_tol_mass,
+            ws = self._ws(lib.flc_split_workspace_bytes(n, 1 if with_rt else 0), "split")
+            check(lib.flc_split_clusters(ptr(labels), ptr(mz), ptr(rt) if with_rt else None, n,
+                                         self.s.precursor_tol_mass,
                                          _lib.TOL_MODES[self.s.precursor_tol_mode],
                                          -1.0 if self.s.rt_tol is None else float(self.s.rt_tol),
                                          self.s.min_samples, 1 if values_sorted else 0, ptr(out),
@@ -440,7 +451,7 @@ class HotPath:
         ivf = None if self.s.exhaustive else self.build_ivf(v, buckets)
         graph = self.knn_graph(v, buckets, ivf)
         db_labels, _ = self.dbscan(graph, n)
-        sorted_labels, n_clusters = self.split(db_labels, buckets.mz, values_sorted=True)
+        sorted_labels, n_clusters = self.split(db_labels, buckets.mz, values_sorted=True, rt=buckets.rt)
         if v.overflow is not None and int(v.overflow.item()) > 0:  # the stream was just synchronised
             raise RuntimeError(f"a spectrum hashed to {int(v.overflow.item())} distinct columns but the sparse rows "
                                f"hold {v.ell_width}: pass the true max_peaks")
@@ -463,6 +474,8 @@ class HotPath:
         -1 = noise) and the number of clusters.  ``keep`` also returns the
         intermediates (bucket order) for parity checks."""
         n = precursor_mz.shape[0]
+        if self.s.rt_tol is not None and rt is None:
+            raise ValueError("rt_tol is set but no retention times were given")
         if n == 0:
             empty = self._empty(0, torch.int32)
             return (empty, 0, {}) if keep else (empty, 0)
@@ -478,6 +491,8 @@ class HotPath:
         first so that bucketing can start while the peak arrays are still crossing
         PCIe; the peaks follow in chunks, one event each."""
         n = int(precursor_mz.shape[0])
+        if self.s.rt_tol is not None and rt is None:
+            raise ValueError("rt_tol is set but no retention times were given")
         if n == 0:
             return None
         dev = self.device

@@ -229,11 +229,17 @@ FLC_API int flc_dbscan(const float* dist, const int32_t* indices, const int64_t*
  * min_samples members become noise; labels renumbered consecutively.
  * values_sorted != 0 promises precursor_mz ascending inside every cluster in
  * row order (true for bucket-sorted rows) and skips the m/z sort.
- * rt_tol >= 0 (retention-time cut, cluster.py:418-429) is not implemented on the
- * device yet: FLC_ERR_UNSUPPORTED.  Synchronises; returns #clusters on the host. */
-FLC_API size_t flc_split_workspace_bytes(int64_t n);
-FLC_API int flc_split_clusters(const int32_t* labels_in, const double* precursor_mz, int64_t n,
-                       double tol, int tol_mode, double rt_tol, int32_t min_samples,
+ * rt_tol >= 0 adds the retention-time cut of cluster.py:418-429: a second 1-D
+ * complete linkage on rt (plain differences, cut at rt_tol), combined with the
+ * m/z cut exactly as the reference does -- np.unique(a_mz * 2 + a_rt * 3) on
+ * scipy fcluster's ids, a map that is not injective, so the ids are reproduced
+ * (depth-first numbering of the dendrogram, scipy _hierarchy.pyx cluster_monocrit).
+ * rt: float64 [n] (the values the caller holds, like precursor_mz), required when
+ * rt_tol >= 0, else ignored / NULL; pass rt_tol < 0 for "None".
+ * Synchronises; returns #clusters on the host. */
+FLC_API size_t flc_split_workspace_bytes(int64_t n, int with_rt);
+FLC_API int flc_split_clusters(const int32_t* labels_in, const double* precursor_mz, const double* rt,
+                       int64_t n, double tol, int tol_mode, double rt_tol, int32_t min_samples,
                        int values_sorted, int32_t* labels_out, int64_t* n_clusters /*host*/,
                        void* workspace, size_t workspace_bytes, flc_stream_t stream);
 

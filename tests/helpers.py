@@ -34,16 +34,18 @@ def oracle_vectors(spectra, low_dim=400, fragment_tol=0.05, min_mz=101.0, max_mz
 
 
 def oracle_pipeline(spectra, exhaustive, centroids=None, vectors=None, low_dim=400, mz_interval=1,
-                    tol=TOL, mode=MODE, eps=EPS, n_probe=32):
+                    tol=TOL, mode=MODE, eps=EPS, n_probe=32, rt_tol=None):
     """Oracle run on bucket-sorted spectra.  Returns dict with order, bucket_ptr,
     vectors, csr (full), csr_cut, labels (bucket order)."""
     order, bptr, keys = oivf.bucket_sort(spectra.precursor_mz, spectra.precursor_charge, mz_interval)
     s2 = spectra.take(order)
     x = oracle_vectors(s2, low_dim) if vectors is None else vectors
+    rts = None if rt_tol is None else np.asarray(s2.retention_time, np.float32)
     mat, cents = oivf.compute_pairwise_distances(
-        x, s2.precursor_mz, None, bptr, tol, mode, None, 64, 128, n_probe, exhaustive, centroids)
+        x, s2.precursor_mz, rts, bptr, tol, mode, rt_tol, 64, 128, n_probe, exhaustive, centroids)
     cut = oivf.eps_cut(mat, eps)
-    labels = odb.generate_clusters(cut.data, cut.indices, cut.indptr, eps, s2.precursor_mz, None, tol, mode)
+    labels = odb.generate_clusters(cut.data, cut.indices, cut.indptr, eps, s2.precursor_mz,
+                                   None if rts is None else rts.astype(np.float64), tol, mode, rt_tol)
     return dict(order=order, bucket_ptr=bptr, keys=keys, sorted=s2, x=x, csr=mat, csr_cut=cut,
                 labels=labels, centroids=cents)
 

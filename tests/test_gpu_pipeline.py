@@ -13,6 +13,7 @@ from falcon_b200 import pipeline, synth  # noqa: E402
 from falcon_b200.cluster import cluster, spectrum  # noqa: E402
 from oracle import dbscan as odb  # noqa: E402
 from oracle import ivf as oivf  # noqa: E402
+from oracle import vectorize as ovec  # noqa: E402
 from tests import helpers  # noqa: E402
 
 
@@ -48,6 +49,23 @@ def test_end_to_end_settings_sweep(low_dim, eps, tol, mode, mz_interval):
     ref[o["order"]] = o["labels"]
     assert nc == ref.max() + 1 and nc > 100
     assert odb.same_partition(labels, ref)
+
+
+@pytest.mark.parametrize("rt_tol", [12.0, 60.0])
+def test_end_to_end_with_rt_tolerance(rt_tol):
+    """``rt_tol`` set: retention-time filter of the neighbours (A.2) and the retention-time cut of the
+    DBSCAN clusters (cluster.py:418-429); identical partitions, and different from the run without it."""
+    n = 20000
+    sp = helpers.dataset(n, 45, 1000.0, 1020.0)
+    labels, nc, _ = pipeline.cluster_host(sp, pipeline.Settings(exhaustive=True, rt_tol=rt_tol))
+    o = helpers.oracle_pipeline(sp, exhaustive=True, rt_tol=rt_tol)
+    ref = np.empty(n, np.int64)
+    ref[o["order"]] = o["labels"]
+    assert nc == ref.max() + 1 and nc > 100
+    assert odb.same_partition(labels, ref)
+    plain, _, _ = pipeline.cluster_host(sp, pipeline.Settings(exhaustive=True))
+    if rt_tol < 20:
+        assert not odb.same_partition(labels, plain)
 
 
 def test_end_to_end_default_nprobe_shared_centroids():
@@ -191,6 +209,9 @@ def test_cli_mgf_to_csv_matches_oracle(tmp_path):
 
     sp = synth.generate(4000, 17, mass_range=(1000.0, 1015.0))
     dicts = sp.as_dicts()
+    for d in dicts[::7]:  # a dominant peak between get_dim's lower bound (100.95) and the raw setting (101.0)
+        d["mz"] = np.r_[np.float32(100.97), d["mz"]].astype(np.float32)
+        d["intensity"] = np.r_[np.float32(50.0 * d["intensity"].max()), d["intensity"]].astype(np.float32)
     path, out = str(tmp_path / "in.mgf"), str(tmp_path / "res")
     mgf_io.write_spectra(path, dicts)
     assert fmain.main([path, out, "--exhaustive", "--export_representatives"]) == 0
@@ -201,7 +222,10 @@ def test_cli_mgf_to_csv_matches_oracle(tmp_path):
     assert list(df.columns) == ["filename", "spectrum_id", "precursor_charge", "precursor_mz", "retention_time", "cluster"]
     # oracle: same preprocessing, same path
     raw, ids, _ = mgf_io.read_mgf(path)
-    valid, mz, it, indptr = opre.process_spectra(raw, min_peaks=5, min_mz_range=250.0, mz_min=101.0, mz_max=1500.0,
+    # falcon.py:120-133: the m/z window the spectra are restricted to is get_dim's, not the raw setting
+    _, lo, hi = ovec.get_dim(101.0, 1500.0, 0.05)
+    assert (lo, hi) != (101.0, 1500.0)
+    valid, mz, it, indptr = opre.process_spectra(raw, min_peaks=5, min_mz_range=250.0, mz_min=lo, mz_max=hi,
                                                  remove_precursor_tolerance=1.5, min_intensity=0.01, max_peaks_used=50,
                                                  scaling=None)
     keep = np.flatnonzero(valid)

@@ -458,26 +458,92 @@ def test_split_clusters(mode, tol, values_sorted):
 
 
 def test_split_golden_cases(hp, golden_dir):
-    """The reference's own _postprocess_cluster outputs (tests/golden/postprocess.npz)."""
+    """The reference's own _postprocess_cluster outputs (tests/golden/postprocess.npz), with and
+    without the retention-time cut (cluster.py:418-429)."""
     g = np.load(os.path.join(golden_dir, "postprocess.npz"))
     dev = hp.device
-    n_checked = 0
+    n_checked = n_rt = 0
     for i in range(int(g["n_post"])):
-        if float(g[f"post_rttol{i}"]) >= 0:
-            continue
+        rt_tol = float(g[f"post_rttol{i}"])
         v, mode, tol = g[f"post_v{i}"], str(g[f"post_mode{i}"]), float(g[f"post_tol{i}"])
-        h = pipeline.HotPath(pipeline.Settings(precursor_tol_mass=tol, precursor_tol_mode=mode))
-        out, nc = h.split(torch.zeros(len(v), dtype=torch.int32, device=dev), torch.from_numpy(v).to(dev), False)
-        assert nc == int(g[f"post_k{i}"])
-        assert odb.same_partition(_cpu(out), g[f"post_labels{i}"])
+        h = pipeline.HotPath(pipeline.Settings(precursor_tol_mass=tol, precursor_tol_mode=mode,
+                                               rt_tol=rt_tol if rt_tol >= 0 else None))
+        rt = torch.from_numpy(g[f"post_rt{i}"]).to(dev) if rt_tol >= 0 else None
+        out, nc = h.split(torch.zeros(len(v), dtype=torch.int32, device=dev), torch.from_numpy(v).to(dev), False, rt=rt)
+        assert nc == int(g[f"post_k{i}"]), i
+        assert odb.same_partition(_cpu(out), g[f"post_labels{i}"]), i
         n_checked += 1
-    assert n_checked >= 30
+        n_rt += rt_tol >= 0
+    assert n_checked >= 120 and n_rt >= 60
 
 
-def test_rt_tolerance_split_is_reported_unsupported(hp):
+def test_split_golden_cases_in_one_call(hp, golden_dir):
+    """All golden retention-time cases as the DBSCAN clusters of ONE call (plus noise rows)."""
+    g = np.load(os.path.join(golden_dir, "postprocess.npz"))
+    cases = [i for i in range(int(g["n_post"])) if float(g[f"post_rttol{i}"]) >= 0 and str(g[f"post_mode{i}"]) == "ppm"]
+    labels, mz, rt, want = [], [], [], []
+    nxt = 0
+    for c, i in enumerate(cases):
+        v = g[f"post_v{i}"]
+        labels.append(np.full(len(v), c))
+        mz.append(v)
+        rt.append(g[f"post_rt{i}"])
+        w = g[f"post_labels{i}"].astype(np.int64)
+        want.append(np.where(w >= 0, w - 7 + nxt, -1))
+        nxt += int(g[f"post_k{i}"])
+    labels.append(np.full(5, -1)); mz.append(np.full(5, 500.0)); rt.append(np.zeros(5)); want.append(np.full(5, -1))
+    labels, mz, rt, want = (np.concatenate(a) for a in (labels, mz, rt, want))
+    perm = np.random.default_rng(5).permutation(len(labels))
+    labels, mz, rt, want = labels[perm], mz[perm], rt[perm], want[perm]
+    h = pipeline.HotPath(pipeline.Settings(precursor_tol_mass=20.0, precursor_tol_mode="ppm", rt_tol=5.0))
+    dev = h.device
+    out, nc = h.split(torch.from_numpy(labels.astype(np.int32)).to(dev), torch.from_numpy(mz).to(dev), False,
+                      rt=torch.from_numpy(rt).to(dev))
+    assert nc == nxt
+    assert odb.same_partition(_cpu(out), want)
+    assert sorted(np.unique(_cpu(out)[_cpu(out) >= 0]).tolist()) == list(range(nc))
+
+
+@pytest.mark.parametrize("mode,tol,rt_tol", [("ppm", 20.0, 3.0), ("Da", 0.02, 0.5), ("ppm", 10.0, 40.0)])
+def test_split_clusters_with_rt(mode, tol, rt_tol):
+    """Random DBSCAN clusters (a few with ~1000 members, exact ties in both columns) against the
+    oracle's postprocess_cluster, which cuts the restated linkage with scipy's fcluster itself."""
+    h = pipeline.HotPath(pipeline.Settings(precursor_tol_mass=tol, precursor_tol_mode=mode, rt_tol=rt_tol))
+    rng = np.random.default_rng(77)
+    n = 20000
+    labels = rng.integers(-1, 3000, n).astype(np.int32)
+    labels[rng.random(n) < 0.2] = -1
+    big = rng.random(n) < 0.1
+    labels[big] = 3000 + rng.integers(0, 2, big.sum())
+    centre = 400.0 + (np.maximum(labels, 0) % 997)
+    mz = centre + rng.normal(0, 1.0, n) * (centre * 12e-6 if mode == "ppm" else 0.012)
+    dup = rng.random(n) < 0.05
+    mz[dup] = centre[dup]
+    rt = rng.uniform(0, 8 * rt_tol, n)
+    rt[labels >= 3000] = rng.uniform(0, 500 * rt_tol, int((labels >= 3000).sum()))
+    rt[rng.random(n) < 0.05] = 2 * rt_tol  # ties
+    if rng.random() < 0.5:
+        rt = rt.astype(np.float32).astype(np.float64)
+    dev = h.device
+    out, nc = h.split(torch.from_numpy(labels).to(dev), torch.from_numpy(mz).to(dev), False,
+                      rt=torch.from_numpy(rt).to(dev))
+    out = _cpu(out)
+    ref = np.full(n, -1, np.int64)
+    nxt = 0
+    for l in np.unique(labels[labels >= 0]):
+        members = np.flatnonzero(labels == l)
+        sub, k = odb.postprocess_cluster(mz[members], rt[members], tol, mode, rt_tol)
+        ref[members[sub >= 0]] = sub[sub >= 0] + nxt
+        nxt += k
+    assert nc == nxt
+    assert odb.same_partition(out, ref)
+    assert sorted(np.unique(out[out >= 0]).tolist()) == list(range(nc))
+
+
+def test_rt_tolerance_needs_retention_times(hp):
     h = pipeline.HotPath(pipeline.Settings(rt_tol=5.0))
     z = torch.zeros(4, dtype=torch.int32, device=h.device)
-    with pytest.raises(NotImplementedError, match="rt_tol"):
+    with pytest.raises(ValueError, match="retention times"):
         h.split(z, torch.ones(4, dtype=torch.float64, device=h.device), False)
 
 
