@@ -14,23 +14,37 @@ import torch
 import torch.distributed as dist
 
 
-def shard_buckets(bucket_sizes, world_size: int, exhaustive: bool = True) -> np.ndarray:
-    """Rank of every bucket: longest-processing-time bin packing by the scan
-    cost ``n_b^2`` (exhaustive) / ``n_b^2 * nprobe / nlist`` (IVF)."""
-    sizes = np.asarray(bucket_sizes, np.float64)
-    cost = sizes * sizes
+def unit_cost(n_queries, n_candidates, exhaustive: bool = True, n_probe: int = 32) -> np.ndarray:
+    """Work of clustering ``n_queries`` rows against a bucket of ``n_candidates`` rows: the scan,
+    ``q * c`` (exhaustive) or ``q * c * nprobe / nlist`` (IVF sizing rule of SURVEY A.2), plus the
+    linear stages."""
+    q = np.asarray(n_queries, np.float64)
+    c = np.asarray(n_candidates, np.float64)
+    cost = q * c
     if not exhaustive:
-        nlist = np.maximum(1.0, 2.0 ** np.floor(np.log2(np.maximum(sizes, 39.0) / 39.0)))
-        nlist[sizes < 100] = 1.0
-        cost = cost * np.maximum(1.0, np.minimum(np.ceil(nlist / 8), 32)) / nlist
-    cost = cost + sizes  # linear stages
-    owner = np.zeros(sizes.shape[0], np.int64)
+        nlist = np.maximum(1.0, 2.0 ** np.floor(np.log2(np.maximum(c, 39.0) / 39.0)))
+        nlist = np.where(c < 100, 1.0, nlist)
+        cost = cost * np.maximum(1.0, np.minimum(np.ceil(nlist / 8), n_probe)) / nlist
+    return cost + q
+
+
+def lpt_assign(cost, world_size: int) -> np.ndarray:
+    """Longest-processing-time bin packing: owner rank of every unit (deterministic)."""
+    cost = np.asarray(cost, np.float64)
+    owner = np.zeros(cost.shape[0], np.int64)
     load = np.zeros(world_size)
     for b in np.argsort(-cost, kind="stable"):
         r = int(np.argmin(load))
         owner[b] = r
         load[r] += cost[b]
     return owner
+
+
+def shard_buckets(bucket_sizes, world_size: int, exhaustive: bool = True) -> np.ndarray:
+    """Rank of every bucket: longest-processing-time bin packing by the scan
+    cost ``n_b^2`` (exhaustive) / ``n_b^2 * nprobe / nlist`` (IVF)."""
+    sizes = np.asarray(bucket_sizes, np.float64)
+    return lpt_assign(unit_cost(sizes, sizes, exhaustive), world_size)
 
 
 def gather_labels(labels: torch.Tensor, n_clusters: int, group=None):
@@ -109,3 +123,257 @@ def gather_representatives(representatives: torch.Tensor, n_spectra: int, group=
     dist.all_gather_into_tensor(out, padded, group=group)
     parts = [out[r * max_len: r * max_len + lens[r]] for r in range(world)]
     return torch.cat(parts) if parts else out
+
+
+# --------------------------------------------------------------------------- one data set over N GPUs
+def same_partition(a, b) -> bool:
+    """Two label arrays describe the same clustering up to renaming (-1 = noise must coincide)."""
+    a, b = np.asarray(a, np.int64), np.asarray(b, np.int64)
+    if a.shape != b.shape or ((a < 0) != (b < 0)).any():
+        return False
+    m = a >= 0
+    if not m.any():
+        return True
+    pa, pb = a[m], b[m]
+    # a -> b and b -> a must both be functions
+    ua, ia = np.unique(pa, return_index=True)
+    ub, ib = np.unique(pb, return_index=True)
+    return bool(ua.shape == ub.shape and (pb[ia][np.searchsorted(ua, pa)] == pb).all()
+                and (pa[ib][np.searchsorted(ub, pb)] == pa).all())
+
+
+def plan_units(bucket_ptr, mz_sorted, world_size: int, tol: float, tol_mode: str, exhaustive: bool = True,
+               bucket_cap=None, n_probe: int = 32):
+    """Work units of one bucket-sorted data set and their owner ranks.
+
+    A precursor bucket is an independent unit (the published pipeline never searches across buckets).
+    A bucket of more than ``bucket_cap`` rows is cut into contiguous pieces of its precursor-m/z order; a
+    piece owns the queries ``[q0, q1)`` and additionally loads the candidates inside one precursor
+    tolerance of its m/z range, ``[c0, c1)`` (the halo), so its sparse rows are complete; DBSCAN of a cut
+    bucket runs on one rank after the rows have been gathered (``cluster_sharded``).  ``bucket_cap=None``
+    picks the cap that keeps any one unit below a rank's fair share of the scan cost.
+
+    Returns a dict of int64 arrays, one entry per unit, in row order: ``bucket, q0, q1, c0, c1, piece
+    (0/1), owner``; rows are positions in the bucket-sorted order."""
+    bptr = np.asarray(bucket_ptr, np.int64)
+    mz = np.asarray(mz_sorted, np.float64)
+    sizes = np.diff(bptr)
+    if bucket_cap is None:
+        total = float(unit_cost(sizes, sizes, exhaustive, n_probe).sum())
+        bucket_cap = max(4096, int(np.sqrt(total / max(world_size, 1)))) if world_size > 1 else int(sizes.max(initial=0)) + 1
+    bucket_cap = max(int(bucket_cap), 1)
+    cols = {k: [] for k in ("bucket", "q0", "q1", "c0", "c1", "piece")}
+
+    def add(b, q0, q1, c0, c1, piece):
+        for k, v in zip(cols, (b, q0, q1, c0, c1, piece)):
+            cols[k].append(v)
+
+    big = sizes > bucket_cap
+    for b in range(sizes.shape[0]):
+        s, e = int(bptr[b]), int(bptr[b + 1])
+        if not big[b]:
+            add(b, s, e, s, e, 0)
+            continue
+        k = -(-(e - s) // bucket_cap)
+        seg = mz[s:e]
+        # |dm| < tol (Da) or |dm| / mz_candidate * 1e6 < tol (ppm): a superset of the candidates in reach
+        halo = tol if tol_mode == "Da" else tol * 1e-6 * float(seg[-1]) * (1.0 + 1e-6)
+        halo = halo * (1.0 + 1e-9) + 1e-12
+        for i in range(k):
+            q0, q1 = s + (e - s) * i // k, s + (e - s) * (i + 1) // k
+            c0 = s + int(np.searchsorted(seg, mz[q0] - halo, "left"))
+            c1 = s + int(np.searchsorted(seg, mz[q1 - 1] + halo, "right"))
+            add(b, q0, q1, c0, c1, 1)
+    units = {k: np.asarray(v, np.int64) for k, v in cols.items()}
+    units["owner"] = lpt_assign(unit_cost(units["q1"] - units["q0"], units["c1"] - units["c0"], exhaustive, n_probe),
+                                world_size)
+    return units
+
+
+def all_gather_var(t: torch.Tensor, group=None):
+    """All ranks' 1-D (or [k, len]) tensors of different lengths along the last axis -> list in rank
+    order.  Two collectives (lengths, padded payload) and one host synchronisation."""
+    world = dist.get_world_size(group)
+    dev = t.device
+    n = t.shape[-1]
+    lens_t = torch.empty(world, dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(lens_t, torch.tensor([n], dtype=torch.int64, device=dev), group=group)
+    lens = [int(x) for x in lens_t.cpu().tolist()]
+    mx = max(lens)
+    lead = tuple(t.shape[:-1])
+    pad = torch.zeros(lead + (mx,), dtype=t.dtype, device=dev)
+    pad[..., :n] = t
+    out = torch.empty(world * pad.numel(), dtype=t.dtype, device=dev)
+    dist.all_gather_into_tensor(out, pad.reshape(-1), group=group)
+    out = out.view((world,) + lead + (mx,))
+    return [out[r][..., : lens[r]] for r in range(world)]
+
+
+def _segments(starts: torch.Tensor, counts: torch.Tensor) -> torch.Tensor:
+    """Concatenation of the index ranges [starts[i], starts[i] + counts[i])."""
+    total = int(counts.sum().item())
+    dev = starts.device
+    if total == 0:
+        return torch.zeros(0, dtype=torch.int64, device=dev)
+    ptr = torch.cumsum(counts, 0) - counts
+    seg = torch.repeat_interleave(torch.arange(counts.shape[0], device=dev), counts)
+    return starts[seg] + (torch.arange(total, device=dev) - ptr[seg])
+
+
+def cluster_sharded(spectra, settings=None, device=None, group=None, bucket_cap=None):
+    """Cluster ONE data set on all ranks of ``group``: every rank holds the same host ``spectra``
+    (a ``synth.SpectrumSet``-like object), takes its share of the precursor buckets
+    (``plan_units``), runs the hot path on them with no data-path communication, and the labels
+    and cluster representatives are gathered at the end (running label offset of
+    /root/reference/falcon/falcon.py:189-193).  A bucket larger than ``bucket_cap`` is cut into
+    pieces with a halo of one precursor tolerance; the pieces' sparse rows are gathered and the
+    bucket's DBSCAN runs on one rank, so the result is the single-GPU partition (in exhaustive mode;
+    with the IVF index a cut bucket trains one index per piece instead of one per bucket).
+
+    Returns ``(labels, n_clusters, representatives)`` on every rank: int32 labels in INPUT order
+    (-1 = noise), the number of clusters, and -- with ``settings.representatives`` -- the input index of
+    every cluster's medoid (label order), else None.  Works without an initialised process group
+    (one rank)."""
+    from . import pipeline
+    from ._lib import check, lib, ptr
+
+    s = settings or pipeline.Settings()
+    hp = pipeline.HotPath(s, device)
+    dev = hp.device
+    multi = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+    world = dist.get_world_size(group) if multi else 1
+    rank = dist.get_rank(group) if multi else 0
+    n = len(spectra.precursor_mz)
+    use_rt = s.rt_tol is not None
+    up = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a, dtype=dt)).to(dev)  # noqa: E731
+    if n == 0:
+        return np.zeros(0, np.int32), 0, (np.zeros(0, np.int64) if s.representatives else None)
+    # ---- every rank: bucket order of the whole data set (12 bytes per spectrum), the plan
+    b = hp.bucket_sort(up(spectra.precursor_mz, np.float64), up(spectra.precursor_charge, np.int32),
+                       up(spectra.retention_time, np.float32) if use_rt else None)
+    order_h = b.order.cpu().numpy().astype(np.int64)
+    units = plan_units(b.bucket_ptr.cpu().numpy(), b.mz.cpu().numpy(), world, s.precursor_tol_mass,
+                       s.precursor_tol_mode, s.exhaustive, bucket_cap, s.n_probe)
+    mine = np.flatnonzero(units["owner"] == rank)
+    whole = mine[units["piece"][mine] == 0]
+    pieces = mine[units["piece"][mine] == 1]
+    # local rows: whole buckets first (their sparse rows never point at a piece), then the pieces' halo ranges
+    lo = np.r_[units["q0"][whole], units["c0"][pieces]]
+    hi = np.r_[units["q1"][whole], units["c1"][pieces]]
+    sizes = hi - lo
+    n_whole = int((units["q1"][whole] - units["q0"][whole]).sum())
+    n_local = int(sizes.sum())
+    l2g_h = np.concatenate([np.arange(a, c) for a, c in zip(lo, hi)] or [np.zeros(0, np.int64)]).astype(np.int64)
+    l2g = up(l2g_h, np.int64)
+    mz_all, rt_all = b.mz, b.rt
+    g = None
+    if n_local:
+        sub = spectra.take(order_h[l2g_h])
+        bptr_l = np.zeros(sizes.shape[0] + 1, np.int64)
+        np.cumsum(sizes, out=bptr_l[1:])
+        lb = pipeline.Buckets(None, None, mz_all[l2g], rt_all[l2g] if use_rt else None, up(bptr_l, np.int64),
+                              int(sizes.shape[0]))
+        v = hp.vectorize(up(sub.mz, np.float32), up(sub.intensity, np.float32), up(sub.indptr, np.int64),
+                         want_f32=False, max_peaks=int(np.diff(sub.indptr).max(initial=0)))
+        ivf = None if s.exhaustive else hp.build_ivf(v, lb)
+        g = hp.knn_graph(v, lb, ivf)
+        if v.overflow is not None and int(v.overflow.item()) > 0:
+            raise RuntimeError("a spectrum hashed to more distinct columns than the sparse rows hold")
+
+    def stage4(graph, rows_g, n_rows):
+        """DBSCAN + split (+ medoids) of complete rows; rows_g = their positions in the global bucket order."""
+        if n_rows == 0:
+            z = torch.zeros(0, dtype=torch.int32, device=dev)
+            return z, 0, torch.zeros(0, dtype=torch.int64, device=dev)
+        db, _ = hp.dbscan(graph, n_rows)
+        lab, nc = hp.split(db, mz_all[rows_g], values_sorted=True, rt=rt_all[rows_g] if use_rt else None)
+        reps = torch.zeros(0, dtype=torch.int64, device=dev)
+        if s.representatives and nc:
+            reps = rows_g[hp.medoids(graph, lab, nc).long()]
+        return lab, nc, reps
+
+    # ---- whole buckets: the prefix of the local matrix
+    if n_whole:
+        nnz_w = int(g.indptr[n_whole].item())
+        gw = pipeline.KnnGraph(g.dist[:nnz_w], g.indices[:nnz_w], g.indptr[: n_whole + 1], nnz_w)
+    lab_w, nc_w, rep_w = stage4(gw if n_whole else None, l2g[:n_whole], n_whole)
+    rows_out, labs_out, reps_out, nc_local = [l2g[:n_whole]], [lab_w], [rep_w], nc_w
+    # ---- cut buckets: gather the pieces' query rows, DBSCAN of a bucket on its home rank
+    cut = np.unique(units["bucket"][units["piece"] == 1])
+    if cut.size:
+        row_parts, ent_parts = [], []
+        off = n_whole
+        for u in pieces:
+            c0, c1, q0, q1 = (int(units[k][u]) for k in ("c0", "c1", "q0", "q1"))
+            ls, le = off + (q0 - c0), off + (q1 - c0)
+            a, e = int(g.indptr[ls].item()), int(g.indptr[le].item())
+            row_parts.append(torch.stack([torch.arange(q0, q1, device=dev, dtype=torch.int32),
+                                          (g.indptr[ls + 1: le + 1] - g.indptr[ls:le]).to(torch.int32)]))
+            ent_parts.append(torch.stack([l2g[g.indices[a:e].long()].to(torch.int32),
+                                          g.dist[a:e].view(torch.int32)]))
+            off += c1 - c0
+        z2 = torch.zeros((2, 0), dtype=torch.int32, device=dev)
+        rows_mine = torch.cat(row_parts, 1) if row_parts else z2
+        ents_mine = torch.cat(ent_parts, 1) if ent_parts else z2
+        if multi:
+            rows_all = torch.cat(all_gather_var(rows_mine, group), 1)
+            ents_all = torch.cat(all_gather_var(ents_mine, group), 1)
+        else:
+            rows_all, ents_all = rows_mine, ents_mine
+        home = cut[np.arange(cut.size) % world == rank]  # buckets whose stage 4 runs here
+        bp_h = b.bucket_ptr.cpu().numpy()
+        if home.size:
+            row_g, cnt = rows_all[0].long(), rows_all[1].long()
+            ent_start = torch.cumsum(cnt, 0) - cnt
+            h_lo, h_hi = up(bp_h[home], np.int64), up(bp_h[home + 1], np.int64)
+            h_off = torch.cumsum(h_hi - h_lo, 0) - (h_hi - h_lo)  # position of a home bucket in the concatenation
+            n_home = int((h_hi - h_lo).sum().item())
+
+            def to_pos(gidx):  # global row -> row of the assembled matrix (-1: not in a home bucket)
+                j = torch.searchsorted(h_lo, gidx, right=True) - 1
+                jc = j.clamp(min=0)
+                ok = (j >= 0) & (gidx < h_hi[jc])
+                return torch.where(ok, gidx - h_lo[jc] + h_off[jc], torch.full_like(gidx, -1))
+
+            pos = to_pos(row_g)
+            sel = torch.nonzero(pos >= 0).squeeze(1)
+            sel = sel[torch.argsort(pos[sel])]
+            if sel.shape[0] != n_home:
+                raise RuntimeError("gathered rows of the cut buckets are incomplete")
+            cnt_s = cnt[sel]
+            indptr = torch.zeros(n_home + 1, dtype=torch.int64, device=dev)
+            torch.cumsum(cnt_s, 0, out=indptr[1:])
+            src = _segments(ent_start[sel], cnt_s)
+            cols = to_pos(ents_all[0][src].long()).to(torch.int32)
+            gh = pipeline.KnnGraph(ents_all[1][src].contiguous().view(torch.float32), cols.contiguous(), indptr,
+                                   int(src.shape[0]))
+            rows_h = _segments(h_lo, h_hi - h_lo)
+            lab_h, nc_h, rep_h = stage4(gh, rows_h, n_home)
+            rows_out.append(rows_h)
+            labs_out.append(torch.where(lab_h >= 0, lab_h + nc_local, lab_h))
+            reps_out.append(rep_h)
+            nc_local += nc_h
+    # ---- final gather: (row, label) of every rank, labels made disjoint by the running offset
+    pay = torch.stack([torch.cat(rows_out).to(torch.int32), torch.cat(labs_out).to(torch.int32)])
+    reps_l = torch.cat(reps_out)
+    if multi:
+        meta = torch.tensor([nc_local], dtype=torch.int64, device=dev)
+        metas = torch.empty(world, dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(metas, meta, group=group)
+        parts = all_gather_var(pay, group)
+        offs = (torch.cumsum(metas, 0) - metas).tolist()
+        parts = [torch.stack([p[0], torch.where(p[1] >= 0, p[1] + int(o), p[1])]) for p, o in zip(parts, offs)]
+        pay = torch.cat(parts, 1)
+        n_clusters = int(metas.sum().item())
+        reps_l = torch.cat(all_gather_var(reps_l, group)) if s.representatives else reps_l
+    else:
+        n_clusters = nc_local
+    if pay.shape[1] != n:
+        raise RuntimeError(f"{pay.shape[1]} labelled rows gathered for {n} spectra")
+    labels_sorted = torch.empty(n, dtype=torch.int32, device=dev)
+    labels_sorted[pay[0].long()] = pay[1]
+    labels = torch.empty(n, dtype=torch.int32, device=dev)
+    check(lib.flc_scatter32(ptr(labels_sorted), ptr(b.order), n, ptr(labels),
+                            torch.cuda.current_stream().cuda_stream))
+    reps = b.order[reps_l].cpu().numpy().astype(np.int64) if s.representatives else None
+    return labels.cpu().numpy(), n_clusters, reps

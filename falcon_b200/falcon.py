@@ -34,14 +34,7 @@ def _read_inputs(filenames: List[str]):
         sets.append(sp)
         idents.extend(ids)
         files.extend(os.path.basename(f) for f in fns)
-    if len(sets) == 1:
-        return sets[0], idents, files
-    cat = np.concatenate
-    indptr = np.zeros(sum(len(s) for s in sets) + 1, np.int64)
-    np.cumsum(cat([np.diff(s.indptr) for s in sets]), out=indptr[1:])
-    return synth.SpectrumSet(cat([s.mz for s in sets]), cat([s.intensity for s in sets]), indptr,
-                             cat([s.precursor_mz for s in sets]), cat([s.precursor_charge for s in sets]),
-                             cat([s.retention_time for s in sets])), idents, files
+    return synth.concat(sets), idents, files
 
 
 def _write_cluster_info(path: str, rows) -> None:

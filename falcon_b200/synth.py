@@ -119,6 +119,19 @@ class SpectrumSet:
         )
 
 
+def concat(sets) -> SpectrumSet:
+    """Concatenation of SpectrumSets (templates are dropped: their ids are per set)."""
+    sets = list(sets)
+    if len(sets) == 1:
+        return sets[0]
+    cat = np.concatenate
+    indptr = np.zeros(sum(len(s) for s in sets) + 1, np.int64)
+    np.cumsum(cat([np.diff(s.indptr) for s in sets]), out=indptr[1:])
+    return SpectrumSet(cat([s.mz for s in sets]), cat([s.intensity for s in sets]), indptr,
+                       cat([s.precursor_mz for s in sets]), cat([s.precursor_charge for s in sets]),
+                       cat([s.retention_time for s in sets]))
+
+
 def generate(
     n: int,
     seed: int = 42,

@@ -28,8 +28,12 @@ def _worker(rank, world, port, q):
     # a rank without spectra (an empty shard) still takes part
     empty = labels if rank == 0 else labels[:0]
     padded2, plens2 = fd.gather_labels_padded(empty, ncl if rank == 0 else 0, max_len=5)
+    # variable-length gather of [k, len] payloads (cluster_sharded's row / entry exchange), empty part included
+    var = fd.all_gather_var(torch.arange(6, dtype=torch.int32).view(2, 3) + 10 * rank if rank == 0
+                            else torch.zeros((2, 0), dtype=torch.int32))
+    var1 = fd.all_gather_var(torch.arange(rank + 1, dtype=torch.int64))
     q.put((rank, out.tolist(), lens, rep_all.tolist(), padded.tolist(), plens.tolist(), padded2.tolist(),
-           plens2.tolist()))
+           plens2.tolist(), [v.tolist() for v in var], [v.tolist() for v in var1]))
     dist.destroy_process_group()
 
 
@@ -44,7 +48,8 @@ def test_gather_labels_gloo_world2():
     for p in procs:
         p.join(60)
         assert p.exitcode == 0
-    for _, out, lens, reps, padded, plens, padded2, plens2 in res:
+    for _, out, lens, reps, padded, plens, padded2, plens2, var, var1 in res:
+        assert var == [[[0, 1, 2], [3, 4, 5]], [[], []]] and var1 == [[0], [0, 1]]
         assert plens2 == [5, 0] and padded2 == [[0, -1, 1, 1, 0], [-1] * 5]
         assert out == [0, -1, 1, 1, 0, -1, 2, 2] and lens == [5, 3]
         # the single-collective variant: same labels, padded to max_len with -1
@@ -94,3 +99,38 @@ def test_sharded_clustering_equals_single_run():
             merged[rows] = np.where(back >= 0, back + offset, -1)
             offset += int(lab.max()) + 1 if lab.size and lab.max() >= 0 else 0
         assert odb.same_partition(merged, np.asarray(whole["labels"], np.int64))
+
+
+def test_plan_units_cuts_oversized_buckets_with_a_tolerance_halo():
+    rng = np.random.default_rng(3)
+    sizes = np.array([50, 3000, 10, 1200, 700])
+    bptr = np.r_[0, np.cumsum(sizes)]
+    mz = np.concatenate([np.sort(500.0 + b + rng.uniform(0, 0.5, s)) for b, s in enumerate(sizes)])
+    for mode, tol in (("ppm", 20.0), ("Da", 0.01)):
+        u = fd.plan_units(bptr, mz, 3, tol, mode, bucket_cap=1000)
+        assert (np.bincount(u["bucket"]) == [1, 3, 1, 2, 1]).all()
+        # queries: every row exactly once, in order; pieces stay inside their bucket
+        assert np.array_equal(np.concatenate([np.arange(a, b) for a, b in zip(u["q0"], u["q1"])]), np.arange(sizes.sum()))
+        assert (u["c0"] <= u["q0"]).all() and (u["c1"] >= u["q1"]).all()
+        assert (u["c0"] >= bptr[u["bucket"]]).all() and (u["c1"] <= bptr[u["bucket"] + 1]).all()
+        assert (u["owner"] >= 0).all() and (u["owner"] < 3).all() and len(set(u["owner"].tolist())) == 3
+        for i in np.flatnonzero(u["piece"] == 1):
+            q = mz[u["q0"][i]: u["q1"][i]]
+            b0, b1 = bptr[u["bucket"][i]], bptr[u["bucket"][i] + 1]
+            cand = mz[b0:b1]
+            d = np.abs(q[:, None] - cand[None, :])
+            reach = (d < tol) if mode == "Da" else (d / cand[None, :] * 1e6 < tol)
+            need = np.flatnonzero(reach.any(axis=0)) + b0  # every candidate some query of the piece can reach
+            assert need.min() >= u["c0"][i] and need.max() < u["c1"][i]
+            assert u["c1"][i] - u["c0"][i] < (b1 - b0)  # and the halo is not the whole bucket
+    # no cap needed on one rank; the automatic cap leaves small buckets whole
+    assert (fd.plan_units(bptr, mz, 1, 20.0, "ppm")["piece"] == 0).all()
+    assert (fd.plan_units(bptr, mz, 2, 20.0, "ppm")["piece"] == 0).all()
+
+
+def test_same_partition():
+    assert fd.same_partition([0, 0, 1, -1, 2], [5, 5, 3, -1, 9])
+    assert not fd.same_partition([0, 0, 1, -1, 2], [5, 5, 5, -1, 9])
+    assert not fd.same_partition([0, 0, 1, -1, 2], [5, 4, 3, -1, 9])
+    assert not fd.same_partition([0, 0, 1, -1, 2], [5, 5, 3, 1, 9])
+    assert fd.same_partition([-1, -1], [-1, -1]) and not fd.same_partition([0], [0, 0])
