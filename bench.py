@@ -36,6 +36,7 @@ if ROOT not in sys.path:
 
 METRIC = "spectra_per_sec_end_to_end"
 UNIT = "spectra/s"
+NCU_TRAFFIC_FILE = "r02_ncu_traffic.json"  # DRAM bytes per launch from this round's ncu --set full captures
 FALLBACK_PEAKS = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}
 
 
@@ -206,10 +207,10 @@ def kernel_rooflines(stats: dict, peaks: dict) -> dict:
                       + n * (stats.get("ell_width", 0) * 6 + 2)),
         # HBM floor of the scan: every bf16 row read once, pairs written once
         "scan_tc": ("hbm", n * ldb * 2 + pairs * 8),
-        # pairs in/out + exact re-score rows (L2-resident in practice) + m/z + row counts
-        # re-score + selection (refine_block and, for the query groups it defers, refine: one logical launch)
-        "refine_block": ("hbm", pairs * 16 + pairs * stats.get("ell_width", 0) * 6
-                   + n * (stats.get("ell_width", 0) * 6 + 8 + 8 + 4)),
+        # re-score + selection (refine_block and, for the query groups it defers, refine: one logical launch):
+        # pairs in / out, every sparse row ONCE (a candidate row is re-read once per pair it takes part in, but
+        # those re-reads are served by L2 -- ncu: 0.38 GB of DRAM reads at 1 M), m/z + row counts, CSR entries out
+        "refine_block": ("hbm", pairs * 16 + n * (stats.get("ell_width", 0) * 6 + 8 + 8 + 4) + nnz * 8),
         "pair_hist": ("hbm", pairs * 8 + pairs * 4),
         "pair_scatter": ("hbm", pairs * 16 + pairs * 12),
         "csr_compact": ("hbm", nnz * 16 + (n + 1) * 24),
@@ -256,14 +257,18 @@ def kernel_rooflines(stats: dict, peaks: dict) -> dict:
         ms, launches = stats["kernels"]["scan_tc"]
         tf = 2.0 * d * stats["required_pairs"] / (ms / launches * 1e-3) / 1e12
         pk = peaks["bf16_tflops"]
-        # `achieved` follows SURVEY 8(d): FLOPs of the (query, member) pairs the IVF semantics require.  The kernel
-        # multiplies `computed_pairs` (whole buckets, but only the tiles at or above the diagonal of the symmetric
-        # product): `executed` is what the tensor pipe really did, the hardware-utilisation view
+        # The tensor roofline is over the FLOPs the tensor pipe EXECUTES (`computed_pairs`: whole buckets, but only
+        # the tiles at or above the diagonal of the symmetric product) -- a fraction of peak by construction <= 1.
+        # `required` is SURVEY 8(d)'s count, the (query, member) pairs the IVF semantics ask for: in exhaustive
+        # mode the symmetric kernel executes about half of them (ratio > 1), with the IVF index it executes a
+        # superset (ratio < 1); it is reported as a rate, not as a fraction of peak.
         ex = 2.0 * d * stats["computed_pairs"] / (ms / launches * 1e-3) / 1e12
-        out["scan_tc"]["tensor"] = {"achieved": tf, "peak": pk, "unit": "TFLOP/s", "frac": tf / pk,
+        out["scan_tc"]["tensor"] = {"achieved": ex, "peak": pk, "unit": "TFLOP/s", "frac": ex / pk,
+                                    "executed_frac": ex / pk,
                                     "required_pairs": stats["required_pairs"],
                                     "computed_pairs": stats["computed_pairs"],
-                                    "executed": ex, "executed_frac": ex / pk}
+                                    "required_tflops": tf,
+                                    "computed_over_required": stats["computed_pairs"] / max(stats["required_pairs"], 1.0)}
     return out
 
 
@@ -291,6 +296,138 @@ def bind_to_gpu_numa_node(torch, local: int) -> None:
 
 
 # --------------------------------------------------------------------------- main arm
+class Workload:
+    """One rank's batch of spectra, resident in HBM and in pinned host memory, and the step functions
+    over it (resident / host API / host API software-pipelined)."""
+
+    def __init__(self, torch, fdist, hp, sp, dev, world):
+        self.torch, self.fdist, self.hp, self.sp, self.dev, self.world = torch, fdist, hp, sp, dev, world
+        self.n = len(sp)
+        self.host = {k: torch.from_numpy(np.ascontiguousarray(v)).pin_memory() for k, v in dict(
+            mz=sp.mz, intensity=sp.intensity, indptr=sp.indptr, precursor_mz=sp.precursor_mz,
+            charge=sp.precursor_charge).items()}
+        self.h2d_bytes = sum(t.numel() * t.element_size() for t in self.host.values())
+        self.d = {k: v.to(dev) for k, v in self.host.items()}
+        self.labels_host = torch.empty(self.n, dtype=torch.int32).pin_memory()
+        self.max_peaks = int(np.diff(sp.indptr).max())  # falcon's max_peaks_used setting (known up front)
+        self.gather_stream = torch.cuda.Stream(device=dev) if world > 1 else None
+        self.peer_gather = None
+        if world > 1 and os.environ.get("FLC_GATHER", "peer") == "peer":
+            try:  # labels stored into the peers' buffers over NVLink by the step's last kernel
+                self.peer_gather = fdist.PeerLabelGather(self.n, dev)
+                hp.label_sink = self.peer_gather
+            except Exception as exc:  # noqa: BLE001 -- no symmetric memory on this platform: NCCL all-gather
+                log(f"[bench] peer-memory label gather unavailable ({exc!r}); using NCCL all_gather")
+        self.gather_mode = "nvlink peer stores (flc_scatter_labels_peers)" if self.peer_gather else \
+            ("nccl all_gather" if world > 1 else "none")
+
+    def gather(self, labels, n_clusters):
+        if self.peer_gather is not None:
+            return self.peer_gather.last[0]
+        # Every rank's batch has the same number of spectra: one collective, label offsets computed on the
+        # device, no host sync.  The collective runs on a side stream behind this batch's labels, so a rank that
+        # finishes its batch early starts the next one instead of idling in the all-gather until its peers
+        # arrive; the timed region ends only after every gather has completed (wait_gathers).
+        if self.world > 1:
+            torch = self.torch
+            done = torch.cuda.Event()
+            done.record()
+            with torch.cuda.stream(self.gather_stream):
+                self.gather_stream.wait_event(done)
+                out = self.fdist.gather_labels_padded(labels, n_clusters, max_len=self.n)[0]
+            labels.record_stream(self.gather_stream)
+            return out
+        return labels
+
+    def wait_gathers(self):
+        if self.peer_gather is not None:
+            self.peer_gather.wait()
+        elif self.gather_stream is not None:
+            self.torch.cuda.current_stream().wait_stream(self.gather_stream)
+
+    def step_resident(self):
+        d = self.d
+        labels, nc = self.hp.run(d["mz"], d["intensity"], d["indptr"], d["precursor_mz"], d["charge"],
+                                 max_peaks=self.max_peaks)
+        return self.gather(labels, nc), nc
+
+    def step_e2e(self):
+        # host (pinned) buffers in, labels back on the host: chunked H2D overlapped with vectorisation
+        h = self.host
+        labels, nc = self.hp.run_host(h["mz"], h["intensity"], h["indptr"], h["precursor_mz"], h["charge"],
+                                      labels_out=self.labels_host, max_peaks=self.max_peaks)
+        out = self.gather(labels, nc)
+        self.torch.cuda.current_stream().synchronize()
+        return out, nc
+
+    def run_e2e_pipelined(self, steps):
+        """K batches through the host API, software-pipelined two deep: batch i + 1 is staged
+        (its H2D copies enqueued on the copy stream) before batch i's kernels run.  Every
+        batch's H2D, kernels and D2H are inside the caller's timed region."""
+        h, hp = self.host, self.hp
+        stage = lambda: hp.stage_host(h["mz"], h["intensity"], h["indptr"], h["precursor_mz"], h["charge"],  # noqa: E731
+                                      max_peaks=self.max_peaks)
+        out = None
+        staged = stage()
+        for i in range(steps):
+            nxt = stage() if i + 1 < steps else None
+            labels, nc = hp.run_staged(staged, labels_out=self.labels_host)
+            out = (self.gather(labels, nc), nc)
+            staged = nxt
+        self.torch.cuda.current_stream().synchronize()
+        return out
+
+    def plain_copy(self):
+        """The same host buffers copied to the device and the labels copied back, nothing else: the PCIe floor
+        of the host API at this number of concurrently copying ranks."""
+        for k, v in self.host.items():
+            self.d[k].copy_(v, non_blocking=True)
+        self.labels_host.copy_(self.d["charge"][: self.n].view(self.torch.int32), non_blocking=True)
+        return None, 0
+
+
+def scan_pair_stats(torch, keep, n, dev):
+    """(computed_pairs, required_pairs, sizes): what the scan multiplies vs what the IVF semantics require."""
+    sizes = (keep["buckets"].bucket_ptr[1:] - keep["buckets"].bucket_ptr[:-1]).double()
+    # pairs the scan actually multiplies: query tile i (128 rows) of a bucket meets the candidate rows from its
+    # own first row to the bucket's end (S = X X^T is symmetric: scan_tc.cu)
+    nb_np = sizes.cpu().numpy()
+    computed_pairs = 0.0
+    for i in range(int(np.ceil(nb_np.max() / 128.0)) if nb_np.size else 0):
+        rows_i = np.clip(nb_np - 128.0 * i, 0.0, 128.0)
+        computed_pairs += float((rows_i * np.maximum(nb_np - 128.0 * i, 0.0)).sum())
+    required_pairs = float((sizes * sizes).sum().item())
+    ivf = keep["ivf"]
+    extra = {}
+    if ivf is not None:
+        bp = keep["buckets"].bucket_ptr
+        b_of_row = torch.searchsorted(bp, torch.arange(n, device=dev), right=True) - 1
+        max_l = int(ivf.nlist.max().item()) + 1
+        lsize = torch.bincount(b_of_row * max_l + ivf.list_id.long(), minlength=int(bp.shape[0]) * max_l)
+        pr = ivf.probes.long()
+        valid = pr >= 0
+        idx = (b_of_row[:, None] * max_l + pr.clamp(min=0))
+        required_pairs = float((lsize[idx] * valid).sum().item())
+        nl = ivf.nlist[:-1].long()
+        row_in_ivf = (nl > 0)[b_of_row]
+        ell_nnz = keep["vectors"].ell_nnz.long() & 0xFFFF
+        extra = {"ell_width": keep["vectors"].ell_width, "max_nprobe": ivf.max_nprobe,
+                 "ivf_rows": int(sizes[nl > 0].sum().item()), "ivf_nnz": int(ell_nnz[row_in_ivf].sum().item()),
+                 "total_centroids": ivf.total_centroids}
+    return computed_pairs, required_pairs, sizes, extra
+
+
+def merge_kernel_classes(kernels: dict) -> dict:
+    if "kmeans_fused_large" in kernels:  # the two size classes of the fused trainer: one logical launch
+        big = kernels.pop("kmeans_fused_large")
+        small = kernels.get("kmeans_fused", (0.0, big[1]))
+        kernels["kmeans_fused"] = (small[0] + big[0], small[1])
+    if "refine_block" in kernels and "refine" in kernels:  # fast path + the query groups it defers
+        rest = kernels.pop("refine")
+        kernels["refine_block"] = (kernels["refine_block"][0] + rest[0], kernels["refine_block"][1])
+    return kernels
+
+
 def run_ours(args):
     import torch
 
@@ -325,71 +462,15 @@ def run_ours(args):
         kw = {"mass_range": (lo + (hi - lo) * rank / world, lo + (hi - lo) * (rank + 1) / world)}
     sp = synth.generate(args.n, 42 + rank, **kw)
     log(f"[rank {rank}] generated {len(sp)} spectra / {sp.n_peaks} peaks in {time.perf_counter() - t0:.1f}s")
-    host = {k: torch.from_numpy(np.ascontiguousarray(v)).pin_memory() for k, v in dict(
-        mz=sp.mz, intensity=sp.intensity, indptr=sp.indptr, precursor_mz=sp.precursor_mz,
-        charge=sp.precursor_charge).items()}
-    h2d_bytes = sum(t.numel() * t.element_size() for t in host.values())
-    d = {k: v.to(dev) for k, v in host.items()}
-    labels_host = torch.empty(len(sp), dtype=torch.int32).pin_memory()
-
-    gather_stream = torch.cuda.Stream(device=dev) if world > 1 else None
-
-    def gather(labels, n_clusters):
-        # Every rank's batch has args.n spectra: one collective, label offsets computed on the device, no host
-        # sync.  The collective runs on a side stream behind this batch's labels, so a rank that finishes its
-        # batch early starts the next one instead of idling in the all-gather until its peers arrive; the timed
-        # region ends only after every gather has completed (wait_gathers).
-        if world > 1:
-            done = torch.cuda.Event()
-            done.record()
-            with torch.cuda.stream(gather_stream):
-                gather_stream.wait_event(done)
-                out = fdist.gather_labels_padded(labels, n_clusters, max_len=args.n)[0]
-            labels.record_stream(gather_stream)
-            return out
-        return labels
-
-    def wait_gathers():
-        if gather_stream is not None:
-            torch.cuda.current_stream().wait_stream(gather_stream)
-
-    max_peaks = int(np.diff(sp.indptr).max())  # falcon's max_peaks_used setting (known up front)
-
-    def step_resident():
-        labels, nc = hp.run(d["mz"], d["intensity"], d["indptr"], d["precursor_mz"], d["charge"],
-                            max_peaks=max_peaks)
-        return gather(labels, nc), nc
-
-    def step_e2e():
-        # host (pinned) buffers in, labels back on the host: chunked H2D overlapped with vectorisation
-        labels, nc = hp.run_host(host["mz"], host["intensity"], host["indptr"], host["precursor_mz"],
-                                 host["charge"], labels_out=labels_host, max_peaks=max_peaks)
-        out = gather(labels, nc)
-        torch.cuda.current_stream().synchronize()
-        return out, nc
-
-    def run_e2e_pipelined(steps):
-        """K batches through the host API, software-pipelined two deep: batch i + 1 is staged
-        (its H2D copies enqueued on the copy stream) before batch i's kernels run.  Every
-        batch's H2D, kernels and D2H are inside the caller's timed region."""
-        out = None
-        staged = hp.stage_host(host["mz"], host["intensity"], host["indptr"], host["precursor_mz"],
-                               host["charge"], max_peaks=max_peaks)
-        for i in range(steps):
-            nxt = hp.stage_host(host["mz"], host["intensity"], host["indptr"], host["precursor_mz"],
-                                host["charge"], max_peaks=max_peaks) if i + 1 < steps else None
-            labels, nc = hp.run_staged(staged, labels_out=labels_host)
-            out = (gather(labels, nc), nc)
-            staged = nxt
-        torch.cuda.current_stream().synchronize()
-        return out
+    wl = Workload(torch, fdist, hp, sp, dev, world)
+    d, h2d_bytes, gather_mode = wl.d, wl.h2d_bytes, wl.gather_mode
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps, warmup, sample_clocks=False, profile=False):
+    def timed(wl_, fn, steps, warmup, sample_clocks=False, profile=False):
         # nvidia-smi takes ~0.1-0.5 s to initialise NVML (longer on a multi-GPU box) and holds driver locks while
         # it does: start it BEFORE the warm-up, wait for its first sample, and only then run warm-up + timed steps,
         # so that it samples during the timed region without its start-up landing inside it.  Rank 0 only.
@@ -409,7 +490,7 @@ def run_ours(args):
         a.record()
         for _ in range(steps):
             out = fn()
-        wait_gathers()
+        wl_.wait_gathers()
         b.record()
         torch.cuda.synchronize()
         launches = _lib.launch_count()
@@ -424,54 +505,24 @@ def run_ours(args):
             ms = float(t.item())
         return ms, out, launches, clocks
 
-    ms, (labels, n_clusters), launches, clocks = timed(step_resident, args.steps, args.warmup,
+    ms, (labels, n_clusters), launches, clocks = timed(wl, wl.step_resident, args.steps, args.warmup,
                                                        sample_clocks=True, profile=True)
-    kernels = _lib.profile_summary()
-    if "kmeans_fused_large" in kernels:  # the two size classes of the fused trainer: one logical launch
-        big = kernels.pop("kmeans_fused_large")
-        small = kernels.get("kmeans_fused", (0.0, big[1]))
-        kernels["kmeans_fused"] = (small[0] + big[0], small[1])
-    if "refine_block" in kernels and "refine" in kernels:  # fast path + the query groups it defers
-        rest = kernels.pop("refine")
-        kernels["refine_block"] = (kernels["refine_block"][0] + rest[0], kernels["refine_block"][1])
-    ms_e2e, _, _, _ = timed(step_e2e, args.steps, max(1, args.warmup - 1))
+    kernels = merge_kernel_classes(_lib.profile_summary())
+    ms_e2e, _, _, _ = timed(wl, wl.step_e2e, args.steps, max(1, args.warmup - 1))
     # the same K batches, software-pipelined two deep (one call = K steps)
-    ms_pipe, _, _, _ = timed(lambda: run_e2e_pipelined(args.steps), 1, 1)
+    ms_pipe, _, _, _ = timed(wl, lambda: wl.run_e2e_pipelined(args.steps), 1, 1)
     ms_pipe /= args.steps
+    # PCIe floor of the host API: the same pinned buffers copied in (and the labels out) by all ranks at once
+    ms_copy, _, _, _ = timed(wl, wl.plain_copy, args.steps, 1)
     total = args.n * world
 
     # one instrumented pass for the roofline statistics (outside the timed regions)
     hp2 = pipeline.HotPath(settings, dev, profile=False)
-    hp2.run(d["mz"], d["intensity"], d["indptr"], d["precursor_mz"], d["charge"], max_peaks=max_peaks)  # warm scratch
+    hp2.run(d["mz"], d["intensity"], d["indptr"], d["precursor_mz"], d["charge"], max_peaks=wl.max_peaks)  # warm scratch
     hp2.timer = pipeline._Timer(True)
     _, _, keep = hp2.run(d["mz"], d["intensity"], d["indptr"], d["precursor_mz"], d["charge"], keep=True)
     stage_ms = hp2.timer.result()
-    sizes = (keep["buckets"].bucket_ptr[1:] - keep["buckets"].bucket_ptr[:-1]).double()
-    # pairs the scan actually multiplies: query tile i (128 rows) of a bucket meets the candidate rows from its
-    # own first row to the bucket's end (S = X X^T is symmetric: scan_tc.cu)
-    nb_np = sizes.cpu().numpy()
-    computed_pairs = 0.0
-    for i in range(int(np.ceil(nb_np.max() / 128.0)) if nb_np.size else 0):
-        rows_i = np.clip(nb_np - 128.0 * i, 0.0, 128.0)
-        computed_pairs += float((rows_i * np.maximum(nb_np - 128.0 * i, 0.0)).sum())
-    required_pairs = float((sizes * sizes).sum().item())
-    ivf = keep["ivf"]
-    stats_extra = {}
-    if ivf is not None:
-        bp = keep["buckets"].bucket_ptr
-        b_of_row = torch.searchsorted(bp, torch.arange(args.n, device=dev), right=True) - 1
-        max_l = int(ivf.nlist.max().item()) + 1
-        lsize = torch.bincount(b_of_row * max_l + ivf.list_id.long(), minlength=int(bp.shape[0]) * max_l)
-        pr = ivf.probes.long()
-        valid = pr >= 0
-        idx = (b_of_row[:, None] * max_l + pr.clamp(min=0))
-        required_pairs = float((lsize[idx] * valid).sum().item())
-        nl = ivf.nlist[:-1].long()
-        row_in_ivf = (nl > 0)[b_of_row]
-        ell_nnz = keep["vectors"].ell_nnz.long() & 0xFFFF
-        stats_extra = {"ell_width": keep["vectors"].ell_width, "max_nprobe": ivf.max_nprobe,
-                       "ivf_rows": int(sizes[nl > 0].sum().item()), "ivf_nnz": int(ell_nnz[row_in_ivf].sum().item()),
-                       "total_centroids": ivf.total_centroids}
+    computed_pairs, required_pairs, sizes, stats_extra = scan_pair_stats(torch, keep, args.n, dev)
     stats = {"n": args.n, "n_peaks": sp.n_peaks, "low_dim": settings.low_dim, "ld_bf16": hp.ld_bf16,
              "dense_f32": 1 if settings.dense_f32 else 0, "ell_width": keep["vectors"].ell_width,
              "n_pairs": keep["graph"].n_pairs, "nnz": keep["graph"].nnz, "kernels": kernels,
@@ -499,7 +550,7 @@ def run_ours(args):
             roofline["note"] = ("fused k-means keeps a bucket's sparse rows in shared memory for all iterations: "
                                 "HBM sees every row once (the algorithmic bytes used here), the kernel itself is "
                                 "bound by shared-memory gathers and barriers -- see profiles/ for the smem-pipe figures")
-    ncu_traffic = os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")
+    ncu_traffic = os.path.join(ROOT, "profiles", NCU_TRAFFIC_FILE)
     if roofline and os.path.exists(ncu_traffic):  # DRAM bytes per launch from the committed ncu --set full capture
         t = json.load(open(ncu_traffic)).get(roofline["kernel"])
         if t and t.get("workload") == ("big" if args.mass_range else "default"):
@@ -517,6 +568,7 @@ def run_ours(args):
                                   f"{dt:.1f}s of CPU work",
                         "stages_s": stages}
 
+    out = None
     if rank == 0:
         bsz = sizes.cpu().numpy()
         out = {
@@ -527,11 +579,17 @@ def run_ours(args):
             "config": workload_config(args),
             "e2e": {"value": total / (ms_pipe * 1e-3), "unit": UNIT, "ms_per_step": ms_pipe,
                     "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": args.n * 4,
+                    "h2d_gbs_per_gpu": h2d_bytes / (ms_pipe * 1e-3) / 1e9,
                     "mode": "host API, batches software-pipelined two deep (stage_host of batch i+1 before "
                             "run_staged of batch i); all K batches' H2D + kernels + D2H inside the timed region",
-                    "unpipelined": {"value": total / (ms_e2e * 1e-3), "ms_per_step": ms_e2e}},
+                    "unpipelined": {"value": total / (ms_e2e * 1e-3), "ms_per_step": ms_e2e},
+                    "copy_floor": {"ms_per_step": ms_copy, "gbs_per_gpu": (h2d_bytes + args.n * 4) / (ms_copy * 1e-3) / 1e9,
+                                   "value": total / (ms_copy * 1e-3),
+                                   "what": "the same pinned buffers copied host->device (labels device->host) and "
+                                           "nothing else, by all ranks at once, max over ranks: the platform's "
+                                           "ceiling for the host API at this GPU count"}},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
-            "n_clusters": int(n_clusters),
+            "n_clusters": int(n_clusters), "label_gather": gather_mode,
             "stage_ms": stage_ms,
             "kernels_ms_per_step": {k: v[0] / args.steps for k, v in kernels.items()},
             "kernel_rooflines": {k: {"frac": v["frac"], "achieved": v["achieved"], "unit": v["unit"],
@@ -543,9 +601,119 @@ def run_ours(args):
                              "p99": float(np.percentile(bsz, 99)), "max": float(bsz.max())},
             "n_pairs": keep["graph"].n_pairs, "nnz": keep["graph"].nnz,
         }
+    # ---- free the headline workload, then the witnesses of the other configurations
+    del keep, hp2, d, wl, labels
+    torch.cuda.empty_cache()
+    mg = multi_gpu_check(args, torch, fdist, pipeline, synth, dev, world, rank) if world > 1 else None
+    ns = north_star_record(args, torch, fdist, pipeline, synth, _lib, dev, world, rank, dist, timed, peaks) \
+        if args.north_star_total else None
+    if rank == 0:
+        out["multi_gpu_check"] = mg
+        out["north_star_10m"] = ns
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def multi_gpu_check(args, torch, fdist, pipeline, synth, dev, world, rank):
+    """Outside every timed region: ONE data set clustered by all ranks through the product's sharded path
+    (`distributed.cluster_sharded`: buckets dealt to the ranks, oversized buckets cut with a tolerance halo,
+    labels + representatives gathered) must give the partition of the single-GPU run (rank 0, same data)."""
+    n = args.check_n
+    a = synth.generate(int(n * 0.6), 50, mass_range=(1000.0, 1012.0))  # buckets of several thousand rows: forced cuts
+    sp = synth.concat([a, synth.generate(n - len(a), 51)])
+    res = {"n": n, "world": world, "bucket_cap": 2000}
+    for exhaustive in (True, False):
+        s = pipeline.Settings(exhaustive=exhaustive, representatives=True)
+        # with the IVF index a cut bucket would train one index per piece: only whole buckets are dealt out
+        cap = 2000 if exhaustive else None
+        labels, nc, reps = fdist.cluster_sharded(sp, s, device=dev, bucket_cap=cap)
+        key = "exhaustive" if exhaustive else "default_nprobe"
+        if rank == 0:
+            ref, nc_ref, _ = pipeline.cluster_host(sp, s, device=dev)
+            units = fdist.plan_units(*_bucket_plan(torch, pipeline, sp, s, dev), world, s.precursor_tol_mass,
+                                     s.precursor_tol_mode, exhaustive, cap)
+            res[key] = {"equal_to_single_gpu": bool(nc == nc_ref and fdist.same_partition(labels, ref)),
+                        "n_clusters": int(nc), "n_clusters_single_gpu": int(nc_ref),
+                        "representatives_ok": bool(reps.shape[0] == nc and (labels[reps] == np.arange(nc)).all()),
+                        "units": int(units["owner"].shape[0]), "halo_pieces": int(units["piece"].sum())}
+        torch.distributed.barrier()
+    if rank == 0:
+        res["equal_to_single_gpu"] = bool(res["exhaustive"]["equal_to_single_gpu"]
+                                          and res["default_nprobe"]["equal_to_single_gpu"])
+    return res
+
+
+def _bucket_plan(torch, pipeline, sp, s, dev):
+    hp = pipeline.HotPath(s, dev)
+    b = hp.bucket_sort(torch.from_numpy(sp.precursor_mz).to(dev), torch.from_numpy(sp.precursor_charge).to(dev))
+    return b.bucket_ptr.cpu().numpy(), b.mz.cpu().numpy()
+
+
+def north_star_record(args, torch, fdist, pipeline, synth, _lib, dev, world, rank, dist, timed, peaks):
+    """BASELINE configs[3] beside the headline: ONE data set of `--north-star-total` spectra (80 bucket-aligned
+    chunks over the whole precursor-mass range, the same data set at every GPU count), chunks dealt to the
+    ranks in order -- whole precursor buckets, so no halo is needed -- each rank clusters its share, labels
+    gathered over NCCL inside the step.  Strong scaling: the total is fixed."""
+    n_chunks = 80
+    total = args.north_star_total // n_chunks * n_chunks
+    mine = range(n_chunks * rank // world, n_chunks * (rank + 1) // world)
+    workers = max(1, min(16, len(os.sched_getaffinity(0)) // world))
+    t0 = time.perf_counter()
+    sp = synth.generate_chunks(total, n_chunks, mine, workers=workers)
+    log(f"[rank {rank}] north star: generated {len(sp)} of {total} spectra in {time.perf_counter() - t0:.1f}s "
+        f"({workers} workers)")
+    settings = pipeline.Settings(exhaustive=args.exhaustive)
+    hp = pipeline.HotPath(settings, dev)
+    wl = Workload(torch, fdist, hp, sp, dev, world)
+    steps, warmup = max(2, min(args.steps, 3)), 3
+    ms, (_, n_clusters), launches, _ = timed(wl, wl.step_resident, steps, warmup, profile=True)
+    kernels = merge_kernel_classes(_lib.profile_summary())
+    ms_pipe, _, _, _ = timed(wl, lambda: wl.run_e2e_pipelined(steps), 1, 1)
+    ms_pipe /= steps
+    d = wl.d
+    hp2 = pipeline.HotPath(settings, dev)
+    labels, nc, keep = hp2.run(d["mz"], d["intensity"], d["indptr"], d["precursor_mz"], d["charge"], keep=True)
+    computed, required, sizes, _ = scan_pair_stats(torch, keep, len(sp), dev)
+    # order-independent fingerprint of the partition: cluster-size histogram (sizes 2..64, 65+) and noise count
+    lab = labels.long()
+    csize = torch.bincount(lab[lab >= 0], minlength=max(int(nc), 1))
+    hist = torch.bincount(csize.clamp(max=65), minlength=66).double()
+    agg = torch.tensor([float(nc), float((lab < 0).sum().item()), computed, required, float(len(sp)),
+                        float(sizes.max().item()), float(sizes.shape[0])], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(agg, op=dist.ReduceOp.SUM)
+        dist.all_reduce(hist, op=dist.ReduceOp.SUM)
+    out = None
+    if rank == 0:
+        import hashlib
+
+        scan_ms = kernels.get("scan_tc", (0.0, 0))[0] / steps
+        ex_tf = 2.0 * settings.low_dim * computed / (scan_ms * 1e-3) / 1e12 if scan_ms > 0 else None
+        out = {
+            "config": f"configs[3]: {total} synthetic spectra in 80 bucket-aligned chunks, chunks (whole precursor "
+                      f"buckets) dealt to {world} GPU(s), falcon defaults" + (" exhaustive" if args.exhaustive else ""),
+            "scaling": "strong", "total_spectra": int(agg[4].item()), "n_gpus": world, "steps": steps, "warmup": warmup,
+            "ms_per_step": ms, "value": agg[4].item() / (ms * 1e-3), "unit": UNIT,
+            "e2e": {"value": agg[4].item() / (ms_pipe * 1e-3), "ms_per_step": ms_pipe, "h2d_bytes_per_step": wl.h2d_bytes,
+                    "d2h_bytes_per_step": len(sp) * 4},
+            "gpu_launches": int(launches),
+            "n_clusters": int(agg[0].item()), "noise": int(agg[1].item()),
+            "partition_fingerprint": hashlib.sha1(hist.cpu().numpy().astype(np.int64).tobytes()).hexdigest()[:16],
+            "buckets": {"n": int(agg[6].item()), "max_rows_rank0": float(sizes.max().item()),
+                        "mean_rows": agg[4].item() / max(agg[6].item(), 1.0)},
+            "scan": {"ms_rank0": scan_ms, "required_pairs": agg[3].item(), "computed_pairs": agg[2].item(),
+                     "computed_over_required": agg[2].item() / max(agg[3].item(), 1.0),
+                     "executed_tflops_rank0": ex_tf,
+                     "executed_frac": (ex_tf / peaks["bf16_tflops"]) if ex_tf else None,
+                     "note": "rank 0's scan_tc time and the pairs of rank 0's share; the fingerprint and the cluster "
+                             "count must not depend on the GPU count (same data set, whole buckets per rank)"},
+            "kernels_ms_per_step_rank0": {k: v[0] / steps for k, v in kernels.items()},
+        }
+        if world > 1:
+            out["scan"]["executed_tflops_rank0"] = (2.0 * settings.low_dim * computed / (scan_ms * 1e-3) / 1e12
+                                                     if scan_ms > 0 else None)
+    return out
 
 
 def main():
@@ -562,6 +730,11 @@ def main():
     ap.add_argument("--total", type=int, default=0,
                     help="strong scaling: this many spectra in total, the precursor-mass range (whole buckets) "
                          "split across the ranks -- BASELINE configs[3] is --total 10000000")
+    ap.add_argument("--north-star-total", type=int, default=10_000_000,
+                    help="spectra of the configs[3] witness record (`north_star_10m`) measured after the headline "
+                         "workload; 0 skips it")
+    ap.add_argument("--check-n", type=int, default=200_000,
+                    help="spectra of the multi-GPU parity self-check (N > 1 only, outside the timed regions)")
     ap.add_argument("--mass-range", type=float, nargs=2, default=None, metavar=("LO", "HI"),
                     help="neutral mass range of the synthetic peptides (default 700-3500 Da); a narrow range "
                          "makes large precursor buckets (tensor-core regime of the scan)")

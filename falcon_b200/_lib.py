@@ -84,6 +84,8 @@ SIGNATURES = {
                               C.POINTER(_i64), _p, _sz, _p]),
     "flc_dbscan_workspace_bytes": (_sz, [_i64]),
     "flc_dbscan": (C.c_int, [_p, _p, _p, _i64, _f32, _i32, _p, C.POINTER(_i64), _p, _sz, _p]),
+    "flc_scatter_labels_peers": (C.c_int, [_p, _p, _i64, _p, _i64, _p, C.c_int, _i64, _p]),
+    "flc_relabel_gathered": (C.c_int, [_p, C.c_int, _i64, _p, _p, _p]),
     "flc_split_workspace_bytes": (_sz, [_i64, C.c_int]),
     "flc_split_clusters": (C.c_int, [_p, _p, _p, _i64, _f64, C.c_int, _f64, _i32, C.c_int, _p,
                                      C.POINTER(_i64), _p, _sz, _p]),

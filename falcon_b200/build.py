@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "csrc", "_obj")
 LIB = os.path.join(HERE, "libfalcon_b200.so")
-SOURCES = ["api.cu", "vectorize.cu", "bucket.cu", "scan.cu", "scan_tc.cu", "refine.cu", "kmeans.cu", "kmeans_tc.cu", "dbscan.cu", "medoids.cu", "preprocess.cu"]
+SOURCES = ["api.cu", "vectorize.cu", "bucket.cu", "scan.cu", "scan_tc.cu", "refine.cu", "kmeans.cu", "kmeans_tc.cu", "dbscan.cu", "medoids.cu", "preprocess.cu", "gather.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",

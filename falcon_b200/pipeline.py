@@ -455,9 +455,13 @@ class HotPath:
         if v.overflow is not None and int(v.overflow.item()) > 0:  # the stream was just synchronised
             raise RuntimeError(f"a spectrum hashed to {int(v.overflow.item())} distinct columns but the sparse rows "
                                f"hold {v.ell_width}: pass the true max_peaks")
-        labels = self._empty(n, torch.int32)
+        sink = getattr(self, "label_sink", None)
         with self.timer("scatter"):
-            check(lib.flc_scatter32(ptr(sorted_labels), ptr(buckets.order), n, ptr(labels), _stream()))
+            if sink is not None:  # multi-GPU: the scatter stores into every peer's gather slot (distributed.PeerLabelGather)
+                labels = sink.scatter(sorted_labels, buckets.order, n_clusters)
+            else:
+                labels = self._empty(n, torch.int32)
+                check(lib.flc_scatter32(ptr(sorted_labels), ptr(buckets.order), n, ptr(labels), _stream()))
         self.representatives = None
         if self.s.representatives:  # input index of every cluster's medoid
             rows = self.medoids(graph, sorted_labels, n_clusters)

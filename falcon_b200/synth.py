@@ -258,3 +258,44 @@ def generate(
     if shuffle:
         out = out.take(rng.permutation(n))
     return out
+
+
+# --------------------------------------------------------------------------- one large data set in bucket-aligned chunks
+BUCKET_WIDTH = 1.0005079  # falcon's precursor bucket rule: round((mz - 1.00794) * z / 1.0005079) // mz_interval
+
+
+def chunk_mass_ranges(n_chunks: int, mass_range: tuple[float, float] = (700.0, 3500.0)):
+    """Neutral-mass slices of ``mass_range`` whose edges sit in the middle between two precursor bucket
+    keys, pulled in by 0.03 Da (precursor jitter of 5 ppm and the proton-mass offset of the rule stay
+    below that): every precursor bucket of the union of the chunks lies inside ONE chunk, so chunks --
+    and any partition of the chunks over GPUs -- are sets of whole buckets."""
+    k_lo = int(np.ceil(mass_range[0] / BUCKET_WIDTH))
+    k_hi = int(np.floor(mass_range[1] / BUCKET_WIDTH)) - 1
+    if k_hi - k_lo < n_chunks:
+        raise ValueError("more chunks than precursor buckets in the mass range")
+    edges = k_lo + (np.arange(n_chunks + 1) * (k_hi - k_lo)) // n_chunks
+    return [((a - 0.5) * BUCKET_WIDTH + 0.03, (b - 0.5) * BUCKET_WIDTH - 0.03) for a, b in zip(edges[:-1], edges[1:])]
+
+
+def _generate_chunk(args):
+    n, seed, rng_ = args
+    return generate(n, seed, mass_range=rng_)
+
+
+def generate_chunks(total: int, n_chunks: int, chunk_ids, seed: int = 1000, workers: int = 1,
+                    mass_range: tuple[float, float] = (700.0, 3500.0)) -> SpectrumSet:
+    """Chunks ``chunk_ids`` of the ``total``-spectrum data set made of ``n_chunks`` bucket-aligned chunks
+    (``chunk_mass_ranges``; chunk c = ``generate(total // n_chunks, seed + c)`` on its mass slice).  The
+    data set is the same however the chunks are dealt out; ``workers`` > 1 generates them in worker
+    processes (spawned: safe next to an initialised CUDA context)."""
+    ranges = chunk_mass_ranges(n_chunks, mass_range)
+    jobs = [(total // n_chunks, seed + int(c), ranges[int(c)]) for c in chunk_ids]
+    if workers > 1 and len(jobs) > 1:
+        import concurrent.futures as cf
+        import multiprocessing as mp
+
+        with cf.ProcessPoolExecutor(min(workers, len(jobs)), mp_context=mp.get_context("spawn")) as ex:
+            parts = list(ex.map(_generate_chunk, jobs))
+    else:
+        parts = [_generate_chunk(j) for j in jobs]
+    return concat(parts)

@@ -88,3 +88,75 @@ def test_sharded_two_ranks_nccl_equal_single_gpu():
     for exhaustive in (True, False):
         same_nc, same, reps_ok, nc = res[0][exhaustive]
         assert same_nc and same and reps_ok and nc > 1000
+
+
+def _peer_worker(rank, world, port, q):
+    import torch.distributed as dist
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    n_max = 30000
+    ok = []
+    hp = pipeline.HotPath(pipeline.Settings(), dev)
+    plain = pipeline.HotPath(pipeline.Settings(), dev)
+    sink = fd.PeerLabelGather(n_max, dev)
+    hp.label_sink = sink
+    for batch in range(5):  # more batches than slot generations; a different length on every rank and batch
+        n = n_max - 1000 * rank - 777 * batch
+        sp = synth.generate(n, 60 + 10 * batch + rank, mass_range=(1000.0, 1030.0))
+        d = helpers.to_device(sp, dev)
+        labels, nc = hp.run(d["mz"], d["intensity"], d["indptr"], d["precursor_mz"], d["charge"])
+        ref, nc_ref = plain.run(d["mz"], d["intensity"], d["indptr"], d["precursor_mz"], d["charge"])
+        want, want_lens = fd.gather_labels_padded(ref, nc_ref, max_len=n_max)  # the NCCL gather
+        sink.wait()
+        got, lens = sink.last
+        ok.append(bool(nc == nc_ref and torch.equal(labels, ref) and torch.equal(got, want)
+                       and torch.equal(lens, want_lens) and int(got.max()) + 1 > nc))
+    dist.barrier()
+    q.put((rank, ok))
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs (gpurun --gpus 2)")
+def test_peer_memory_label_gather_equals_nccl_gather():
+    """flc_scatter_labels_peers + barrier + flc_relabel_gathered (NVLink peer stores from the step's last kernel)
+    give exactly the labels of the NCCL all-gather, batch after batch (slot reuse), ragged lengths."""
+    import torch.multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_peer_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=600) for _ in procs)
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert res[0] == [True] * 5 and res[1] == [True] * 5
+
+
+def test_relabel_gathered_single_process():
+    """The relabel kernel on hand-made slots (any GPU count): offsets from the headers, -1 kept, padding -1."""
+    from falcon_b200._lib import check, lib, ptr
+
+    dev = torch.device("cuda", 0)
+    max_len = 6
+    slots = torch.tensor([[5, 2, 0, -1, 1, 1, 0, 99], [3, 1, -1, 0, 0, 77, 77, 77], [0, 0, 9, 9, 9, 9, 9, 9]],
+                         dtype=torch.int32, device=dev)
+    out = torch.empty((3, max_len), dtype=torch.int32, device=dev)
+    lens = torch.empty(3, dtype=torch.int64, device=dev)
+    check(lib.flc_relabel_gathered(ptr(slots), 3, max_len, ptr(out), ptr(lens), None))
+    assert out.cpu().tolist() == [[0, -1, 1, 1, 0, -1], [-1, 2, 2, -1, -1, -1], [-1] * 6]
+    assert lens.cpu().tolist() == [5, 3, 0]
+    # one "peer" (this GPU): the scatter kernel writes header + labels in input order
+    buf = torch.full((10,), -7, dtype=torch.int32, device=dev)
+    import ctypes as C
+
+    ptrs = (C.c_void_p * 1)(buf.data_ptr())
+    lab = torch.tensor([4, -1, 2], dtype=torch.int32, device=dev)
+    order = torch.tensor([2, 0, 1], dtype=torch.int32, device=dev)
+    check(lib.flc_scatter_labels_peers(ptr(lab), ptr(order), 3, None, 5, ptrs, 1, 1, None))
+    assert buf.cpu().tolist() == [-7, 3, 5, -1, 2, 4, -7, -7, -7, -7]
