@@ -59,12 +59,13 @@ SIGNATURES = {
     "flc_vectorize": (C.c_int, [_p, _p, _p, _p, _p, _i64, _f64, _f64, _u32, _u32, _u32, C.c_int,
                                 _p, _i64, _p, _i64, _p, _p, _p, _p, _i32, _p, _p]),
     "flc_bucket_sort_workspace_bytes": (_sz, [_i64]),
-    "flc_bucket_sort": (C.c_int, [_p, _p, _i64, _i32, _p, _p, _p, _p, C.POINTER(_i64), _p, _sz, _p]),
+    "flc_bucket_sort": (C.c_int, [_p, _p, _i64, _i32, _p, _p, _p, _p, C.POINTER(_i64), _i64, _p, _p, _sz, _p]),
     "flc_gather": (C.c_int, [_p, _p, _i64, C.c_int, _p, _p]),
     "flc_scatter32": (C.c_int, [_p, _p, _i64, _p, _p]),
     "flc_ivf_plan": (C.c_int, [_p, _i64, _i32, C.c_int, _p, _p, _p, C.POINTER(_i64), C.POINTER(_i32),
                                C.POINTER(_i64), _p]),
     "flc_kmeans_workspace_bytes": (_sz, [_i64, _i64, _i64, _i64, _i32, _u32]),
+    "flc_kmeans_needs_tiled": (C.c_int, [_i64, _i64, _i32, _u32]),
     "flc_kmeans_train": (C.c_int, [_p, _p, _p, _i32, _p, _i64, _i64, _u32, _p, _i64, _p, _p, _i64, _i64, C.c_int,
                                    _p, _p, _i32, _p, _p, _p, _sz, _p]),
     "flc_ivf_assign": (C.c_int, [_p, _i64, _i64, _u32, _p, _i64, _p, _p, _p, _p, _i32,
@@ -83,12 +84,13 @@ SIGNATURES = {
                               _f64, C.c_int, _f64, _i32, _i32, _f32, _p, _p, _u64, _p,
                               C.POINTER(_i64), _p, _sz, _p]),
     "flc_dbscan_workspace_bytes": (_sz, [_i64]),
-    "flc_dbscan": (C.c_int, [_p, _p, _p, _i64, _f32, _i32, _p, C.POINTER(_i64), _p, _sz, _p]),
+    "flc_dbscan": (C.c_int, [_p, _p, _p, _i64, _f32, _i32, _p, C.POINTER(_i64), _p, _i32, C.POINTER(_i32), _p,
+                             _p, _sz, _p]),
     "flc_scatter_labels_peers": (C.c_int, [_p, _p, _i64, _p, _i64, _p, C.c_int, _i64, _p]),
     "flc_relabel_gathered": (C.c_int, [_p, C.c_int, _i64, _p, _p, _p]),
     "flc_split_workspace_bytes": (_sz, [_i64, C.c_int]),
     "flc_split_clusters": (C.c_int, [_p, _p, _p, _i64, _f64, C.c_int, _f64, _i32, C.c_int, _p,
-                                     C.POINTER(_i64), _p, _sz, _p]),
+                                     C.POINTER(_i64), _p, _p, _sz, _p]),
 }
 
 for _name, (_res, _args) in SIGNATURES.items():

@@ -49,8 +49,14 @@ __global__ void bucket_head_kernel(const uint32_t* __restrict__ key, int64_t n,
   if (i < n) flag[i] = (i == 0) || (key[i] != key[i - 1]);
 }
 
-__global__ void bucket_close_kernel(int64_t* bucket_ptr, const int64_t* n_buckets, int64_t n) {
-  bucket_ptr[*n_buckets] = n;
+// bucket_ptr[n_buckets .. max(n_buckets, pad_to)] = n: the end of the last bucket, and (pad_to) empty
+// buckets behind it so that later stages can run with a host-side upper bound of the bucket count.
+__global__ void bucket_close_kernel(int64_t* bucket_ptr, const int64_t* n_buckets, int64_t n, int64_t pad_to,
+                                    int64_t* n_buckets_dev) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t nb = *n_buckets;
+  if (i == 0 && n_buckets_dev) *n_buckets_dev = nb;
+  if (i == 0 || nb + i <= pad_to) bucket_ptr[nb + i] = n;
 }
 
 struct BucketSortLayout {
@@ -103,18 +109,18 @@ size_t flc_bucket_sort_workspace_bytes(int64_t n) {
 
 int flc_bucket_sort(const double* precursor_mz, const int32_t* charge, int64_t n,
                     int32_t mz_interval, int32_t* order, uint32_t* key_sorted, double* mz_sorted,
-                    int64_t* bucket_ptr, int64_t* n_buckets, void* workspace,
-                    size_t workspace_bytes, flc_stream_t stream_) {
+                    int64_t* bucket_ptr, int64_t* n_buckets, int64_t pad_buckets, int64_t* n_buckets_dev,
+                    void* workspace, size_t workspace_bytes, flc_stream_t stream_) {
   using namespace flc;
   FLC_REQUIRE(n >= 0 && n < (int64_t(1) << 31), "n out of range");
   FLC_REQUIRE(mz_interval > 0, "mz_interval must be positive");
-  FLC_REQUIRE(n_buckets != nullptr, "null n_buckets");
+  FLC_REQUIRE(n_buckets != nullptr || n_buckets_dev != nullptr, "no output for n_buckets");
+  FLC_REQUIRE(pad_buckets >= 0 && pad_buckets <= n, "pad_buckets must be in [0, n]");
   cudaStream_t stream = as_stream(stream_);
   if (n == 0) {
-    *n_buckets = 0;
-    int64_t zero = 0;
-    FLC_CUDA(cudaMemcpyAsync(bucket_ptr, &zero, sizeof(zero), cudaMemcpyHostToDevice, stream));
-    FLC_CUDA(cudaStreamSynchronize(stream));
+    if (n_buckets) *n_buckets = 0;
+    FLC_CUDA(cudaMemsetAsync(bucket_ptr, 0, sizeof(int64_t), stream));
+    if (n_buckets_dev) FLC_CUDA(cudaMemsetAsync(n_buckets_dev, 0, sizeof(int64_t), stream));
     return FLC_OK;
   }
   Workspace ws(workspace, workspace_bytes);
@@ -144,10 +150,14 @@ int flc_bucket_sort(const double* precursor_mz, const int32_t* charge, int64_t n
   FLC_CUDA(cub::DeviceSelect::Flagged(L.cub_tmp, tmp, cub::CountingInputIterator<int64_t>(0), L.flag,
                                       bucket_ptr, L.n_sel, num, stream));
   count_launch(2);
-  timed("bucket_close", stream, [&] { bucket_close_kernel<<<1, 1, 0, stream>>>(bucket_ptr, L.n_sel, n); });
+  timed("bucket_close", stream, [&] {
+    bucket_close_kernel<<<static_cast<unsigned>((pad_buckets + 1 + 255) / 256), 256, 0, stream>>>(
+        bucket_ptr, L.n_sel, n, pad_buckets, n_buckets_dev); });
   FLC_LAUNCH_CHECK();
-  FLC_CUDA(cudaMemcpyAsync(n_buckets, L.n_sel, sizeof(int64_t), cudaMemcpyDeviceToHost, stream));
-  FLC_CUDA(cudaStreamSynchronize(stream));
+  if (n_buckets) {  // NULL: no synchronisation, the count stays on the device (n_buckets_dev)
+    FLC_CUDA(cudaMemcpyAsync(n_buckets, L.n_sel, sizeof(int64_t), cudaMemcpyDeviceToHost, stream));
+    FLC_CUDA(cudaStreamSynchronize(stream));
+  }
   return FLC_OK;
 }
 

@@ -86,6 +86,8 @@ __global__ void dbscan_propagate_kernel(const float* __restrict__ dist, const in
   if (any) *changed = 1;
 }
 
+__global__ void copy_count_kernel(const int32_t* __restrict__ src, int64_t* __restrict__ dst) { *dst = *src; }
+
 __global__ void dbscan_seed_kernel(const int32_t* __restrict__ m, const uint8_t* __restrict__ core, int64_t n,
                                    int32_t* __restrict__ seed) {
   const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -116,7 +118,7 @@ static void dbscan_layout(Workspace& ws, int64_t n, DbscanLayout& L) {
   L.core = ws.take<uint8_t>(n + 1);
   L.seed = ws.take<int32_t>(n + 1);
   L.rank = ws.take<int32_t>(n + 1);
-  L.changed = ws.take<int32_t>(1);
+  L.changed = ws.take<int32_t>(4);
   size_t b = 0;
   cub::DeviceScan::ExclusiveSum(nullptr, b, (int32_t*)nullptr, (int32_t*)nullptr, static_cast<int>(n + 1));
   L.cub_bytes = b;
@@ -551,15 +553,21 @@ size_t flc_dbscan_workspace_bytes(int64_t n) {
 }
 
 int flc_dbscan(const float* dist, const int32_t* indices, const int64_t* indptr, int64_t n, float eps,
-               int32_t min_samples, int32_t* labels, int64_t* n_clusters, void* workspace,
-               size_t workspace_bytes, flc_stream_t stream_) {
+               int32_t min_samples, int32_t* labels, int64_t* n_clusters, int64_t* n_clusters_dev,
+               int32_t n_sweeps, int32_t* sweeps_used, int32_t* unsettled_dev,
+               void* workspace, size_t workspace_bytes, flc_stream_t stream_) {
   using namespace flc;
   FLC_REQUIRE(n >= 0 && n < (int64_t(1) << 31) - 1, "n out of range");
   FLC_REQUIRE(min_samples >= 1, "min_samples must be >= 1");
-  FLC_REQUIRE(n_clusters != nullptr, "null n_clusters");
+  FLC_REQUIRE(n_clusters != nullptr || n_clusters_dev != nullptr, "no output for n_clusters");
+  FLC_REQUIRE(n_sweeps >= 0 && (n_sweeps == 0 || unsettled_dev != nullptr),
+              "a fixed number of sweeps needs unsettled_dev to report whether it was enough");
   cudaStream_t stream = as_stream(stream_);
   if (n == 0) {
-    *n_clusters = 0;
+    if (n_clusters) *n_clusters = 0;
+    if (sweeps_used) *sweeps_used = 0;
+    if (n_clusters_dev) FLC_CUDA(cudaMemsetAsync(n_clusters_dev, 0, sizeof(int64_t), stream));
+    if (unsettled_dev) FLC_CUDA(cudaMemsetAsync(unsettled_dev, 0, sizeof(int32_t), stream));
     return FLC_OK;
   }
   Workspace ws(workspace, workspace_bytes);
@@ -570,20 +578,30 @@ int flc_dbscan(const float* dist, const int32_t* indices, const int64_t* indptr,
   const unsigned tblocks = static_cast<unsigned>((n + 1 + 255) / 256);
   timed("dbscan_core", stream, [&] { dbscan_core_kernel<<<wblocks, 256, 0, stream>>>(dist, indptr, n, eps, min_samples, L.m, L.core); });
   FLC_LAUNCH_CHECK();
-  int32_t changed = 1;
-  int sweeps = 0;
-  while (changed) {
-    // two sweeps before the first look at the flag (only the second one's changes count: the first
-    // always changes something), one sweep per look afterwards
-    for (int rep = 0; rep < (sweeps == 0 ? 2 : 1); ++rep) {
-      FLC_CUDA(cudaMemsetAsync(L.changed, 0, sizeof(int32_t), stream));
-      timed("dbscan_propagate", stream, [&] { dbscan_propagate_kernel<<<wblocks, 256, 0, stream>>>(dist, indices, indptr, n, eps, L.core, L.m,
-                                                           L.changed); });
-      FLC_LAUNCH_CHECK();
+  auto sweep = [&](int32_t* flag) -> int {
+    FLC_CUDA(cudaMemsetAsync(flag, 0, sizeof(int32_t), stream));
+    timed("dbscan_propagate", stream, [&] { dbscan_propagate_kernel<<<wblocks, 256, 0, stream>>>(dist, indices, indptr, n, eps, L.core, L.m,
+                                                         flag); });
+    FLC_LAUNCH_CHECK();
+    return FLC_OK;
+  };
+  if (n_sweeps > 0) {
+    // a fixed number of sweeps, nothing read back: the flag of the last one (did it still change something?)
+    // is left in unsettled_dev for the caller's next synchronisation
+    for (int i = 0; i < n_sweeps; ++i) FLC_TRY(sweep(unsettled_dev));
+  } else {
+    int32_t changed = 1;
+    int sweeps = 0, launched = 0;
+    while (changed) {
+      // two sweeps before the first look at the flag (only the second one's changes count: the first
+      // always changes something), one sweep per look afterwards
+      for (int rep = 0; rep < (sweeps == 0 ? 2 : 1); ++rep, ++launched) FLC_TRY(sweep(L.changed));
+      FLC_CUDA(cudaMemcpyAsync(&changed, L.changed, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+      FLC_CUDA(cudaStreamSynchronize(stream));
+      if (++sweeps > 100000) return set_error(FLC_ERR_CUDA, "dbscan propagation did not converge");
     }
-    FLC_CUDA(cudaMemcpyAsync(&changed, L.changed, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
-    FLC_CUDA(cudaStreamSynchronize(stream));
-    if (++sweeps > 100000) return set_error(FLC_ERR_CUDA, "dbscan propagation did not converge");
+    if (sweeps_used) *sweeps_used = launched;
+    if (unsettled_dev) FLC_CUDA(cudaMemsetAsync(unsettled_dev, 0, sizeof(int32_t), stream));
   }
   timed("dbscan_seed", stream, [&] { dbscan_seed_kernel<<<tblocks, 256, 0, stream>>>(L.m, L.core, n, L.seed); });
   FLC_LAUNCH_CHECK();
@@ -592,10 +610,16 @@ int flc_dbscan(const float* dist, const int32_t* indices, const int64_t* indptr,
   count_launch(2);
   timed("dbscan_label", stream, [&] { dbscan_label_kernel<<<tblocks, 256, 0, stream>>>(L.m, L.rank, n, labels); });
   FLC_LAUNCH_CHECK();
-  int32_t total = 0;
-  FLC_CUDA(cudaMemcpyAsync(&total, L.rank + n, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
-  FLC_CUDA(cudaStreamSynchronize(stream));
-  *n_clusters = total;
+  if (n_clusters_dev) {
+    copy_count_kernel<<<1, 1, 0, stream>>>(L.rank + n, n_clusters_dev);
+    FLC_LAUNCH_CHECK();
+  }
+  if (n_clusters) {  // NULL: no synchronisation, the count stays on the device
+    int32_t total = 0;
+    FLC_CUDA(cudaMemcpyAsync(&total, L.rank + n, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+    FLC_CUDA(cudaStreamSynchronize(stream));
+    *n_clusters = total;
+  }
   return FLC_OK;
 }
 
@@ -609,19 +633,20 @@ size_t flc_split_workspace_bytes(int64_t n, int with_rt) {
 
 int flc_split_clusters(const int32_t* labels_in, const double* precursor_mz, const double* rt, int64_t n,
                        double tol, int tol_mode, double rt_tol, int32_t min_samples, int values_sorted,
-                       int32_t* labels_out, int64_t* n_clusters, void* workspace, size_t workspace_bytes,
-                       flc_stream_t stream_) {
+                       int32_t* labels_out, int64_t* n_clusters, int64_t* n_clusters_dev, void* workspace,
+                       size_t workspace_bytes, flc_stream_t stream_) {
   using namespace flc;
   FLC_REQUIRE(n >= 0 && n < (int64_t(1) << 31) - 1, "n out of range");
   FLC_REQUIRE(tol_mode == FLC_TOL_DA || tol_mode == FLC_TOL_PPM, "Unknown precursor tolerance mode");
-  FLC_REQUIRE(n_clusters != nullptr, "null n_clusters");
+  FLC_REQUIRE(n_clusters != nullptr || n_clusters_dev != nullptr, "no output for n_clusters");
   const bool with_rt = rt_tol >= 0.0;
   FLC_REQUIRE(!with_rt || rt != nullptr, "rt_tol is set but no retention times were given");
   // combined key = label << 32 | (a_mz * 2 + a_rt * 3), a_* < n
   FLC_REQUIRE(!with_rt || n < (int64_t(1) << 29), "n out of range for the retention-time cut");
   cudaStream_t stream = as_stream(stream_);
   if (n == 0) {
-    *n_clusters = 0;
+    if (n_clusters) *n_clusters = 0;
+    if (n_clusters_dev) FLC_CUDA(cudaMemsetAsync(n_clusters_dev, 0, sizeof(int64_t), stream));
     return FLC_OK;
   }
   Workspace ws(workspace, workspace_bytes);
@@ -716,10 +741,16 @@ int flc_split_clusters(const int32_t* labels_in, const double* precursor_mz, con
   count_launch(2);
   timed("split_label", stream, [&] { split_label_kernel<<<tblocks, 256, 0, stream>>>(L.run_id, L.kept, L.new_id, perm, n, labels_out); });
   FLC_LAUNCH_CHECK();
-  int32_t total = 0;
-  FLC_CUDA(cudaMemcpyAsync(&total, L.new_id + n, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
-  FLC_CUDA(cudaStreamSynchronize(stream));
-  *n_clusters = total;
+  if (n_clusters_dev) {
+    copy_count_kernel<<<1, 1, 0, stream>>>(L.new_id + n, n_clusters_dev);
+    FLC_LAUNCH_CHECK();
+  }
+  if (n_clusters) {  // NULL: no synchronisation, the count stays on the device
+    int32_t total = 0;
+    FLC_CUDA(cudaMemcpyAsync(&total, L.new_id + n, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+    FLC_CUDA(cudaStreamSynchronize(stream));
+    *n_clusters = total;
+  }
   return FLC_OK;
 }
 

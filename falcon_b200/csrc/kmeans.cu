@@ -158,7 +158,7 @@ ivf_assign_kernel(const float* __restrict__ x, int64_t ld, int64_t n, uint32_t l
     if (lane < max_nprobe) probes[i * max_nprobe + lane] = lane == 0 ? 0 : -1;
     return;
   }
-  const int32_t P = nprobe[b];
+  const int32_t P = min(nprobe[b], max_nprobe);  // max_nprobe may be a caller-side bound (checked by the caller)
   float* xi = smem_x + static_cast<size_t>(warp) * low_dim;
   if (ell_idx == nullptr) {
     for (uint32_t t = lane; t < low_dim; t += 32) xi[t] = x[i * ld + t];
@@ -211,14 +211,17 @@ __global__ void __launch_bounds__(256)
 kmeans_classify_kernel(const uint16_t* __restrict__ ell_nnz, uint32_t low_dim,
                        const int64_t* __restrict__ bucket_ptr, int64_t n_buckets,
                        const int32_t* __restrict__ nlist, TrainQueues q, int force_tiled, int32_t max_nprobe,
-                       int32_t* __restrict__ list_id, int32_t* __restrict__ probes) {
+                       int32_t* __restrict__ list_id, int32_t* __restrict__ probes,
+                       const int64_t* __restrict__ centroid_ptr, int64_t total_centroids) {
   const int lane = threadIdx.x & 31;
   const int64_t b = static_cast<int64_t>(blockIdx.x) * 8 + (threadIdx.x >> 5);
   if (b >= n_buckets) return;
   const int32_t L = nlist[b];
   const int64_t s = bucket_ptr[b];
   const int64_t nb = bucket_ptr[b + 1] - s;
-  if (L <= 0) {
+  // total_centroids may be a caller-side bound that turned out too small (sync-free callers check the true
+  // total afterwards and redo the batch): buckets whose centroids would not fit are left untrained
+  if (L <= 0 || centroid_ptr[b] + L > total_centroids) {
     if (lane == 0) q.bclass[b] = kClsFlat;
     if (list_id != nullptr) {
       for (int64_t t = lane; t < nb; t += 32) list_id[s + t] = 0;
@@ -709,7 +712,7 @@ kmeans_fused_kernel(FusedArgs A, int cls) {
       if (j < rnnz[row]) C[idx[row * pitch + j] * pl.lp + c] = val[row * pitch + j];
     }
     __syncthreads();
-    const int P = A.list_id != nullptr ? min(A.nprobe[b], L) : 0;
+    const int P = A.list_id != nullptr ? min(min(A.nprobe[b], L), A.max_nprobe) : 0;
     clk.mark(2);
     if (pl.lp == 4)
       fused_train_bucket<4, NT>(A, pl, smem, S, nb, L, pitch, s, c0, P, clk);
@@ -776,6 +779,7 @@ kmeans_tiled_init_kernel(TiledArgs A, int64_t total) {
   const int64_t c0 = A.centroid_ptr[b];
   const int64_t c = gc - c0;
   const int32_t L = A.nlist[b];
+  if (c >= L) return;  // `total` may be an upper bound of the centroid count (sync-free callers)
   const int64_t s = A.bucket_ptr[b], nb = A.bucket_ptr[b + 1] - s;
   const int64_t row = s + (c * nb) / L;
   const uint32_t d = A.low_dim;
@@ -1230,7 +1234,7 @@ ivf_assign_tiled_f32_kernel(TiledArgs A, const int32_t* __restrict__ nprobe, int
     seg = seg_end;
     if (A.q.bclass[b] != kClsTiled) continue;
     const int32_t L = A.nlist[b];
-    const int32_t P = min(nprobe[b], L);
+    const int32_t P = min(min(nprobe[b], L), max_nprobe);
     bool slow = active;
     if (L <= 32 && P <= 8) {
       __syncthreads();  // the previous bucket's centroids are no longer read
@@ -1342,7 +1346,7 @@ ivf_assign_tiled_kernel(TiledArgs A, const int32_t* __restrict__ nprobe, int32_t
   const int64_t i = rows[w];
   const int64_t b = find_segment(A.bucket_ptr, A.n_buckets, i);
   const int32_t L = A.nlist[b];
-  const int32_t P = min(nprobe[b], L);
+  const int32_t P = min(min(nprobe[b], L), max_nprobe);
   const int d = static_cast<int>(A.low_dim);
   const float* ctb = A.ct + A.centroid_ptr[b] * d;
   const int m = min(static_cast<int>(A.ell_nnz[i]), A.W);
@@ -1468,11 +1472,12 @@ int flc_ivf_plan(const int64_t* bucket_ptr, int64_t n_buckets, int32_t n_probe, 
   using namespace flc;
   FLC_REQUIRE(n_buckets >= 0, "n_buckets must be non-negative");
   FLC_REQUIRE(n_probe >= 1, "n_probe must be >= 1");
-  FLC_REQUIRE(total_centroids && max_nprobe, "null host outputs");
+  FLC_REQUIRE((total_centroids == nullptr) == (max_nprobe == nullptr), "total_centroids and max_nprobe go together");
   cudaStream_t stream = as_stream(stream_);
   timed("ivf_plan", stream, [&] { ivf_plan_kernel<<<1, 1024, 0, stream>>>(
       bucket_ptr, n_buckets, n_probe, exhaustive, nlist, nprobe, centroid_ptr); });
   FLC_LAUNCH_CHECK();
+  if (total_centroids == nullptr) return FLC_OK;  // no synchronisation: the totals stay in centroid_ptr[n_buckets ..]
   int64_t tail[3] = {0, 0, 0};
   FLC_CUDA(cudaMemcpyAsync(tail, centroid_ptr + n_buckets, 3 * sizeof(int64_t), cudaMemcpyDeviceToHost, stream));
   FLC_CUDA(cudaStreamSynchronize(stream));
@@ -1491,6 +1496,12 @@ size_t flc_kmeans_workspace_bytes(int64_t n, int64_t n_buckets, int64_t total_ce
   flc::kmeans_layout(ws, n, n_buckets, total_centroids, low_dim,
                      force_tiled || flc::kmeans_needs_tiled(n, max_ivf_bucket, ell_width, low_dim), L);
   return ws.used + 256;
+}
+
+int flc_kmeans_needs_tiled(int64_t n, int64_t max_ivf_bucket, int32_t ell_width, uint32_t low_dim) {
+  const char* force_env = getenv("FLC_KMEANS_FORCE_TILED");
+  if (force_env != nullptr && force_env[0] == '1') return 1;
+  return flc::kmeans_needs_tiled(n, max_ivf_bucket, ell_width, low_dim) ? 1 : 0;
 }
 
 int flc_kmeans_train(const uint16_t* ell_idx, const float* ell_val, const uint16_t* ell_nnz, int32_t ell_width,
@@ -1527,7 +1538,8 @@ int flc_kmeans_train(const uint16_t* ell_idx, const float* ell_val, const uint16
   FLC_CUDA(cudaMemsetAsync(K.qctr, 0, 16 * sizeof(int32_t), stream));
   timed("kmeans_classify", stream, [&] {
     kmeans_classify_kernel<<<static_cast<unsigned>((n_buckets + 7) / 8), 256, 0, stream>>>(
-        ell_nnz, low_dim, bucket_ptr, n_buckets, nlist, q, force_tiled, max_nprobe, list_id, probes); });
+        ell_nnz, low_dim, bucket_ptr, n_buckets, nlist, q, force_tiled, max_nprobe, list_id, probes, centroid_ptr,
+        total_centroids); });
   FLC_LAUNCH_CHECK();
   if (total_centroids == 0) return FLC_OK;
   // ---- fused classes

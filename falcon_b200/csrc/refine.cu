@@ -551,12 +551,11 @@ int flc_knn_csr(const uint64_t* pairs, const uint64_t* pair_count, uint64_t pair
   FLC_REQUIRE((list_id == nullptr) == (probes == nullptr), "list_id and probes go together");
   FLC_REQUIRE((ell_idx == nullptr) == (ell_val == nullptr), "ell_idx and ell_val go together");
   FLC_REQUIRE(x != nullptr || ell_idx != nullptr, "need dense or ELL rows");
-  FLC_REQUIRE(nnz != nullptr, "null nnz");
   cudaStream_t stream = as_stream(stream_);
   if (n == 0) {
-    *nnz = 0;
+    if (nnz) *nnz = 0;
     FLC_CUDA(cudaMemsetAsync(indptr, 0, sizeof(int64_t), stream));
-    FLC_CUDA(cudaStreamSynchronize(stream));
+    if (nnz) FLC_CUDA(cudaStreamSynchronize(stream));
     return FLC_OK;
   }
   // The workspace is laid out for pair_capacity pairs; whether the scan overflowed it is
@@ -629,18 +628,25 @@ int flc_knn_csr(const uint64_t* pairs, const uint64_t* pair_count, uint64_t pair
   tmp = L.cub_bytes;
   FLC_CUDA(cub::DeviceScan::ExclusiveSum(L.cub_tmp, tmp, L.row_count, indptr, static_cast<int>(n + 1), stream));
   count_launch(2);
-  int64_t total_nnz = 0;
-  uint64_t n_pairs = 0;
-  FLC_CUDA(cudaMemcpyAsync(&total_nnz, indptr + n, sizeof(int64_t), cudaMemcpyDeviceToHost, stream));
-  FLC_CUDA(cudaMemcpyAsync(&n_pairs, pair_count, sizeof(n_pairs), cudaMemcpyDeviceToHost, stream));
-  FLC_CUDA(cudaStreamSynchronize(stream));
-  if (n_pairs > pair_capacity)
-    return set_error(FLC_ERR_CAPACITY, "scan produced %llu candidate pairs, capacity %llu",
-                     static_cast<unsigned long long>(n_pairs), static_cast<unsigned long long>(pair_capacity));
-  *nnz = total_nnz;
-  if (static_cast<uint64_t>(total_nnz) > nnz_capacity)
-    return set_error(FLC_ERR_CAPACITY, "CSR needs %lld entries, capacity %llu",
-                     static_cast<long long>(total_nnz), static_cast<unsigned long long>(nnz_capacity));
+  if (nnz != nullptr) {
+    int64_t total_nnz = 0;
+    uint64_t n_pairs = 0;
+    FLC_CUDA(cudaMemcpyAsync(&total_nnz, indptr + n, sizeof(int64_t), cudaMemcpyDeviceToHost, stream));
+    FLC_CUDA(cudaMemcpyAsync(&n_pairs, pair_count, sizeof(n_pairs), cudaMemcpyDeviceToHost, stream));
+    FLC_CUDA(cudaStreamSynchronize(stream));
+    if (n_pairs > pair_capacity)
+      return set_error(FLC_ERR_CAPACITY, "scan produced %llu candidate pairs, capacity %llu",
+                       static_cast<unsigned long long>(n_pairs), static_cast<unsigned long long>(pair_capacity));
+    *nnz = total_nnz;
+    if (static_cast<uint64_t>(total_nnz) > nnz_capacity)
+      return set_error(FLC_ERR_CAPACITY, "CSR needs %lld entries, capacity %llu",
+                       static_cast<long long>(total_nnz), static_cast<unsigned long long>(nnz_capacity));
+  } else {
+    // No synchronisation: the caller checks *pair_count <= pair_capacity (and reads indptr[n]) when it next
+    // synchronises.  nnz <= min(pairs, n * n_neighbors), so the CSR arrays cannot overflow unless the pairs did.
+    FLC_REQUIRE(nnz_capacity >= std::min<uint64_t>(pair_capacity, static_cast<uint64_t>(n) * n_neighbors),
+                "nnz_capacity must be at least min(pair_capacity, n * n_neighbors) without a synchronisation");
+  }
   const unsigned cblocks = static_cast<unsigned>((n + 255) / 256);
   timed("csr_compact", stream, [&] { csr_compact_kernel<<<cblocks, 256, 0, stream>>>(L.grouped, L.off, indptr, n, nnz_capacity, dist, indices); });
   FLC_LAUNCH_CHECK();

@@ -52,6 +52,8 @@ class Settings:
     eps_cut: bool = True  # keep only dist <= eps in the CSR (what generate_clusters reads)
     representatives: bool = False  # also pick every cluster's medoid (HotPath.representatives, input indices)
     dense_f32: bool = False  # also materialise the dense float32 rows (no stage needs them: all read the sparse copy)
+    speculate: bool = True  # steady state: size every stage by the previous batch's counts (upper bounds) and read the
+    #                         true counts back once at the end of the step instead of after every stage (HotPath._finish)
 
 
 def get_dim(min_mz: float, max_mz: float, bin_size: float):
@@ -138,6 +140,7 @@ class KnnGraph:
     indptr: torch.Tensor  # int64 [n + 1]
     nnz: int
     pair_count: object = 0  # candidate pairs the scan produced (int, or the device-side counter)
+    pair_capacity: int = 0  # size of the candidate buffer the scan wrote into (sync=False: to be checked by the caller)
 
     @property
     def n_pairs(self) -> int:
@@ -153,7 +156,9 @@ class Buckets:
     mz: torch.Tensor  # float64 [n] precursor m/z in bucket order
     rt: Optional[torch.Tensor]  # float32 [n] in bucket order
     bucket_ptr: torch.Tensor  # int64 [n_buckets + 1] (view of an [n + 1] buffer)
-    n_buckets: int
+    n_buckets: int  # the true count, or a host-side upper bound (trailing buckets empty)
+    n_buckets_dev: Optional[torch.Tensor] = None  # int64 [1]: the true count on the device
+    bucket_ptr_full: Optional[torch.Tensor] = None  # the [n + 1] buffer bucket_ptr is a view of
 
 
 @dataclasses.dataclass
@@ -166,6 +171,7 @@ class IvfIndex:
     probes: torch.Tensor
     max_nprobe: int
     total_centroids: int
+    max_ivf_bucket: int = 0
 
 
 class HotPath:
@@ -199,23 +205,31 @@ class HotPath:
 
     # ------------------------------------------------------------------ a5
     def bucket_sort(self, precursor_mz: torch.Tensor, charge: torch.Tensor,
-                    rt: Optional[torch.Tensor] = None) -> Buckets:
+                    rt: Optional[torch.Tensor] = None, n_buckets_cap: Optional[int] = None) -> Buckets:
+        """Bucket order of the spectra.  With ``n_buckets_cap`` (a host-side upper bound of the bucket count)
+        nothing is read back: ``bucket_ptr`` is padded with empty buckets up to the cap, ``n_buckets`` is the
+        cap, and the true count stays on the device in ``Buckets.n_buckets_dev`` (the caller must check it
+        against the cap when it next synchronises)."""
         n = precursor_mz.shape[0]
         order = self._empty(n, torch.int32)
         key = self._empty(n, torch.int32)
         mz_sorted = self._empty(n, torch.float64)
         bucket_ptr = self._empty(n + 1, torch.int64)
         nb = C.c_int64(0)
+        nb_dev = self._empty(1, torch.int64)
+        cap = None if n_buckets_cap is None else max(0, min(int(n_buckets_cap), n))
         with self.timer("bucket_sort"):
             ws = self._ws(lib.flc_bucket_sort_workspace_bytes(n), "bucket_sort")
             check(lib.flc_bucket_sort(ptr(precursor_mz), ptr(charge), n, self.s.mz_interval,
                                       ptr(order), ptr(key), ptr(mz_sorted), ptr(bucket_ptr),
-                                      C.byref(nb), ptr(ws), ws.numel(), _stream()))
+                                      C.byref(nb) if cap is None else None, 0 if cap is None else cap, ptr(nb_dev),
+                                      ptr(ws), ws.numel(), _stream()))
             rt_sorted = None
             if rt is not None:
                 rt_sorted = self._empty(n, torch.float32)
                 check(lib.flc_gather(ptr(rt), ptr(order), n, 4, ptr(rt_sorted), _stream()))
-        return Buckets(order, key, mz_sorted, rt_sorted, bucket_ptr[: nb.value + 1], int(nb.value))
+        count = int(nb.value) if cap is None else cap
+        return Buckets(order, key, mz_sorted, rt_sorted, bucket_ptr[: count + 1], count, nb_dev, bucket_ptr)
 
     # ------------------------------------------------------------------ 8f-1: preprocessing
     def preprocess(self, mz: torch.Tensor, intensity: torch.Tensor, indptr: torch.Tensor,
@@ -301,25 +315,32 @@ class HotPath:
         return out
 
     # ------------------------------------------------------------------ a6
-    def ivf_plan(self, buckets: Buckets):
+    def ivf_plan(self, buckets: Buckets, caps: Optional[dict] = None):
+        """nlist / nprobe / centroid offsets of every bucket and the totals (total centroids, largest nprobe,
+        largest IVF bucket).  With ``caps`` (host-side upper bounds of the three totals) nothing is read back:
+        the true totals stay in ``cptr[n_buckets : n_buckets + 3]``."""
         nb = buckets.n_buckets
         nlist = self._empty(nb + 1, torch.int32)
         nprobe = self._empty(nb + 1, torch.int32)
         cptr = self._empty(nb + 3, torch.int64)
         total, maxp, maxb = C.c_int64(0), C.c_int32(0), C.c_int64(0)
+        if caps is not None:
+            check(lib.flc_ivf_plan(ptr(buckets.bucket_ptr), nb, self.s.n_probe, 0, ptr(nlist), ptr(nprobe),
+                                   ptr(cptr), None, None, None, _stream()))
+            return nlist, nprobe, cptr, int(caps["total"]), int(caps["maxp"]), int(caps["maxb"])
         check(lib.flc_ivf_plan(ptr(buckets.bucket_ptr), nb, self.s.n_probe, 0, ptr(nlist), ptr(nprobe),
                                ptr(cptr), C.byref(total), C.byref(maxp), C.byref(maxb), _stream()))
         return nlist, nprobe, cptr, int(total.value), int(maxp.value), int(maxb.value)
 
     def build_ivf(self, v: Vectors, buckets: Buckets,
-                  centroids: Optional[torch.Tensor] = None) -> IvfIndex:
+                  centroids: Optional[torch.Tensor] = None, caps: Optional[dict] = None) -> IvfIndex:
         """IVF index of every bucket: trained here (sparse rows needed), or coarse
         assignment against the given ``centroids`` (dense or sparse rows)."""
         n, d = v.n, v.low_dim
         x = v.x
         ld = x.stride(0) if x is not None else d
         with self.timer("ivf_train"):
-            nlist, nprobe, cptr, total, maxp, maxb = self.ivf_plan(buckets)
+            nlist, nprobe, cptr, total, maxp, maxb = self.ivf_plan(buckets, caps)
             list_id = self._empty(n, torch.int32)
             probes = torch.empty((n, maxp), dtype=torch.int32, device=self.device)
             if centroids is None:
@@ -332,7 +353,7 @@ class HotPath:
                                            ptr(buckets.bucket_ptr), buckets.n_buckets, ptr(nlist), ptr(cptr),
                                            total, maxb, self.s.kmeans_iters, ptr(centroids), ptr(nprobe), maxp,
                                            ptr(list_id), ptr(probes), ptr(ws), ws.numel(), _stream()))
-                return IvfIndex(nlist, nprobe, cptr, centroids, list_id, probes, maxp, total)
+                return IvfIndex(nlist, nprobe, cptr, centroids, list_id, probes, maxp, total, maxb)
             if centroids.shape[0] < total:
                 raise ValueError("centroids array too small for the bucket plan")
         with self.timer("ivf_assign"):
@@ -349,7 +370,11 @@ class HotPath:
         return float(np.float32(1.0) - np.float32(self.s.eps) - np.float32(SCAN_MARGIN))
 
     def knn_graph(self, v: Vectors, buckets: Buckets,
-                  ivf: Optional[IvfIndex] = None, pair_capacity: Optional[int] = None) -> KnnGraph:
+                  ivf: Optional[IvfIndex] = None, pair_capacity: Optional[int] = None, sync: bool = True) -> KnnGraph:
+        """Sparse k-NN matrix.  ``sync=False``: nothing is read back -- ``dist`` / ``indices`` keep their
+        capacity, ``nnz`` is -1 (it is ``indptr[n]``), and the caller must compare ``pair_count`` with
+        ``pair_capacity`` when it next synchronises (a scan that overflowed its buffer produced an
+        incomplete matrix)."""
         n, d = v.n, v.low_dim
         x, xb = v.x, v.xb
         s = self.s
@@ -392,8 +417,10 @@ class HotPath:
                                           -1.0 if s.rt_tol is None else float(s.rt_tol),
                                           s.n_neighbors, s.n_neighbors_ann,
                                           float(np.float32(s.eps)) if s.eps_cut else float("nan"),
-                                          ptr(dist), ptr(indices), nnz_cap, ptr(indptr), C.byref(nnz),
-                                          ptr(ws2), ws2.numel(), _stream()))
+                                          ptr(dist), ptr(indices), nnz_cap, ptr(indptr),
+                                          C.byref(nnz) if sync else None, ptr(ws2), ws2.numel(), _stream()))
+                if not sync:
+                    return KnnGraph(dist, indices, indptr, -1, pair_count, pair_capacity)
                 break
             except _lib.CapacityError:
                 n_pairs = int(pair_count.item())
@@ -403,24 +430,35 @@ class HotPath:
         return KnnGraph(dist[: nnz.value], indices[: nnz.value], indptr, int(nnz.value), pair_count)
 
     # ------------------------------------------------------------------ a10
-    def dbscan(self, g: KnnGraph, n: int):
+    def dbscan(self, g: KnnGraph, n: int, n_sweeps: int = 0):
+        """DBSCAN labels and the number of clusters.  ``n_sweeps`` > 0: exactly that many propagation sweeps
+        and nothing read back -- returns (labels, n_clusters int64 device tensor, unsettled int32 device
+        tensor: non-zero if the sweeps were not enough)."""
         labels = self._empty(n, torch.int32)
-        nc = C.c_int64(0)
+        nc, used = C.c_int64(0), C.c_int32(0)
+        sync = n_sweeps <= 0
+        nc_dev = None if sync else self._empty(1, torch.int64)
+        unsettled = None if sync else self._empty(1, torch.int32)
         with self.timer("dbscan"):
             ws = self._ws(lib.flc_dbscan_workspace_bytes(n), "dbscan")
             check(lib.flc_dbscan(ptr(g.dist), ptr(g.indices), ptr(g.indptr), n,
                                  float(np.float32(self.s.eps)), self.s.min_samples, ptr(labels),
-                                 C.byref(nc), ptr(ws), ws.numel(), _stream()))
-        return labels, int(nc.value)
+                                 C.byref(nc) if sync else None, ptr(nc_dev), max(0, int(n_sweeps)), C.byref(used),
+                                 ptr(unsettled), ptr(ws), ws.numel(), _stream()))
+        if sync:
+            self.dbscan_sweeps = int(used.value)
+            return labels, int(nc.value)
+        return labels, nc_dev, unsettled
 
     # ------------------------------------------------------------------ a11-a15
     def split(self, labels: torch.Tensor, mz: torch.Tensor, values_sorted: bool,
-              rt: Optional[torch.Tensor] = None):
+              rt: Optional[torch.Tensor] = None, sync: bool = True):
         """``_postprocess_cluster`` of every DBSCAN cluster (/root/reference/falcon/cluster/cluster.py:362-455);
         with ``Settings.rt_tol`` also the retention-time cut (:418-429), which needs ``rt``."""
         n = labels.shape[0]
         out = self._empty(n, torch.int32)
         nc = C.c_int64(0)
+        nc_dev = None if sync else self._empty(1, torch.int64)
         with_rt = self.s.rt_tol is not None
         if with_rt:
             if rt is None:
@@ -433,8 +471,8 @@ class HotPath:
                                          _lib.TOL_MODES[self.s.precursor_tol_mode],
                                          -1.0 if self.s.rt_tol is None else float(self.s.rt_tol),
                                          self.s.min_samples, 1 if values_sorted else 0, ptr(out),
-                                         C.byref(nc), ptr(ws), ws.numel(), _stream()))
-        return out, int(nc.value)
+                                         C.byref(nc) if sync else None, ptr(nc_dev), ptr(ws), ws.numel(), _stream()))
+        return out, (int(nc.value) if sync else nc_dev)
 
     # ------------------------------------------------------------------ a16
     def medoids(self, g: KnnGraph, labels: torch.Tensor, n_clusters: int) -> torch.Tensor:
@@ -447,7 +485,23 @@ class HotPath:
         return out
 
     # ------------------------------------------------------------------ whole path
-    def _cluster_vectors(self, v: Vectors, buckets: Buckets, n: int, keep: bool):
+    def _spec_for(self, n: int, keep: bool) -> Optional[dict]:
+        """Upper bounds learnt from the previous batch of this size (None: run with a read-back per stage)."""
+        if keep or not self.s.speculate or self.s.representatives or not self.s.eps_cut:
+            return None
+        return self.__dict__.setdefault("_spec", {}).get(n)
+
+    def _learn(self, n: int, nb: int, total: int, maxp: int, maxb: int, pairs: int, sweeps: int) -> None:
+        grow = lambda x, lo: int(x + x // 8 + lo)  # noqa: E731 -- 12 % head-room: consecutive batches of a run are alike
+        # maxb only decides whether k-means also runs its tiled path: kept exact, and what is checked later is that
+        # decision, not the bound.  sweeps: DBSCAN propagation sweeps to launch blind (the last one must change nothing)
+        self.__dict__.setdefault("_spec", {})[n] = dict(
+            nb=min(n, grow(nb, 64)), total=grow(total, 64), maxp=maxp, maxb=maxb,
+            pairs=max(grow(pairs, 1 << 16) + pairs // 2, 1 << 20), sweeps=max(2, sweeps))
+
+    def _cluster_vectors(self, v: Vectors, buckets: Buckets, n: int, keep: bool, spec: Optional[dict] = None):
+        if spec is not None:
+            return self._cluster_vectors_spec(v, buckets, n, spec)
         ivf = None if self.s.exhaustive else self.build_ivf(v, buckets)
         graph = self.knn_graph(v, buckets, ivf)
         db_labels, _ = self.dbscan(graph, n)
@@ -455,6 +509,8 @@ class HotPath:
         if v.overflow is not None and int(v.overflow.item()) > 0:  # the stream was just synchronised
             raise RuntimeError(f"a spectrum hashed to {int(v.overflow.item())} distinct columns but the sparse rows "
                                f"hold {v.ell_width}: pass the true max_peaks")
+        self._learn(n, buckets.n_buckets, ivf.total_centroids if ivf else 0, ivf.max_nprobe if ivf else 1,
+                    ivf.max_ivf_bucket if ivf else 0, graph.n_pairs, self.dbscan_sweeps + 1)
         sink = getattr(self, "label_sink", None)
         with self.timer("scatter"):
             if sink is not None:  # multi-GPU: the scatter stores into every peer's gather slot (distributed.PeerLabelGather)
@@ -473,6 +529,46 @@ class HotPath:
                                             representatives=self.representatives)
         return labels, n_clusters
 
+    def _cluster_vectors_spec(self, v: Vectors, buckets: Buckets, n: int, spec: dict):
+        """The stages after vectorisation with NO read-back between them: buffers and grids are sized by
+        ``spec`` (upper bounds from the previous batch; the bucket list is padded with empty buckets), every
+        count stays on the device, and ONE synchronisation at the end fetches them all.  If a bound turns out
+        too small the batch is redone with exact sizes (and the bounds are re-learnt)."""
+        ivf = None if self.s.exhaustive else self.build_ivf(v, buckets, caps=spec)
+        graph = self.knn_graph(v, buckets, ivf, pair_capacity=spec["pairs"], sync=False)
+        db_labels, _, unsettled = self.dbscan(graph, n, n_sweeps=spec["sweeps"])
+        sorted_labels, nc_dev = self.split(db_labels, buckets.mz, values_sorted=True, rt=buckets.rt, sync=False)
+        nb_cap = buckets.n_buckets
+        tail = ivf.centroid_ptr[nb_cap: nb_cap + 3] if ivf is not None else torch.zeros(3, dtype=torch.int64, device=self.device)
+        counts = torch.cat([buckets.n_buckets_dev, tail, graph.pair_count.view(torch.int64).view(1), nc_dev,
+                            v.overflow.to(torch.int64) if v.overflow is not None else tail[:1] * 0,
+                            unsettled.to(torch.int64)]).cpu().tolist()
+        nb, total, maxp, maxb, pairs, n_clusters, overflow, unsettled = (int(c) for c in counts)  # the step's one read-back
+        if overflow > 0:
+            raise RuntimeError(f"a spectrum hashed to {overflow} distinct columns but the sparse rows "
+                               f"hold {v.ell_width}: pass the true max_peaks")
+        tiled = lambda mb: bool(lib.flc_kmeans_needs_tiled(n, mb, v.ell_width, v.low_dim))  # noqa: E731
+        if (nb > nb_cap or total > spec["total"] or maxp > spec["maxp"] or pairs > spec["pairs"] or unsettled
+                or (maxb > spec["maxb"] and tiled(maxb) and not tiled(spec["maxb"]))):
+            # a bound was too small (or DBSCAN needed more sweeps): this batch again with exact sizes
+            exact = dataclasses.replace(buckets, bucket_ptr=buckets.bucket_ptr_full[: nb + 1], n_buckets=nb)
+            self.__dict__.get("_spec", {}).pop(n, None)
+            self.spec_misses = getattr(self, "spec_misses", 0) + 1
+            return self._cluster_vectors(v, exact, n, False, None)
+        self._learn(n, nb, total, max(maxp, 1), max(maxb, spec["maxb"]) if not tiled(maxb) else maxb, pairs,
+                    spec["sweeps"])
+        # the last kernel goes out after the check: with a label sink it also stores into the peers' gather
+        # slots, which must happen exactly once per batch
+        sink = getattr(self, "label_sink", None)
+        with self.timer("scatter"):
+            if sink is not None:
+                labels = sink.scatter(sorted_labels, buckets.order, n_clusters)
+            else:
+                labels = self._empty(n, torch.int32)
+                check(lib.flc_scatter32(ptr(sorted_labels), ptr(buckets.order), n, ptr(labels), _stream()))
+        self.representatives = None
+        return labels, n_clusters
+
     def run(self, mz, intensity, indptr, precursor_mz, charge, rt=None, keep=False, max_peaks=None):
         """All stages on device tensors; returns labels in INPUT order (int32,
         -1 = noise) and the number of clusters.  ``keep`` also returns the
@@ -483,10 +579,12 @@ class HotPath:
         if n == 0:
             empty = self._empty(0, torch.int32)
             return (empty, 0, {}) if keep else (empty, 0)
-        buckets = self.bucket_sort(precursor_mz, charge, rt if self.s.rt_tol is not None else None)
+        spec = self._spec_for(n, keep)
+        buckets = self.bucket_sort(precursor_mz, charge, rt if self.s.rt_tol is not None else None,
+                                   n_buckets_cap=spec["nb"] if spec else None)
         v = self.vectorize(mz, intensity, indptr, buckets.order, want_f32=keep or self.s.dense_f32,
                            max_peaks=max_peaks)
-        return self._cluster_vectors(v, buckets, n, keep)
+        return self._cluster_vectors(v, buckets, n, keep, spec)
 
     def stage_host(self, mz, intensity, indptr, precursor_mz, charge, rt=None,
                    max_peaks: Optional[int] = None, n_chunks: int = 8) -> Optional[dict]:
@@ -561,7 +659,8 @@ class HotPath:
         compute = torch.cuda.current_stream()
         try:
             compute.wait_event(st["ev_meta"])
-            buckets = self.bucket_sort(st["pmz"], st["z"], st["rt"])
+            spec = self._spec_for(n, False)
+            buckets = self.bucket_sort(st["pmz"], st["z"], st["rt"], n_buckets_cap=spec["nb"] if spec else None)
             rank = self._empty(n, torch.int32)  # input position -> bucket-order row
             check(lib.flc_scatter32(None, ptr(buckets.order), n, ptr(rank), _stream()))
             v = self.alloc_vectors(n, st["width"], want_f32=self.s.dense_f32)
@@ -579,7 +678,7 @@ class HotPath:
             st["slot"]["free"] = torch.cuda.Event()
             st["slot"]["free"].record(compute)
             st["slot"]["pending"] = False
-        labels, n_clusters = self._cluster_vectors(v, buckets, n, False)
+        labels, n_clusters = self._cluster_vectors(v, buckets, n, False, spec)
         if labels_out is not None:
             labels_out.copy_(labels, non_blocking=True)
         return labels, n_clusters

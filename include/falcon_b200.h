@@ -108,7 +108,10 @@ FLC_API size_t flc_bucket_sort_workspace_bytes(int64_t n);
 FLC_API int flc_bucket_sort(const double* precursor_mz, const int32_t* charge, int64_t n,
                     int32_t mz_interval,
                     int32_t* order, uint32_t* key_sorted, double* mz_sorted,
-                    int64_t* bucket_ptr, int64_t* n_buckets /*host*/,
+                    int64_t* bucket_ptr, int64_t* n_buckets /*host; NULL = do not synchronise*/,
+                    int64_t pad_buckets /*bucket_ptr[n_buckets .. pad_buckets] = n: empty buckets up to a
+                                          host-side upper bound of the count (0 = none; <= n)*/,
+                    int64_t* n_buckets_dev /*device, nullable*/,
                     void* workspace, size_t workspace_bytes, flc_stream_t stream);
 /* out[i] = in[order[i]] for 4- or 8-byte elements. */
 FLC_API int flc_gather(const void* in, const int32_t* order, int64_t n, int elem_bytes,
@@ -153,8 +156,14 @@ FLC_API int flc_ivf_plan(const int64_t* bucket_ptr, int64_t n_buckets, int32_t n
                  int64_t* centroid_ptr /*[n_buckets+3]: scan, total, max nprobe, max IVF bucket*/,
                  int64_t* total_centroids /*host*/, int32_t* max_nprobe /*host*/,
                  int64_t* max_ivf_bucket /*host, nullable*/, flc_stream_t stream);
+/*  (total_centroids == max_nprobe == NULL: no synchronisation; the three totals stay in
+ *  centroid_ptr[n_buckets .. n_buckets + 2].) */
 FLC_API size_t flc_kmeans_workspace_bytes(int64_t n, int64_t n_buckets, int64_t total_centroids,
                                   int64_t max_ivf_bucket, int32_t ell_width, uint32_t low_dim);
+/*  Whether flc_kmeans_train runs its tiled multi-launch path when the largest IVF bucket has
+ *  max_ivf_bucket rows (monotone in max_ivf_bucket).  For callers that pass flc_kmeans_train an upper
+ *  bound instead of the value read back from flc_ivf_plan. */
+FLC_API int flc_kmeans_needs_tiled(int64_t n, int64_t max_ivf_bucket, int32_t ell_width, uint32_t low_dim);
 FLC_API int flc_kmeans_train(const uint16_t* ell_idx, const float* ell_val, const uint16_t* ell_nnz,
                      int32_t ell_width,
                      const uint16_t* x_bf16, int64_t ld_bf16 /*nullable: bf16 copy of the (unit-norm) rows; lets
@@ -223,7 +232,9 @@ FLC_API int flc_knn_csr(const uint64_t* pairs, const uint64_t* pair_count, uint6
                 double tol, int tol_mode, double rt_tol,
                 int32_t n_neighbors, int32_t n_neighbors_ann, float eps_cut,
                 float* dist, int32_t* indices, uint64_t nnz_capacity, int64_t* indptr /*[n+1]*/,
-                int64_t* nnz /*host*/,
+                int64_t* nnz /*host; NULL = do not synchronise: nnz stays in indptr[n], the caller checks
+                               *pair_count <= pair_capacity itself, and nnz_capacity must be at least
+                               min(pair_capacity, n * n_neighbors)*/,
                 void* workspace, size_t workspace_bytes, flc_stream_t stream);
 
 /* ------------------------------------------------------------------ a10: DBSCAN
@@ -234,7 +245,13 @@ FLC_API int flc_knn_csr(const uint64_t* pairs, const uint64_t* pair_count, uint6
  * returns the number of clusters on the host. */
 FLC_API size_t flc_dbscan_workspace_bytes(int64_t n);
 FLC_API int flc_dbscan(const float* dist, const int32_t* indices, const int64_t* indptr, int64_t n,
-               float eps, int32_t min_samples, int32_t* labels, int64_t* n_clusters /*host*/,
+               float eps, int32_t min_samples, int32_t* labels,
+               int64_t* n_clusters /*host; NULL = do not synchronise*/, int64_t* n_clusters_dev /*device, nullable*/,
+               int32_t n_sweeps /*0: propagate until a sweep changes nothing (the host looks at a flag after
+                                  each sweep); > 0: exactly this many sweeps and no look -- then
+                                  *unsettled_dev != 0 afterwards means they were not enough*/,
+               int32_t* sweeps_used /*host, nullable: sweeps the n_sweeps = 0 loop launched*/,
+               int32_t* unsettled_dev /*device int32, required with n_sweeps > 0*/,
                void* workspace, size_t workspace_bytes, flc_stream_t stream);
 
 /* ------------------------------------------------------------------ a11-a15: precursor split
@@ -250,11 +267,13 @@ FLC_API int flc_dbscan(const float* dist, const int32_t* indices, const int64_t*
  * (depth-first numbering of the dendrogram, scipy _hierarchy.pyx cluster_monocrit).
  * rt: float64 [n] (the values the caller holds, like precursor_mz), required when
  * rt_tol >= 0, else ignored / NULL; pass rt_tol < 0 for "None".
- * Synchronises; returns #clusters on the host. */
+ * Returns #clusters on the host (synchronises) and / or on the device. */
 FLC_API size_t flc_split_workspace_bytes(int64_t n, int with_rt);
 FLC_API int flc_split_clusters(const int32_t* labels_in, const double* precursor_mz, const double* rt,
                        int64_t n, double tol, int tol_mode, double rt_tol, int32_t min_samples,
-                       int values_sorted, int32_t* labels_out, int64_t* n_clusters /*host*/,
+                       int values_sorted, int32_t* labels_out,
+                       int64_t* n_clusters /*host; NULL = do not synchronise*/,
+                       int64_t* n_clusters_dev /*device, nullable*/,
                        void* workspace, size_t workspace_bytes, flc_stream_t stream);
 
 /* ------------------------------------------------------------------ a16: representatives

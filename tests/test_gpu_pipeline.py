@@ -68,6 +68,37 @@ def test_end_to_end_with_rt_tolerance(rt_tol):
         assert not odb.same_partition(labels, plain)
 
 
+@pytest.mark.parametrize("exhaustive", [False, True])
+def test_sync_free_steady_state_equals_the_stage_by_stage_run(exhaustive):
+    """Batches of one size through ONE HotPath: from the second batch on the stages are sized by the previous
+    batch's counts and nothing is read back until the end of the step.  Labels must equal a fresh
+    HotPath's (read-back after every stage), also when the new batch breaks the bounds learnt from the
+    previous one (more buckets, more centroids, larger buckets, more pairs) and the step is redone."""
+    n = 30000
+    ranges = [(1000.0, 1010.0), (1000.0, 1010.0), (1002.0, 1012.5), (700.0, 3500.0), (1000.0, 1003.0),
+              (1000.0, 1003.0), (900.0, 1100.0)]
+    hp = pipeline.HotPath(pipeline.Settings(exhaustive=exhaustive))
+    modes = []
+    for i, (lo, hi) in enumerate(ranges):
+        sp = synth.generate(n, 70 + i, mass_range=(lo, hi))
+        d = helpers.to_device(sp, hp.device)
+        fresh = pipeline.HotPath(pipeline.Settings(exhaustive=exhaustive, speculate=False))
+        ref, nc_ref = fresh.run(d["mz"], d["intensity"], d["indptr"], d["precursor_mz"], d["charge"])
+        before = getattr(hp, "spec_misses", 0)
+        speculated = hp._spec_for(n, False) is not None
+        if i % 2:
+            labels, nc = hp.run(d["mz"], d["intensity"], d["indptr"], d["precursor_mz"], d["charge"])
+        else:  # the host API shares the learnt bounds
+            out = torch.empty(n, dtype=torch.int32).pin_memory()
+            labels, nc = hp.run_host(*(t.cpu().pin_memory() for t in (d["mz"], d["intensity"], d["indptr"],
+                                                                        d["precursor_mz"], d["charge"])), labels_out=out)
+            torch.cuda.synchronize()
+            assert np.array_equal(out.numpy(), _cpu(ref))
+        assert nc == nc_ref and torch.equal(labels, ref), (i, lo, hi)
+        modes.append("first" if not speculated else ("redo" if getattr(hp, "spec_misses", 0) > before else "ok"))
+    assert modes[0] == "first" and modes[1] == "ok" and "redo" in modes[2:] and modes.count("ok") >= 3, modes
+
+
 def test_end_to_end_default_nprobe_shared_centroids():
     sp = helpers.dataset(20000, 43, 1000.0, 1020.0)
     h = pipeline.HotPath(pipeline.Settings(exhaustive=False))
