@@ -9,6 +9,8 @@ box, gloo in the CPU tests.
 """
 from __future__ import annotations
 
+import dataclasses
+
 import numpy as np
 import torch
 import torch.distributed as dist
@@ -354,8 +356,9 @@ def cluster_sharded(spectra, settings=None, device=None, group=None, bucket_cap=
         if v.overflow is not None and int(v.overflow.item()) > 0:
             raise RuntimeError("a spectrum hashed to more distinct columns than the sparse rows hold")
 
-    def stage4(graph, rows_g, n_rows):
-        """DBSCAN + split (+ medoids) of complete rows; rows_g = their positions in the global bucket order."""
+    def stage4(graph, rows_g, n_rows, medoid_rows):
+        """DBSCAN + split (+ medoids) of complete rows; rows_g = their positions in the global bucket order.
+        medoid_rows(labels, n_clusters) -> row of every cluster's representative."""
         if n_rows == 0:
             z = torch.zeros(0, dtype=torch.int32, device=dev)
             return z, 0, torch.zeros(0, dtype=torch.int64, device=dev)
@@ -363,14 +366,31 @@ def cluster_sharded(spectra, settings=None, device=None, group=None, bucket_cap=
         lab, nc = hp.split(db, mz_all[rows_g], values_sorted=True, rt=rt_all[rows_g] if use_rt else None)
         reps = torch.zeros(0, dtype=torch.int64, device=dev)
         if s.representatives and nc:
-            reps = rows_g[hp.medoids(graph, lab, nc).long()]
+            reps = rows_g[medoid_rows(lab, nc).long()]
         return lab, nc, reps
+
+    def vectors_of(rows_h, bptr_h):
+        """Vectors + bucket descriptor of the given rows of the global bucket order (host index array)."""
+        sub_ = spectra.take(order_h[rows_h])
+        rows_d = up(rows_h, np.int64)
+        bk = pipeline.Buckets(None, None, mz_all[rows_d], rt_all[rows_d] if use_rt else None, up(bptr_h, np.int64),
+                              int(bptr_h.shape[0]) - 1)
+        vv = hp.vectorize(up(sub_.mz, np.float32), up(sub_.intensity, np.float32), up(sub_.indptr, np.int64),
+                          want_f32=False, max_peaks=int(np.diff(sub_.indptr).max(initial=0)))
+        return vv, bk
+
+    def whole_medoids(lab, nc):
+        # the published rule reads the uncut matrix (HotPath.representatives_exact); whole buckets are the first
+        # len(whole) buckets of the local rows, the pieces behind them carry no label here
+        full = torch.cat([lab, torch.full((n_local - n_whole,), -1, dtype=torch.int32, device=dev)])
+        wb = dataclasses.replace(lb, bucket_ptr=lb.bucket_ptr[: len(whole) + 1], n_buckets=len(whole))
+        return hp.representatives_exact(v, wb, ivf, full, nc)
 
     # ---- whole buckets: the prefix of the local matrix
     if n_whole:
         nnz_w = int(g.indptr[n_whole].item())
         gw = pipeline.KnnGraph(g.dist[:nnz_w], g.indices[:nnz_w], g.indptr[: n_whole + 1], nnz_w)
-    lab_w, nc_w, rep_w = stage4(gw if n_whole else None, l2g[:n_whole], n_whole)
+    lab_w, nc_w, rep_w = stage4(gw if n_whole else None, l2g[:n_whole], n_whole, whole_medoids)
     rows_out, labs_out, reps_out, nc_local = [l2g[:n_whole]], [lab_w], [rep_w], nc_w
     # ---- cut buckets: gather the pieces' query rows, DBSCAN of a bucket on its home rank
     cut = np.unique(units["bucket"][units["piece"] == 1])
@@ -422,7 +442,18 @@ def cluster_sharded(spectra, settings=None, device=None, group=None, bucket_cap=
             gh = pipeline.KnnGraph(ents_all[1][src].contiguous().view(torch.float32), cols.contiguous(), indptr,
                                    int(src.shape[0]))
             rows_h = _segments(h_lo, h_hi - h_lo)
-            lab_h, nc_h, rep_h = stage4(gh, rows_h, n_home)
+
+            def home_medoids(lab, nc):
+                # uncut rows rank their candidates over the WHOLE bucket before the tolerance filter, which the
+                # pieces' halo ranges cannot reproduce: the home rank builds the uncut matrix of its cut buckets
+                # itself (exhaustive: a cut bucket has no bucket-wide index)
+                sz = bp_h[home + 1] - bp_h[home]
+                hb = np.zeros(home.size + 1, np.int64)
+                np.cumsum(sz, out=hb[1:])
+                vh, bk = vectors_of(rows_h.cpu().numpy(), hb)
+                return hp.representatives_exact(vh, bk, None, lab, nc)
+
+            lab_h, nc_h, rep_h = stage4(gh, rows_h, n_home, home_medoids)
             rows_out.append(rows_h)
             labs_out.append(torch.where(lab_h >= 0, lab_h + nc_local, lab_h))
             reps_out.append(rep_h)

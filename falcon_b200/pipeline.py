@@ -364,13 +364,14 @@ class HotPath:
         return IvfIndex(nlist, nprobe, cptr, centroids, list_id, probes, maxp, total)
 
     # ------------------------------------------------------------------ a7-a9
-    def scan_threshold(self) -> float:
-        if not self.s.eps_cut:
+    def scan_threshold(self, eps_cut: Optional[bool] = None) -> float:
+        if not (self.s.eps_cut if eps_cut is None else eps_cut):
             return -math.inf
         return float(np.float32(1.0) - np.float32(self.s.eps) - np.float32(SCAN_MARGIN))
 
     def knn_graph(self, v: Vectors, buckets: Buckets,
-                  ivf: Optional[IvfIndex] = None, pair_capacity: Optional[int] = None, sync: bool = True) -> KnnGraph:
+                  ivf: Optional[IvfIndex] = None, pair_capacity: Optional[int] = None, sync: bool = True,
+                  eps_cut: Optional[bool] = None) -> KnnGraph:
         """Sparse k-NN matrix.  ``sync=False``: nothing is read back -- ``dist`` / ``indices`` keep their
         capacity, ``nnz`` is -1 (it is ``indptr[n]``), and the caller must compare ``pair_count`` with
         ``pair_capacity`` when it next synchronises (a scan that overflowed its buffer produced an
@@ -380,9 +381,10 @@ class HotPath:
         s = self.s
         if s.rt_tol is not None and buckets.rt is None:
             raise ValueError("rt_tol is set but no retention times were given")
-        thr = self.scan_threshold()
+        cut = s.eps_cut if eps_cut is None else eps_cut
+        thr = self.scan_threshold(cut)
         if pair_capacity is None:
-            pair_capacity = 32 * n + (1 << 20) if s.eps_cut else None
+            pair_capacity = 32 * n + (1 << 20) if cut else None
         if pair_capacity is None:
             sizes = (buckets.bucket_ptr[1:] - buckets.bucket_ptr[:-1])
             pair_capacity = int((sizes * sizes).sum().item()) + 1024
@@ -416,7 +418,7 @@ class HotPath:
                                           s.precursor_tol_mass, _lib.TOL_MODES[s.precursor_tol_mode],
                                           -1.0 if s.rt_tol is None else float(s.rt_tol),
                                           s.n_neighbors, s.n_neighbors_ann,
-                                          float(np.float32(s.eps)) if s.eps_cut else float("nan"),
+                                          float(np.float32(s.eps)) if cut else float("nan"),
                                           ptr(dist), ptr(indices), nnz_cap, ptr(indptr),
                                           C.byref(nnz) if sync else None, ptr(ws2), ws2.numel(), _stream()))
                 if not sync:
@@ -484,6 +486,40 @@ class HotPath:
                                   n_clusters, ptr(out), ptr(ws), ws.numel(), _stream()))
         return out
 
+    def representatives_exact(self, v: Vectors, buckets: Buckets, ivf: Optional[IvfIndex], labels: torch.Tensor,
+                              n_clusters: int, max_pairs: int = 1 << 27) -> torch.Tensor:
+        """Medoid row of every cluster by the published rule: mean distance to the cluster
+        members present in the row of the FULL ``n_neighbors`` matrix -- members beyond ``eps`` count as
+        well, so the eps-cut matrix the clustering uses is not enough.  The uncut matrix is built for a
+        range of buckets at a time (a bucket of b rows yields b * b candidate pairs; ``max_pairs`` bounds a
+        range), its medoids taken, and dropped again.  ``labels``: final labels in row order, numbered in
+        bucket order (what ``split`` returns)."""
+        out = torch.full((max(n_clusters, 1),), -1, dtype=torch.int32, device=self.device)[:n_clusters]
+        if n_clusters == 0:
+            return out
+        bptr = buckets.bucket_ptr.cpu().numpy()
+        sizes = np.diff(bptr).astype(np.float64)
+        n = labels.shape[0]
+        b0 = 0
+        while b0 < sizes.shape[0]:
+            b1, acc = b0, 0.0
+            while b1 < sizes.shape[0] and (b1 == b0 or acc + sizes[b1] ** 2 <= max_pairs):
+                acc += sizes[b1] ** 2
+                b1 += 1
+            r0, r1 = int(bptr[b0]), int(bptr[b1])
+            lab = labels[r0:r1]
+            lab = lab[lab >= 0]
+            if lab.numel():
+                lo, hi = int(lab.min().item()), int(lab.max().item())
+                sub = dataclasses.replace(buckets, bucket_ptr=buckets.bucket_ptr[b0: b1 + 1], n_buckets=b1 - b0)
+                sub_ivf = None if ivf is None else dataclasses.replace(ivf, nlist=ivf.nlist[b0:], nprobe=ivf.nprobe[b0:],
+                                                                        centroid_ptr=ivf.centroid_ptr[b0:])
+                g = self.knn_graph(v, sub, sub_ivf, pair_capacity=int(acc) + 1024, eps_cut=False)
+                out[lo: hi + 1] = self.medoids(g, labels, n_clusters)[lo: hi + 1]
+                del g
+            b0 = b1
+        return out
+
     # ------------------------------------------------------------------ whole path
     def _spec_for(self, n: int, keep: bool) -> Optional[dict]:
         """Upper bounds learnt from the previous batch of this size (None: run with a read-back per stage)."""
@@ -520,7 +556,7 @@ class HotPath:
                 check(lib.flc_scatter32(ptr(sorted_labels), ptr(buckets.order), n, ptr(labels), _stream()))
         self.representatives = None
         if self.s.representatives:  # input index of every cluster's medoid
-            rows = self.medoids(graph, sorted_labels, n_clusters)
+            rows = self.representatives_exact(v, buckets, ivf, sorted_labels, n_clusters)
             self.representatives = self._empty(n_clusters, torch.int32)
             check(lib.flc_gather(ptr(buckets.order), ptr(rows), n_clusters, 4, ptr(self.representatives), _stream()))
         if keep:

@@ -392,24 +392,56 @@ def test_medoids_match_oracle(hp):
 
 
 def test_representatives_end_to_end():
+    """Representatives follow the published rule on the FULL n_neighbors matrix: cluster members
+    beyond eps count in the mean and in the quarter-of-the-cluster test.  Reference: the oracle's medoids on
+    the oracle's uncut matrix.  Also in bucket ranges (max_pairs) and through the facade."""
     from falcon_b200.cluster import cluster as fcluster
     from oracle import medoids as omed
 
-    h = pipeline.HotPath(pipeline.Settings(exhaustive=True, representatives=True))
+    h = pipeline.HotPath(pipeline.Settings(exhaustive=True, representatives=True, eps=0.2))
     sp = helpers.dataset(6000, 41, 1000.0, 1010.0)
     d = helpers.to_device(sp, h.device)
     labels, nc, keep = h.run(d["mz"], d["intensity"], d["indptr"], d["precursor_mz"], d["charge"], keep=True)
     reps = _cpu(keep["representatives"])
     assert reps.shape == (nc,) and np.array_equal(_cpu(labels)[reps], np.arange(nc))
+    o = helpers.oracle_pipeline(sp, exhaustive=True, eps=0.2)
+    full = o["csr"]
+    ref_rows = omed.cluster_medoids(full.data, full.indices, full.indptr, np.asarray(o["labels"]))
+    assert odb.same_partition(_cpu(keep["sorted_labels"]), o["labels"])
+    order = _cpu(keep["buckets"].order)
+    assert sorted(reps.tolist()) == sorted(order[ref_rows].tolist())
+    # the eps-cut matrix would pick other representatives for some clusters: the test can tell the two rules apart
     g = keep["graph"]
-    ref_rows = omed.cluster_medoids(_cpu(g.dist), _cpu(g.indices), _cpu(g.indptr), _cpu(keep["sorted_labels"]))
-    assert np.array_equal(reps, _cpu(keep["buckets"].order)[ref_rows])
-    # the facade with the published signature gives the same rows
-    rows = fcluster.get_cluster_representatives(_cpu(keep["sorted_labels"]), _cpu(g.indptr), _cpu(g.indices),
-                                                _cpu(g.dist))
-    assert np.array_equal(rows, ref_rows)
+    cut_rows = omed.cluster_medoids(_cpu(g.dist), _cpu(g.indices), _cpu(g.indptr), _cpu(keep["sorted_labels"]))
+    assert sorted(order[cut_rows].tolist()) != sorted(reps.tolist())
+    # bucket ranges of at most ~2 buckets at a time give the same rows
+    rows = h.representatives_exact(keep["vectors"], keep["buckets"], None, keep["sorted_labels"], nc, max_pairs=800_000)
+    assert np.array_equal(order[_cpu(rows)], reps)
+    # the facade with the published signature, fed the uncut matrix
+    got = fcluster.get_cluster_representatives(np.asarray(o["labels"]), full.indptr, full.indices, full.data)
+    assert np.array_equal(got, ref_rows)
     assert fcluster.get_cluster_representatives(np.full(3, -1), np.zeros(4, np.int64), np.zeros(0, np.int32),
                                                 np.zeros(0, np.float32)) is None
+
+
+def test_representatives_default_nprobe():
+    """With the IVF index the uncut rows hold only members of probed lists; rule and ranges as above."""
+    h = pipeline.HotPath(pipeline.Settings(representatives=True))
+    sp = helpers.dataset(20000, 43, 1000.0, 1020.0)
+    d = helpers.to_device(sp, h.device)
+    labels, nc, keep = h.run(d["mz"], d["intensity"], d["indptr"], d["precursor_mz"], d["charge"], keep=True)
+    reps = _cpu(keep["representatives"])
+    assert reps.shape == (nc,) and np.array_equal(_cpu(labels)[reps], np.arange(nc))
+    ivf = keep["ivf"]
+    rows = h.representatives_exact(keep["vectors"], keep["buckets"], ivf, keep["sorted_labels"], nc, max_pairs=3_000_000)
+    assert np.array_equal(_cpu(keep["buckets"].order)[_cpu(rows)], reps)
+    # against the oracle's medoids on the uncut matrix the device builds (same index, no eps cut)
+    from oracle import medoids as omed
+
+    g = h.knn_graph(keep["vectors"], keep["buckets"], ivf, pair_capacity=int((np.diff(_cpu(keep["buckets"].bucket_ptr)) ** 2).sum()) + 1024,
+                    eps_cut=False)
+    ref = omed.cluster_medoids(_cpu(g.dist), _cpu(g.indices), _cpu(g.indptr), _cpu(keep["sorted_labels"]))
+    assert np.array_equal(_cpu(rows), ref)
 
 
 def test_dbscan_long_chain(hp):
