@@ -601,6 +601,30 @@ def run_ours(args):
                              "p99": float(np.percentile(bsz, 99)), "max": float(bsz.max())},
             "n_pairs": keep["graph"].n_pairs, "nnz": keep["graph"].nnz,
         }
+    # ---- the same step with cluster representatives (medoids by the published rule: uncut matrix), gathered
+    # over NCCL with the labels when there are several ranks -- north_star's "final gather of labels and cluster
+    # representatives"; kept beside the headline because building the uncut matrix multiplies the step time
+    reps_rec = None
+    if not args.no_representatives:
+        hp_r = pipeline.HotPath(pipeline.Settings(exhaustive=args.exhaustive, representatives=True), dev)
+
+        def step_reps():
+            lab, nc = hp_r.run(d["mz"], d["intensity"], d["indptr"], d["precursor_mz"], d["charge"],
+                               max_peaks=wl.max_peaks)
+            reps = hp_r.representatives
+            if world > 1:
+                lab = fdist.gather_labels_padded(lab, nc, max_len=args.n)[0]
+                reps = fdist.gather_representatives(reps, args.n)
+            return (lab, reps), nc
+
+        ms_reps, ((_, reps), _), _, _ = timed(wl, step_reps, 2, 1)
+        if rank == 0:
+            reps_rec = {"ms_per_step": ms_reps, "value": total / (ms_reps * 1e-3), "unit": UNIT,
+                        "n_representatives": int(reps.shape[0]),
+                        "what": "whole step + medoid of every cluster from the uncut n_neighbors matrix "
+                                "(HotPath.representatives_exact)" + (", labels and representatives gathered over NCCL"
+                                                                     if world > 1 else "")}
+        del hp_r, reps
     # ---- free the headline workload, then the witnesses of the other configurations
     del keep, hp2, d, wl, labels
     torch.cuda.empty_cache()
@@ -608,6 +632,7 @@ def run_ours(args):
     ns = north_star_record(args, torch, fdist, pipeline, synth, _lib, dev, world, rank, dist, timed, peaks) \
         if args.north_star_total else None
     if rank == 0:
+        out["representatives"] = reps_rec
         out["multi_gpu_check"] = mg
         out["north_star_10m"] = ns
         print(json.dumps(out), flush=True)
@@ -727,6 +752,7 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=1_000_000,
                     help="spectra in the CPU-baseline sample (whole buckets; ~10 s of CPU work at 1M)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-representatives", action="store_true", help="skip the step-with-representatives record")
     ap.add_argument("--total", type=int, default=0,
                     help="strong scaling: this many spectra in total, the precursor-mass range (whole buckets) "
                          "split across the ranks -- BASELINE configs[3] is --total 10000000")

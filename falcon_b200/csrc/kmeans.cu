@@ -135,6 +135,82 @@ __device__ __forceinline__ int64_t find_segment(const int64_t* __restrict__ ptr,
   return lo;
 }
 
+
+// Best-P list of one row's (score, list) stream, fed in ascending list order by a whole warp; order:
+// score descending, ties to the lower (= earlier) list.  Up to 32 probes lane j holds the j-th best in
+// registers; beyond that (n_probe > 32, buckets of >= 512 lists) the list lives in the warp's slice of shared
+// memory: a score that does not beat the current P-th best is rejected by one compare, the others are
+// inserted by a warp-wide shift.
+struct ProbeList {
+  double my_score;
+  int32_t my_id;
+  double* s;
+  int32_t* ids;
+  int cnt, P;
+  double worst;
+  bool big;
+  __device__ __forceinline__ void init(int P_, double* s_, int32_t* ids_) {
+    P = P_;
+    big = P_ > 32;
+    s = s_;
+    ids = ids_;
+    cnt = 0;
+    worst = -INFINITY;
+    my_score = -INFINITY;
+    my_id = -1;
+  }
+  // all lanes pass the same (sc, cid)
+  __device__ __forceinline__ void push(double sc, int32_t cid, int lane) {
+    if (!big) {
+      const uint32_t ahead = __ballot_sync(0xffffffffu, my_id >= 0 && my_score >= sc);
+      const int pos = __popc(ahead);
+      if (pos < P) {
+        const double up_s = __shfl_up_sync(0xffffffffu, my_score, 1);
+        const int32_t up_i = __shfl_up_sync(0xffffffffu, my_id, 1);
+        if (lane > pos) { my_score = up_s; my_id = up_i; }
+        if (lane == pos) { my_score = sc; my_id = cid; }
+      }
+      return;
+    }
+    if (cnt == P && !(sc > worst)) return;  // equal scores: the earlier list stays
+    int pos = 0;
+    for (int j0 = 0; j0 < cnt; j0 += 32) {
+      const int j = j0 + lane;
+      const uint32_t ahead = __ballot_sync(0xffffffffu, j < cnt && s[j] >= sc);
+      pos += __popc(ahead);
+      if (ahead != 0xffffffffu) break;
+    }
+    const int ncnt = min(cnt + 1, P);
+    for (int hi = ncnt - 1; hi > pos; hi -= 32) {  // shift [pos, ncnt - 1) up by one, from the top
+      const int j = hi - lane;
+      double ts = 0.0;
+      int32_t ti = 0;
+      if (j > pos) { ts = s[j - 1]; ti = ids[j - 1]; }
+      __syncwarp();
+      if (j > pos) { s[j] = ts; ids[j] = ti; }
+      __syncwarp();
+    }
+    if (lane == 0) { s[pos] = sc; ids[pos] = cid; }
+    __syncwarp();
+    cnt = ncnt;
+    if (cnt == P) worst = s[P - 1];
+  }
+  // probes[0 .. max_nprobe) of the row and its list
+  __device__ __forceinline__ void store(int32_t* probes_row, int32_t max_nprobe, int32_t* list_id_row, int lane) {
+    if (!big) {
+      if (lane < max_nprobe) probes_row[lane] = lane < P ? my_id : -1;
+      for (int t = 32 + lane; t < max_nprobe; t += 32) probes_row[t] = -1;
+      if (lane == 0) *list_id_row = my_id;
+    } else {
+      for (int t = lane; t < max_nprobe; t += 32) probes_row[t] = t < cnt ? ids[t] : -1;
+      if (lane == 0) *list_id_row = ids[0];
+    }
+  }
+};
+__host__ __device__ inline size_t probe_list_bytes(int32_t max_nprobe) {  // per warp
+  return max_nprobe > 32 ? ((static_cast<size_t>(max_nprobe) * 12 + 15) & ~size_t(15)) : 0;
+}
+
 // Final assignment + probe list: one warp per row, float64 inner products,
 // best-first insertion into a warp-resident list (lane j holds the j-th best so
 // far).  With `bclass` only rows of tiled buckets are handled.
@@ -155,18 +231,20 @@ ivf_assign_kernel(const float* __restrict__ x, int64_t ld, int64_t n, uint32_t l
   const int32_t L = nlist[b];
   if (L == 0) {
     if (lane == 0) list_id[i] = 0;
-    if (lane < max_nprobe) probes[i * max_nprobe + lane] = lane == 0 ? 0 : -1;
+    for (int t = lane; t < max_nprobe; t += 32) probes[i * max_nprobe + t] = t == 0 ? 0 : -1;
     return;
   }
   const int32_t P = min(nprobe[b], max_nprobe);  // max_nprobe may be a caller-side bound (checked by the caller)
   float* xi = smem_x + static_cast<size_t>(warp) * low_dim;
+  unsigned char* pl_mem = reinterpret_cast<unsigned char*>(smem_x + static_cast<size_t>(8) * low_dim) +
+                          warp * probe_list_bytes(max_nprobe);
+  ProbeList top;
+  top.init(P, reinterpret_cast<double*>(pl_mem), reinterpret_cast<int32_t*>(pl_mem + static_cast<size_t>(max_nprobe) * 8));
   if (ell_idx == nullptr) {
     for (uint32_t t = lane; t < low_dim; t += 32) xi[t] = x[i * ld + t];
     __syncwarp();
   }
   const float* cent = centroids + centroid_ptr[b] * low_dim;
-  double my_score = -INFINITY;
-  int32_t my_id = -1;
   for (int32_t c = 0; c < L; ++c) {
     const float* cr = cent + static_cast<int64_t>(c) * low_dim;
     double acc = 0.0;
@@ -182,18 +260,9 @@ ivf_assign_kernel(const float* __restrict__ x, int64_t ld, int64_t n, uint32_t l
         acc = fma(static_cast<double>(xi[t]), static_cast<double>(__ldg(cr + t)), acc);
     }
     acc = warp_sum_f64(acc);
-    // entries ahead of the newcomer: strictly better, or equal (earlier id wins)
-    const uint32_t ahead = __ballot_sync(0xffffffffu, my_id >= 0 && my_score >= acc);
-    const int pos = __popc(ahead);
-    if (pos < P) {
-      const double up_s = __shfl_up_sync(0xffffffffu, my_score, 1);
-      const int32_t up_i = __shfl_up_sync(0xffffffffu, my_id, 1);
-      if (lane > pos) { my_score = up_s; my_id = up_i; }
-      if (lane == pos) { my_score = acc; my_id = c; }
-    }
+    top.push(acc, c, lane);  // entries ahead of the newcomer: strictly better, or equal (earlier id wins)
   }
-  if (lane < max_nprobe) probes[i * max_nprobe + lane] = lane < P ? my_id : -1;
-  if (lane == 0) list_id[i] = my_id;
+  top.store(probes + i * max_nprobe, max_nprobe, list_id + i, lane);
 }
 
 // ---------------------------------------------------------------- classification
@@ -1340,7 +1409,9 @@ __global__ void __launch_bounds__(256)
 ivf_assign_tiled_kernel(TiledArgs A, const int32_t* __restrict__ nprobe, int32_t max_nprobe,
                         const int32_t* __restrict__ rows, const int32_t* __restrict__ n_rows,
                         int32_t* __restrict__ list_id, int32_t* __restrict__ probes) {
+  extern __shared__ __align__(16) unsigned char pl_smem[];
   const int lane = threadIdx.x & 31;
+  unsigned char* pl_mem = pl_smem + (threadIdx.x >> 5) * probe_list_bytes(max_nprobe);
   const int32_t total_rows = *n_rows;
   for (int32_t w = blockIdx.x * 8 + (threadIdx.x >> 5); w < total_rows; w += gridDim.x * 8) {
   const int64_t i = rows[w];
@@ -1350,8 +1421,8 @@ ivf_assign_tiled_kernel(TiledArgs A, const int32_t* __restrict__ nprobe, int32_t
   const int d = static_cast<int>(A.low_dim);
   const float* ctb = A.ct + A.centroid_ptr[b] * d;
   const int m = min(static_cast<int>(A.ell_nnz[i]), A.W);
-  double my_score = -INFINITY;  // lane j: j-th best so far
-  int32_t my_id = -1;
+  ProbeList top;
+  top.init(P, reinterpret_cast<double*>(pl_mem), reinterpret_cast<int32_t*>(pl_mem + static_cast<size_t>(max_nprobe) * 8));
   for (int32_t s0 = 0; s0 < L; s0 += 32) {
     const int32_t c = s0 + lane;
     double acc = 0.0;
@@ -1380,26 +1451,22 @@ ivf_assign_tiled_kernel(TiledArgs A, const int32_t* __restrict__ nprobe, int32_t
           const int oc = __shfl_xor_sync(0xffffffffu, bc, o);
           if (oc != 0x7fffffff && (bc == 0x7fffffff || ov > bv || (ov == bv && oc < bc))) { bv = ov; bc = oc; }
         }
-        if (lane == t) { my_score = bv; my_id = bc; }
+        if (lane == t) { top.my_score = bv; top.my_id = bc; }
         if (static_cast<int>(c) == bc) taken = true;
       }
       break;
     }
-    for (int t = 0; t < n_here; ++t) {
-      const double sc = __shfl_sync(0xffffffffu, acc, t);
-      // entries ahead of the newcomer: strictly better, or equal (earlier id wins)
-      const uint32_t ahead = __ballot_sync(0xffffffffu, my_id >= 0 && my_score >= sc);
-      const int pos = __popc(ahead);
-      if (pos < P) {
-        const double up_s = __shfl_up_sync(0xffffffffu, my_score, 1);
-        const int32_t up_i = __shfl_up_sync(0xffffffffu, my_id, 1);
-        if (lane > pos) { my_score = up_s; my_id = up_i; }
-        if (lane == pos) { my_score = sc; my_id = s0 + t; }
+    if (top.big && top.cnt == top.P) {
+      // only the scores that beat the current P-th best need the list
+      for (uint32_t rest = __ballot_sync(0xffffffffu, c < L && acc > top.worst); rest != 0u; rest &= rest - 1u) {
+        const int t = __ffs(rest) - 1;
+        top.push(__shfl_sync(0xffffffffu, acc, t), s0 + t, lane);
       }
+    } else {
+      for (int t = 0; t < n_here; ++t) top.push(__shfl_sync(0xffffffffu, acc, t), s0 + t, lane);
     }
   }
-  if (lane < max_nprobe) probes[i * max_nprobe + lane] = lane < P ? my_id : -1;
-  if (lane == 0) list_id[i] = my_id;
+  top.store(probes + i * max_nprobe, max_nprobe, list_id + i, lane);
   }
 }
 
@@ -1528,8 +1595,7 @@ int flc_kmeans_train(const uint16_t* ell_idx, const float* ell_val, const uint16
   const char* force_env = getenv("FLC_KMEANS_FORCE_TILED");
   const int force_tiled = (force_env != nullptr && force_env[0] == '1') ? 1 : 0;
   const bool tiled = force_tiled || kmeans_needs_tiled(n, max_ivf_bucket, W, low_dim);
-  if (tiled && list_id != nullptr && max_nprobe > 32)
-    return set_error(FLC_ERR_UNSUPPORTED, "n_probe > 32 is not supported by the device probe selection");
+  FLC_REQUIRE(max_nprobe <= 1024, "n_probe > 1024 not supported");
   Workspace ws(workspace, workspace_bytes);
   KmeansLayout K;
   kmeans_layout(ws, n, n_buckets, total_centroids, low_dim, tiled, K);
@@ -1649,7 +1715,11 @@ int flc_kmeans_train(const uint16_t* ell_idx, const float* ell_val, const uint16
       ivf_assign_tiled_f32_kernel<<<static_cast<unsigned>((n + kAssignRows - 1) / kAssignRows), kAssignRows, asmem, stream>>>(
           T, nprobe, max_nprobe, gap, list_id, probes, K.tc_unsure, T.tc_counts + 1); });
     FLC_LAUNCH_CHECK();
-    timed("ivf_assign_tiled", stream, [&] { ivf_assign_tiled_kernel<<<kNumSMs * 8, 256, 0, stream>>>(
+    const size_t plsmem = 8 * probe_list_bytes(max_nprobe);
+    if (plsmem > 48 * 1024)
+      FLC_CUDA(cudaFuncSetAttribute(ivf_assign_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    static_cast<int>(plsmem)));
+    timed("ivf_assign_tiled", stream, [&] { ivf_assign_tiled_kernel<<<kNumSMs * 8, 256, plsmem, stream>>>(
         T, nprobe, max_nprobe, K.tc_unsure, T.tc_counts + 1, list_id, probes); });
     FLC_LAUNCH_CHECK();
   }
@@ -1678,11 +1748,10 @@ int flc_ivf_assign(const float* x, int64_t ld, int64_t n, uint32_t low_dim, cons
   FLC_REQUIRE(max_nprobe >= 1, "max_nprobe must be >= 1");
   FLC_REQUIRE((ell_idx == nullptr) == (ell_val == nullptr), "ell_idx and ell_val go together");
   FLC_REQUIRE(ell_idx != nullptr || x != nullptr, "need dense or ELL rows");
-  if (max_nprobe > 32)
-    return set_error(FLC_ERR_UNSUPPORTED, "n_probe > 32 is not supported by the device probe selection");
+  FLC_REQUIRE(max_nprobe <= 1024, "n_probe > 1024 not supported");
   if (n == 0) return FLC_OK;
   cudaStream_t stream = as_stream(stream_);
-  const size_t smem = static_cast<size_t>(8) * low_dim * sizeof(float);
+  const size_t smem = static_cast<size_t>(8) * low_dim * sizeof(float) + 8 * probe_list_bytes(max_nprobe);
   if (smem > 48 * 1024)
     FLC_CUDA(cudaFuncSetAttribute(ivf_assign_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   static_cast<int>(smem)));

@@ -16,6 +16,12 @@ import torch
 import torch.distributed as dist
 
 
+# Largest bucket that is clustered as ONE unit.  The published sizing rule gives a bucket of >= 10^6 vectors
+# 65 536 inverted lists; the device trainer is built for buckets up to that point, and larger
+# buckets are cut into pieces with a precursor-tolerance halo (plan_units), each piece indexed on its own.
+MAX_BUCKET_ROWS = 1 << 19
+
+
 def unit_cost(n_queries, n_candidates, exhaustive: bool = True, n_probe: int = 32) -> np.ndarray:
     """Work of clustering ``n_queries`` rows against a bucket of ``n_candidates`` rows: the scan,
     ``q * c`` (exhaustive) or ``q * c * nprobe / nlist`` (IVF sizing rule of SURVEY A.2), plus the
@@ -235,8 +241,10 @@ def plan_units(bucket_ptr, mz_sorted, world_size: int, tol: float, tol_mode: str
     mz = np.asarray(mz_sorted, np.float64)
     sizes = np.diff(bptr)
     if bucket_cap is None:
+        # no unit above a rank's fair share of the scan cost, and none above MAX_BUCKET_ROWS (also on one GPU)
         total = float(unit_cost(sizes, sizes, exhaustive, n_probe).sum())
-        bucket_cap = max(4096, int(np.sqrt(total / max(world_size, 1)))) if world_size > 1 else int(sizes.max(initial=0)) + 1
+        bucket_cap = min(MAX_BUCKET_ROWS, max(4096, int(np.sqrt(total / max(world_size, 1))))) if world_size > 1 \
+            else MAX_BUCKET_ROWS
     bucket_cap = max(int(bucket_cap), 1)
     cols = {k: [] for k in ("bucket", "q0", "q1", "c0", "c1", "piece")}
 
@@ -304,7 +312,15 @@ def cluster_sharded(spectra, settings=None, device=None, group=None, bucket_cap=
     /root/reference/falcon/falcon.py:189-193).  A bucket larger than ``bucket_cap`` is cut into
     pieces with a halo of one precursor tolerance; the pieces' sparse rows are gathered and the
     bucket's DBSCAN runs on one rank, so the result is the single-GPU partition (in exhaustive mode;
-    with the IVF index a cut bucket trains one index per piece instead of one per bucket).
+    with the IVF index a cut bucket trains one index per piece instead of one per bucket).  Buckets of
+    more than ``MAX_BUCKET_ROWS`` rows are always cut, also on one GPU: this is the entry point for data
+    whose buckets exceed what ``HotPath.run`` indexes as one unit.
+
+    Exactness of a cut (exhaustive mode): the reference ranks a query's candidates over the whole bucket,
+    keeps ``n_neighbors_ann``, and only then applies the precursor tolerance; a piece ranks the candidates
+    inside its halo.  Both agree whenever fewer than ``n_neighbors_ann`` rows of the bucket lie within
+    ``eps`` (+ the scan margin) of a query -- the eps-cut matrix only holds such rows -- which is the
+    regime falcon's defaults (128 candidates, eps 0.1) are chosen for.
 
     Returns ``(labels, n_clusters, representatives)`` on every rank: int32 labels in INPUT order
     (-1 = noise), the number of clusters, and -- with ``settings.representatives`` -- the input index of

@@ -341,6 +341,9 @@ class HotPath:
         ld = x.stride(0) if x is not None else d
         with self.timer("ivf_train"):
             nlist, nprobe, cptr, total, maxp, maxb = self.ivf_plan(buckets, caps)
+            if maxb >= (1 << 20):
+                raise ValueError(f"a precursor bucket holds {maxb} spectra: buckets of 2^20 rows and more are clustered "
+                                 "through falcon_b200.distributed.cluster_sharded, which cuts them (also on one GPU)")
             list_id = self._empty(n, torch.int32)
             probes = torch.empty((n, maxp), dtype=torch.int32, device=self.device)
             if centroids is None:

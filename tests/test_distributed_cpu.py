@@ -123,6 +123,10 @@ def test_plan_units_cuts_oversized_buckets_with_a_tolerance_halo():
             need = np.flatnonzero(reach.any(axis=0)) + b0  # every candidate some query of the piece can reach
             assert need.min() >= u["c0"][i] and need.max() < u["c1"][i]
             assert u["c1"][i] - u["c0"][i] < (b1 - b0)  # and the halo is not the whole bucket
+    # a bucket beyond MAX_BUCKET_ROWS is cut whatever the number of ranks
+    big = np.sort(700.0 + np.random.default_rng(1).uniform(0, 0.5, fd.MAX_BUCKET_ROWS * 2 + 10))
+    u1 = fd.plan_units(np.array([0, big.shape[0]]), big, 1, 20.0, "ppm")
+    assert (u1["piece"] == 1).all() and u1["piece"].shape[0] == 3 and (u1["q1"] - u1["q0"]).max() <= fd.MAX_BUCKET_ROWS
     # no cap needed on one rank; the automatic cap leaves small buckets whole
     assert (fd.plan_units(bptr, mz, 1, 20.0, "ppm")["piece"] == 0).all()
     assert (fd.plan_units(bptr, mz, 2, 20.0, "ppm")["piece"] == 0).all()

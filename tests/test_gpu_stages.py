@@ -259,6 +259,36 @@ def test_ivf_shared_centroids_exact_and_recall(sparse):
     assert np.array_equal(gp, ref.indptr) and np.array_equal(gi, ref.indices)
 
 
+def test_ivf_more_than_32_probes():
+    """n_probe = 64 on a bucket of > 20 000 rows (512 lists, min(ceil(512 / 8), 64) = 64 probes): probe lists
+    from the trainer's final assignment and from flc_ivf_assign both equal the oracle's for the same centroids;
+    neighbours at that n_probe equal the oracle's."""
+    h = pipeline.HotPath(pipeline.Settings(exhaustive=False, n_probe=64))
+    sp = synth.generate(44000, 29, mass_range=(1000.05, 1000.85))
+    d = helpers.to_device(sp, h.device)
+    b = h.bucket_sort(d["precursor_mz"], d["charge"])
+    v = h.vectorize(d["mz"], d["intensity"], d["indptr"], b.order)
+    ivf = h.build_ivf(v, b)
+    nlist, cptr, bptr = _cpu(ivf.nlist), _cpu(ivf.centroid_ptr), _cpu(b.bucket_ptr)
+    assert np.diff(bptr).max() > 20000 and nlist[: b.n_buckets].max() == 512 and ivf.max_nprobe == 64
+    again = h.build_ivf(_drop_ell(v), b, centroids=ivf.centroids)  # flc_ivf_assign on the dense rows
+    assert torch.equal(again.list_id, ivf.list_id) and torch.equal(again.probes, ivf.probes)
+    cents, xs = _cpu(ivf.centroids), _cpu(v.x)
+    shared = [cents[cptr[i]: cptr[i] + nlist[i]] if nlist[i] else None for i in range(b.n_buckets)]
+    lid, probes = _cpu(ivf.list_id), _cpu(ivf.probes)
+    for i in range(b.n_buckets):
+        if nlist[i]:
+            s, e = bptr[i], bptr[i + 1]
+            p = oivf.n_probe_rule(int(nlist[i]), 64)
+            assert np.array_equal(lid[s:e], oivf.assign_lists(xs[s:e], shared[i]))
+            assert np.array_equal(probes[s:e, :p], oivf.probe_lists(xs[s:e], shared[i], p))
+            assert (probes[s:e, p:] == -1).all()
+    g = h.knn_graph(v, b, ivf)
+    o = helpers.oracle_pipeline(sp, exhaustive=False, centroids=shared, vectors=xs, n_probe=64)
+    ref = o["csr_cut"]
+    assert np.array_equal(_cpu(g.indptr), ref.indptr) and np.array_equal(_cpu(g.indices), ref.indices)
+
+
 def _train(n, seed, lo, hi, force_tiled=False, monkeypatch=None, want_bf16=False, tc_all=False, tc_dense=False,
            low_dim=400, negate=False):
     if monkeypatch is not None:

@@ -136,3 +136,38 @@ def test_preprocess_oracle_hand_example():
     assert opre.process_spectrum(mz, it, 300.0, 2, scaling=None, **{**kw, "min_peaks": 5}) is None
     m, i = opre.process_spectrum(mz, it, 300.0, 2, scaling="root", **{**kw, "max_peaks_used": None})
     assert m.tolist() == [150.0, 200.5, 400.0, 700.0] and abs(float((i.astype(np.float64) ** 2).sum()) - 1) < 1e-6
+
+
+def test_oracle_kmeans_against_sklearn_kmeans():
+    """An independent second source for the IVF trainer the oracle restates (faiss itself is not installable
+    here): scikit-learn's Lloyd k-means, started from the same rows, on the same unit vectors.  For unit
+    vectors the Euclidean objective is 2 - 2 * (mean inner product with the own centroid direction), so the
+    two must reach the same quality; the assignments of the oracle's spherical variant and sklearn's centroids
+    (normalised) must largely agree."""
+    from sklearn.cluster import KMeans
+
+    sp = helpers.dataset(4000, 9, 1000.0, 1001.0)
+    x = helpers.oracle_vectors(sp)
+    order, bptr, _ = oivf.bucket_sort(sp.precursor_mz, sp.precursor_charge)
+    sizes = np.diff(bptr)
+    b = int(np.argmax(sizes))
+    xb = x[order[bptr[b]: bptr[b + 1]]]
+    k = oivf.n_list_rule(xb.shape[0])
+    assert k >= 16
+    cent = oivf.kmeans_train(xb, k, 10)
+    init = xb[(np.arange(k, dtype=np.int64) * xb.shape[0]) // k]
+    km = KMeans(n_clusters=k, init=init, n_init=1, max_iter=10, algorithm="lloyd", tol=0.0).fit(xb.astype(np.float64))
+    sk = km.cluster_centers_ / np.linalg.norm(km.cluster_centers_, axis=1, keepdims=True)
+
+    def quality(c):
+        return float((xb.astype(np.float64) @ c.T).max(axis=1).mean())
+
+    q_oracle, q_sklearn, q_init = quality(cent.astype(np.float64)), quality(sk), quality(init.astype(np.float64))
+    assert q_oracle > q_init + 0.02 and q_sklearn > q_init + 0.02  # training does something on this data
+    assert abs(q_oracle - q_sklearn) < 0.03 * q_sklearn  # spherical vs Euclidean means: not the same fixed point
+    # same rows grouped together by both solutions (adjusted Rand index of the two assignments)
+    from sklearn.metrics import adjusted_rand_score
+
+    a = oivf.assign_lists(xb, cent)
+    s = np.argmax(xb.astype(np.float64) @ sk.T, axis=1)
+    assert adjusted_rand_score(a, s) > 0.5  # 64 lists over ~600 templates: many equally good groupings
