@@ -5,4 +5,4 @@ Drop-in for the ``falcon.cluster`` entry points named by the north star
 see ``falcon_b200.cluster``.  All compute runs in hand-written sm_100a CUDA
 kernels behind the C ABI of ``include/falcon_b200.h``; there is no CPU fallback.
 """
-__version__ = "0.1.0"
+__version__ = "0.2.0+b200"

@@ -9,7 +9,7 @@ import argparse
 import os
 from typing import List, Optional
 
-__version__ = "0.1.0+b200"
+from . import __version__  # noqa: E402  (one version string for the package and the CSV header)
 
 
 def _ini_args(path: str) -> List[str]:
@@ -61,6 +61,14 @@ class Config:
         p.add_argument("--batch_size", type=int, default=2 ** 16, help="Batch size (kept for compatibility).")
         p.add_argument("--n_probe", type=int, default=32, help="Maximum number of lists to probe per query.")
         p.add_argument("--exhaustive", action="store_true", help="Probe every list (n_probe = n_list).")
+        p.add_argument("--singletons_as_clusters", action="store_true",
+                       help="Give every unclustered spectrum its own cluster id in the CSV, as the development "
+                            "head of falcon does (cluster.py:144-155), instead of -1 (published releases).")
+        # The development head of falcon replaced the nearest-neighbour + DBSCAN pipeline by exact
+        # hierarchical clustering (config.py:96-124).  This build implements the published pipeline: those
+        # flags are recognised and refused, not silently ignored.
+        p.add_argument("--linkage", default=None, help=argparse.SUPPRESS)
+        p.add_argument("--min_matched_peaks", default=None, help=argparse.SUPPRESS)
         # preprocessing (config.py:127-183)
         p.add_argument("--min_peaks", default=5, type=int)
         p.add_argument("--min_mz_range", default=250.0, type=float)
@@ -89,6 +97,11 @@ class Config:
         ns["precursor_tol"] = [float(ns["precursor_tol"][0]), str(ns["precursor_tol"][1])]
         if ns["precursor_tol"][1] not in ("ppm", "Da"):
             raise ValueError("Unknown precursor tolerance mode")
+        for flag in ("linkage", "min_matched_peaks"):
+            if ns[flag] is not None:
+                raise ValueError(f"--{flag} belongs to the hierarchical-clustering pipeline of falcon's development "
+                                 "head; this build clusters with the published nearest-neighbour + DBSCAN pipeline "
+                                 "(--eps, --n_probe, ...)")
         if ns["distance_threshold"] is not None:
             ns["eps"] = ns["distance_threshold"]
         if ns["n_neighbors_ann"] < ns["n_neighbors"]:

@@ -17,8 +17,11 @@ from typing import List, Optional
 import numpy as np
 import torch
 
-from . import pipeline, synth
-from .config import __version__, config
+import glob
+import re
+
+from . import __version__, pipeline, synth
+from .config import config
 from .ms_io import mgf_io
 
 logger = logging.getLogger("falcon")
@@ -65,12 +68,18 @@ def main(args: Optional[List[str]] = None) -> int:
                         style="{", level=logging.INFO)
     config.parse(args)
     csv_path = f"{config.output_filename}.csv"
-    if os.path.isfile(csv_path) and not config.overwrite:
-        logger.warning("Output file %s already exists, skipping (use --overwrite)", csv_path)
-        return 0
+    # existing results are an error unless --overwrite (/root/reference/falcon/falcon.py:90-122), the representatives file included
+    outputs = [csv_path] + ([f"{config.output_filename}.mgf"] if config.export_representatives else [])
+    if not config.overwrite:
+        for path in outputs:
+            if os.path.isfile(path):
+                logger.error("Output file %s already exists (use --overwrite)", path)
+                return 1
     logger.info("falcon version %s", __version__)
-    raw, idents, files = _read_inputs(config.input_filenames)
-    logger.info("Read %d spectra from %d peak file(s)", len(raw), len(config.input_filenames))
+    # input patterns are expanded like the reference does (/root/reference/falcon/falcon.py:262-264)
+    input_filenames = [fn for pattern in config.input_filenames for fn in (sorted(glob.glob(pattern)) or [pattern])]
+    raw, idents, files = _read_inputs(input_filenames)
+    logger.info("Read %d spectra from %d peak file(s)", len(raw), len(input_filenames))
     settings = pipeline.Settings(
         precursor_tol_mass=config.precursor_tol[0], precursor_tol_mode=config.precursor_tol[1], rt_tol=config.rt_tol,
         fragment_tol=config.fragment_tol, eps=config.eps, mz_interval=config.mz_interval, low_dim=config.low_dim,
@@ -134,7 +143,17 @@ def main(args: Optional[List[str]] = None) -> int:
     if not rows["cluster"]:
         logger.error("No valid spectra found for clustering")
         return 1
-    order = sorted(range(len(rows["cluster"])), key=lambda i: (rows["filename"][i], rows["spectrum_id"][i]))
+    if config.singletons_as_clusters:  # development-head convention: noise -> new singleton cluster ids
+        lab = np.asarray(rows["cluster"], np.int64)
+        noise = np.flatnonzero(lab < 0)
+        lab[noise] = current_label + np.arange(noise.shape[0])
+        rows["cluster"] = lab.tolist()
+
+    def natural(text):  # natsort's order (/root/reference/falcon/falcon.py:206-208): digit runs compare as numbers
+        return [(0, int(t), "") if t.isdigit() else (1, 0, t) for t in re.split(r"(\d+)", str(text)) if t != ""]
+
+    order = sorted(range(len(rows["cluster"])),
+                   key=lambda i: (natural(rows["filename"][i]), natural(rows["spectrum_id"][i])))
     rows = {k: [v[i] for i in order] for k, v in rows.items()}
     logger.info("Export cluster assignments of %d spectra to %d unique clusters to output file %s",
                 len(rows["cluster"]), current_label, csv_path)

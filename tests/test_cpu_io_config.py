@@ -79,3 +79,26 @@ def test_config_defaults_ini_and_command_line(tmp_path):
         cfg.parse(["in.mgf", "out", "--n_neighbors", "64", "--n_neighbors_ann", "32"])
     cfg.parse(["in.mgf", "out", "--distance_threshold", "0.15"])
     assert cfg.eps == 0.15
+
+
+def test_config_refuses_the_development_heads_flags_and_maps_its_alias():
+    cfg = fconfig.Config()
+    cfg.parse(["a.mgf", "out", "--distance_threshold", "0.25", "--singletons_as_clusters"])
+    assert cfg.eps == 0.25 and cfg.singletons_as_clusters
+    for flag, val in (("--linkage", "complete"), ("--min_matched_peaks", "6")):
+        with pytest.raises(ValueError, match="hierarchical-clustering pipeline"):
+            fconfig.Config().parse(["a.mgf", "out", flag, val])
+
+
+def test_cli_refuses_existing_outputs_before_doing_any_work(tmp_path):
+    """falcon.py:90-122: an existing .csv (or .mgf with --export_representatives) without --overwrite is an
+    error (return code 1), checked before anything is read or computed -- no GPU is needed to get there."""
+    from falcon_b200 import falcon as fmain
+
+    out = tmp_path / "res"
+    (tmp_path / "res.csv").write_text("old")
+    assert fmain.main([str(tmp_path / "missing.mgf"), str(out)]) == 1
+    (tmp_path / "res.csv").unlink()
+    (tmp_path / "res.mgf").write_text("old")
+    assert fmain.main([str(tmp_path / "missing.mgf"), str(out), "--export_representatives"]) == 1
+    assert (tmp_path / "res.mgf").read_text() == "old"

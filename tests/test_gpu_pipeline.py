@@ -251,6 +251,11 @@ def test_cli_mgf_to_csv_matches_oracle(tmp_path):
     assert header[0].startswith("# falcon version") and any(l.startswith("# eps = 0.100") for l in header)
     df = pd.read_csv(out + ".csv", comment="#")
     assert list(df.columns) == ["filename", "spectrum_id", "precursor_charge", "precursor_mz", "retention_time", "cluster"]
+    # rows in natural order of (filename, spectrum_id) like natsort (falcon.py:206-208): synth:2 before synth:10
+    nums = [int(t.split(":")[1]) for t in df["spectrum_id"]]
+    assert nums == sorted(nums) and nums != sorted(nums, key=str)
+    # a second run without --overwrite refuses (return code 1) and leaves the files alone
+    assert fmain.main([path, out, "--exhaustive"]) == 1
     # oracle: same preprocessing, same path
     raw, ids, _ = mgf_io.read_mgf(path)
     # falcon.py:120-133: the m/z window the spectra are restricted to is get_dim's, not the raw setting
