@@ -182,15 +182,20 @@ refine_kernel(RefineParams P, const int64_t* __restrict__ off, uint64_t* __restr
   uint64_t* buf = reinterpret_cast<uint64_t*>(smem_raw + warp * per_warp);
   float* xq = reinterpret_cast<float*>(buf + 2 * P.ka_pow2);
   const bool sparse = P.ell_idx != nullptr;
-  // With `deferred` this kernel only finishes the query blocks refine_block_kernel passed on.
-  if (deferred != nullptr && deferred[0] == 0) return;
+  // With `deferred` this kernel only finishes the query groups refine_block_kernel passed on:
+  // deferred[0] = how many, deferred[1 ..] = their group numbers (kWarpQueries queries each).
+  const int64_t n_work = deferred != nullptr ? static_cast<int64_t>(deferred[0]) * kWarpQueries : P.n;
+  if (n_work == 0) return;
   if (sparse) {
     for (uint32_t i = lane; i < P.low_dim; i += 32) xq[i] = 0.f;
     __syncwarp();
   }
   const int64_t warps_total = static_cast<int64_t>(gridDim.x) * kRefineWarps;
-  for (int64_t q = static_cast<int64_t>(blockIdx.x) * kRefineWarps + warp; q < P.n; q += warps_total) {
-    if (deferred != nullptr && deferred[1 + q / kWarpQueries] == 0) continue;
+  for (int64_t w = static_cast<int64_t>(blockIdx.x) * kRefineWarps + warp; w < n_work; w += warps_total) {
+    const int64_t q = deferred != nullptr
+                          ? static_cast<int64_t>(deferred[1 + w / kWarpQueries]) * kWarpQueries + (w % kWarpQueries)
+                          : w;
+    if (q >= P.n) continue;
     const int64_t base = off[q];
     const int64_t m = off[q + 1] - base;
     if (m == 0) {
@@ -323,7 +328,7 @@ refine_kernel(RefineParams P, const int64_t* __restrict__ off, uint64_t* __restr
 // zero), products accumulate in float64, two shuffles join the quad.  Ranks come
 // from counting smaller keys among the query's pairs, then the same top-k_ann /
 // tolerance / first-k selection as refine_kernel.  Query groups with more than
-// kWarpPairs pairs are flagged in `deferred` (deferred[0] = any) and left to
+// kWarpPairs pairs are appended to `deferred` (deferred[0] = how many) and left to
 // refine_kernel.
 __global__ void __launch_bounds__(kBlockWarps * 32)
 refine_block_kernel(RefineParams P, const int64_t* __restrict__ off, uint64_t* __restrict__ grouped,
@@ -349,7 +354,7 @@ refine_block_kernel(RefineParams P, const int64_t* __restrict__ off, uint64_t* _
     const int64_t base = __shfl_sync(0xffffffffu, my_off, 0);
     const int64_t pb64 = __shfl_sync(0xffffffffu, my_off, nq) - base;
     if (pb64 > kWarpPairs) {  // uniform
-      if (lane == 0) { deferred[1 + grp] = 1; deferred[0] = 1; }
+      if (lane == 0) deferred[1 + atomicAdd(deferred, 1)] = static_cast<int32_t>(grp);
       continue;
     }
     const int pb = static_cast<int>(pb64);
@@ -611,7 +616,7 @@ int flc_knn_csr(const uint64_t* pairs, const uint64_t* pair_count, uint64_t pair
                           (reinterpret_cast<uintptr_t>(ell_idx) % 16) == 0 && (reinterpret_cast<uintptr_t>(ell_val) % 16) == 0;
   if (block_path) {
     const int64_t n_groups = (n + kWarpQueries - 1) / kWarpQueries;
-    FLC_CUDA(cudaMemsetAsync(L.deferred, 0, sizeof(int32_t) * (1 + n_groups), stream));
+    FLC_CUDA(cudaMemsetAsync(L.deferred, 0, sizeof(int32_t), stream));  // [0] = count, [1 ..] = deferred groups
     FLC_CUDA(cudaFuncSetAttribute(refine_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   static_cast<int>(bsmem)));
     const int64_t per_sm = std::max<int64_t>(1, (227 * 1024) / static_cast<int64_t>(bsmem + 1024));

@@ -280,8 +280,11 @@ def test_cli_mgf_to_csv_matches_oracle(tmp_path):
     # one representative per cluster, each a member of its cluster
     reps = list(mgf_io.get_spectra(out + ".mgf"))
     assert len(reps) == lab["cluster"].nunique()
-    # second run without --overwrite leaves the result alone
-    assert fmain.main([path, out, "--exhaustive"]) == 0
+    # --overwrite runs again; every unclustered spectrum can get its own id (development-head convention)
+    assert fmain.main([path, out, "--exhaustive", "--overwrite", "--singletons_as_clusters"]) == 0
+    df2 = pd.read_csv(out + ".csv", comment="#")
+    assert (df2["cluster"] >= 0).all() and df2["cluster"].nunique() == lab["cluster"].nunique() + int((df["cluster"] < 0).sum())
+    assert (df2["cluster"][df["cluster"] >= 0] == df["cluster"][df["cluster"] >= 0]).all()
 
 
 @pytest.mark.gpu
