@@ -318,7 +318,7 @@ class Workload:
                 hp.label_sink = self.peer_gather
             except Exception as exc:  # noqa: BLE001 -- no symmetric memory on this platform: NCCL all-gather
                 log(f"[bench] peer-memory label gather unavailable ({exc!r}); using NCCL all_gather")
-        self.gather_mode = "nvlink peer stores (flc_scatter_labels_peers)" if self.peer_gather else \
+        self.gather_mode = "nvlink peer memory (flc_scatter_labels_peers + barrier + flc_relabel_gathered pull)" if self.peer_gather else \
             ("nccl all_gather" if world > 1 else "none")
 
     def gather(self, labels, n_clusters):
@@ -651,6 +651,7 @@ def multi_gpu_check(args, torch, fdist, pipeline, synth, dev, world, rank):
     for exhaustive in (True, False):
         s = pipeline.Settings(exhaustive=exhaustive, representatives=True)
         # with the IVF index a cut bucket would train one index per piece: only whole buckets are dealt out
+        # (cluster_sharded's default there)
         cap = 2000 if exhaustive else None
         labels, nc, reps = fdist.cluster_sharded(sp, s, device=dev, bucket_cap=cap)
         key = "exhaustive" if exhaustive else "default_nprobe"

@@ -134,42 +134,46 @@ def gather_representatives(representatives: torch.Tensor, n_spectra: int, group=
 
 
 class PeerLabelGather:
-    """Label gather over NVLink peer memory, fused into the step's last kernel.
+    """Label gather over NVLink peer memory, without a collective kernel.
 
     One symmetric buffer per rank (``torch.distributed._symmetric_memory``: CUDA VMM allocations mapped
-    into every peer over NVLink / NVSwitch) holds ``depth`` x ``world`` slots of ``max_len + 2`` int32.
-    ``scatter`` replaces the single-GPU path's final ``flc_scatter32``: the kernel that puts the labels
-    back into input order stores them straight into slot ``rank`` of every peer's buffer
-    (``flc_scatter_labels_peers``), so the transfer is part of the producing kernel -- no NCCL kernel
-    competing for SMs with the persistent kernels of the next batch, no staging copy.  On a side stream a
-    barrier on the peers' signal pads follows, then ``flc_relabel_gathered`` applies the running label
-    offsets (/root/reference/falcon/falcon.py:189-193) from the slot headers.  The compute stream never
-    waits for a peer within a batch; it waits for the barrier of batch k - 1 before it overwrites the
-    slots of batch k - 2 (``depth`` = 2), which is what makes reusing them safe.
+    into every peer over NVLink / NVSwitch) holds ``depth`` slots of ``4 + max_len`` int32.  ``scatter``
+    replaces the single-GPU path's final ``flc_scatter32``: the kernel that puts the labels back into input
+    order writes them into this rank's slot (``flc_scatter_labels_peers``, local stores).  On a side stream a
+    barrier on the peers' signal pads follows, then ``flc_relabel_gathered`` pulls every peer's slot with
+    coalesced loads over NVLink and applies the running label offsets
+    (/root/reference/falcon/falcon.py:189-193) from the slot headers.  The transfer is off the compute
+    stream, which never waits for a peer within a batch -- no NCCL kernel competing for SMs with the
+    persistent kernels of the next batch, no staging copy; the compute stream only waits for the barrier of
+    batch k - 1 before it overwrites the slot of batch k - 2 (``depth`` = 2): passing that barrier means
+    every peer has finished pulling the older slot.
 
     Raises if symmetric memory cannot be set up (callers fall back to ``gather_labels_padded``)."""
 
     def __init__(self, max_len: int, device, group=None, depth: int = 2):
+        import ctypes as C
+
         import torch.distributed._symmetric_memory as symm
 
         self.group = group if group is not None else dist.group.WORLD
         self.world = dist.get_world_size(self.group)
         self.rank = dist.get_rank(self.group)
-        self.max_len, self.slot, self.depth = int(max_len), int(max_len) + 2, depth
+        self.max_len = (int(max_len) + 3) // 4 * 4
+        self.slot, self.depth = self.max_len + 4, depth
         self.device = torch.device(device)
-        self.buf = symm.empty(depth * self.world * self.slot, dtype=torch.int32, device=self.device)
+        self.buf = symm.empty(depth * self.slot, dtype=torch.int32, device=self.device)
         self.hdl = symm.rendezvous(self.buf, self.group)
-        import ctypes as C
-
-        self._ptrs = (C.c_void_p * self.world)(*[int(p) for p in self.hdl.buffer_ptrs])
+        ptrs = [int(p) for p in self.hdl.buffer_ptrs]
+        self._own = (C.c_void_p * 1)(ptrs[self.rank])
+        self._slots = [(C.c_void_p * self.world)(*[p + 4 * b * self.slot for p in ptrs]) for b in range(depth)]
         self.side = torch.cuda.Stream(device=self.device)
         self.k = 0
         self.events = [None] * depth
         self.last = None
 
     def scatter(self, sorted_labels: torch.Tensor, order, n_clusters) -> torch.Tensor:
-        """Labels of this batch in input order (a view of this rank's own slot); the gathered, globally
-        unique labels of all ranks arrive in ``self.last`` = (padded [world, max_len], lens) on ``self.side``."""
+        """Labels of this batch in input order (a view of this rank's slot); the gathered, globally unique
+        labels of all ranks arrive in ``self.last`` = (padded [world, max_len], lens) on ``self.side``."""
         from ._lib import check, lib, ptr
 
         n = int(sorted_labels.shape[0])
@@ -179,13 +183,12 @@ class PeerLabelGather:
         main = torch.cuda.current_stream()
         prev = self.events[(self.k - 1) % self.depth]
         if prev is not None:
-            main.wait_event(prev)  # every peer has read the slots about to be overwritten (class docstring)
-        base = b * self.world * self.slot
-        offset = base + self.rank * self.slot
+            main.wait_event(prev)  # every peer has pulled the slot about to be overwritten (class docstring)
+        offset = b * self.slot
         nc_dev = n_clusters if isinstance(n_clusters, torch.Tensor) else None
         check(lib.flc_scatter_labels_peers(ptr(sorted_labels), ptr(order), n, ptr(nc_dev),
-                                           0 if nc_dev is not None else int(n_clusters), self._ptrs, self.world,
-                                           offset, main.cuda_stream))
+                                           0 if nc_dev is not None else int(n_clusters), self._own, 1, offset,
+                                           main.cuda_stream))
         ev = torch.cuda.Event()
         ev.record(main)
         with torch.cuda.stream(self.side):
@@ -193,14 +196,14 @@ class PeerLabelGather:
             self.hdl.barrier(channel=0)
             out = torch.empty((self.world, self.max_len), dtype=torch.int32, device=self.device)
             lens = torch.empty(self.world, dtype=torch.int64, device=self.device)
-            check(lib.flc_relabel_gathered(ptr(self.buf[base:]), self.world, self.max_len, ptr(out), ptr(lens),
+            check(lib.flc_relabel_gathered(self._slots[b], self.world, self.max_len, ptr(out), ptr(lens),
                                            self.side.cuda_stream))
             done = torch.cuda.Event()
             done.record(self.side)
         self.events[b] = done
         self.k += 1
         self.last = (out, lens)
-        return self.buf[offset + 2: offset + 2 + n]
+        return self.buf[offset + 4: offset + 4 + n]
 
     def wait(self):
         """Make the current stream wait for the gathers issued so far."""
@@ -243,8 +246,10 @@ def plan_units(bucket_ptr, mz_sorted, world_size: int, tol: float, tol_mode: str
     if bucket_cap is None:
         # no unit above a rank's fair share of the scan cost, and none above MAX_BUCKET_ROWS (also on one GPU)
         total = float(unit_cost(sizes, sizes, exhaustive, n_probe).sum())
-        bucket_cap = min(MAX_BUCKET_ROWS, max(4096, int(np.sqrt(total / max(world_size, 1))))) if world_size > 1 \
-            else MAX_BUCKET_ROWS
+        # (with the IVF index a cut bucket would train one index per piece and no longer give the single-GPU
+        # result, so there only MAX_BUCKET_ROWS cuts)
+        bucket_cap = min(MAX_BUCKET_ROWS, max(4096, int(np.sqrt(total / max(world_size, 1))))) \
+            if (world_size > 1 and exhaustive) else MAX_BUCKET_ROWS
     bucket_cap = max(int(bucket_cap), 1)
     cols = {k: [] for k in ("bucket", "q0", "q1", "c0", "c1", "piece")}
 

@@ -123,16 +123,19 @@ FLC_API int flc_scatter32(const void* in, const int32_t* order, int64_t n, void*
 
 /* ------------------------------------------------------------------ 8e: label gather over NVLink peer memory
  * The path's only exchange (running label offset of falcon/falcon.py:189-193).
- * peer_buffers: HOST array of `world` device pointers, entry r = rank r's symmetric int32 buffer
- * (peer-mapped: CUDA P2P / NVLink); this rank's own pointer included.  The kernel stores
- * [n, n_clusters, out...] with out[order[i]] = labels[i] (order == NULL: out[i]) at element offset
- * slot_offset of EVERY buffer.  n_clusters_dev (device int64, nullable) overrides n_clusters. */
+ * A slot = [n, n_clusters, 0, 0, labels ...] (int32).  flc_scatter_labels_peers writes a slot at element
+ * offset slot_offset of each of the `world` buffers in peer_buffers (HOST array of device pointers) with
+ * labels in input order: out[order[i]] = labels[i] (order == NULL: out[i]).  The product passes only the
+ * rank's own symmetric buffer (world = 1: local stores); n_clusters_dev (device int64, nullable)
+ * overrides n_clusters. */
 FLC_API int flc_scatter_labels_peers(const int32_t* labels, const int32_t* order, int64_t n,
                              const int64_t* n_clusters_dev, int64_t n_clusters, void* const* peer_buffers,
                              int world, int64_t slot_offset, flc_stream_t stream);
-/* slots: `world` consecutive slots of max_len + 2 int32 as written above.  out[r, i] = slot r's label i
- * plus the cluster counts of slots < r (-1 stays -1, also beyond slot r's length); lens[r] = its length. */
-FLC_API int flc_relabel_gathered(const int32_t* slots, int world, int64_t max_len, int32_t* out /*[world, max_len]*/,
+/* slots: HOST array of `world` device pointers, entry r = rank r's slot as mapped into this rank (peer
+ * memory: the kernel pulls it with 16-byte loads); slots 16-byte aligned, max_len % 4 == 0 and every slot
+ * holds at least 4 + max_len int32.  out[r, i] = slot r's label i plus the cluster counts of slots < r
+ * (-1 stays -1, also beyond slot r's length); lens[r] = its length. */
+FLC_API int flc_relabel_gathered(const void* const* slots, int world, int64_t max_len, int32_t* out /*[world, max_len]*/,
                          int64_t* lens /*[world]*/, flc_stream_t stream);
 
 /* ------------------------------------------------------------------ a6: IVF train / assign

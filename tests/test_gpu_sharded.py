@@ -140,23 +140,25 @@ def test_peer_memory_label_gather_equals_nccl_gather():
 
 def test_relabel_gathered_single_process():
     """The relabel kernel on hand-made slots (any GPU count): offsets from the headers, -1 kept, padding -1."""
+    import ctypes as C
+
     from falcon_b200._lib import check, lib, ptr
 
     dev = torch.device("cuda", 0)
-    max_len = 6
-    slots = torch.tensor([[5, 2, 0, -1, 1, 1, 0, 99], [3, 1, -1, 0, 0, 77, 77, 77], [0, 0, 9, 9, 9, 9, 9, 9]],
-                         dtype=torch.int32, device=dev)
+    max_len = 8
+    raw = [[5, 2, 0, 0, 0, -1, 1, 1, 0, 99, 99, 99], [3, 1, 0, 0, -1, 0, 0, 77, 77, 77, 77, 77],
+           [0, 0, 0, 0, 9, 9, 9, 9, 9, 9, 9, 9]]
+    slots = [torch.tensor(r, dtype=torch.int32, device=dev) for r in raw]
     out = torch.empty((3, max_len), dtype=torch.int32, device=dev)
     lens = torch.empty(3, dtype=torch.int64, device=dev)
-    check(lib.flc_relabel_gathered(ptr(slots), 3, max_len, ptr(out), ptr(lens), None))
-    assert out.cpu().tolist() == [[0, -1, 1, 1, 0, -1], [-1, 2, 2, -1, -1, -1], [-1] * 6]
+    ptrs = (C.c_void_p * 3)(*[t.data_ptr() for t in slots])
+    check(lib.flc_relabel_gathered(ptrs, 3, max_len, ptr(out), ptr(lens), None))
+    assert out.cpu().tolist() == [[0, -1, 1, 1, 0, -1, -1, -1], [-1, 2, 2, -1, -1, -1, -1, -1], [-1] * 8]
     assert lens.cpu().tolist() == [5, 3, 0]
-    # one "peer" (this GPU): the scatter kernel writes header + labels in input order
-    buf = torch.full((10,), -7, dtype=torch.int32, device=dev)
-    import ctypes as C
-
-    ptrs = (C.c_void_p * 1)(buf.data_ptr())
+    # the scatter kernel writes header + labels in input order into the slot
+    buf = torch.full((12,), -7, dtype=torch.int32, device=dev)
+    own = (C.c_void_p * 1)(buf.data_ptr())
     lab = torch.tensor([4, -1, 2], dtype=torch.int32, device=dev)
     order = torch.tensor([2, 0, 1], dtype=torch.int32, device=dev)
-    check(lib.flc_scatter_labels_peers(ptr(lab), ptr(order), 3, None, 5, ptrs, 1, 1, None))
-    assert buf.cpu().tolist() == [-7, 3, 5, -1, 2, 4, -7, -7, -7, -7]
+    check(lib.flc_scatter_labels_peers(ptr(lab), ptr(order), 3, None, 5, own, 1, 1, None))
+    assert buf.cpu().tolist() == [-7, 3, 5, 0, 0, -1, 2, 4, -7, -7, -7, -7]
