@@ -655,6 +655,9 @@ int flc_split_clusters(const int32_t* labels_in, const double* precursor_mz, con
   if (!ws.ok) return set_error(FLC_ERR_WORKSPACE, "split workspace too small: need %zu", ws.used);
   const int num = static_cast<int>(n);
   const unsigned tblocks = static_cast<unsigned>((n + 255) / 256);
+  int label_bits = 1;
+  while (label_bits < 32 && (int64_t(1) << label_bits) <= n) ++label_bits;  // labels_in[i] < n
+  label_bits = std::min(32, label_bits + 1);
   size_t tmp;
   // Rows grouped by label, ascending in `values` inside a group (stable sorts): L.key_b = sorted
   // keys, *perm_out = sorted position -> row, L.vs = values, L.ghead / L.gstart / L.n_groups.
@@ -679,7 +682,8 @@ int flc_split_clusters(const int32_t* labels_in, const double* precursor_mz, con
     }
     int32_t* perm = (idx_in == L.idx_a) ? L.idx_b : L.idx_a;
     size_t t = L.cub_bytes;
-    FLC_CUDA(cub::DeviceRadixSort::SortPairs(L.cub_tmp, t, L.key_a, L.key_b, idx_in, perm, num, 0, 32, stream));
+    // labels are < n: only their significant bits are sorted on (the noise key is all ones, so it still comes last)
+    FLC_CUDA(cub::DeviceRadixSort::SortPairs(L.cub_tmp, t, L.key_a, L.key_b, idx_in, perm, num, 0, label_bits, stream));
     count_launch(5);
     timed("split_prepare", stream, [&] { split_prepare_kernel<<<tblocks, 256, 0, stream>>>(L.key_b, perm, values, n, L.vs, L.ghead,
                                                       L.runhead); });

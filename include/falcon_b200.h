@@ -258,7 +258,7 @@ FLC_API int flc_dbscan(const float* dist, const int32_t* indices, const int64_t*
                void* workspace, size_t workspace_bytes, flc_stream_t stream);
 
 /* ------------------------------------------------------------------ a11-a15: precursor split
- * falcon/cluster/cluster.py:334-509: inside every DBSCAN cluster, 1-D complete
+ * falcon/cluster/cluster.py:334-509: inside every DBSCAN cluster (labels_in[i] in [0, n) or -1), 1-D complete
  * linkage on precursor m/z cut at tol (inclusive); sub-clusters with fewer than
  * min_samples members become noise; labels renumbered consecutively.
  * values_sorted != 0 promises precursor_mz ascending inside every cluster in
