@@ -551,10 +551,16 @@ def run_ours(args):
                                 "HBM sees every row once (the algorithmic bytes used here), the kernel itself is "
                                 "bound by shared-memory gathers and barriers -- see profiles/ for the smem-pipe figures")
     ncu_traffic = os.path.join(ROOT, "profiles", NCU_TRAFFIC_FILE)
-    if roofline and os.path.exists(ncu_traffic):  # DRAM bytes per launch from the committed ncu --set full capture
-        t = json.load(open(ncu_traffic)).get(roofline["kernel"])
-        if t and t.get("workload") == ("big" if args.mass_range else "default"):
+    if os.path.exists(ncu_traffic) and not args.mass_range and not args.total and args.n == 1_000_000:
+        # DRAM bytes per launch from the committed ncu --set full capture of this workload's steady-state step
+        traffic = json.load(open(ncu_traffic))
+        for name, r in roof_all.items():
+            if name in traffic and traffic[name].get("workload") == "default":
+                r["traffic"] = traffic[name]["dram_bytes_per_launch"]
+        t = traffic.get(roofline["kernel"]) if roofline else None
+        if t and t.get("workload") == "default":
             roofline["traffic"] = t["dram_bytes_per_launch"]
+            roofline["traffic_over_algorithmic"] = t["dram_bytes_per_launch"] / roof_all[roofline["kernel"]]["algorithmic_bytes_per_launch"]
             roofline["traffic_source"] = t.get("source")
 
     cpu_baseline = None
@@ -594,6 +600,8 @@ def run_ours(args):
             "kernels_ms_per_step": {k: v[0] / args.steps for k, v in kernels.items()},
             "kernel_rooflines": {k: {"frac": v["frac"], "achieved": v["achieved"], "unit": v["unit"],
                                      "ms_per_launch": v["ms_per_launch"],
+                                     "algorithmic_bytes_per_launch": v["algorithmic_bytes_per_launch"],
+                                     **({"traffic": v["traffic"]} if "traffic" in v else {}),
                                      **({"survey_8d": v["survey_8d"]} if "survey_8d" in v else {}),
                                      **({"tensor": v["tensor"]} if "tensor" in v else {})}
                                  for k, v in roof_all.items()},
