@@ -102,3 +102,19 @@ def test_cli_refuses_existing_outputs_before_doing_any_work(tmp_path):
     (tmp_path / "res.mgf").write_text("old")
     assert fmain.main([str(tmp_path / "missing.mgf"), str(out), "--export_representatives"]) == 1
     assert (tmp_path / "res.mgf").read_text() == "old"
+
+
+def test_console_script_is_declared_like_the_reference():
+    """setup.cfg:47-49 of the reference declares `falcon = falcon.falcon:main`; pyproject.toml declares the same
+    command on this package's main, and that object exists and takes an argument list."""
+    import inspect
+    import os
+    import tomllib
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    with open(os.path.join(root, "pyproject.toml"), "rb") as fh:
+        meta = tomllib.load(fh)
+    assert meta["project"]["scripts"]["falcon"] == "falcon_b200.falcon:main"
+    from falcon_b200 import falcon as fmain
+
+    assert list(inspect.signature(fmain.main).parameters) == ["args"]
