@@ -105,7 +105,7 @@ def test_cli_refuses_existing_outputs_before_doing_any_work(tmp_path):
 
 
 def test_console_script_is_declared_like_the_reference():
-    """setup.cfg:47-49 of the reference declares `falcon = falcon.falcon:main`; pyproject.toml declares the same
+    """setup.cfg:43-45 of the reference declares `falcon = falcon.falcon:main`; pyproject.toml declares the same
     command on this package's main, and that object exists and takes an argument list."""
     import inspect
     import os
