@@ -1296,7 +1296,9 @@ ivf_assign_tiled_f32_kernel(TiledArgs A, const int32_t* __restrict__ nprobe, int
   const int64_t row1 = min(A.n, row0 + kAssignRows);
   if (row0 >= row1) return;
   int64_t b = find_segment(A.bucket_ptr, A.n_buckets, row0);
-  for (int64_t seg = row0; seg < row1; ++b) {
+  // b < n_buckets: with a caller-side bound of the bucket count that turned out too small the bucket list does not
+  // end at row n (the caller redoes the batch; this kernel must only stay inside the list)
+  for (int64_t seg = row0; seg < row1 && b < A.n_buckets; ++b) {
     const int64_t seg_end = min(row1, A.bucket_ptr[b + 1]);
     const int64_t i = seg + tid;
     const bool active = i < seg_end;
