@@ -194,6 +194,7 @@ struct ProbeList {
     __syncwarp();
     cnt = ncnt;
     if (cnt == P) worst = s[P - 1];
+    __syncwarp();  // every lane has read the new P-th best before the next push may overwrite it
   }
   // probes[0 .. max_nprobe) of the row and its list
   __device__ __forceinline__ void store(int32_t* probes_row, int32_t max_nprobe, int32_t* list_id_row, int lane) {
