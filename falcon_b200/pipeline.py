@@ -40,7 +40,7 @@ class Settings:
     low_dim: int = 400
     n_neighbors: int = 64
     n_neighbors_ann: int = 128
-    batch_size: int = 2 ** 16
+    batch_size: int = 2 ** 16  # falcon's flag, accepted for compatibility: the device path has no search batches
     n_probe: int = 32
     min_mz: float = 101.0
     max_mz: float = 1500.0
