@@ -86,7 +86,21 @@ def main(args: Optional[List[str]] = None) -> int:
         n_neighbors=config.n_neighbors, n_neighbors_ann=config.n_neighbors_ann, batch_size=config.batch_size,
         n_probe=config.n_probe, min_mz=config.min_mz, max_mz=config.max_mz, exhaustive=config.exhaustive,
         representatives=config.export_representatives)
-    hp = pipeline.HotPath(settings)
+    # Under torchrun (one process per GPU) every charge is clustered by all GPUs together
+    # (distributed.cluster_sharded: buckets dealt to the ranks, labels and representatives gathered); every rank
+    # reads and preprocesses the input, rank 0 writes the results.
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    device = None
+    if world > 1:
+        import torch.distributed as dist
+
+        device = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(device)
+        if not dist.is_initialized():
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            dist.init_process_group("nccl", device_id=torch.device("cuda", device))
+    hp = pipeline.HotPath(settings, device)
     dev = hp.device
     up = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a, dtype=dt)).to(dev)  # noqa: E731
     if len(raw) == 0:
@@ -118,12 +132,21 @@ def main(args: Optional[List[str]] = None) -> int:
         owner = torch.repeat_interleave(torch.arange(sel.shape[0], device=dev), cnt)
         src = indptr_d[:-1][sel_d][owner] + (torch.arange(int(sub_indptr[-1]), device=dev) - sub_indptr[:-1][owner])
         rt = up(raw.retention_time[sel], np.float32) if config.rt_tol is not None else None
-        labels, n_clusters = hp.run(mz_d[src], in_d[src], sub_indptr, pmz_d[sel_d], z_d[sel_d], rt,
-                                    max_peaks=int(cnt.max().item()))
-        labels_h = labels.cpu().numpy().astype(np.int64)
+        if world > 1:
+            from . import distributed as fdist
+
+            part = synth.SpectrumSet(mz_d[src].cpu().numpy(), in_d[src].cpu().numpy(), sub_indptr.cpu().numpy(),
+                                     raw.precursor_mz[sel], raw.precursor_charge[sel], raw.retention_time[sel])
+            labels_np, n_clusters, reps_np = fdist.cluster_sharded(part, settings, device=dev)
+            labels_h = labels_np.astype(np.int64)
+        else:
+            labels, n_clusters = hp.run(mz_d[src], in_d[src], sub_indptr, pmz_d[sel_d], z_d[sel_d], rt,
+                                        max_peaks=int(cnt.max().item()))
+            labels_h = labels.cpu().numpy().astype(np.int64)
+            reps_np = hp.representatives.cpu().numpy() if config.export_representatives and n_clusters > 0 else None
         labels_h[labels_h >= 0] += current_label  # disjoint labels across charges, noise stays -1
         if config.export_representatives and n_clusters > 0:
-            for r in hp.representatives.cpu().numpy():
+            for r in reps_np:
                 i = int(sel[r])
                 a, b = int(raw.indptr[i]), int(raw.indptr[i + 1])
                 representatives.append({
@@ -143,6 +166,8 @@ def main(args: Optional[List[str]] = None) -> int:
     if not rows["cluster"]:
         logger.error("No valid spectra found for clustering")
         return 1
+    if rank != 0:  # rank 0 exports
+        return 0
     if config.singletons_as_clusters:  # development-head convention: noise -> new singleton cluster ids
         lab = np.asarray(rows["cluster"], np.int64)
         noise = np.flatnonzero(lab < 0)

@@ -162,3 +162,52 @@ def test_relabel_gathered_single_process():
     order = torch.tensor([2, 0, 1], dtype=torch.int32, device=dev)
     check(lib.flc_scatter_labels_peers(ptr(lab), ptr(order), 3, None, 5, own, 1, 1, None))
     assert buf.cpu().tolist() == [-7, 3, 5, 0, 0, -1, 2, 4, -7, -7, -7, -7]
+
+
+def _cli_worker(rank, world, port, argv, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    from falcon_b200 import falcon as fmain
+
+    rc = fmain.main(list(argv))
+    q.put((rank, rc))
+    import torch.distributed as dist
+
+    if dist.is_initialized():
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs (gpurun --gpus 2)")
+def test_falcon_command_on_two_gpus_equals_one_gpu(tmp_path):
+    """The `falcon` command under a 2-rank launch (what torchrun sets up): every charge clustered by both GPUs
+    through cluster_sharded, rank 0 writes.  Same partition, same number of representatives as the 1-GPU run."""
+    import pandas as pd
+    import torch.multiprocessing as mp
+
+    from falcon_b200 import falcon as fmain
+    from falcon_b200.ms_io import mgf_io
+
+    sp = synth.generate(6000, 19, mass_range=(1000.0, 1010.0))
+    path = str(tmp_path / "in.mgf")
+    mgf_io.write_spectra(path, sp.as_dicts())
+    one, two = str(tmp_path / "one"), str(tmp_path / "two")
+    assert fmain.main([path, one, "--exhaustive", "--export_representatives"]) == 0
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_cli_worker, args=(r, 2, port, [path, two, "--exhaustive", "--export_representatives"], q))
+             for r in range(2)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=600) for _ in procs)
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert res == {0: 0, 1: 0}
+    a = pd.read_csv(one + ".csv", comment="#")
+    b = pd.read_csv(two + ".csv", comment="#")
+    assert a["spectrum_id"].tolist() == b["spectrum_id"].tolist()
+    assert fd.same_partition(a["cluster"].to_numpy(), b["cluster"].to_numpy())
+    ra, rb = list(mgf_io.get_spectra(one + ".mgf")), list(mgf_io.get_spectra(two + ".mgf"))
+    assert len(ra) == len(rb) == a["cluster"][a["cluster"] >= 0].nunique()
+    assert sorted(r["identifier"] for r in ra) == sorted(r["identifier"] for r in rb)
