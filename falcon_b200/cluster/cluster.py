@@ -119,13 +119,27 @@ def compute_pairwise_distances(
     v = hp.vectorize(up(spectra.mz, np.float32), up(spectra.intensity, np.float32),
                      up(spectra.indptr, np.int64), buckets.order)
     ivf = None if exhaustive else hp.build_ivf(v, buckets)
-    g = hp.knn_graph(v, buckets, ivf)
     order = buckets.order.cpu().numpy()
     idx_dtype = np.int32 if n * n_neighbors < 2 ** 31 else np.int64
     mat = ss.csr_matrix((n, n), dtype=np.float32)
-    mat.data = g.dist.cpu().numpy()
-    mat.indices = g.indices.cpu().numpy().astype(idx_dtype, copy=False)
-    mat.indptr = g.indptr.cpu().numpy().astype(idx_dtype, copy=False)
+    if eps is not None:
+        g = hp.knn_graph(v, buckets, ivf)
+        mat.data = g.dist.cpu().numpy()
+        mat.indices = g.indices.cpu().numpy().astype(idx_dtype, copy=False)
+        mat.indptr = g.indptr.cpu().numpy().astype(idx_dtype, copy=False)
+    else:
+        # the full matrix: every bucket yields rows^2 candidate pairs, so it is built range by range
+        data, indices, counts = [], [], []
+        for r0, r1, g in hp.uncut_graph_ranges(v, buckets, ivf):
+            ptr_ = g.indptr[r0: r1 + 1].cpu().numpy()
+            data.append(g.dist[int(ptr_[0]): int(ptr_[-1])].cpu().numpy())
+            indices.append(g.indices[int(ptr_[0]): int(ptr_[-1])].cpu().numpy())
+            counts.append(np.diff(ptr_))
+        indptr = np.zeros(n + 1, np.int64)
+        np.cumsum(np.concatenate(counts), out=indptr[1:])
+        mat.data = np.concatenate(data)
+        mat.indices = np.concatenate(indices).astype(idx_dtype, copy=False)
+        mat.indptr = indptr.astype(idx_dtype, copy=False)
     metadata = pd.DataFrame({
         "identifier": [idents[i] for i in order],
         "precursor_charge": spectra.precursor_charge[order],

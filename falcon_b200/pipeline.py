@@ -489,38 +489,42 @@ class HotPath:
                                   n_clusters, ptr(out), ptr(ws), ws.numel(), _stream()))
         return out
 
-    def representatives_exact(self, v: Vectors, buckets: Buckets, ivf: Optional[IvfIndex], labels: torch.Tensor,
-                              n_clusters: int, max_pairs: int = 1 << 27) -> torch.Tensor:
-        """Medoid row of every cluster by the published rule (SURVEY A.5): mean distance to the cluster
-        members present in the row of the FULL ``n_neighbors`` matrix -- members beyond ``eps`` count as
-        well, so the eps-cut matrix the clustering uses is not enough.  The uncut matrix is built for a
-        range of buckets at a time (a bucket of b rows yields b * b candidate pairs; ``max_pairs`` bounds a
-        range), its medoids taken, and dropped again.  ``labels``: final labels in row order, numbered in
-        bucket order (what ``split`` returns)."""
-        out = torch.full((max(n_clusters, 1),), -1, dtype=torch.int32, device=self.device)[:n_clusters]
-        if n_clusters == 0:
-            return out
+    def uncut_graph_ranges(self, v: Vectors, buckets: Buckets, ivf: Optional[IvfIndex], max_pairs: int = 1 << 27):
+        """The FULL ``n_neighbors`` matrix (no eps cut) one range of buckets at a time: a bucket of b rows yields
+        b * b candidate pairs, ``max_pairs`` bounds a range (at least one bucket).  Yields ``(r0, r1, graph)``:
+        ``graph`` has n rows, of which rows ``r0 .. r1`` (the range's buckets) are populated."""
         bptr = buckets.bucket_ptr.cpu().numpy()
         sizes = np.diff(bptr).astype(np.float64)
-        n = labels.shape[0]
         b0 = 0
         while b0 < sizes.shape[0]:
             b1, acc = b0, 0.0
             while b1 < sizes.shape[0] and (b1 == b0 or acc + sizes[b1] ** 2 <= max_pairs):
                 acc += sizes[b1] ** 2
                 b1 += 1
-            r0, r1 = int(bptr[b0]), int(bptr[b1])
+            sub = dataclasses.replace(buckets, bucket_ptr=buckets.bucket_ptr[b0: b1 + 1], n_buckets=b1 - b0)
+            sub_ivf = None if ivf is None else dataclasses.replace(ivf, nlist=ivf.nlist[b0:], nprobe=ivf.nprobe[b0:],
+                                                                    centroid_ptr=ivf.centroid_ptr[b0:])
+            g = self.knn_graph(v, sub, sub_ivf, pair_capacity=int(acc) + 1024, eps_cut=False)
+            yield int(bptr[b0]), int(bptr[b1]), g
+            del g
+            b0 = b1
+
+    def representatives_exact(self, v: Vectors, buckets: Buckets, ivf: Optional[IvfIndex], labels: torch.Tensor,
+                              n_clusters: int, max_pairs: int = 1 << 27) -> torch.Tensor:
+        """Medoid row of every cluster by the published rule (SURVEY A.5): mean distance to the cluster
+        members present in the row of the FULL ``n_neighbors`` matrix -- members beyond ``eps`` count as
+        well, so the eps-cut matrix the clustering uses is not enough.  The uncut matrix is built for a
+        range of buckets at a time (``uncut_graph_ranges``), its medoids taken, and dropped again.
+        ``labels``: final labels in row order, numbered in bucket order (what ``split`` returns)."""
+        out = torch.full((max(n_clusters, 1),), -1, dtype=torch.int32, device=self.device)[:n_clusters]
+        if n_clusters == 0:
+            return out
+        for r0, r1, g in self.uncut_graph_ranges(v, buckets, ivf, max_pairs):
             lab = labels[r0:r1]
             lab = lab[lab >= 0]
             if lab.numel():
                 lo, hi = int(lab.min().item()), int(lab.max().item())
-                sub = dataclasses.replace(buckets, bucket_ptr=buckets.bucket_ptr[b0: b1 + 1], n_buckets=b1 - b0)
-                sub_ivf = None if ivf is None else dataclasses.replace(ivf, nlist=ivf.nlist[b0:], nprobe=ivf.nprobe[b0:],
-                                                                        centroid_ptr=ivf.centroid_ptr[b0:])
-                g = self.knn_graph(v, sub, sub_ivf, pair_capacity=int(acc) + 1024, eps_cut=False)
                 out[lo: hi + 1] = self.medoids(g, labels, n_clusters)[lo: hi + 1]
-                del g
-            b0 = b1
         return out
 
     # ------------------------------------------------------------------ whole path

@@ -177,6 +177,17 @@ def test_facade_compute_pairwise_distances_and_generate_clusters(tmp_path):
     assert np.array_equal(meta["precursor_mz"].values, o["sorted"].precursor_mz)
     labels = cluster.generate_clusters(mat, 0.1, meta["precursor_mz"].values, None, 20.0, "ppm", None)
     assert odb.same_partition(labels, o["labels"])
+    # eps=None: the full n_neighbors matrix like the reference's (built bucket range by bucket range), with
+    # get_cluster_representatives on it
+    full, _ = cluster.compute_pairwise_distances(len(sp), files, None, vectorize, 20.0, "ppm", None, 64, 128,
+                                                 2 ** 16, 32, eps=None, exhaustive=True)
+    assert np.array_equal(full.indptr, o["csr"].indptr) and np.array_equal(full.indices, o["csr"].indices)
+    np.testing.assert_allclose(full.data, o["csr"].data, rtol=0, atol=1e-5)
+    assert full.nnz > 2 * mat.nnz  # beyond-eps neighbours inside the precursor tolerance are there as well
+    from oracle import medoids as omed
+
+    reps = cluster.get_cluster_representatives(labels, full.indptr, full.indices, full.data)
+    assert np.array_equal(reps, omed.cluster_medoids(o["csr"].data, o["csr"].indices, o["csr"].indptr, labels))
     # the oracle's own full matrix through the GPU generate_clusters
     labels2 = cluster.generate_clusters(o["csr"], 0.1, o["sorted"].precursor_mz, None, 20.0, "ppm")
     assert odb.same_partition(labels2, o["labels"])
