@@ -103,7 +103,8 @@ FLC_API int flc_vectorize(const float* mz, const float* intensity, const int64_t
  *   key_sorted [n] uint32  charge << 24 | interval, in sorted order
  *   mz_sorted  [n] float64 precursor m/z in sorted order
  *   bucket_ptr [n + 1] int64, first *n_buckets + 1 entries valid
- * Synchronises the stream (returns *n_buckets on the host). */
+ * With a host pointer for n_buckets the stream is synchronised and the count returned; with NULL nothing is
+ * read back and the count is left in *n_buckets_dev (see DESIGN.md section 5 for how callers use that). */
 FLC_API size_t flc_bucket_sort_workspace_bytes(int64_t n);
 FLC_API int flc_bucket_sort(const double* precursor_mz, const int32_t* charge, int64_t n,
                     int32_t mz_interval,
@@ -153,7 +154,7 @@ FLC_API int flc_relabel_gathered(const void* const* slots, int world, int64_t ma
  * FLC_KMEANS_NO_TC, FLC_KMEANS_TC_DENSE, FLC_KMEANS_SIMT_SMALL, FLC_KMEANS_TIMING. */
 /*  nlist[b], nprobe[b] (int32) and centroid_ptr[b] (int64 exclusive scan of nlist)
  *  for every bucket; exhaustive != 0 lifts the nprobe cap (nprobe = nlist).
- *  Synchronises the stream; returns the total number of centroids on the host. */
+ *  Synchronises the stream and returns the totals on the host -- unless the host pointers are NULL (below). */
 FLC_API int flc_ivf_plan(const int64_t* bucket_ptr, int64_t n_buckets, int32_t n_probe,
                  int exhaustive, int32_t* nlist, int32_t* nprobe,
                  int64_t* centroid_ptr /*[n_buckets+3]: scan, total, max nprobe, max IVF bucket*/,
@@ -224,7 +225,7 @@ FLC_API int flc_scan_pairs(const uint16_t* x_bf16, int64_t ld_bf16, int64_t n, u
  * keep n_neighbors_ann, precursor (Da: |d| < tol; ppm: |d| / mz_cand * 1e6 < tol)
  * and RT (|d| < rt_tol, rt == NULL or rt_tol < 0: off) filter in that order,
  * keep n_neighbors, write CSR (float32 dist, int32 column, int64 indptr).
- * Synchronises the stream; returns nnz on the host. */
+ * Synchronises the stream and returns nnz on the host -- unless nnz is NULL (below). */
 FLC_API size_t flc_knn_csr_workspace_bytes(int64_t n, uint64_t n_pairs);
 FLC_API int flc_knn_csr(const uint64_t* pairs, const uint64_t* pair_count, uint64_t pair_capacity,
                 const float* x, int64_t ld /*dense rows, nullable if ELL given*/,
@@ -244,8 +245,8 @@ FLC_API int flc_knn_csr(const uint64_t* pairs, const uint64_t* pair_count, uint6
  * A.4 + sklearn dbscan_inner semantics (sklearn/cluster/_dbscan_inner.pyx:11-41):
  * neighbourhood = row entries with dist <= eps, core = |neighbourhood| >= min_samples,
  * label = rank of the minimum-index core point the point is reachable from
- * along edges leaving core points; -1 = noise.  Synchronises the stream;
- * returns the number of clusters on the host. */
+ * along edges leaving core points; -1 = noise.  Returns the number of clusters on the host
+ * (synchronises) and / or on the device. */
 FLC_API size_t flc_dbscan_workspace_bytes(int64_t n);
 FLC_API int flc_dbscan(const float* dist, const int32_t* indices, const int64_t* indptr, int64_t n,
                float eps, int32_t min_samples, int32_t* labels,
