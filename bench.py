@@ -25,7 +25,6 @@ import os
 import subprocess
 import sys
 import tempfile
-import threading
 import time
 
 import numpy as np
@@ -744,9 +743,6 @@ def north_star_record(args, torch, fdist, pipeline, synth, _lib, dev, world, ran
                              "count must not depend on the GPU count (same data set, whole buckets per rank)"},
             "kernels_ms_per_step_rank0": {k: v[0] / steps for k, v in kernels.items()},
         }
-        if world > 1:
-            out["scan"]["executed_tflops_rank0"] = (2.0 * settings.low_dim * computed / (scan_ms * 1e-3) / 1e12
-                                                     if scan_ms > 0 else None)
     return out
 
 

@@ -18,7 +18,6 @@ import scipy.sparse as ss
 import torch
 
 from .. import pipeline, synth
-from . import spectrum as _spectrum
 
 logger = logging.getLogger("falcon")
 
