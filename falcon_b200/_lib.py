@@ -81,7 +81,7 @@ SIGNATURES = {
                                  _p, _u64, _p, _p, _sz, _p]),
     "flc_knn_csr_workspace_bytes": (_sz, [_i64, _u64]),
     "flc_knn_csr": (C.c_int, [_p, _p, _u64, _p, _i64, _p, _p, _i32, _i64, _u32, _p, _p, _p, _p, _i32,
-                              _f64, C.c_int, _f64, _i32, _i32, _f32, _p, _p, _u64, _p,
+                              _f64, C.c_int, _f64, _i32, _i32, _f32, _p, _p, _p, _u64, _p,
                               C.POINTER(_i64), _p, _sz, _p]),
     "flc_dbscan_workspace_bytes": (_sz, [_i64]),
     "flc_dbscan": (C.c_int, [_p, _p, _p, _i64, _f32, _i32, _p, C.POINTER(_i64), _p, _i32, C.POINTER(_i32), _p,

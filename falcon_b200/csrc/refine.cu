@@ -37,25 +37,28 @@ __device__ __forceinline__ int qo_at(const int (&qo)[kWarpQueries + 1], int r) {
   return v;
 }
 
+// query_mask (nullable): queries with a zero byte keep no pairs -- their rows of the matrix stay empty
 __global__ void pair_hist_kernel(const uint64_t* __restrict__ pairs, const uint64_t* __restrict__ pair_count,
-                                 uint64_t capacity, int64_t n, uint32_t* __restrict__ cnt) {
+                                 uint64_t capacity, int64_t n, const uint8_t* __restrict__ query_mask,
+                                 uint32_t* __restrict__ cnt) {
   const uint64_t total = min(*pair_count, capacity);
   for (uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
        i += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
     const uint32_t q = static_cast<uint32_t>(pairs[i] >> 32);
-    if (q < n) atomicAdd(cnt + q, 1u);
+    if (q < n && (query_mask == nullptr || query_mask[q])) atomicAdd(cnt + q, 1u);
   }
 }
 
 __global__ void pair_scatter_kernel(const uint64_t* __restrict__ pairs, const uint64_t* __restrict__ pair_count,
-                                    uint64_t capacity, int64_t n, const int64_t* __restrict__ off,
+                                    uint64_t capacity, int64_t n, const uint8_t* __restrict__ query_mask,
+                                    const int64_t* __restrict__ off,
                                     uint32_t* __restrict__ cursor, uint64_t* __restrict__ grouped) {
   const uint64_t total = min(*pair_count, capacity);
   for (uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
        i += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
     const uint64_t p = pairs[i];
     const uint32_t q = static_cast<uint32_t>(p >> 32);
-    if (q < n) {
+    if (q < n && (query_mask == nullptr || query_mask[q])) {
       const uint32_t slot = atomicAdd(cursor + q, 1u);
       grouped[off[q] + slot] = p & 0xffffffffull;
     }
@@ -544,8 +547,8 @@ int flc_knn_csr(const uint64_t* pairs, const uint64_t* pair_count, uint64_t pair
                 int32_t ell_width, int64_t n, uint32_t low_dim,
                 const double* precursor_mz, const float* rt, const int32_t* list_id,
                 const int32_t* probes, int32_t max_nprobe, double tol, int tol_mode, double rt_tol,
-                int32_t n_neighbors, int32_t n_neighbors_ann, float eps_cut, float* dist,
-                int32_t* indices, uint64_t nnz_capacity, int64_t* indptr, int64_t* nnz,
+                int32_t n_neighbors, int32_t n_neighbors_ann, float eps_cut, const uint8_t* query_mask,
+                float* dist, int32_t* indices, uint64_t nnz_capacity, int64_t* indptr, int64_t* nnz,
                 void* workspace, size_t workspace_bytes, flc_stream_t stream_) {
   using namespace flc;
   FLC_REQUIRE(n >= 0 && n < (int64_t(1) << 31), "n out of range");
@@ -577,12 +580,12 @@ int flc_knn_csr(const uint64_t* pairs, const uint64_t* pair_count, uint64_t pair
   FLC_CUDA(cudaMemsetAsync(L.row_count, 0, sizeof(int32_t) * (n + 1), stream));
   const unsigned pair_blocks =
       static_cast<unsigned>(std::min<uint64_t>((total + 255) / 256 + 1, uint64_t(kNumSMs) * 32));
-  timed("pair_hist", stream, [&] { pair_hist_kernel<<<pair_blocks, 256, 0, stream>>>(pairs, pair_count, pair_capacity, n, L.cnt); });
+  timed("pair_hist", stream, [&] { pair_hist_kernel<<<pair_blocks, 256, 0, stream>>>(pairs, pair_count, pair_capacity, n, query_mask, L.cnt); });
   FLC_LAUNCH_CHECK();
   size_t tmp = L.cub_bytes;
   FLC_CUDA(cub::DeviceScan::ExclusiveSum(L.cub_tmp, tmp, L.cnt, L.off, static_cast<int>(n + 1), stream));
   count_launch(2);
-  timed("pair_scatter", stream, [&] { pair_scatter_kernel<<<pair_blocks, 256, 0, stream>>>(pairs, pair_count, pair_capacity, n, L.off,
+  timed("pair_scatter", stream, [&] { pair_scatter_kernel<<<pair_blocks, 256, 0, stream>>>(pairs, pair_count, pair_capacity, n, query_mask, L.off,
                                                        L.cursor, L.grouped); });
   FLC_LAUNCH_CHECK();
 

@@ -374,7 +374,7 @@ class HotPath:
 
     def knn_graph(self, v: Vectors, buckets: Buckets,
                   ivf: Optional[IvfIndex] = None, pair_capacity: Optional[int] = None, sync: bool = True,
-                  eps_cut: Optional[bool] = None) -> KnnGraph:
+                  eps_cut: Optional[bool] = None, query_mask: Optional[torch.Tensor] = None) -> KnnGraph:
         """Sparse k-NN matrix.  ``sync=False``: nothing is read back -- ``dist`` / ``indices`` keep their
         capacity, ``nnz`` is -1 (it is ``indptr[n]``), and the caller must compare ``pair_count`` with
         ``pair_capacity`` when it next synchronises (a scan that overflowed its buffer produced an
@@ -421,7 +421,7 @@ class HotPath:
                                           s.precursor_tol_mass, _lib.TOL_MODES[s.precursor_tol_mode],
                                           -1.0 if s.rt_tol is None else float(s.rt_tol),
                                           s.n_neighbors, s.n_neighbors_ann,
-                                          float(np.float32(s.eps)) if cut else float("nan"),
+                                          float(np.float32(s.eps)) if cut else float("nan"), ptr(query_mask),
                                           ptr(dist), ptr(indices), nnz_cap, ptr(indptr),
                                           C.byref(nnz) if sync else None, ptr(ws2), ws2.numel(), _stream()))
                 if not sync:
@@ -489,10 +489,12 @@ class HotPath:
                                   n_clusters, ptr(out), ptr(ws), ws.numel(), _stream()))
         return out
 
-    def uncut_graph_ranges(self, v: Vectors, buckets: Buckets, ivf: Optional[IvfIndex], max_pairs: int = 1 << 27):
+    def uncut_graph_ranges(self, v: Vectors, buckets: Buckets, ivf: Optional[IvfIndex], max_pairs: int = 1 << 27,
+                           query_mask: Optional[torch.Tensor] = None):
         """The FULL ``n_neighbors`` matrix (no eps cut) one range of buckets at a time: a bucket of b rows yields
         b * b candidate pairs, ``max_pairs`` bounds a range (at least one bucket).  Yields ``(r0, r1, graph)``:
-        ``graph`` has n rows, of which rows ``r0 .. r1`` (the range's buckets) are populated."""
+        ``graph`` has n rows, of which rows ``r0 .. r1`` (the range's buckets) are populated -- only those with a
+        non-zero byte in ``query_mask`` (uint8 [n]) when one is given."""
         bptr = buckets.bucket_ptr.cpu().numpy()
         sizes = np.diff(bptr).astype(np.float64)
         b0 = 0
@@ -504,7 +506,7 @@ class HotPath:
             sub = dataclasses.replace(buckets, bucket_ptr=buckets.bucket_ptr[b0: b1 + 1], n_buckets=b1 - b0)
             sub_ivf = None if ivf is None else dataclasses.replace(ivf, nlist=ivf.nlist[b0:], nprobe=ivf.nprobe[b0:],
                                                                     centroid_ptr=ivf.centroid_ptr[b0:])
-            g = self.knn_graph(v, sub, sub_ivf, pair_capacity=int(acc) + 1024, eps_cut=False)
+            g = self.knn_graph(v, sub, sub_ivf, pair_capacity=int(acc) + 1024, eps_cut=False, query_mask=query_mask)
             yield int(bptr[b0]), int(bptr[b1]), g
             del g
             b0 = b1
@@ -519,7 +521,13 @@ class HotPath:
         out = torch.full((max(n_clusters, 1),), -1, dtype=torch.int32, device=self.device)[:n_clusters]
         if n_clusters == 0:
             return out
-        for r0, r1, g in self.uncut_graph_ranges(v, buckets, ivf, max_pairs):
+        # clusters of one or two members take their first member whatever the matrix says: only the rows of
+        # larger clusters need their uncut neighbour lists
+        member = labels >= 0
+        size = torch.bincount(labels[member].long(), minlength=n_clusters)
+        need = torch.zeros(labels.shape[0], dtype=torch.uint8, device=self.device)
+        need[member] = (size[labels[member].long()] > 2).to(torch.uint8)
+        for r0, r1, g in self.uncut_graph_ranges(v, buckets, ivf, max_pairs, query_mask=need):
             lab = labels[r0:r1]
             lab = lab[lab >= 0]
             if lab.numel():

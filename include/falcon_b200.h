@@ -235,6 +235,8 @@ FLC_API int flc_knn_csr(const uint64_t* pairs, const uint64_t* pair_count, uint6
                 const int32_t* list_id, const int32_t* probes, int32_t max_nprobe,
                 double tol, int tol_mode, double rt_tol,
                 int32_t n_neighbors, int32_t n_neighbors_ann, float eps_cut,
+                const uint8_t* query_mask /*nullable [n]: rows with a zero byte are left empty (their pairs are
+                                            dropped before the re-score) -- callers that need only some rows*/,
                 float* dist, int32_t* indices, uint64_t nnz_capacity, int64_t* indptr /*[n+1]*/,
                 int64_t* nnz /*host; NULL = do not synchronise: nnz stays in indptr[n], the caller checks
                                *pair_count <= pair_capacity itself, and nnz_capacity must be at least
