@@ -248,15 +248,63 @@ __device__ void split_group_one(int64_t g, int64_t n_groups, const int64_t* __re
   for (int32_t j = lane; j < r; j += 32) runhead[s + __ldcg(cur + j)] = 1;
 }
 
-// Warps stride over the groups (their number is only known on the device).
+// Four groups of at most eight members side by side in one warp (eight lanes each): the register
+// algorithm of split_group_one at width 8.  Most DBSCAN clusters are this small.
+__device__ __forceinline__ void split_groups_quad(int64_t s, int32_t m, bool active, const double* __restrict__ vs,
+                                                  double tol, int tol_mode, uint8_t* __restrict__ runhead) {
+  const int lane = threadIdx.x & 31;
+  const int sl = lane & 7, base = lane & ~7;
+  const double val = (active && sl < m) ? vs[s + sl] : 0.0;
+  uint32_t heads = active ? ((1u << m) - 1u) : 0u;
+  while (true) {
+    const bool is_b = active && sl >= 1 && sl < m && ((heads >> sl) & 1u);
+    const uint32_t lower = heads & ((1u << sl) - 1u);
+    const int ps = lower ? 31 - __clz(lower) : 0;
+    const uint32_t above = heads >> (sl + 1);
+    const int ne = above ? min(sl + __ffs(above), m) : m;
+    const double d = split_distance(__shfl_sync(0xffffffffu, val, base + ps),
+                                    __shfl_sync(0xffffffffu, val, base + max(ne - 1, 0)), tol_mode);
+    const double dl = __shfl_sync(0xffffffffu, d, base + ps);
+    const double dr = __shfl_sync(0xffffffffu, d, base + (ne < m ? ne : 0));
+    bool merge = is_b && d <= tol;
+    if (merge && ps >= 1 && !(d < dl)) merge = false;
+    if (merge && ne < m && !(d <= dr)) merge = false;
+    const uint32_t mb = __ballot_sync(0xffffffffu, merge);
+    if (mb == 0u) break;
+    heads &= ~((mb >> base) & 0xffu);
+  }
+  if (active && sl < m && ((heads >> sl) & 1u)) runhead[s + sl] = 1;
+}
+
+// Warps stride over the groups, four at a time (their number is only known on the device).
 __global__ void __launch_bounds__(256)
 split_group_kernel(const int64_t* __restrict__ gstart, const int64_t* __restrict__ n_groups_ptr,
                    const uint32_t* __restrict__ key_sorted, const double* __restrict__ vs, int64_t n, double tol,
                    int tol_mode, int32_t* list_a, int32_t* list_b, uint8_t* __restrict__ runhead) {
   const int64_t n_groups = *n_groups_ptr;
+  const int lane = threadIdx.x & 31;
   const int64_t warps_total = static_cast<int64_t>(gridDim.x) * (blockDim.x >> 5);
-  for (int64_t g = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5; g < n_groups; g += warps_total) {
-    split_group_one(g, n_groups, gstart, key_sorted, vs, n, tol, tol_mode, list_a, list_b, runhead);
+  for (int64_t g0 = ((static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5) * 4; g0 < n_groups;
+       g0 += warps_total * 4) {
+    const int64_t g = g0 + (lane >> 3);
+    int64_t s = 0;
+    int32_t m = 0;
+    bool active = false;
+    if (g < n_groups) {
+      s = gstart[g];
+      const int64_t e = (g + 1 < n_groups) ? gstart[g + 1] : n;
+      const bool noise = key_sorted[s] == kNoiseKey;
+      m = noise ? 0 : static_cast<int32_t>(min(e - s, static_cast<int64_t>(1 << 30)));
+      active = m >= 2;
+    }
+    if (__all_sync(0xffffffffu, m <= 8)) {
+      split_groups_quad(s, m, active, vs, tol, tol_mode, runhead);
+    } else {
+      for (int t = 0; t < 4; ++t) {
+        if (g0 + t < n_groups) split_group_one(g0 + t, n_groups, gstart, key_sorted, vs, n, tol, tol_mode, list_a, list_b, runhead);
+        __syncwarp();
+      }
+    }
     __syncwarp();
   }
 }
@@ -699,7 +747,7 @@ int flc_split_clusters(const int32_t* labels_in, const double* precursor_mz, con
   FLC_TRY(group_rows(precursor_mz, values_sorted != 0, &perm));
   const uint32_t* key_sorted = L.key_b;
   // The number of groups is only known on the device: a resident grid of warps strides over them.
-  const unsigned gblocks = static_cast<unsigned>(std::min<int64_t>((n * 32 + 255) / 256, static_cast<int64_t>(kNumSMs) * 8));
+  const unsigned gblocks = static_cast<unsigned>(std::min<int64_t>((n * 8 + 255) / 256 + 1, static_cast<int64_t>(kNumSMs) * 8));
   if (!with_rt) {
     timed("split_group", stream, [&] { split_group_kernel<<<gblocks, 256, 0, stream>>>(L.gstart, L.n_groups, key_sorted, L.vs, n, tol, tol_mode,
                                                     L.list_a, L.list_b, L.runhead); });
