@@ -9,11 +9,13 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-fil
     python bench.py --steps 2 --warmup 1 --north-star-total 0 --no-representatives --no-cpu-baseline \
     > $OUT/${TAG}_launches_bench.log 2>&1
 # step 3 of run_step.py = steady state (sizes learnt, one read-back); our kernels all end in "_kernel"
-ncu --set full --clock-control none -k regex:"_kernel" -s 104 -c 52 -o /tmp/${TAG}_default \
+# (the first step has 35 launches that match, a steady-state step 40)
+ncu --set full --clock-control none -k regex:"_kernel" -s 75 -c 40 -o /tmp/${TAG}_default \
     python tools/run_step.py --steps 3 > $OUT/${TAG}_prof_default.log 2>&1
 python tools/ncu_summary.py /tmp/${TAG}_default.ncu-rep > $OUT/${TAG}_ncu_default.jsonl
+if [ "${2:-}" != "nodense" ]; then
 ncu --set full --clock-control none -k regex:"kmeans_t|ivf_assign|scan_tc|refine_block|vectorize_kernel" -s 40 -c 45 \
     -o /tmp/${TAG}_dense python tools/run_step.py --steps 2 --mass-range 1000 1280 > $OUT/${TAG}_prof_dense.log 2>&1
 python tools/ncu_summary.py /tmp/${TAG}_dense.ncu-rep > $OUT/${TAG}_ncu_dense.jsonl
-wc -l $OUT/${TAG}_ncu_default.jsonl $OUT/${TAG}_ncu_dense.jsonl
-tail -2 $OUT/${TAG}_prof_default.log $OUT/${TAG}_prof_dense.log
+fi
+wc -l $OUT/${TAG}_ncu_*.jsonl
