@@ -138,3 +138,30 @@ def test_same_partition():
     assert not fd.same_partition([0, 0, 1, -1, 2], [5, 4, 3, -1, 9])
     assert not fd.same_partition([0, 0, 1, -1, 2], [5, 5, 3, 1, 9])
     assert fd.same_partition([-1, -1], [-1, -1]) and not fd.same_partition([0], [0, 0])
+
+
+def test_bucket_aligned_chunks_hold_whole_buckets():
+    """`synth.generate_chunks` (the 10 M / 30 M data sets of bench.py and tools/sweep_30m.py): no precursor bucket
+    (charge, interval of the published rule) has spectra in two chunks, whatever subset of chunks a rank takes,
+    and the union does not depend on how the chunks are dealt out."""
+    from falcon_b200 import synth
+    from oracle import ivf as oivf
+
+    total, n_chunks = 48000, 16
+    whole = synth.generate_chunks(total, n_chunks, range(n_chunks))
+    assert len(whole) == total
+    per = total // n_chunks
+    keys = oivf.bucket_ids(whole.precursor_mz, whole.precursor_charge)
+    owner = {}
+    for c in range(n_chunks):
+        sl = slice(c * per, (c + 1) * per)
+        for k in set(zip(whole.precursor_charge[sl].tolist(), keys[sl].tolist())):
+            assert owner.setdefault(k, c) == c, f"bucket {k} in chunks {owner[k]} and {c}"
+    # two ranks' shares concatenate to the same data set
+    a = synth.generate_chunks(total, n_chunks, range(0, 8))
+    b = synth.generate_chunks(total, n_chunks, range(8, 16))
+    both = synth.concat([a, b])
+    assert np.array_equal(both.mz, whole.mz) and np.array_equal(both.precursor_mz, whole.precursor_mz)
+    # chunk edges sit between bucket keys, 0.03 Da away from them
+    for lo, hi in synth.chunk_mass_ranges(n_chunks):
+        assert abs(((lo - 0.03) / synth.BUCKET_WIDTH) % 1.0 - 0.5) < 1e-9 and hi > lo
