@@ -130,6 +130,49 @@ def split_sorted_1d(sorted_values: np.ndarray, tol: float, mode=None) -> np.ndar
     return np.cumsum(gid) - 1
 
 
+def fcluster_ids_by_range_additions(sorted_values: np.ndarray, tol: float, mode=None) -> np.ndarray:
+    """0-based ids scipy's ``fcluster(linkage_1d(v), tol, 'distance')`` gives the elements of an ascending 1-D
+    array, computed the way the CUDA kernel does (``csrc/dbscan.cu:linkage_ids_one``) instead of by walking the
+    dendrogram: ``fcluster`` numbers flat clusters in a depth-first walk from the root -- left subtree, right
+    subtree, then the children that are single observations, left before right; a subtree at or below the cut
+    gets one id when it is entered (scipy/cluster/_hierarchy.pyx:cluster_monocrit).  Merging nodes A (left) and B
+    (right) above the cut therefore shifts the ids of A's flat clusters by off(A) and B's by off(B):
+        A, B both single observations: 0, 1     A single only: |B|, 0
+        B single only: 0, |A|                   neither: 0, |A|
+    (|X| = flat clusters in X), and a flat cluster's id is the sum of the shifts on its path to the root: a
+    difference array over the flat clusters (contiguous in sorted order) and one prefix sum.  Checked against
+    scipy in tests/test_oracle_golden.py; the kernel is checked against the reference's goldens."""
+    v = np.asarray(sorted_values, np.float64)
+    m = v.shape[0]
+    if m < 2:
+        return np.zeros(m, np.int64)
+    flat = split_sorted_1d(v, tol, mode)  # flat cluster of every element (ids in sorted order)
+    r0 = int(flat[-1]) + 1
+    starts = [int(np.searchsorted(flat, k, "left")) for k in range(r0)]  # element offset of every node
+    first = list(range(r0))                                               # first flat cluster of every node
+    delta = np.zeros(r0 + 1, np.int64)
+    while len(starts) > 1:
+        best, bi = np.inf, -1
+        for i in range(len(starts) - 1):
+            end = starts[i + 2] if i + 2 < len(starts) else m
+            d = _tolerance_distance(v[starts[i]], v[end - 1], mode)
+            if d < best:
+                best, bi = d, i
+        sa, sb = starts[bi], starts[bi + 1]
+        eb = starts[bi + 2] if bi + 2 < len(starts) else m
+        fa, fb = first[bi], first[bi + 1]
+        fe = first[bi + 2] if bi + 2 < len(first) else r0
+        ca, cb = fb - fa, fe - fb
+        single_a, single_b = sb - sa == 1, eb - sb == 1
+        off_a = (0 if single_b else cb) if single_a else 0
+        off_b = (1 if single_a else ca) if single_b else (0 if single_a else ca)
+        delta[fa] += off_a
+        delta[fb] += off_b - off_a
+        delta[fe] -= off_b
+        del starts[bi + 1], first[bi + 1]
+    return np.cumsum(delta[:r0])[flat]
+
+
 def postprocess_cluster(mzs, rts, tol, mode, rt_tol, min_samples: int = MIN_SAMPLES):
     """Sub-cluster id (or -1) of every member of ONE DBSCAN cluster and the
     number of sub-clusters kept.  Restates

@@ -137,3 +137,27 @@ def test_split_equals_scipy_fcluster():
 def test_group_idx_golden(golden_dir):
     g = _cases(golden_dir)
     assert g["groups_out"].tolist() == [[0, 1], [1, 2], [2, 4], [4, 5], [5, 8]]
+
+
+def test_fcluster_numbering_as_range_additions():
+    """The id numbering the CUDA kernel reproduces for the retention-time cut (cluster.py:418-429 combines two
+    fcluster assignments through a non-injective map, so the ids themselves matter): the range-addition
+    formulation equals scipy's fcluster on the linkage the reference builds, on random 1-D data with ties."""
+    import scipy.cluster.hierarchy as sch
+
+    rng = np.random.default_rng(11)
+    for case in range(300):
+        m = int(rng.integers(2, 60))
+        mode = "ppm" if case % 3 == 0 else None
+        base = rng.uniform(300, 1500) if mode == "ppm" else rng.uniform(0, 100)
+        spread = base * 20e-6 if mode == "ppm" else 5.0
+        v = base + rng.normal(0, spread * rng.uniform(0.2, 4.0), m)
+        if case % 4 == 0:
+            v[rng.integers(0, m, m // 3)] = v[0]  # ties
+        if case % 5 == 0:
+            v = np.round(v, 3 if mode is None else 5)  # more ties
+        v = np.sort(v)
+        tol = 20.0 if mode == "ppm" else 5.0
+        want = sch.fcluster(odb.linkage_1d(v, mode), tol, "distance").astype(np.int64) - 1
+        got = odb.fcluster_ids_by_range_additions(v, tol, mode)
+        assert np.array_equal(got, want), (case, v.tolist())
