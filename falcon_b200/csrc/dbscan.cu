@@ -86,8 +86,6 @@ __global__ void dbscan_propagate_kernel(const float* __restrict__ dist, const in
   if (any) *changed = 1;
 }
 
-__global__ void copy_count_kernel(const int32_t* __restrict__ src, int64_t* __restrict__ dst) { *dst = *src; }
-
 __global__ void dbscan_seed_kernel(const int32_t* __restrict__ m, const uint8_t* __restrict__ core, int64_t n,
                                    int32_t* __restrict__ seed) {
   const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -95,8 +93,9 @@ __global__ void dbscan_seed_kernel(const int32_t* __restrict__ m, const uint8_t*
 }
 
 __global__ void dbscan_label_kernel(const int32_t* __restrict__ m, const int32_t* __restrict__ rank, int64_t n,
-                                    int32_t* __restrict__ labels) {
+                                    int32_t* __restrict__ labels, int64_t* __restrict__ n_clusters_dev) {
   const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i == n && n_clusters_dev != nullptr) *n_clusters_dev = rank[n];  // the grid covers n + 1 threads
   if (i < n) {
     const int32_t r = m[i];
     labels[i] = r == kInf ? -1 : rank[r];
@@ -329,17 +328,17 @@ __global__ void split_keep_kernel(const int64_t* __restrict__ rstart, const int6
 
 __global__ void split_label_kernel(const int32_t* __restrict__ run_id_incl, const int32_t* __restrict__ kept,
                                    const int32_t* __restrict__ new_id, const int32_t* __restrict__ perm,
-                                   int64_t n, int32_t* __restrict__ labels_out) {
+                                   int64_t n, int32_t* __restrict__ labels_out, int64_t* __restrict__ n_clusters_dev) {
   const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i == 0 && n_clusters_dev != nullptr) *n_clusters_dev = new_id[n];
   if (i >= n) return;
   const int32_t r = run_id_incl[i] - 1;
   labels_out[perm[i]] = kept[r] ? new_id[r] : -1;
 }
 
-__global__ void u8_to_i32_kernel(const uint8_t* __restrict__ in, int64_t n, int32_t* __restrict__ out) {
-  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i < n) out[i] = in[i];
-}
+struct U8ToI32 {
+  __host__ __device__ __forceinline__ int32_t operator()(uint8_t v) const { return static_cast<int32_t>(v); }
+};
 
 
 // ---------------------------------------------------------------- RT cut (cluster.py:418-429)
@@ -577,7 +576,8 @@ static void split_layout(Workspace& ws, int64_t n, bool with_rt, SplitLayout& L)
                                   (int32_t*)nullptr, num);
   cub::DeviceSelect::Flagged(nullptr, b3, cub::CountingInputIterator<int64_t>(0), (uint8_t*)nullptr,
                              (int64_t*)nullptr, (int64_t*)nullptr, num);
-  cub::DeviceScan::InclusiveSum(nullptr, b4, (int32_t*)nullptr, (int32_t*)nullptr, num);
+  cub::DeviceScan::InclusiveSum(nullptr, b4, cub::TransformInputIterator<int32_t, U8ToI32, const uint8_t*>(nullptr, U8ToI32()),
+                                (int32_t*)nullptr, num);
   cub::DeviceScan::ExclusiveSum(nullptr, b5, (int32_t*)nullptr, (int32_t*)nullptr, num + 1);
   size_t b = b1;
   if (b2 > b) b = b2;
@@ -656,12 +656,8 @@ int flc_dbscan(const float* dist, const int32_t* indices, const int64_t* indptr,
   size_t tmp = L.cub_bytes;
   FLC_CUDA(cub::DeviceScan::ExclusiveSum(L.cub_tmp, tmp, L.seed, L.rank, static_cast<int>(n + 1), stream));
   count_launch(2);
-  timed("dbscan_label", stream, [&] { dbscan_label_kernel<<<tblocks, 256, 0, stream>>>(L.m, L.rank, n, labels); });
+  timed("dbscan_label", stream, [&] { dbscan_label_kernel<<<tblocks, 256, 0, stream>>>(L.m, L.rank, n, labels, n_clusters_dev); });
   FLC_LAUNCH_CHECK();
-  if (n_clusters_dev) {
-    copy_count_kernel<<<1, 1, 0, stream>>>(L.rank + n, n_clusters_dev);
-    FLC_LAUNCH_CHECK();
-  }
   if (n_clusters) {  // NULL: no synchronisation, the count stays on the device
     int32_t total = 0;
     FLC_CUDA(cudaMemcpyAsync(&total, L.rank + n, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
@@ -779,10 +775,9 @@ int flc_split_clusters(const int32_t* labels_in, const double* precursor_mz, con
   FLC_CUDA(cub::DeviceSelect::Flagged(L.cub_tmp, tmp, cub::CountingInputIterator<int64_t>(0), L.runhead,
                                       L.rstart, L.n_runs, num, stream));
   count_launch(2);
-  timed("u8_to_i32", stream, [&] { u8_to_i32_kernel<<<tblocks, 256, 0, stream>>>(L.runhead, n, L.run_i32); });
-  FLC_LAUNCH_CHECK();
   tmp = L.cub_bytes;
-  FLC_CUDA(cub::DeviceScan::InclusiveSum(L.cub_tmp, tmp, L.run_i32, L.run_id, num, stream));
+  FLC_CUDA(cub::DeviceScan::InclusiveSum(L.cub_tmp, tmp, cub::TransformInputIterator<int32_t, U8ToI32, const uint8_t*>(L.runhead, U8ToI32()),
+                                         L.run_id, num, stream));
   count_launch(2);
   timed("split_keep", stream, [&] { split_keep_kernel<<<static_cast<unsigned>((n + 1 + 255) / 256), 256, 0, stream>>>(L.rstart, L.n_runs,
                                                                                    key_sorted, n, min_samples,
@@ -791,12 +786,9 @@ int flc_split_clusters(const int32_t* labels_in, const double* precursor_mz, con
   tmp = L.cub_bytes;
   FLC_CUDA(cub::DeviceScan::ExclusiveSum(L.cub_tmp, tmp, L.kept, L.new_id, num + 1, stream));
   count_launch(2);
-  timed("split_label", stream, [&] { split_label_kernel<<<tblocks, 256, 0, stream>>>(L.run_id, L.kept, L.new_id, perm, n, labels_out); });
+  timed("split_label", stream, [&] { split_label_kernel<<<tblocks, 256, 0, stream>>>(L.run_id, L.kept, L.new_id, perm, n, labels_out,
+                                                  n_clusters_dev); });
   FLC_LAUNCH_CHECK();
-  if (n_clusters_dev) {
-    copy_count_kernel<<<1, 1, 0, stream>>>(L.new_id + n, n_clusters_dev);
-    FLC_LAUNCH_CHECK();
-  }
   if (n_clusters) {  // NULL: no synchronisation, the count stays on the device
     int32_t total = 0;
     FLC_CUDA(cudaMemcpyAsync(&total, L.new_id + n, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
