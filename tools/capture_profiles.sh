@@ -9,8 +9,8 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-fil
     python bench.py --steps 2 --warmup 1 --north-star-total 0 --no-representatives --no-cpu-baseline \
     > $OUT/${TAG}_launches_bench.log 2>&1
 # step 3 of run_step.py = steady state (sizes learnt, one read-back); our kernels all end in "_kernel"
-# (the first step has 35 launches that match, a steady-state step 40)
-ncu --set full --clock-control none -k regex:"_kernel" -s 75 -c 40 -o /tmp/${TAG}_default \
+# (the first step has 32 launches that match, a steady-state step 37)
+ncu --set full --clock-control none -k regex:"_kernel" -s 69 -c 37 -o /tmp/${TAG}_default \
     python tools/run_step.py --steps 3 > $OUT/${TAG}_prof_default.log 2>&1
 python tools/ncu_summary.py /tmp/${TAG}_default.ncu-rep > $OUT/${TAG}_ncu_default.jsonl
 if [ "${2:-}" != "nodense" ]; then
