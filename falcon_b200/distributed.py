@@ -309,6 +309,39 @@ def _segments(starts: torch.Tensor, counts: torch.Tensor) -> torch.Tensor:
     return starts[seg] + (torch.arange(total, device=dev) - ptr[seg])
 
 
+def assemble_bucket_rows(rows_all: torch.Tensor, ents_all: torch.Tensor, h_lo: torch.Tensor, h_hi: torch.Tensor):
+    """Sparse matrix of the buckets ``[h_lo[j], h_hi[j])`` (row ranges of the global bucket order, ascending) from
+    the sparse rows the pieces gathered: ``rows_all`` = int32 [2, R] (global row, entry count) in any order,
+    ``ents_all`` = int32 [2, E] (global column, float32 distance bits), a row's entries consecutive and rows'
+    entries in the order of ``rows_all``.  Rows outside the given buckets are ignored.  Returns
+    ``(dist float32 [nnz], cols int32 [nnz], indptr int64 [n + 1], rows int64 [n])``: the buckets concatenated,
+    rows in global order, columns renumbered to positions in that concatenation, ``rows`` = their global rows."""
+    dev = rows_all.device
+    row_g, cnt = rows_all[0].long(), rows_all[1].long()
+    ent_start = torch.cumsum(cnt, 0) - cnt
+    h_off = torch.cumsum(h_hi - h_lo, 0) - (h_hi - h_lo)  # position of a bucket in the concatenation
+    n_home = int((h_hi - h_lo).sum().item())
+
+    def to_pos(gidx):  # global row -> row of the assembled matrix (-1: not in one of the buckets)
+        j = torch.searchsorted(h_lo, gidx, right=True) - 1
+        jc = j.clamp(min=0)
+        ok = (j >= 0) & (gidx < h_hi[jc])
+        return torch.where(ok, gidx - h_lo[jc] + h_off[jc], torch.full_like(gidx, -1))
+
+    pos = to_pos(row_g)
+    sel = torch.nonzero(pos >= 0).squeeze(1)
+    sel = sel[torch.argsort(pos[sel])]
+    if sel.shape[0] != n_home or (n_home and not torch.equal(pos[sel], torch.arange(n_home, device=dev))):
+        raise RuntimeError("gathered rows of the cut buckets are incomplete")
+    cnt_s = cnt[sel]
+    indptr = torch.zeros(n_home + 1, dtype=torch.int64, device=dev)
+    torch.cumsum(cnt_s, 0, out=indptr[1:])
+    src = _segments(ent_start[sel], cnt_s)
+    cols = to_pos(ents_all[0][src].long()).to(torch.int32)
+    return (ents_all[1][src].contiguous().view(torch.float32), cols.contiguous(), indptr,
+            _segments(h_lo, h_hi - h_lo))
+
+
 def cluster_sharded(spectra, settings=None, device=None, group=None, bucket_cap=None):
     """Cluster ONE data set on all ranks of ``group``: every rank holds the same host ``spectra``
     (a ``synth.SpectrumSet``-like object), takes its share of the precursor buckets
@@ -438,31 +471,10 @@ def cluster_sharded(spectra, settings=None, device=None, group=None, bucket_cap=
         home = cut[np.arange(cut.size) % world == rank]  # buckets whose stage 4 runs here
         bp_h = b.bucket_ptr.cpu().numpy()
         if home.size:
-            row_g, cnt = rows_all[0].long(), rows_all[1].long()
-            ent_start = torch.cumsum(cnt, 0) - cnt
             h_lo, h_hi = up(bp_h[home], np.int64), up(bp_h[home + 1], np.int64)
-            h_off = torch.cumsum(h_hi - h_lo, 0) - (h_hi - h_lo)  # position of a home bucket in the concatenation
-            n_home = int((h_hi - h_lo).sum().item())
-
-            def to_pos(gidx):  # global row -> row of the assembled matrix (-1: not in a home bucket)
-                j = torch.searchsorted(h_lo, gidx, right=True) - 1
-                jc = j.clamp(min=0)
-                ok = (j >= 0) & (gidx < h_hi[jc])
-                return torch.where(ok, gidx - h_lo[jc] + h_off[jc], torch.full_like(gidx, -1))
-
-            pos = to_pos(row_g)
-            sel = torch.nonzero(pos >= 0).squeeze(1)
-            sel = sel[torch.argsort(pos[sel])]
-            if sel.shape[0] != n_home:
-                raise RuntimeError("gathered rows of the cut buckets are incomplete")
-            cnt_s = cnt[sel]
-            indptr = torch.zeros(n_home + 1, dtype=torch.int64, device=dev)
-            torch.cumsum(cnt_s, 0, out=indptr[1:])
-            src = _segments(ent_start[sel], cnt_s)
-            cols = to_pos(ents_all[0][src].long()).to(torch.int32)
-            gh = pipeline.KnnGraph(ents_all[1][src].contiguous().view(torch.float32), cols.contiguous(), indptr,
-                                   int(src.shape[0]))
-            rows_h = _segments(h_lo, h_hi - h_lo)
+            dist_h, cols_h, indptr_h, rows_h = assemble_bucket_rows(rows_all, ents_all, h_lo, h_hi)
+            n_home = int(rows_h.shape[0])
+            gh = pipeline.KnnGraph(dist_h, cols_h, indptr_h, int(dist_h.shape[0]))
 
             def home_medoids(lab, nc):
                 # uncut rows rank their candidates over the WHOLE bucket before the tolerance filter, which the

@@ -3,6 +3,7 @@ import os
 import socket
 
 import numpy as np
+import pytest
 import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
@@ -165,3 +166,30 @@ def test_bucket_aligned_chunks_hold_whole_buckets():
     # chunk edges sit between bucket keys, 0.03 Da away from them
     for lo, hi in synth.chunk_mass_ranges(n_chunks):
         assert abs(((lo - 0.03) / synth.BUCKET_WIDTH) % 1.0 - 0.5) < 1e-9 and hi > lo
+
+
+def test_assemble_bucket_rows_from_gathered_pieces():
+    """The row gather of a cut bucket (cluster_sharded): pieces arrive in rank order, not in row order; rows of
+    buckets another rank is home of are ignored; columns are renumbered to the concatenation of the home buckets."""
+    # global rows 10..15 = bucket A, 20..23 = bucket B (home here), 30..32 = bucket C (someone else's)
+    rows = {10: [(10, .0), (12, .5)], 11: [(11, .0)], 12: [(12, .0), (10, .5), (14, .25)], 13: [], 14: [(14, .0), (12, .25)],
+            20: [(20, .0), (22, .125)], 21: [(21, .0)], 22: [(22, .0), (20, .125)],
+            30: [(30, .0), (31, .75)], 31: [(31, .0)]}
+    order = [14, 20, 30, 21, 10, 11, 31, 12, 13, 22]  # as two "ranks" would send them
+    rows_all = torch.tensor([[r for r in order], [len(rows[r]) for r in order]], dtype=torch.int32)
+    cols = [c for r in order for c, _ in rows[r]]
+    dist = np.float32([d for r in order for _, d in rows[r]])
+    ents_all = torch.stack([torch.tensor(cols, dtype=torch.int32), torch.from_numpy(dist.view(np.int32))])
+    h_lo, h_hi = torch.tensor([10, 20]), torch.tensor([15, 23])
+    d, c, indptr, rg = fd.assemble_bucket_rows(rows_all, ents_all, h_lo, h_hi)
+    assert rg.tolist() == [10, 11, 12, 13, 14, 20, 21, 22]
+    assert indptr.tolist() == [0, 2, 3, 6, 6, 8, 10, 11, 13]
+    pos = {g: i for i, g in enumerate(rg.tolist())}
+    want_c = [pos[cc] for r in rg.tolist() for cc, _ in rows[r]]
+    want_d = [dd for r in rg.tolist() for _, dd in rows[r]]
+    assert c.tolist() == want_c and d.tolist() == want_d
+    # a missing row is an error, not a silently shorter matrix
+    keep = [i for i, r in enumerate(order) if r != 13]
+    sub = rows_all[:, keep]
+    with pytest.raises(RuntimeError, match="incomplete"):
+        fd.assemble_bucket_rows(sub, ents_all, h_lo, h_hi)
